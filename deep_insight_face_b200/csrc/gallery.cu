@@ -1,0 +1,952 @@
+// 1:N gallery search (new API - the reference only has the 1:1 verify of
+// deep_insight_face/predictions.py:104-150 and api.py:94-104).
+//
+// Pipeline of one dif_gallery_search call (all on `stream`, no host synchronisation):
+//   1. prep_rows_kernel       queries -> canonical planes (normalised for cosine)            [HBM-bound]
+//   2. nt_gemm_rowscan_kernel tensor-core filter: approximate scores of every (query, row) with a
+//                             per-query top-k list per gallery split kept in shared memory; the Q x N
+//                             score matrix never exists in HBM                               [tensor-bound]
+//   3. rerank_kernel          per query: window of candidates that can still be in the true top-k,
+//                             canonical fp32 scores for them, final order (score, row asc);
+//                             proves from the error bound of pass 2 that nothing outside the
+//                             candidate lists can belong to the top-k, else flags the query    [HBM-bound]
+//   4. exact_scan_kernel +    flagged queries only (normally none): canonical brute force over the
+//      exact_merge_kernel     whole shard
+// The result is therefore bit-identical to oracle/dif_oracle.c:dif_or_gallery_search in every
+// precision mode; the mode only changes how fast pass 2 runs and how often pass 4 is needed.
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "dif_canon.cuh"
+#include "nt_gemm.cuh"
+
+namespace dif {
+
+constexpr int kGalBN = 256;
+constexpr int kRerankThreads = 128;
+constexpr int kRerankCap = 256;     // candidates inside the 2*eps window before a query is flagged
+constexpr int kExactChunks = 64;    // row chunks per flagged query in the exact scan
+constexpr int kExactThreads = 256;
+
+// Error bound of the tensor-core pass relative to |q| * |g| (cosine: both are 1).
+//   3xTF32: dropped lo*lo terms + truncation of lo (2^-20) + <= 3*D/8 fp32 accumulations
+//   1xTF32: operand truncation 2 * 2^-10;   bf16: operand rounding 2 * 2^-9
+__host__ __device__ inline float mode_eps(int precision) {
+  return precision == DIF_PREC_TF32X3 ? 1.0e-4f : (precision == DIF_PREC_BF16 ? 5.0e-3f : 2.5e-3f);
+}
+
+__device__ __forceinline__ float key_score(uint64_t key) {
+  const uint32_t o = (uint32_t)(key >> 32);
+  return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: rows -> canonical planes.  One warp per row.
+//   SRC 0: rows read from `src`; SRC 1: synthetic rows (seed, row0 + r).
+//   p0/p1: fp32 planes (TF32x3: p0 = tf32(x), p1 = x - p0 exactly; otherwise p0 = x, p1 unused)
+//   pb   : bf16 plane (bf16 mode only);  sq[r] = canonical sum of squares of the STORED row
+//   gmax : running max of sq (orderable uint), may be NULL
+// ------------------------------------------------------------------------------------------
+struct PrepParams {
+  const float* src;
+  uint64_t seed;
+  int64_t row0;
+  int64_t n;
+  int D;
+  int normalize;
+  int split;  // 1: write hi/lo planes
+  float* p0;
+  float* p1;
+  __nv_bfloat16* pb;
+  float* sq;
+  unsigned int* gmax;
+};
+
+template <int SRC>
+__global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < p.n; r += warps) {
+    const float* s = SRC == 0 ? p.src + r * p.D : nullptr;
+    float acc = 0.f;
+    for (int d = lane; d < p.D; d += 32) {
+      const float x = SRC == 0 ? s[d] : synth_value(p.seed, (uint64_t)(p.row0 + r), (uint64_t)d, (uint64_t)p.D);
+      acc = __fmaf_rn(x, x, acc);
+    }
+    const float ss = canon_tree(acc);
+    const float inv = p.normalize ? canon_inv_norm(ss) : 1.0f;
+    float acc2 = 0.f;
+    for (int d = lane; d < p.D; d += 32) {
+      float x = SRC == 0 ? s[d] : synth_value(p.seed, (uint64_t)(p.row0 + r), (uint64_t)d, (uint64_t)p.D);
+      if (p.normalize) x = __fmul_rn(x, inv);
+      acc2 = __fmaf_rn(x, x, acc2);
+      if (p.split) {
+        const float hi = tf32_round(x);
+        p.p0[r * p.D + d] = hi;
+        p.p1[r * p.D + d] = __fsub_rn(x, hi);
+      } else {
+        p.p0[r * p.D + d] = x;
+      }
+      if (p.pb) p.pb[r * p.D + d] = __float2bfloat16_rn(x);
+    }
+    const float ss2 = canon_tree(acc2);
+    if (lane == 0) {
+      if (p.sq) p.sq[r] = ss2;
+      if (p.gmax) atomicMax(p.gmax, float_orderable(ss2));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K6 epilogue: per-query top-KP list per split, kept in shared memory ([slot][thread] layout so a
+// warp's accesses to one slot are 256 contiguous bytes).  A thread replaces the current minimum
+// of its list when a score beats it and rescans for the new minimum; after the first few tiles
+// this happens rarely, and the common path per 32 columns is a max-reduction and one compare.
+// ------------------------------------------------------------------------------------------
+template <int METRIC>
+struct TopkEpi {
+  struct Params {
+    uint64_t* cand;      // [rows padded][n_splits][kp]
+    const float* gnorm;  // [n_rows padded to tile] canonical |g|^2 (METRIC 0)
+    int n_rows;
+    int n_splits;
+    int kp;
+  };
+  static constexpr int kSmemBytes = DIF_MAX_TOPK * GEMM_BM * 8;
+
+  const Params& p;
+  uint64_t* keys;  // this thread's slot 0; slot s at keys[s * GEMM_BM]
+  float thr;
+  int min_slot;
+
+  __device__ TopkEpi(const Params& pp, uint8_t* smem, int row)
+      : p(pp), keys(reinterpret_cast<uint64_t*>(smem) + row), thr(0.f), min_slot(0) {}
+
+  __device__ void begin_item(int, int, int) {
+    for (int s = 0; s < p.kp; ++s) keys[s * GEMM_BM] = 0ull;
+    thr = -INFINITY;
+    min_slot = 0;
+  }
+
+  __device__ __forceinline__ void insert(float v, int col) {
+    keys[min_slot * GEMM_BM] = make_key(v, (uint32_t)col);
+    uint64_t mn = keys[0];
+    int ms = 0;
+    for (int s = 1; s < p.kp; ++s) {
+      const uint64_t k2 = keys[s * GEMM_BM];
+      if (k2 < mn) {
+        mn = k2;
+        ms = s;
+      }
+    }
+    min_slot = ms;
+    thr = (mn == 0ull) ? -INFINITY : key_score(mn);
+  }
+
+  __device__ __forceinline__ void consume(int col0, const uint32_t (&acc)[32]) {
+    float v[32];
+    if (METRIC == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+    } else {
+      const float4* gn = reinterpret_cast<const float4*>(p.gnorm + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 g = __ldg(gn + i);
+        v[4 * i + 0] = __fmaf_rn(2.f, __uint_as_float(acc[4 * i + 0]), -g.x);
+        v[4 * i + 1] = __fmaf_rn(2.f, __uint_as_float(acc[4 * i + 1]), -g.y);
+        v[4 * i + 2] = __fmaf_rn(2.f, __uint_as_float(acc[4 * i + 2]), -g.z);
+        v[4 * i + 3] = __fmaf_rn(2.f, __uint_as_float(acc[4 * i + 3]), -g.w);
+      }
+    }
+    if (col0 + 32 > p.n_rows) {
+      // ragged last tile: TMA zero-filled the rows past the end, they must not compete
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.n_rows && v[i] > thr) insert(v[i], col0 + i);
+      return;
+    }
+    float m = v[0];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) m = fmaxf(m, v[i]);
+    if (m > thr) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (v[i] > thr) insert(v[i], col0 + i);
+    }
+  }
+
+  __device__ void end_item(int m_row, int split) {
+    uint64_t* out = p.cand + ((size_t)m_row * p.n_splits + split) * p.kp;
+    for (int s = 0; s < p.kp; ++s) out[s] = keys[s * GEMM_BM];
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// Selection helpers on unique 64-bit keys held in shared memory.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t block_max_u64(uint64_t v, uint64_t* red /* [32] */) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const uint64_t w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w > v ? w : v;
+  }
+  const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[warp] = v;
+  __syncthreads();
+  uint64_t r = red[0];
+  for (int i = 1; i < nw; ++i) r = red[i] > r ? red[i] : r;
+  return r;
+}
+
+struct RerankParams {
+  const uint64_t* cand;  // [rows padded][S][kp] approximate keys from pass 2
+  int S, kp, k, n_queries;
+  const float* q0;
+  const float* q1;
+  const float* g0;
+  const float* g1;
+  const float* q_sq;          // canonical |q|^2 per query (sq-L2 bound)
+  const unsigned int* gmax;   // orderable max |g|^2
+  int D, metric;
+  float eps_rel;
+  const int64_t* ids;
+  int64_t id_base;
+  int64_t n_rows;
+  float* out_scores;
+  int64_t* out_ids;
+  int32_t* out_rows;
+  int* flagged_count;
+  int* flagged_list;
+  int force_flag;
+};
+
+__device__ __forceinline__ float exact_score_warp(const float* __restrict__ q0, const float* __restrict__ q1,
+                                                  const float* __restrict__ g0, const float* __restrict__ g1, int D,
+                                                  int metric) {
+  // every operand is rebuilt as p0 + p1 (exact) when a lo plane exists
+  float acc = 0.f;
+  for (int d = (int)(threadIdx.x & 31u); d < D; d += 32) {
+    const float a = q1 ? __fadd_rn(q0[d], q1[d]) : q0[d];
+    const float b = g1 ? __fadd_rn(g0[d], g1[d]) : g0[d];
+    if (metric == 1) {
+      acc = __fmaf_rn(a, b, acc);
+    } else {
+      const float t = __fsub_rn(a, b);
+      acc = __fmaf_rn(t, t, acc);
+    }
+  }
+  return canon_tree(acc);
+}
+
+__device__ __forceinline__ void emit_result(const RerankParams& p, int q, int slot, uint64_t key) {
+  const size_t at = (size_t)q * p.k + slot;
+  if (key == 0ull) {
+    p.out_scores[at] = 0.f;
+    p.out_ids[at] = -1;
+    if (p.out_rows) p.out_rows[at] = -1;
+    return;
+  }
+  const uint32_t row = key_index(key);
+  const float better = key_score(key);
+  p.out_scores[at] = p.metric == 1 ? better : -better;
+  p.out_ids[at] = p.ids ? p.ids[row] : p.id_base + (int64_t)row;
+  if (p.out_rows) p.out_rows[at] = (int32_t)row;
+}
+
+// K7: one block per query.
+__global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) {
+  extern __shared__ uint64_t sm_keys[];  // [S * kp]
+  __shared__ uint64_t red[32];
+  __shared__ uint64_t ekeys[kRerankCap];
+  __shared__ uint32_t rrows[kRerankCap];
+  __shared__ int n_r;
+  __shared__ int flag;
+
+  const int q = blockIdx.x;
+  const int n = p.S * p.kp;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    n_r = 0;
+    flag = p.force_flag;
+  }
+  const uint64_t* src = p.cand + (size_t)q * n;
+  for (int i = tid; i < n; i += blockDim.x) sm_keys[i] = src[i];
+  __syncthreads();
+
+  // k-th largest approximate key (keys are unique: the row index is part of the key)
+  uint64_t prev = ~0ull;
+  for (int r = 0; r < p.k; ++r) {
+    uint64_t best = 0ull;
+    for (int i = tid; i < n; i += blockDim.x) {
+      const uint64_t key = sm_keys[i];
+      if (key < prev && key > best) best = key;
+    }
+    prev = block_max_u64(best, red);
+    if (prev == 0ull) break;
+  }
+  float eps = p.eps_rel;
+  if (p.metric == 0) {
+    const float qn = sqrtf(p.q_sq[q]);
+    const uint32_t o = *p.gmax;
+    const float gn = sqrtf(fmaxf(__uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o), 0.f));
+    eps = 2.f * p.eps_rel * qn * gn + 4e-6f * (qn + gn) * (qn + gn);
+  } else {
+    eps += 4e-6f;
+  }
+  const float lim = prev == 0ull ? -INFINITY : key_score(prev) - 2.f * eps;
+
+  // a full list whose minimum reaches the window may hide a better row that was evicted
+  for (int s = tid; s < p.S; s += blockDim.x) {
+    uint64_t mn = ~0ull;
+    for (int i = 0; i < p.kp; ++i) {
+      const uint64_t key = sm_keys[s * p.kp + i];
+      mn = key < mn ? key : mn;
+    }
+    if (mn != 0ull && !(key_score(mn) < lim)) flag = 1;
+  }
+  for (int i = tid; i < n; i += blockDim.x) {
+    const uint64_t key = sm_keys[i];
+    if (key != 0ull && key_score(key) >= lim) {
+      const int at = atomicAdd(&n_r, 1);
+      if (at < kRerankCap) rrows[at] = key_index(key);
+      else flag = 1;
+    }
+  }
+  __syncthreads();
+  const int nr = min(n_r, kRerankCap);
+
+  // canonical scores of the window
+  const int warp = tid >> 5, nw = blockDim.x >> 5;
+  for (int i = warp; i < nr; i += nw) {
+    const uint32_t row = rrows[i];
+    const float s = exact_score_warp(p.q0 + (size_t)q * p.D, p.q1 ? p.q1 + (size_t)q * p.D : nullptr,
+                                     p.g0 + (size_t)row * p.D, p.g1 ? p.g1 + (size_t)row * p.D : nullptr, p.D,
+                                     p.metric);
+    if ((tid & 31) == 0) ekeys[i] = make_key(p.metric == 1 ? s : -s, row);
+  }
+  __syncthreads();
+  // rank by counting (|window| is small); unique keys -> unique ranks
+  for (int i = tid; i < nr; i += blockDim.x) {
+    const uint64_t key = ekeys[i];
+    int rank = 0;
+    for (int j = 0; j < nr; ++j) rank += ekeys[j] > key;
+    if (rank < p.k) emit_result(p, q, rank, key);
+  }
+  for (int i = nr + tid; i < p.k; i += blockDim.x) emit_result(p, q, i, 0ull);
+  if (tid == 0 && flag) p.flagged_list[atomicAdd(p.flagged_count, 1)] = q;
+}
+
+// Exact scan of flagged queries: work item = (flagged index, row chunk); 8 warps interleave rows,
+// each keeps a top-k list in shared memory; the block merges and writes k canonical keys.
+__global__ void __launch_bounds__(kExactThreads) exact_scan_kernel(RerankParams p, uint64_t* ex_keys) {
+  extern __shared__ float sm_q[];  // [D]
+  __shared__ uint64_t lists[kExactThreads / 32][DIF_MAX_TOPK];
+  const int n_flag = *p.flagged_count;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int64_t chunk_rows = (p.n_rows + kExactChunks - 1) / kExactChunks;
+  for (int item = blockIdx.x; item < n_flag * kExactChunks; item += gridDim.x) {
+    const int fi = item / kExactChunks, chunk = item - fi * kExactChunks;
+    const int q = p.flagged_list[fi];
+    __syncthreads();
+    for (int d = threadIdx.x; d < p.D; d += blockDim.x)
+      sm_q[d] = p.q1 ? __fadd_rn(p.q0[(size_t)q * p.D + d], p.q1[(size_t)q * p.D + d]) : p.q0[(size_t)q * p.D + d];
+    if (lane < p.k) lists[warp][lane] = 0ull;
+    __syncthreads();
+    uint64_t thr_key = 0ull;  // minimum of this warp's list (0 while it is not full)
+    int min_slot = 0;
+    const int64_t r0 = chunk * chunk_rows, r1 = min(r0 + chunk_rows, p.n_rows);
+    for (int64_t r = r0 + warp; r < r1; r += nw) {
+      const float s = exact_score_warp(sm_q, nullptr, p.g0 + (size_t)r * p.D, p.g1 ? p.g1 + (size_t)r * p.D : nullptr,
+                                       p.D, p.metric);
+      const uint64_t key = make_key(p.metric == 1 ? s : -s, (uint32_t)r);
+      if (key > thr_key) {  // warp-uniform
+        if (lane == 0) lists[warp][min_slot] = key;
+        __syncwarp();
+        uint64_t mn = lists[warp][0];
+        int ms = 0;
+        for (int i = 1; i < p.k; ++i) {
+          const uint64_t k2 = lists[warp][i];
+          if (k2 < mn) {
+            mn = k2;
+            ms = i;
+          }
+        }
+        thr_key = mn;
+        min_slot = ms;
+        __syncwarp();
+      }
+    }
+    uint64_t* dst = ex_keys + ((size_t)fi * kExactChunks + chunk) * p.k;
+    if (threadIdx.x < p.k) dst[threadIdx.x] = 0ull;
+    __syncthreads();
+    // merge nw lists by rank counting
+    uint64_t* all = &lists[0][0];
+    if (threadIdx.x < nw * DIF_MAX_TOPK) {
+      const int w = threadIdx.x / DIF_MAX_TOPK, i = threadIdx.x - w * DIF_MAX_TOPK;
+      const uint64_t key = i < p.k ? all[threadIdx.x] : 0ull;
+      if (key != 0ull) {
+        int rank = 0;
+        for (int w2 = 0; w2 < nw; ++w2)
+          for (int j = 0; j < p.k; ++j) rank += lists[w2][j] > key;
+        if (rank < p.k) dst[rank] = key;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kRerankThreads) exact_merge_kernel(RerankParams p, const uint64_t* ex_keys) {
+  extern __shared__ uint64_t sm_keys[];
+  const int n_flag = *p.flagged_count;
+  const int n = kExactChunks * p.k;
+  for (int fi = blockIdx.x; fi < n_flag; fi += gridDim.x) {
+    const int q = p.flagged_list[fi];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sm_keys[i] = ex_keys[(size_t)fi * n + i];
+    __syncthreads();
+    int n_valid = 0;
+    for (int i = 0; i < n; ++i) n_valid += sm_keys[i] != 0ull;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint64_t key = sm_keys[i];
+      if (key == 0ull) continue;
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += sm_keys[j] > key;
+      if (rank < p.k) emit_result(p, q, rank, key);
+    }
+    for (int i = n_valid + threadIdx.x; i < p.k; i += blockDim.x) emit_result(p, q, i, 0ull);
+  }
+}
+
+// Cross-shard merge: candidates carry (score, global row, id); order (better score, global row asc).
+__global__ void __launch_bounds__(128) topk_merge_kernel(const float* scores, const int64_t* grows, const int64_t* ids,
+                                                         int world, int n_queries, int k, int metric,
+                                                         float* out_scores, int64_t* out_grows, int64_t* out_ids) {
+  extern __shared__ uint8_t sm_raw[];
+  const int n = world * k;
+  uint32_t* so = reinterpret_cast<uint32_t*>(sm_raw);                 // orderable "better" score
+  int64_t* sr = reinterpret_cast<int64_t*>(sm_raw + ((n * 4 + 7) & ~7));  // global row, -1 = empty
+  for (int q = blockIdx.x; q < n_queries; q += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int w = i / k, j = i - w * k;
+      const size_t at = ((size_t)w * n_queries + q) * k + j;
+      const float s = scores[at];
+      so[i] = float_orderable(metric == 1 ? s : -s);
+      sr[i] = grows[at];
+    }
+    __syncthreads();
+    int n_valid = 0;
+    for (int i = 0; i < n; ++i) n_valid += sr[i] >= 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      if (sr[i] < 0) continue;
+      int rank = 0;
+      for (int j = 0; j < n; ++j)
+        rank += sr[j] >= 0 && (so[j] > so[i] || (so[j] == so[i] && (sr[j] < sr[i] || (sr[j] == sr[i] && j < i))));
+      if (rank < k) {
+        const int w = i / k, jj = i - w * k;
+        const size_t at = ((size_t)w * n_queries + q) * k + jj;
+        out_scores[(size_t)q * k + rank] = scores[at];
+        out_grows[(size_t)q * k + rank] = sr[i];
+        if (out_ids) out_ids[(size_t)q * k + rank] = ids ? ids[at] : sr[i];
+      }
+    }
+    for (int i = n_valid + threadIdx.x; i < k; i += blockDim.x) {
+      out_scores[(size_t)q * k + i] = 0.f;
+      out_grows[(size_t)q * k + i] = -1;
+      if (out_ids) out_ids[(size_t)q * k + i] = -1;
+    }
+  }
+}
+
+__global__ void gather_rows_kernel(const float* p0, const float* p1, int64_t row0, int64_t n, int D, float* out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * D; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t at = row0 * D + i;
+    out[i] = p1 ? __fadd_rn(p0[at], p1[at]) : p0[at];
+  }
+}
+
+}  // namespace dif
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+using namespace dif;
+
+struct dif_gallery {
+  int device = 0;
+  int64_t capacity = 0;
+  int64_t size = 0;
+  int D = 0;
+  int metric = 1;
+  int precision = 0;
+  int64_t id_base = 0;
+  bool has_ids = false;
+  float* g0 = nullptr;
+  float* g1 = nullptr;
+  __nv_bfloat16* gb = nullptr;
+  float* gsq = nullptr;  // [capacity + kGalBN]
+  unsigned int* gmax = nullptr;
+  int64_t* ids = nullptr;
+  // query-side workspace (grown on demand)
+  int q_cap = 0;
+  float* q0 = nullptr;
+  float* q1 = nullptr;
+  __nv_bfloat16* qb = nullptr;
+  float* qsq = nullptr;
+  uint64_t* cand = nullptr;
+  size_t cand_elems = 0;
+  int* flagged = nullptr;  // [0] = count, [1..] = list
+  uint64_t* ex_keys = nullptr;
+  size_t ex_elems = 0;
+  // host staging for the *_host entry points
+  void* h_pin = nullptr;
+  size_t h_pin_bytes = 0;
+  void* d_stage = nullptr;
+  size_t d_stage_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int64_t stats[4] = {0, 0, 0, 0};
+  int opt_ctas = 2;
+  int opt_force_fallback = 0;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(T** p, size_t n) {
+  DIF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  return DIF_OK;
+}
+
+int prep_launch(const PrepParams& pp, bool synth, cudaStream_t st) {
+  if (pp.n == 0) return DIF_OK;
+  const int warps_per_block = 8;
+  int64_t blocks = (pp.n + warps_per_block - 1) / warps_per_block;
+  blocks = std::min<int64_t>(blocks, 148 * 16);
+  if (synth) prep_rows_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(pp);
+  else prep_rows_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(pp);
+  DIF_LAUNCH_OK();
+  return DIF_OK;
+}
+
+int ensure_query_ws(dif_gallery* g, int Q, int S, int kp) {
+  const int q_pad = (int)round_up(Q, GEMM_BM * 2);
+  if (q_pad > g->q_cap) {
+    cudaFree(g->q0); cudaFree(g->q1); cudaFree(g->qb); cudaFree(g->qsq); cudaFree(g->flagged);
+    g->q0 = g->q1 = nullptr; g->qb = nullptr; g->qsq = nullptr; g->flagged = nullptr;
+    g->q_cap = 0;
+    if (int rc = dev_alloc(&g->q0, (size_t)q_pad * g->D)) return rc;
+    if (g->precision == DIF_PREC_TF32X3)
+      if (int rc = dev_alloc(&g->q1, (size_t)q_pad * g->D)) return rc;
+    if (g->precision == DIF_PREC_BF16)
+      if (int rc = dev_alloc(&g->qb, (size_t)q_pad * g->D)) return rc;
+    if (int rc = dev_alloc(&g->qsq, (size_t)q_pad)) return rc;
+    if (int rc = dev_alloc(&g->flagged, (size_t)q_pad + 1)) return rc;
+    g->q_cap = q_pad;
+  }
+  const size_t need = (size_t)q_pad * S * kp;
+  if (need > g->cand_elems) {
+    cudaFree(g->cand);
+    g->cand = nullptr;
+    g->cand_elems = 0;
+    if (int rc = dev_alloc(&g->cand, need)) return rc;
+    g->cand_elems = need;
+  }
+  return DIF_OK;
+}
+
+template <int PREC, int CTAS>
+int launch_search(dif_gallery* g, const CUtensorMap* maps, const GemmShape& shape, int kp, cudaStream_t st) {
+  const int n_units = std::max(1, device_sm_count() / CTAS);
+  if (g->metric == DIF_METRIC_COSINE) {
+    TopkEpi<1>::Params ep{g->cand, g->gsq, (int)g->size, shape.n_splits, kp};
+    return launch_nt_gemm<PREC, kGalBN, CTAS, TopkEpi<1>>(maps, shape, ep, n_units, st);
+  }
+  TopkEpi<0>::Params ep{g->cand, g->gsq, (int)g->size, shape.n_splits, kp};
+  return launch_nt_gemm<PREC, kGalBN, CTAS, TopkEpi<0>>(maps, shape, ep, n_units, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+dif_gallery_t* dif_gallery_create(int device, int64_t capacity_rows, int dim, int metric, int precision) {
+  if (dif_init(device) != DIF_OK) return nullptr;
+  if (capacity_rows <= 0 || capacity_rows >= (int64_t)0x7FFFFF00 || dim < 32 || dim % 4 != 0 || dim > 8192 ||
+      (metric != DIF_METRIC_SQL2 && metric != DIF_METRIC_COSINE) || precision < 0 || precision > 2 ||
+      (precision == DIF_PREC_BF16 && (dim % 8 != 0 || dim < 64))) {
+    set_error("dif_gallery_create: invalid argument (capacity %lld, dim %d (multiple of 4 and >= 32; of 8 and >= 64 for "
+              "bf16), metric %d, precision %d)", (long long)capacity_rows, dim, metric, precision);
+    return nullptr;
+  }
+  dif_gallery* g = new (std::nothrow) dif_gallery();
+  if (!g) return nullptr;
+  g->device = device;
+  g->capacity = capacity_rows;
+  g->D = dim;
+  g->metric = metric;
+  g->precision = precision;
+  const size_t elems = (size_t)capacity_rows * dim;
+  bool ok = cudaMalloc((void**)&g->g0, elems * 4) == cudaSuccess;
+  if (ok && precision == DIF_PREC_TF32X3) ok = cudaMalloc((void**)&g->g1, elems * 4) == cudaSuccess;
+  if (ok && precision == DIF_PREC_BF16) ok = cudaMalloc((void**)&g->gb, elems * 2) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&g->gsq, ((size_t)capacity_rows + kGalBN) * 4) == cudaSuccess;
+  ok = ok && cudaMalloc((void**)&g->gmax, 4) == cudaSuccess;
+  ok = ok && cudaMemset(g->gsq, 0, ((size_t)capacity_rows + kGalBN) * 4) == cudaSuccess;
+  ok = ok && cudaMemset(g->gmax, 0, 4) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&g->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreate(&g->ev0) == cudaSuccess && cudaEventCreate(&g->ev1) == cudaSuccess;
+  if (!ok) {
+    set_error("dif_gallery_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    dif_gallery_destroy(g);
+    return nullptr;
+  }
+  return g;
+}
+
+void dif_gallery_destroy(dif_gallery_t* g) {
+  if (!g) return;
+  cudaFree(g->g0); cudaFree(g->g1); cudaFree(g->gb); cudaFree(g->gsq); cudaFree(g->gmax); cudaFree(g->ids);
+  cudaFree(g->q0); cudaFree(g->q1); cudaFree(g->qb); cudaFree(g->qsq); cudaFree(g->cand); cudaFree(g->flagged);
+  cudaFree(g->ex_keys); cudaFree(g->d_stage);
+  if (g->h_pin) cudaFreeHost(g->h_pin);
+  if (g->own_stream) cudaStreamDestroy(g->own_stream);
+  if (g->ev0) cudaEventDestroy(g->ev0);
+  if (g->ev1) cudaEventDestroy(g->ev1);
+  delete g;
+}
+
+int dif_gallery_set_option(dif_gallery_t* g, const char* name, int value) {
+  DIF_REQUIRE(g && name, DIF_ERR_INVALID, "dif_gallery_set_option: null argument");
+  if (!strcmp(name, "gemm_ctas")) {
+    DIF_REQUIRE(value == 1 || value == 2, DIF_ERR_INVALID, "gemm_ctas must be 1 or 2");
+    g->opt_ctas = value;
+  } else if (!strcmp(name, "force_fallback")) {
+    g->opt_force_fallback = value != 0;
+  } else {
+    DIF_REQUIRE(false, DIF_ERR_INVALID, "unknown option '%s'", name);
+  }
+  return DIF_OK;
+}
+
+static int gallery_append(dif_gallery_t* g, const float* rows, bool synth, uint64_t seed, int64_t row0,
+                          const int64_t* ids, int64_t n, cudaStream_t st) {
+  DIF_REQUIRE(g, DIF_ERR_INVALID, "null gallery");
+  DIF_REQUIRE(n >= 0 && g->size + n <= g->capacity, DIF_ERR_CAPACITY, "gallery full: %lld + %lld > capacity %lld",
+              (long long)g->size, (long long)n, (long long)g->capacity);
+  if (n == 0) return DIF_OK;
+  DIF_REQUIRE(synth || rows, DIF_ERR_INVALID, "rows is NULL");
+  PrepParams pp{};
+  pp.src = rows;
+  pp.seed = seed;
+  pp.row0 = row0;
+  pp.n = n;
+  pp.D = g->D;
+  pp.normalize = g->metric == DIF_METRIC_COSINE;
+  pp.split = g->precision == DIF_PREC_TF32X3;
+  pp.p0 = g->g0 + (size_t)g->size * g->D;
+  pp.p1 = g->g1 ? g->g1 + (size_t)g->size * g->D : nullptr;
+  pp.pb = g->gb ? g->gb + (size_t)g->size * g->D : nullptr;
+  pp.sq = g->gsq + g->size;
+  pp.gmax = g->gmax;
+  if (int rc = prep_launch(pp, synth, st)) return rc;
+  if (ids) {
+    if (!g->ids) {
+      DIF_CUDA_OK(cudaMalloc((void**)&g->ids, (size_t)g->capacity * 8));
+      DIF_CUDA_OK(cudaMemsetAsync(g->ids, 0xFF, (size_t)g->capacity * 8, st));
+    }
+    DIF_CUDA_OK(cudaMemcpyAsync(g->ids + g->size, ids, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    g->has_ids = true;
+  } else {
+    DIF_REQUIRE(!g->has_ids, DIF_ERR_STATE, "this gallery was built with explicit ids; ids must be given on every add");
+  }
+  g->size += n;
+  return DIF_OK;
+}
+
+int dif_gallery_add(dif_gallery_t* g, const float* rows, const int64_t* ids, int64_t n, void* stream) {
+  return gallery_append(g, rows, false, 0, 0, ids, n, static_cast<cudaStream_t>(stream));
+}
+
+int dif_gallery_fill_synth(dif_gallery_t* g, uint64_t seed, int64_t row0, int64_t n, void* stream) {
+  return gallery_append(g, nullptr, true, seed, row0, nullptr, n, static_cast<cudaStream_t>(stream));
+}
+
+static int ensure_stage(dif_gallery_t* g, size_t bytes) {
+  if (bytes > g->h_pin_bytes) {
+    if (g->h_pin) cudaFreeHost(g->h_pin);
+    g->h_pin = nullptr;
+    g->h_pin_bytes = 0;
+    DIF_CUDA_OK(cudaMallocHost(&g->h_pin, bytes));
+    g->h_pin_bytes = bytes;
+  }
+  if (bytes > g->d_stage_bytes) {
+    cudaFree(g->d_stage);
+    g->d_stage = nullptr;
+    g->d_stage_bytes = 0;
+    DIF_CUDA_OK(cudaMalloc(&g->d_stage, bytes));
+    g->d_stage_bytes = bytes;
+  }
+  return DIF_OK;
+}
+
+int dif_gallery_add_host(dif_gallery_t* g, const float* rows_host, const int64_t* ids_host, int64_t n) {
+  DIF_REQUIRE(g && (rows_host || n == 0), DIF_ERR_INVALID, "dif_gallery_add_host: null argument");
+  const int64_t chunk = std::max<int64_t>(1, (int64_t)(64u << 20) / (g->D * 4));
+  for (int64_t done = 0; done < n; done += chunk) {
+    const int64_t m = std::min(chunk, n - done);
+    const size_t rb = (size_t)m * g->D * 4, ib = ids_host ? (size_t)m * 8 : 0;
+    if (int rc = ensure_stage(g, rb + ib)) return rc;
+    memcpy(g->h_pin, rows_host + (size_t)done * g->D, rb);
+    if (ids_host) memcpy((char*)g->h_pin + rb, ids_host + done, ib);
+    DIF_CUDA_OK(cudaMemcpyAsync(g->d_stage, g->h_pin, rb + ib, cudaMemcpyHostToDevice, g->own_stream));
+    if (int rc = gallery_append(g, (const float*)g->d_stage, false, 0, 0,
+                                ids_host ? (const int64_t*)((char*)g->d_stage + rb) : nullptr, m, g->own_stream))
+      return rc;
+    DIF_CUDA_OK(cudaStreamSynchronize(g->own_stream));
+  }
+  return DIF_OK;
+}
+
+int dif_gallery_set_id_base(dif_gallery_t* g, int64_t id_base) {
+  DIF_REQUIRE(g, DIF_ERR_INVALID, "null gallery");
+  g->id_base = id_base;
+  return DIF_OK;
+}
+
+int64_t dif_gallery_size(const dif_gallery_t* g) { return g ? g->size : -1; }
+
+int dif_gallery_reset(dif_gallery_t* g) {
+  DIF_REQUIRE(g, DIF_ERR_INVALID, "null gallery");
+  g->size = 0;
+  g->has_ids = false;
+  DIF_CUDA_OK(cudaMemset(g->gsq, 0, ((size_t)g->capacity + kGalBN) * 4));
+  DIF_CUDA_OK(cudaMemset(g->gmax, 0, 4));
+  return DIF_OK;
+}
+
+int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, int k, float* scores, int64_t* ids,
+                       int32_t* rows, void* stream) {
+  DIF_REQUIRE(g && queries && scores && ids, DIF_ERR_INVALID, "dif_gallery_search: null argument");
+  DIF_REQUIRE(n_queries > 0 && k >= 1 && k <= DIF_MAX_TOPK, DIF_ERR_INVALID,
+              "dif_gallery_search: n_queries %d, k %d (1..%d)", n_queries, k, DIF_MAX_TOPK);
+  DIF_REQUIRE(device_sm_count() > 0, DIF_ERR_STATE, "dif_init has not succeeded on this process");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = g->D, kp = k;
+  const int ctas = g->opt_ctas;
+  const int64_t launches0 = dif_launch_count();
+
+  // work decomposition: items = splits x query blocks, a whole number of items per persistent unit
+  GemmShape shape{};
+  shape.m_blocks = (n_queries + GEMM_BM * ctas - 1) / (GEMM_BM * ctas);
+  shape.n_tiles = (int)((g->size + kGalBN - 1) / kGalBN);
+  const int chunk = g->precision == DIF_PREC_BF16 ? 64 : 32;
+  shape.k_chunks = (D + chunk - 1) / chunk;
+  const int units = std::max(1, device_sm_count() / ctas);
+  int splits = 1;
+  if (shape.n_tiles > 0) {
+    const int rounds = std::max(1, std::min(8, (shape.n_tiles * shape.m_blocks) / (units * 8)));
+    splits = std::max(1, (units * rounds + shape.m_blocks - 1) / shape.m_blocks);
+    splits = std::min(splits, shape.n_tiles);
+    splits = std::min(splits, 512);
+  }
+  shape.n_splits = splits;
+  shape.tiles_per_split = shape.n_tiles > 0 ? (shape.n_tiles + splits - 1) / splits : 0;
+  if (shape.tiles_per_split > 0) shape.n_splits = splits = (shape.n_tiles + shape.tiles_per_split - 1) / shape.tiles_per_split;
+
+  if (int rc = ensure_query_ws(g, n_queries, splits, kp)) return rc;
+
+  // 1. queries -> canonical planes
+  PrepParams pp{};
+  pp.src = queries;
+  pp.n = n_queries;
+  pp.D = D;
+  pp.normalize = g->metric == DIF_METRIC_COSINE;
+  pp.split = g->precision == DIF_PREC_TF32X3;
+  pp.p0 = g->q0;
+  pp.p1 = g->q1;
+  pp.pb = g->qb;
+  pp.sq = g->qsq;
+  pp.gmax = nullptr;
+  if (int rc = prep_launch(pp, false, st)) return rc;
+  DIF_CUDA_OK(cudaMemsetAsync(g->flagged, 0, sizeof(int), st));
+
+  // 2. tensor-core filter
+  if (shape.n_tiles > 0) {
+    CUtensorMap maps[4];
+    const bool bf = g->precision == DIF_PREC_BF16;
+    const void* a0 = bf ? (const void*)g->qb : (const void*)g->q0;
+    const void* b0 = bf ? (const void*)g->gb : (const void*)g->g0;
+    const int esz = bf ? 2 : 4;
+    const uint32_t bcols = (uint32_t)(128 / esz);
+    if (int rc = make_tmap_2d(&maps[0], a0, n_queries, D, (uint64_t)D * esz, GEMM_BM, bcols, bf)) return rc;
+    if (int rc = make_tmap_2d(&maps[2], b0, g->size, D, (uint64_t)D * esz, kGalBN / ctas, bcols, bf)) return rc;
+    maps[1] = maps[0];
+    maps[3] = maps[2];
+    if (g->precision == DIF_PREC_TF32X3) {
+      if (int rc = make_tmap_2d(&maps[1], g->q1, n_queries, D, (uint64_t)D * 4, GEMM_BM, bcols, 0)) return rc;
+      if (int rc = make_tmap_2d(&maps[3], g->g1, g->size, D, (uint64_t)D * 4, kGalBN / ctas, bcols, 0)) return rc;
+    }
+    DIF_CUDA_OK(cudaEventRecord(g->ev0, st));
+    int rc;
+    if (ctas == 2) {
+      rc = g->precision == DIF_PREC_TF32X3 ? launch_search<0, 2>(g, maps, shape, kp, st)
+           : g->precision == DIF_PREC_BF16 ? launch_search<1, 2>(g, maps, shape, kp, st)
+                                           : launch_search<2, 2>(g, maps, shape, kp, st);
+    } else {
+      rc = g->precision == DIF_PREC_TF32X3 ? launch_search<0, 1>(g, maps, shape, kp, st)
+           : g->precision == DIF_PREC_BF16 ? launch_search<1, 1>(g, maps, shape, kp, st)
+                                           : launch_search<2, 1>(g, maps, shape, kp, st);
+    }
+    if (rc) return rc;
+    DIF_CUDA_OK(cudaEventRecord(g->ev1, st));
+  } else {
+    DIF_CUDA_OK(cudaMemsetAsync(g->cand, 0, (size_t)g->q_cap * splits * kp * 8, st));
+  }
+
+  // 3. window + canonical re-rank
+  RerankParams rp{};
+  rp.cand = g->cand;
+  rp.S = splits;
+  rp.kp = kp;
+  rp.k = k;
+  rp.n_queries = n_queries;
+  rp.q0 = g->q0;
+  rp.q1 = g->q1;
+  rp.g0 = g->g0;
+  rp.g1 = g->g1;
+  rp.q_sq = g->qsq;
+  rp.gmax = g->gmax;
+  rp.D = D;
+  rp.metric = g->metric;
+  rp.eps_rel = mode_eps(g->precision);
+  rp.ids = g->has_ids ? g->ids : nullptr;
+  rp.id_base = g->id_base;
+  rp.n_rows = g->size;
+  rp.out_scores = scores;
+  rp.out_ids = ids;
+  rp.out_rows = rows;
+  rp.flagged_count = g->flagged;
+  rp.flagged_list = g->flagged + 1;
+  rp.force_flag = g->opt_force_fallback;
+  const size_t rr_smem = (size_t)splits * kp * 8;
+  DIF_REQUIRE(rr_smem <= 160 * 1024, DIF_ERR_CAPACITY, "candidate lists too large for the re-rank kernel");
+  if (rr_smem > 40 * 1024)
+    DIF_CUDA_OK(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
+  rerank_kernel<<<n_queries, kRerankThreads, rr_smem, st>>>(rp);
+  DIF_LAUNCH_OK();
+
+  // 4. exact path for flagged queries (grids sized for the hardware, work read from the device counter)
+  if (g->size > 0) {
+    const size_t need = (size_t)g->q_cap * kExactChunks * k;
+    if (need > g->ex_elems) {
+      // allocated lazily but before it can be needed: the flagged count is only known on the device
+      cudaFree(g->ex_keys);
+      g->ex_keys = nullptr;
+      g->ex_elems = 0;
+      if (int rc = dev_alloc(&g->ex_keys, need)) return rc;
+      g->ex_elems = need;
+    }
+    exact_scan_kernel<<<device_sm_count() * 4, kExactThreads, (size_t)D * 4, st>>>(rp, g->ex_keys);
+    DIF_LAUNCH_OK();
+    exact_merge_kernel<<<device_sm_count() * 2, kRerankThreads, (size_t)kExactChunks * k * 8, st>>>(rp, g->ex_keys);
+    DIF_LAUNCH_OK();
+  }
+  g->stats[1] = dif_launch_count() - launches0;
+  g->stats[2] = splits;
+  g->stats[3] = kp;
+  return DIF_OK;
+}
+
+int dif_gallery_search_host(dif_gallery_t* g, const float* queries_host, int n_queries, int k, float* scores_host,
+                            int64_t* ids_host, int32_t* rows_host) {
+  DIF_REQUIRE(g && queries_host && scores_host && ids_host, DIF_ERR_INVALID, "dif_gallery_search_host: null argument");
+  DIF_REQUIRE(n_queries > 0 && k >= 1 && k <= DIF_MAX_TOPK, DIF_ERR_INVALID, "n_queries %d, k %d", n_queries, k);
+  const size_t qb = (size_t)n_queries * g->D * 4;
+  const size_t nk = (size_t)n_queries * k;
+  const size_t ob = nk * (4 + 8 + 4);
+  const size_t qb_al = (qb + 255) & ~(size_t)255;
+  if (int rc = ensure_stage(g, qb_al + ob + 256)) return rc;
+  char* hp = (char*)g->h_pin;
+  char* dp = (char*)g->d_stage;
+  memcpy(hp, queries_host, qb);
+  cudaStream_t st = g->own_stream;
+  DIF_CUDA_OK(cudaMemcpyAsync(dp, hp, qb, cudaMemcpyHostToDevice, st));
+  int64_t* d_ids = (int64_t*)(dp + qb_al);
+  float* d_scores = (float*)(dp + qb_al + nk * 8);
+  int32_t* d_rows = (int32_t*)(dp + qb_al + nk * 12);
+  if (int rc = dif_gallery_search(g, (const float*)dp, n_queries, k, d_scores, d_ids, d_rows, st)) return rc;
+  DIF_CUDA_OK(cudaMemcpyAsync(hp + qb_al, dp + qb_al, ob, cudaMemcpyDeviceToHost, st));
+  DIF_CUDA_OK(cudaStreamSynchronize(st));
+  memcpy(ids_host, hp + qb_al, nk * 8);
+  memcpy(scores_host, hp + qb_al + nk * 8, nk * 4);
+  if (rows_host) memcpy(rows_host, hp + qb_al + nk * 12, nk * 4);
+  return DIF_OK;
+}
+
+int dif_gallery_last_stats(const dif_gallery_t* g, int64_t out[4]) {
+  DIF_REQUIRE(g && out, DIF_ERR_INVALID, "null argument");
+  int n_flag = 0;
+  if (g->flagged) DIF_CUDA_OK(cudaMemcpy(&n_flag, g->flagged, sizeof(int), cudaMemcpyDeviceToHost));
+  out[0] = n_flag;
+  out[1] = g->stats[1];
+  out[2] = g->stats[2];
+  out[3] = g->stats[3];
+  return DIF_OK;
+}
+
+int dif_gallery_last_kernel_ms(dif_gallery_t* g, float* ms) {
+  DIF_REQUIRE(g && ms, DIF_ERR_INVALID, "null argument");
+  DIF_CUDA_OK(cudaEventElapsedTime(ms, g->ev0, g->ev1));
+  return DIF_OK;
+}
+
+int dif_gallery_get_rows(dif_gallery_t* g, int64_t row0, int64_t n, float* out, void* stream) {
+  DIF_REQUIRE(g && out && row0 >= 0 && n >= 0 && row0 + n <= g->size, DIF_ERR_INVALID, "dif_gallery_get_rows: range");
+  if (n == 0) return DIF_OK;
+  gather_rows_kernel<<<(unsigned)std::min<int64_t>((n * g->D + 255) / 256, 148 * 8), 256, 0,
+                       static_cast<cudaStream_t>(stream)>>>(g->g0, g->g1, row0, n, g->D, out);
+  DIF_LAUNCH_OK();
+  return DIF_OK;
+}
+
+int dif_topk_merge(const float* scores, const int64_t* grows, const int64_t* ids, int world, int n_queries, int k,
+                   int metric, float* out_scores, int64_t* out_grows, int64_t* out_ids, void* stream) {
+  DIF_REQUIRE(scores && grows && out_scores && out_grows, DIF_ERR_INVALID, "dif_topk_merge: null argument");
+  DIF_REQUIRE(world >= 1 && world <= 64 && n_queries > 0 && k >= 1 && k <= DIF_MAX_TOPK, DIF_ERR_INVALID,
+              "dif_topk_merge: world %d, n_queries %d, k %d", world, n_queries, k);
+  const int n = world * k;
+  const size_t smem = ((n * 4 + 7) & ~7) + (size_t)n * 8;
+  topk_merge_kernel<<<std::min(n_queries, 148 * 8), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      scores, grows, ids, world, n_queries, k, metric, out_scores, out_grows, out_ids);
+  DIF_LAUNCH_OK();
+  return DIF_OK;
+}
+
+// raw synthetic rows (no normalisation): out[n*D] = synth_value(seed, row, d, D); rows_idx NULL -> row0 + r
+int dif_synth_fill(float* out, uint64_t seed, int64_t row0, const int64_t* rows_idx, int64_t n, int D, void* stream);
+
+}  // extern "C"
+
+namespace dif {
+__global__ void synth_fill_kernel(float* out, uint64_t seed, int64_t row0, const int64_t* rows_idx, int64_t n, int D) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * D; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / D;
+    const int d = (int)(i - r * D);
+    const int64_t row = rows_idx ? rows_idx[r] : row0 + r;
+    out[i] = synth_value(seed, (uint64_t)row, (uint64_t)d, (uint64_t)D);
+  }
+}
+}  // namespace dif
+
+extern "C" int dif_synth_fill(float* out, uint64_t seed, int64_t row0, const int64_t* rows_idx, int64_t n, int D,
+                              void* stream) {
+  DIF_REQUIRE(out && n >= 0 && D > 0, DIF_ERR_INVALID, "dif_synth_fill: invalid argument");
+  if (n == 0) return DIF_OK;
+  dif::synth_fill_kernel<<<(unsigned)std::min<int64_t>((n * D + 255) / 256, 148 * 16), 256, 0,
+                           static_cast<cudaStream_t>(stream)>>>(out, seed, row0, rows_idx, n, D);
+  DIF_LAUNCH_OK();
+  return DIF_OK;
+}

@@ -1,0 +1,157 @@
+/* dif_b200.h - C ABI of libdif_b200.so: the embedding-space distance path of
+ * sandyz1000/deep-insight-face, rebuilt for NVIDIA B200 (sm_100a).
+ *
+ * The reference has no FFI for this path: its boundary is plain Python (a Keras Loss subclass,
+ * numpy evaluators, verify()).  Each entry point below names the reference function whose
+ * arithmetic it replaces (paths relative to the reference repo root).  The Python mirror in
+ * deep_insight_face_b200/ binds these with ctypes; INTEGRATION.md shows the stub a maintainer of
+ * the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 (DIF_OK) or a negative DIF_ERR_* code and never throws;
+ *     dif_last_error() returns a thread-local description of the last failure;
+ *   - pointers are caller-owned DEVICE pointers unless the function name ends in _host;
+ *   - functions are stream-ordered on `stream` (a cudaStream_t, NULL = default stream) and
+ *     return without synchronising, except the *_host variants, which synchronise before returning;
+ *   - a handle must not be used from two threads at once;
+ *   - there is no CPU fallback: without a usable sm_100 device every compute call fails.
+ */
+#ifndef DIF_B200_H_
+#define DIF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIF_OK 0
+#define DIF_ERR_INVALID (-1)  /* bad argument */
+#define DIF_ERR_CUDA (-2)     /* CUDA runtime / driver error */
+#define DIF_ERR_NO_DEVICE (-3)
+#define DIF_ERR_CAPACITY (-4) /* gallery full / workspace too small */
+#define DIF_ERR_STATE (-5)
+
+/* metric codes follow deep_insight_face/evaluation/utility.py:52-66 (`distance_metric`) */
+#define DIF_METRIC_SQL2 0   /* sum((a-b)^2)                      utility.py:55-56 */
+#define DIF_METRIC_COSINE 1 /* arccos(cos_sim)/pi for pairs; cosine similarity for search */
+
+/* Precision of the tensor-core pass.  Gallery search re-ranks every surviving candidate with the
+ * canonical fp32 reduction and proves the candidate lists complete from the pass's error bound, so
+ * its RESULTS are identical in all three modes; the losses report values of the chosen precision. */
+#define DIF_PREC_TF32X3 0 /* fp32-exact: hi/lo TF32 planes, 3 tensor-core products per term (default) */
+#define DIF_PREC_BF16 1   /* bf16 operands, fp32 accumulate (reported separately) */
+#define DIF_PREC_TF32X1 2 /* fp32 storage read as TF32 by the tensor cores, one product per term */
+
+#define DIF_MAX_TOPK 24
+
+/* ---- library ------------------------------------------------------------------------------ */
+int dif_init(int device);             /* selects the device, checks it is sm_100, warms the context */
+const char* dif_last_error(void);
+int dif_sync(void* stream);
+const char* dif_version(void);
+int64_t dif_launch_count(void);       /* kernels launched by this library since load (bench evidence) */
+
+/* ---- 1:N gallery search -------------------------------------------------------------------
+ * New API (the reference only has 1:1 verify: predictions.py:104-150 `TripletPrediction.verify`,
+ * api.py:94-104 `face_distance`).  Rows are L2-normalised on add for DIF_METRIC_COSINE
+ * (networks/inceptionv3.py:305, networks/triplet.py:138 contract) and stored raw for DIF_METRIC_SQL2.
+ * Search returns, per query, the k best rows ordered by (score best-first, row index ascending);
+ * scores are cosine similarity (descending) or squared L2 distance (ascending), computed with the
+ * canonical fp32 reduction of oracle/dif_oracle.c so results are bit-reproducible on the CPU. */
+typedef struct dif_gallery dif_gallery_t;
+
+dif_gallery_t* dif_gallery_create(int device, int64_t capacity_rows, int dim, int metric, int precision);
+void dif_gallery_destroy(dif_gallery_t* g);
+int dif_gallery_add(dif_gallery_t* g, const float* rows, const int64_t* ids /* NULL: id = row index + id_base */,
+                    int64_t n, void* stream);
+int dif_gallery_add_host(dif_gallery_t* g, const float* rows_host, const int64_t* ids_host, int64_t n);
+/* rows [row0, row0+n) of the synthetic gallery of oracle/dif_oracle.c:dif_synth_value (seed, dim) */
+int dif_gallery_fill_synth(dif_gallery_t* g, uint64_t seed, int64_t row0, int64_t n, void* stream);
+int dif_gallery_set_id_base(dif_gallery_t* g, int64_t id_base); /* default ids = id_base + local row */
+int64_t dif_gallery_size(const dif_gallery_t* g);
+/* tuning / test knobs: "gemm_ctas" = 1 | 2 (CTA pair, default), "force_fallback" = 0 | 1 (send every
+ * query through the exact brute-force path as well) */
+int dif_gallery_set_option(dif_gallery_t* g, const char* name, int value);
+int dif_gallery_reset(dif_gallery_t* g);
+/* scores [Q*k] fp32, ids [Q*k] int64, rows [Q*k] int32 local row index (may be NULL).
+ * Slots beyond the gallery size hold id -1 / row -1. */
+int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, int k, float* scores,
+                       int64_t* ids, int32_t* rows, void* stream);
+/* same call with HOST buffers: pinned staging, H2D of queries, D2H of results, synchronises */
+int dif_gallery_search_host(dif_gallery_t* g, const float* queries_host, int n_queries, int k,
+                            float* scores_host, int64_t* ids_host, int32_t* rows_host);
+/* counters of the last search: [0] queries that took the exact fallback, [1] kernels launched,
+ * [2] candidate splits, [3] candidates per split */
+int dif_gallery_last_stats(const dif_gallery_t* g, int64_t out[4]);
+/* duration in ms of the last search's tensor-core kernel (CUDA events on the launch stream);
+ * only valid after the stream has been synchronised */
+int dif_gallery_last_kernel_ms(dif_gallery_t* g, float* ms);
+/* copy canonical stored rows (normalised for cosine) back out: out [n*dim] fp32 */
+int dif_gallery_get_rows(dif_gallery_t* g, int64_t row0, int64_t n, float* out, void* stream);
+
+/* merge `world` per-shard results (each [Q*k], shard-major) into the global top-k, ordering
+ * (score best-first, global row ascending).  grows = global row index of each candidate. */
+int dif_topk_merge(const float* scores, const int64_t* grows, const int64_t* ids, int world, int n_queries,
+                   int k, int metric, float* out_scores, int64_t* out_grows, int64_t* out_ids, void* stream);
+
+/* raw synthetic rows shared with the oracle (oracle/dif_oracle.c:dif_or_synth_value):
+ * out[r*D + d] = synth(seed, row, d, D) with row = rows_idx ? rows_idx[r] : row0 + r (device pointers) */
+int dif_synth_fill(float* out, uint64_t seed, int64_t row0, const int64_t* rows_idx, int64_t n, int D, void* stream);
+
+/* diagnostic: C[M,N] (row-major, ldc = N) = A[M,K] * B[N,K]^T through the same tcgen05/TMA skeleton the
+ * search and loss kernels use.  precision as above; ctas = 1 | 2.  Used by tests/test_gemm_gpu.py. */
+int dif_debug_nt_gemm(const float* A, const float* B, int M, int N, int K, float* C, int precision, int ctas,
+                      int n_splits, void* stream);
+
+/* ---- batch-hard / batch-all triplet losses ------------------------------------------------
+ * deep_insight_face/common/losses.py:33-51 (BatchHardTripletLoss, cosine),
+ * :54-85 (BatchHardTripletLossEuclidean), :88-128 (...AutoAlpha: pass the current auto_alpha as
+ * `alpha`; stats[0]*alpha_scale is the caller's next value), :131-148 (BatchAllTripletLoss).
+ * labels are int32 class ids (argmax of the one-hot, losses.py:35).  Outputs:
+ *   loss [B]; pos_idx/neg_idx [B] mined column (first index on ties, -1 if a filler won);
+ *   stats [4] = mean(dists), mean(hardest_pos), mean(hardest_neg), max(dists) (losses.py:72-80,70);
+ *   demb [B*D] gradient of sum_i dloss[i]*loss[i] (dloss NULL -> 1/B each, Keras AUTO mean); NULL skips backward. */
+#define DIF_LOSS_BH_COSINE 0
+#define DIF_LOSS_BH_EUCLIDEAN 1
+#define DIF_LOSS_BATCH_ALL 2
+int dif_batch_hard(const float* emb, const int32_t* labels, int B, int D, int variant, float alpha, float* loss,
+                   int32_t* pos_idx, int32_t* neg_idx, float* stats, const float* dloss, float* demb,
+                   int precision, void* stream);
+int dif_batch_hard_host(const float* emb_host, const int32_t* labels_host, int B, int D, int variant, float alpha,
+                        float* loss_host, int32_t* pos_idx_host, int32_t* neg_idx_host, float* stats_host,
+                        const float* dloss_host, float* demb_host, int precision);
+
+/* explicit-triplet loss on [B, 3D] rows (anchor|positive|negative):
+ * deep_insight_face/networks/triplet.py:16-46 `triplet_loss`; loss [B]; dy [B*3D] optional (dloss NULL -> 1) */
+int dif_triplet_apn(const float* y_pred, int B, int D, float alpha, float* loss, const float* dloss, float* dy,
+                    void* stream);
+/* deep_insight_face/networks/siamese.py:22-24 `euclidean_distance`: out [B] = sqrt(max(sum((x-y)^2), eps)) */
+int dif_euclidean_distance(const float* x, const float* y, int B, int D, float eps, float* out, void* stream);
+/* deep_insight_face/networks/siamese.py:32-39 `contrastive_loss` (margin 1): out [1] mean loss; dd [B] optional */
+int dif_contrastive_loss(const float* y_true, const float* dist, int B, float margin, float* out, float* dd,
+                         void* stream);
+
+/* ---- ArcFace additive-angular-margin logits + softmax cross-entropy ------------------------
+ * Absent from the reference; spec in DESIGN.md (arXiv 1801.07698): logits = s*cos(theta + m*onehot)
+ * over L2-normalised X [B,D] and W [C,D]; loss [B]; dX [B*D], dW [C*D] gradients of mean(loss)
+ * (either may be NULL to skip the backward pass). */
+int dif_arcface(const float* X, const float* W, const int32_t* y, int B, int C, int D, float s, float m,
+                float* loss, float* dX, float* dW, int precision, void* stream);
+
+/* ---- pair verification --------------------------------------------------------------------
+ * deep_insight_face/evaluation/utility.py:52-66 `distance`: out [N]; metric 0 squared L2,
+ * metric 1 arccos(cosine)/pi. */
+int dif_pair_distance(const float* e1, const float* e2, int64_t N, int D, int metric, float* out, void* stream);
+int dif_pair_distance_host(const float* e1_host, const float* e2_host, int64_t N, int D, int metric,
+                           float* out_host);
+/* deep_insight_face/evaluation/utility.py:36-49 `calculate_accuracy` / :69-77 `calculate_val_far`
+ * for T thresholds in one pass: counts [T*4] int64 = tp, fp, tn, fn with predict = dist < thr
+ * (strict, np.less); `select` (uint8 [N], may be NULL) restricts to a fold's train or test set. */
+int dif_threshold_sweep(const float* dist, const uint8_t* issame, const uint8_t* select, int64_t N,
+                        const float* thresholds, int T, int64_t* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIF_B200_H_ */
