@@ -1,0 +1,104 @@
+"""In-tree build of libdif_b200.so (nvcc, sm_100a only) and of the CPU oracle used by the tests.
+
+The shared objects stay next to their sources (git-ignored) so a `gpurun` snapshot carries them to
+the GPU box, where nothing is compiled.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_DIR = os.path.dirname(PKG_DIR)
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libdif_b200.so")
+ORACLE_DIR = os.path.join(REPO_DIR, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "libdif_oracle.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libdif_b200.so cannot be built")
+
+
+def _digest(paths) -> str:
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        h.update(p.encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _sources():
+    cu = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    hdr = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    hdr.append(os.path.join(REPO_DIR, "include", "dif_b200.h"))
+    return cu, hdr
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile every csrc/*.cu for sm_100a and link libdif_b200.so.  Returns its path."""
+    cu, hdr = _sources()
+    stamp = os.path.join(PKG_DIR, "build", "stamp")
+    digest = _digest(cu + hdr + [os.path.abspath(__file__)])
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return LIB_PATH
+    nvcc = _nvcc()
+    obj_dir = os.path.join(PKG_DIR, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v", "-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        with open(obj + ".ptxas.log", "w") as f:
+            f.write(r.stderr)
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(cu))) as ex:
+        objs = list(ex.map(compile_one, cu))
+    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return LIB_PATH
+
+
+def build_oracle(force: bool = False) -> str:
+    """gcc build of oracle/dif_oracle.c (test infrastructure, never loaded by the package)."""
+    src = os.path.join(ORACLE_DIR, "dif_oracle.c")
+    stamp = os.path.join(ORACLE_DIR, ".stamp")
+    digest = _digest([src])
+    if not force and os.path.exists(ORACLE_LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return ORACLE_LIB
+    cmd = ["gcc", "-O3", "-fopenmp", "-ffp-contract=off", "-mfma", "-mavx2", "-fPIC", "-shared",
+           "-fvisibility=hidden", "-o", ORACLE_LIB, src, "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"gcc failed for the oracle:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return ORACLE_LIB
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_oracle(force="--force" in sys.argv))
