@@ -82,6 +82,7 @@ SIGNATURES = {
     "dif_topk_merge": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "dif_synth_fill": (_i32, [_vp, _u64, _i64, _vp, _i64, _i32, _vp]),
     "dif_debug_nt_gemm": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
+    "dif_debug_gemm_time": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_f32)]),
     "dif_batch_hard": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "dif_batch_hard_host": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
     "dif_triplet_apn": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
@@ -89,10 +90,11 @@ SIGNATURES = {
     "dif_contrastive_loss": (_i32, [_vp, _vp, _i32, _f32, _vp, _vp, _vp]),
     "dif_arcface": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _i32, _vp]),
     "dif_arcface_host": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _i32]),
-    "dif_pair_distance": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
-    "dif_pair_distance_host": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp]),
-    "dif_threshold_sweep": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp]),
-    "dif_threshold_sweep_host": (_i32, [_vp, _vp, _vp, _i64, _vp, _i32, _vp]),
+    "dif_pair_distance": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "dif_pair_distance_host": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "dif_fold_mean": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "dif_threshold_sweep": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "dif_threshold_sweep_host": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _i32, _vp]),
 }
 
 _lib = None

@@ -228,6 +228,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// One column: this warp's 32 lanes x 1 fp32 column (slow paths re-read single accumulator columns).
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(v) : : "memory");
+  return v;
+}
 // Wait for this thread's outstanding tcgen05.ld; the registers are listed as in/out operands so
 // the compiler cannot schedule a use of them above the wait.
 __device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {

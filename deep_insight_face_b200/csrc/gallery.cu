@@ -18,28 +18,14 @@
 #include <new>
 #include <vector>
 
-#include "dif_canon.cuh"
-#include "nt_gemm.cuh"
+#include "gallery_epi.cuh"
 
 namespace dif {
 
-constexpr int kGalBN = 256;
 constexpr int kRerankThreads = 128;
 constexpr int kRerankCap = 256;     // candidates inside the 2*eps window before a query is flagged
 constexpr int kExactChunks = 64;    // row chunks per flagged query in the exact scan
 constexpr int kExactThreads = 256;
-
-// Error bound of the tensor-core pass relative to |q| * |g| (cosine: both are 1).
-//   3xTF32: dropped lo*lo terms + truncation of lo (2^-20) + <= 3*D/8 fp32 accumulations
-//   1xTF32: operand truncation 2 * 2^-10;   bf16: operand rounding 2 * 2^-9
-__host__ __device__ inline float mode_eps(int precision) {
-  return precision == DIF_PREC_TF32X3 ? 1.0e-4f : (precision == DIF_PREC_BF16 ? 5.0e-3f : 2.5e-3f);
-}
-
-__device__ __forceinline__ float key_score(uint64_t key) {
-  const uint32_t o = (uint32_t)(key >> 32);
-  return __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
-}
 
 // ------------------------------------------------------------------------------------------
 // K5: rows -> canonical planes.  One warp per row.
@@ -97,91 +83,6 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
     }
   }
 }
-
-// ------------------------------------------------------------------------------------------
-// K6 epilogue: per-query top-KP list per split, kept in shared memory ([slot][thread] layout so a
-// warp's accesses to one slot are 256 contiguous bytes).  A thread replaces the current minimum
-// of its list when a score beats it and rescans for the new minimum; after the first few tiles
-// this happens rarely, and the common path per 32 columns is a max-reduction and one compare.
-// ------------------------------------------------------------------------------------------
-template <int METRIC>
-struct TopkEpi {
-  struct Params {
-    uint64_t* cand;      // [rows padded][n_splits][kp]
-    const float* gnorm;  // [n_rows padded to tile] canonical |g|^2 (METRIC 0)
-    int n_rows;
-    int n_splits;
-    int kp;
-  };
-  static constexpr int kSmemBytes = DIF_MAX_TOPK * GEMM_BM * 8;
-
-  const Params& p;
-  uint64_t* keys;  // this thread's slot 0; slot s at keys[s * GEMM_BM]
-  float thr;
-  int min_slot;
-
-  __device__ TopkEpi(const Params& pp, uint8_t* smem, int row)
-      : p(pp), keys(reinterpret_cast<uint64_t*>(smem) + row), thr(0.f), min_slot(0) {}
-
-  __device__ void begin_item(int, int, int) {
-    for (int s = 0; s < p.kp; ++s) keys[s * GEMM_BM] = 0ull;
-    thr = -INFINITY;
-    min_slot = 0;
-  }
-
-  __device__ __forceinline__ void insert(float v, int col) {
-    keys[min_slot * GEMM_BM] = make_key(v, (uint32_t)col);
-    uint64_t mn = keys[0];
-    int ms = 0;
-    for (int s = 1; s < p.kp; ++s) {
-      const uint64_t k2 = keys[s * GEMM_BM];
-      if (k2 < mn) {
-        mn = k2;
-        ms = s;
-      }
-    }
-    min_slot = ms;
-    thr = (mn == 0ull) ? -INFINITY : key_score(mn);
-  }
-
-  __device__ __forceinline__ void consume(int col0, const uint32_t (&acc)[32]) {
-    float v[32];
-    if (METRIC == 1) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
-    } else {
-      const float4* gn = reinterpret_cast<const float4*>(p.gnorm + col0);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 g = __ldg(gn + i);
-        v[4 * i + 0] = __fmaf_rn(2.f, __uint_as_float(acc[4 * i + 0]), -g.x);
-        v[4 * i + 1] = __fmaf_rn(2.f, __uint_as_float(acc[4 * i + 1]), -g.y);
-        v[4 * i + 2] = __fmaf_rn(2.f, __uint_as_float(acc[4 * i + 2]), -g.z);
-        v[4 * i + 3] = __fmaf_rn(2.f, __uint_as_float(acc[4 * i + 3]), -g.w);
-      }
-    }
-    if (col0 + 32 > p.n_rows) {
-      // ragged last tile: TMA zero-filled the rows past the end, they must not compete
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (col0 + i < p.n_rows && v[i] > thr) insert(v[i], col0 + i);
-      return;
-    }
-    float m = v[0];
-#pragma unroll
-    for (int i = 1; i < 32; ++i) m = fmaxf(m, v[i]);
-    if (m > thr) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (v[i] > thr) insert(v[i], col0 + i);
-    }
-  }
-
-  __device__ void end_item(int m_row, int split) {
-    uint64_t* out = p.cand + ((size_t)m_row * p.n_splits + split) * p.kp;
-    for (int s = 0; s < p.kp; ++s) out[s] = keys[s * GEMM_BM];
-  }
-};
 
 // ------------------------------------------------------------------------------------------
 // Selection helpers on unique 64-bit keys held in shared memory.
@@ -287,15 +188,8 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
     prev = block_max_u64(best, red);
     if (prev == 0ull) break;
   }
-  float eps = p.eps_rel;
-  if (p.metric == 0) {
-    const float qn = sqrtf(p.q_sq[q]);
-    const uint32_t o = *p.gmax;
-    const float gn = sqrtf(fmaxf(__uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o), 0.f));
-    eps = 2.f * p.eps_rel * qn * gn + 4e-6f * (qn + gn) * (qn + gn);
-  } else {
-    eps += 4e-6f;
-  }
+  const float eps = window_eps(p.metric, p.eps_rel, p.metric == 0 ? p.q_sq[q] : 1.f,
+                               p.metric == 0 ? orderable_to_float(*p.gmax) : 1.f);
   const float lim = prev == 0ull ? -INFINITY : key_score(prev) - 2.f * eps;
 
   // a full list whose minimum reaches the window may hide a better row that was evicted
@@ -498,6 +392,7 @@ struct dif_gallery {
   uint64_t* cand = nullptr;
   size_t cand_elems = 0;
   int* flagged = nullptr;  // [0] = count, [1..] = list
+  unsigned int* bound = nullptr;  // [q_cap] shared per-query lower bound on the k-th best score
   uint64_t* ex_keys = nullptr;
   size_t ex_elems = 0;
   // host staging for the *_host entry points
@@ -507,9 +402,11 @@ struct dif_gallery {
   size_t d_stage_bytes = 0;
   cudaStream_t own_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int64_t stats[4] = {0, 0, 0, 0};
+  int64_t stats[6] = {0, 0, 0, 0, 0, 0};
   int opt_ctas = 2;
   int opt_force_fallback = 0;
+  int opt_resident = -1;   // -1 auto, 0 never, 1 whenever it fits
+  int opt_splits = 0;      // 0 auto
 };
 
 namespace {
@@ -534,8 +431,8 @@ int prep_launch(const PrepParams& pp, bool synth, cudaStream_t st) {
 int ensure_query_ws(dif_gallery* g, int Q, int S, int kp) {
   const int q_pad = (int)round_up(Q, GEMM_BM * 2);
   if (q_pad > g->q_cap) {
-    cudaFree(g->q0); cudaFree(g->q1); cudaFree(g->qb); cudaFree(g->qsq); cudaFree(g->flagged);
-    g->q0 = g->q1 = nullptr; g->qb = nullptr; g->qsq = nullptr; g->flagged = nullptr;
+    cudaFree(g->q0); cudaFree(g->q1); cudaFree(g->qb); cudaFree(g->qsq); cudaFree(g->flagged); cudaFree(g->bound);
+    g->q0 = g->q1 = nullptr; g->qb = nullptr; g->qsq = nullptr; g->flagged = nullptr; g->bound = nullptr;
     g->q_cap = 0;
     if (int rc = dev_alloc(&g->q0, (size_t)q_pad * g->D)) return rc;
     if (g->precision == DIF_PREC_TF32X3)
@@ -544,6 +441,8 @@ int ensure_query_ws(dif_gallery* g, int Q, int S, int kp) {
       if (int rc = dev_alloc(&g->qb, (size_t)q_pad * g->D)) return rc;
     if (int rc = dev_alloc(&g->qsq, (size_t)q_pad)) return rc;
     if (int rc = dev_alloc(&g->flagged, (size_t)q_pad + 1)) return rc;
+    if (int rc = dev_alloc(&g->bound, (size_t)q_pad)) return rc;
+    DIF_CUDA_OK(cudaMemset(g->qsq, 0, (size_t)q_pad * 4));
     g->q_cap = q_pad;
   }
   const size_t need = (size_t)q_pad * S * kp;
@@ -557,15 +456,14 @@ int ensure_query_ws(dif_gallery* g, int Q, int S, int kp) {
   return DIF_OK;
 }
 
-template <int PREC, int CTAS>
-int launch_search(dif_gallery* g, const CUtensorMap* maps, const GemmShape& shape, int kp, cudaStream_t st) {
-  const int n_units = std::max(1, device_sm_count() / CTAS);
-  if (g->metric == DIF_METRIC_COSINE) {
-    TopkEpi<1>::Params ep{g->cand, g->gsq, (int)g->size, shape.n_splits, kp};
-    return launch_nt_gemm<PREC, kGalBN, CTAS, TopkEpi<1>>(maps, shape, ep, n_units, st);
-  }
-  TopkEpi<0>::Params ep{g->cand, g->gsq, (int)g->size, shape.n_splits, kp};
-  return launch_nt_gemm<PREC, kGalBN, CTAS, TopkEpi<0>>(maps, shape, ep, n_units, st);
+// resident-A schedule whenever the query block (all of K) fits beside a >= 3-stage B ring
+bool ares_fits(int precision, int k_chunks) {
+  GemmSmemPlan plan;
+  const int epi = TopkEpi<1>::kSmemBytes;
+  bool ok = false;
+  if (precision == DIF_PREC_BF16) ok = plan_gemm_smem<1, kGalBN, 2, 1>(k_chunks, epi, &plan);
+  else if (precision == DIF_PREC_TF32X1) ok = plan_gemm_smem<2, kGalBN, 2, 1>(k_chunks, epi, &plan);
+  return ok && plan.stages >= 3;
 }
 
 }  // namespace
@@ -610,7 +508,7 @@ void dif_gallery_destroy(dif_gallery_t* g) {
   if (!g) return;
   cudaFree(g->g0); cudaFree(g->g1); cudaFree(g->gb); cudaFree(g->gsq); cudaFree(g->gmax); cudaFree(g->ids);
   cudaFree(g->q0); cudaFree(g->q1); cudaFree(g->qb); cudaFree(g->qsq); cudaFree(g->cand); cudaFree(g->flagged);
-  cudaFree(g->ex_keys); cudaFree(g->d_stage);
+  cudaFree(g->bound); cudaFree(g->ex_keys); cudaFree(g->d_stage);
   if (g->h_pin) cudaFreeHost(g->h_pin);
   if (g->own_stream) cudaStreamDestroy(g->own_stream);
   if (g->ev0) cudaEventDestroy(g->ev0);
@@ -625,6 +523,10 @@ int dif_gallery_set_option(dif_gallery_t* g, const char* name, int value) {
     g->opt_ctas = value;
   } else if (!strcmp(name, "force_fallback")) {
     g->opt_force_fallback = value != 0;
+  } else if (!strcmp(name, "resident_queries")) {
+    g->opt_resident = value < 0 ? -1 : (value != 0);
+  } else if (!strcmp(name, "splits")) {
+    g->opt_splits = value < 0 ? 0 : value;
   } else {
     DIF_REQUIRE(false, DIF_ERR_INVALID, "unknown option '%s'", name);
   }
@@ -751,6 +653,7 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
     splits = std::max(1, (units * rounds + shape.m_blocks - 1) / shape.m_blocks);
     splits = std::min(splits, shape.n_tiles);
     splits = std::min(splits, 512);
+    if (g->opt_splits > 0) splits = std::min(g->opt_splits, shape.n_tiles);
   }
   shape.n_splits = splits;
   shape.tiles_per_split = shape.n_tiles > 0 ? (shape.n_tiles + splits - 1) / splits : 0;
@@ -789,17 +692,14 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
       if (int rc = make_tmap_2d(&maps[1], g->q1, n_queries, D, (uint64_t)D * 4, GEMM_BM, bcols, 0)) return rc;
       if (int rc = make_tmap_2d(&maps[3], g->g1, g->size, D, (uint64_t)D * 4, kGalBN / ctas, bcols, 0)) return rc;
     }
+    DIF_CUDA_OK(cudaMemsetAsync(g->bound, 0, (size_t)g->q_cap * sizeof(unsigned int), st));
+    TopkEpi<1>::Params ep{g->cand, g->gsq, g->bound, g->qsq, g->gmax, (int)g->size, splits, kp, mode_eps(g->precision)};
+    const int ares = ctas == 2 && g->opt_resident != 0 && ares_fits(g->precision, shape.k_chunks);
+    g->stats[4] = ares;
     DIF_CUDA_OK(cudaEventRecord(g->ev0, st));
-    int rc;
-    if (ctas == 2) {
-      rc = g->precision == DIF_PREC_TF32X3 ? launch_search<0, 2>(g, maps, shape, kp, st)
-           : g->precision == DIF_PREC_BF16 ? launch_search<1, 2>(g, maps, shape, kp, st)
-                                           : launch_search<2, 2>(g, maps, shape, kp, st);
-    } else {
-      rc = g->precision == DIF_PREC_TF32X3 ? launch_search<0, 1>(g, maps, shape, kp, st)
-           : g->precision == DIF_PREC_BF16 ? launch_search<1, 1>(g, maps, shape, kp, st)
-                                           : launch_search<2, 1>(g, maps, shape, kp, st);
-    }
+    const int rc = g->precision == DIF_PREC_TF32X3 ? launch_search_tf32x3(g->metric, ctas, ares, maps, shape, ep, units, st)
+                   : g->precision == DIF_PREC_BF16 ? launch_search_bf16(g->metric, ctas, ares, maps, shape, ep, units, st)
+                                                   : launch_search_tf32x1(g->metric, ctas, ares, maps, shape, ep, units, st);
     if (rc) return rc;
     DIF_CUDA_OK(cudaEventRecord(g->ev1, st));
   } else {
@@ -886,7 +786,7 @@ int dif_gallery_search_host(dif_gallery_t* g, const float* queries_host, int n_q
   return DIF_OK;
 }
 
-int dif_gallery_last_stats(const dif_gallery_t* g, int64_t out[4]) {
+int dif_gallery_last_stats(const dif_gallery_t* g, int64_t out[6]) {
   DIF_REQUIRE(g && out, DIF_ERR_INVALID, "null argument");
   int n_flag = 0;
   if (g->flagged) DIF_CUDA_OK(cudaMemcpy(&n_flag, g->flagged, sizeof(int), cudaMemcpyDeviceToHost));
@@ -894,6 +794,8 @@ int dif_gallery_last_stats(const dif_gallery_t* g, int64_t out[4]) {
   out[1] = g->stats[1];
   out[2] = g->stats[2];
   out[3] = g->stats[3];
+  out[4] = g->stats[4];
+  out[5] = 0;
   return DIF_OK;
 }
 

@@ -17,13 +17,34 @@ struct StoreEpi {
   int m_row;
   __device__ StoreEpi(const Params& pp, uint8_t*, int) : p(pp), m_row(0) {}
   __device__ void begin_item(int m, int, int) { m_row = m; }
-  __device__ void consume(int col0, const uint32_t (&acc)[32]) {
+  __device__ void begin_tile() {}
+  __device__ void consume(int col0, const uint32_t (&acc)[32], uint32_t, uint32_t (&)[32]) {
     if (m_row >= p.M) return;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
       if (col0 + i < p.N) p.C[(size_t)m_row * p.N + col0 + i] = __uint_as_float(acc[i]);
   }
   __device__ void end_item(int, int) {}
+};
+
+// Epilogue that only folds the tile into one checksum per row: isolates main-loop speed.
+struct SumEpi {
+  struct Params {
+    float* row_sum;  // [rows padded]
+  };
+  static constexpr int kSmemBytes = 16;
+  const Params& p;
+  float acc_sum;
+  __device__ SumEpi(const Params& pp, uint8_t*, int) : p(pp), acc_sum(0.f) {}
+  __device__ void begin_item(int, int, int) { acc_sum = 0.f; }
+  __device__ void begin_tile() {}
+  __device__ void consume(int, const uint32_t (&acc)[32], uint32_t, uint32_t (&)[32]) {
+    float m = __uint_as_float(acc[0]);
+#pragma unroll
+    for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(acc[i]));
+    acc_sum += m;
+  }
+  __device__ void end_item(int m_row, int) { atomicAdd(p.row_sum + m_row, acc_sum); }
 };
 
 __global__ void split_planes_kernel(const float* x, int64_t n, float* hi, float* lo, __nv_bfloat16* bf) {
@@ -40,7 +61,7 @@ __global__ void split_planes_kernel(const float* x, int64_t n, float* hi, float*
 
 template <int PREC, int CTAS>
 static int run_debug(const void* a0, const void* a1, const void* b0, const void* b1, int M, int N, int K, float* C,
-                     int n_splits, cudaStream_t st) {
+                     int n_splits, int ares, cudaStream_t st) {
   constexpr int BN = 256;
   const bool bf = PREC == 1;
   const int esz = bf ? 2 : 4;
@@ -59,17 +80,108 @@ static int run_debug(const void* a0, const void* a1, const void* b0, const void*
   shape.n_splits = (shape.n_tiles + shape.tiles_per_split - 1) / shape.tiles_per_split;
   StoreEpi::Params ep{C, M, N};
   const int units = std::max(1, device_sm_count() / CTAS);
-  return launch_nt_gemm<PREC, BN, CTAS, StoreEpi>(maps, shape, ep, units, st);
+  if (ares) {
+    if constexpr (PREC != 0 && CTAS == 2) return launch_nt_gemm<PREC, BN, CTAS, 1, StoreEpi>(maps, shape, ep, units, st);
+  }
+  return launch_nt_gemm<PREC, BN, CTAS, 0, StoreEpi>(maps, shape, ep, units, st);
+}
+
+template <int PREC, int CTAS>
+static int run_time(const void* a0, const void* a1, const void* b0, const void* b1, int M, int N, int K, float* rs,
+                    int n_splits, int ares, cudaStream_t st) {
+  constexpr int BN = 256;
+  const bool bf = PREC == 1;
+  const int esz = bf ? 2 : 4;
+  const uint32_t bcols = 128 / esz;
+  CUtensorMap maps[4];
+  if (int rc = make_tmap_2d(&maps[0], a0, M, K, (uint64_t)K * esz, GEMM_BM, bcols, bf)) return rc;
+  if (int rc = make_tmap_2d(&maps[1], a1, M, K, (uint64_t)K * esz, GEMM_BM, bcols, bf)) return rc;
+  if (int rc = make_tmap_2d(&maps[2], b0, N, K, (uint64_t)K * esz, BN / CTAS, bcols, bf)) return rc;
+  if (int rc = make_tmap_2d(&maps[3], b1, N, K, (uint64_t)K * esz, BN / CTAS, bcols, bf)) return rc;
+  GemmShape shape{};
+  shape.m_blocks = (M + GEMM_BM * CTAS - 1) / (GEMM_BM * CTAS);
+  shape.n_tiles = (N + BN - 1) / BN;
+  shape.k_chunks = (K + (int)bcols - 1) / (int)bcols;
+  shape.n_splits = std::max(1, std::min(n_splits, shape.n_tiles));
+  shape.tiles_per_split = (shape.n_tiles + shape.n_splits - 1) / shape.n_splits;
+  shape.n_splits = (shape.n_tiles + shape.tiles_per_split - 1) / shape.tiles_per_split;
+  SumEpi::Params ep{rs};
+  const int units = std::max(1, device_sm_count() / CTAS);
+  if (ares) {
+    if constexpr (PREC != 0 && CTAS == 2) return launch_nt_gemm<PREC, BN, CTAS, 1, SumEpi>(maps, shape, ep, units, st);
+  }
+  return launch_nt_gemm<PREC, BN, CTAS, 0, SumEpi>(maps, shape, ep, units, st);
 }
 
 }  // namespace dif
 
 using namespace dif;
 
+// diagnostic: time the NT-GEMM main loop (checksum epilogue, nothing written per element) on synthetic
+// operands; ms_out = average over `iters` launches (CUDA events on `stream`).
+extern "C" int dif_debug_gemm_time(int M, int N, int K, int precision, int ctas, int n_splits, int iters,
+                                   float* ms_out) {
+  const int ares = (ctas & 16) ? 1 : 0;
+  ctas &= 15;
+  DIF_REQUIRE(M > 0 && N > 0 && K >= 64 && K % 8 == 0 && ms_out && iters > 0, DIF_ERR_INVALID, "dif_debug_gemm_time: bad shape");
+  DIF_REQUIRE(precision >= 0 && precision <= 2 && (ctas == 1 || ctas == 2), DIF_ERR_INVALID, "bad precision/ctas");
+  DIF_REQUIRE(!ares || (ctas == 2 && precision != DIF_PREC_TF32X3), DIF_ERR_INVALID, "resident-A needs ctas 2, bf16/tf32");
+  DIF_REQUIRE(device_sm_count() > 0, DIF_ERR_STATE, "dif_init has not succeeded on this process");
+  const size_t na = (size_t)M * K, nb = (size_t)N * K;
+  float *a = nullptr, *b = nullptr, *rs = nullptr;
+  __nv_bfloat16 *ab = nullptr, *bb = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto cleanup = [&] {
+    cudaFree(a); cudaFree(b); cudaFree(rs); cudaFree(ab); cudaFree(bb);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  };
+  if (cudaMalloc((void**)&a, na * 4) || cudaMalloc((void**)&b, nb * 4) || cudaMalloc((void**)&rs, ((size_t)M + 512) * 4) ||
+      cudaMalloc((void**)&ab, na * 2) || cudaMalloc((void**)&bb, nb * 2) || cudaEventCreate(&e0) || cudaEventCreate(&e1)) {
+    cleanup();
+    set_error("dif_debug_gemm_time: allocation failed");
+    return DIF_ERR_CUDA;
+  }
+  cudaMemset(rs, 0, ((size_t)M + 512) * 4);
+  if (int rc = dif_synth_fill(a, 11, 0, nullptr, M, K, nullptr)) { cleanup(); return rc; }
+  if (int rc = dif_synth_fill(b, 12, 0, nullptr, N, K, nullptr)) { cleanup(); return rc; }
+  split_planes_kernel<<<148 * 4, 256>>>(a, (int64_t)na, nullptr, nullptr, ab);
+  split_planes_kernel<<<148 * 4, 256>>>(b, (int64_t)nb, nullptr, nullptr, bb);
+  int rc = DIF_OK;
+  for (int i = 0; i < iters + 2 && rc == DIF_OK; ++i) {
+    if (i == 2) cudaEventRecord(e0, nullptr);
+    if (precision == DIF_PREC_BF16)
+      rc = ctas == 2 ? run_time<1, 2>(ab, ab, bb, bb, M, N, K, rs, n_splits, ares, nullptr)
+                     : run_time<1, 1>(ab, ab, bb, bb, M, N, K, rs, n_splits, ares, nullptr);
+    else if (precision == DIF_PREC_TF32X1)
+      rc = ctas == 2 ? run_time<2, 2>(a, a, b, b, M, N, K, rs, n_splits, ares, nullptr)
+                     : run_time<2, 1>(a, a, b, b, M, N, K, rs, n_splits, ares, nullptr);
+    else  // 3xTF32 timing uses the same plane for hi and lo: identical instruction stream and traffic
+      rc = ctas == 2 ? run_time<0, 2>(a, a, b, b, M, N, K, rs, n_splits, ares, nullptr)
+                     : run_time<0, 1>(a, a, b, b, M, N, K, rs, n_splits, ares, nullptr);
+  }
+  cudaEventRecord(e1, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  float ms = 0.f;
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  *ms_out = ms / (float)iters;
+  cleanup();
+  if (rc) return rc;
+  if (e != cudaSuccess) {
+    set_error("dif_debug_gemm_time: %s", cudaGetErrorString(e));
+    return DIF_ERR_CUDA;
+  }
+  return DIF_OK;
+}
+
 extern "C" int dif_debug_nt_gemm(const float* A, const float* B, int M, int N, int K, float* C, int precision, int ctas,
                                  int n_splits, void* stream) {
   DIF_REQUIRE(A && B && C && M > 0 && N > 0 && K >= 32 && K % 4 == 0, DIF_ERR_INVALID, "dif_debug_nt_gemm: bad shape");
+  // ctas = 1 | 2 selects the CTA-pair mode; ctas + 16 additionally asks for the resident-A schedule
+  const int ares = (ctas & 16) ? 1 : 0;
+  ctas &= 15;
   DIF_REQUIRE(precision >= 0 && precision <= 2 && (ctas == 1 || ctas == 2), DIF_ERR_INVALID, "bad precision/ctas");
+  DIF_REQUIRE(!ares || (ctas == 2 && precision != DIF_PREC_TF32X3), DIF_ERR_INVALID, "resident-A needs ctas 2, bf16/tf32");
   DIF_REQUIRE(precision != DIF_PREC_BF16 || (K % 8 == 0 && K >= 64), DIF_ERR_INVALID, "bf16 needs K %% 8 == 0, K >= 64");
   DIF_REQUIRE(device_sm_count() > 0, DIF_ERR_STATE, "dif_init has not succeeded on this process");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -88,8 +200,8 @@ extern "C" int dif_debug_nt_gemm(const float* A, const float* B, int M, int N, i
     split_planes_kernel<<<148 * 4, 256, 0, st>>>(A, (int64_t)na, ah, al, nullptr);
     split_planes_kernel<<<148 * 4, 256, 0, st>>>(B, (int64_t)nb, bh, bl, nullptr);
     count_launch(2);
-    rc = ctas == 2 ? run_debug<0, 2>(ah, al, bh, bl, M, N, K, C, n_splits, st)
-                   : run_debug<0, 1>(ah, al, bh, bl, M, N, K, C, n_splits, st);
+    rc = ctas == 2 ? run_debug<0, 2>(ah, al, bh, bl, M, N, K, C, n_splits, ares, st)
+                   : run_debug<0, 1>(ah, al, bh, bl, M, N, K, C, n_splits, ares, st);
   } else if (precision == DIF_PREC_BF16) {
     if (cudaMalloc((void**)&ab, na * 2) || cudaMalloc((void**)&bb, nb * 2)) {
       cleanup();
@@ -99,11 +211,11 @@ extern "C" int dif_debug_nt_gemm(const float* A, const float* B, int M, int N, i
     split_planes_kernel<<<148 * 4, 256, 0, st>>>(A, (int64_t)na, nullptr, nullptr, ab);
     split_planes_kernel<<<148 * 4, 256, 0, st>>>(B, (int64_t)nb, nullptr, nullptr, bb);
     count_launch(2);
-    rc = ctas == 2 ? run_debug<1, 2>(ab, ab, bb, bb, M, N, K, C, n_splits, st)
-                   : run_debug<1, 1>(ab, ab, bb, bb, M, N, K, C, n_splits, st);
+    rc = ctas == 2 ? run_debug<1, 2>(ab, ab, bb, bb, M, N, K, C, n_splits, ares, st)
+                   : run_debug<1, 1>(ab, ab, bb, bb, M, N, K, C, n_splits, ares, st);
   } else {
-    rc = ctas == 2 ? run_debug<2, 2>(A, A, B, B, M, N, K, C, n_splits, st)
-                   : run_debug<2, 1>(A, A, B, B, M, N, K, C, n_splits, st);
+    rc = ctas == 2 ? run_debug<2, 2>(A, A, B, B, M, N, K, C, n_splits, ares, st)
+                   : run_debug<2, 1>(A, A, B, B, M, N, K, C, n_splits, ares, st);
   }
   cudaError_t e = cudaStreamSynchronize(st);
   cleanup();

@@ -7,12 +7,16 @@
 // Precision modes (PREC):
 //   0  3xTF32: A = Ahi + Alo, B = Bhi + Blo pre-split into TF32 planes; Alo*Bhi + Ahi*Blo + Ahi*Bhi
 //   1  bf16  : single bf16 plane per operand
-//   2  1xTF32: hi planes only
+//   2  1xTF32: fp32 storage read as TF32 by the tensor cores
 //
 // Structure: persistent CTAs (or cta_group::2 CTA pairs), 6 warps: warps 0-3 epilogue (TMEM lane
 // quarter = warp index), warp 4 TMA producer, warp 5 TMEM allocator + single-thread MMA issuer.
-// smem ring of STAGES K-chunks (one 128-byte swizzle row of K per chunk), NBUF accumulator
-// buffers in TMEM so the epilogue of tile t overlaps the MMAs of tile t+1.
+// A work item is (A row block, range of B tiles).  Two operand schedules:
+//   ARES = 0  A and B K-chunks stream together through a ring of smem stages;
+//   ARES = 1  the item's whole A block (all K) is loaded once and stays resident in smem while only
+//             B streams through the ring: halves the L2->smem traffic per MMA, which is what bounds a
+//             128x256 tile at tensor-core speed ("operand feed").
+// NBUF accumulator buffers in TMEM let the epilogue of tile t overlap the MMAs of tile t+1.
 #pragma once
 #include <cuda.h>
 
@@ -25,41 +29,60 @@ constexpr int GEMM_BM = 128;          // A rows per CTA == epilogue threads == T
 constexpr int GEMM_THREADS = 192;     // 4 epilogue warps + producer + MMA
 constexpr int GEMM_SWZ = 128;         // bytes of K per smem row (SWIZZLE_128B)
 constexpr int GEMM_SMEM_MAX = 232448; // 227 KB opt-in limit per CTA
+constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_BAR_BYTES = 1024;
 
 template <int PREC>
 struct PrecTraits {
   static constexpr bool kTf32 = (PREC != 1);
   static constexpr int kElemBytes = kTf32 ? 4 : 2;
   static constexpr int kPlanes = (PREC == 0) ? 2 : 1;
-  static constexpr int kChunkElems = GEMM_SWZ / kElemBytes;  // K elements per stage
-  static constexpr int kKSteps = GEMM_SWZ / 32;               // MMAs (per product) per stage: 32 B of K each
+  static constexpr int kChunkElems = GEMM_SWZ / kElemBytes;  // K elements per chunk
+  static constexpr int kKSteps = GEMM_SWZ / 32;               // MMAs (per product) per chunk: 32 B of K each
   static constexpr uint32_t kFmt = kTf32 ? 2u : 1u;
 };
 
 struct GemmShape {
   int m_blocks;         // number of (128*CTAS)-row blocks of A
   int n_tiles;          // number of BN-row tiles of B
-  int k_chunks;         // K / chunk elems
+  int k_chunks;         // ceil(K / chunk elems)
   int n_splits;         // B tile range is cut into n_splits pieces -> items = n_splits * m_blocks
   int tiles_per_split;  // ceil(n_tiles / n_splits)
+  int stages;           // smem ring depth (host-computed from the shared-memory budget)
 };
 
-template <int PREC, int BN, int CTAS, int EPI_SMEM>
-struct GemmLayout {
+template <int PREC, int BN, int CTAS>
+struct GemmTiles {
   using PT = PrecTraits<PREC>;
-  static constexpr int kATile = GEMM_BM * GEMM_SWZ;       // bytes per plane per stage
+  static constexpr int kATile = GEMM_BM * GEMM_SWZ;       // bytes per plane per K chunk
   static constexpr int kBTile = (BN / CTAS) * GEMM_SWZ;   // each CTA of a pair stages half of B's rows
-  static constexpr int kStage = PT::kPlanes * (kATile + kBTile);
   static constexpr int kAccBufs = 512 / BN;
-  static constexpr int kBarBytes = 1024;
-  static constexpr int kAvail = GEMM_SMEM_MAX - 1024 /*align slack*/ - kBarBytes - EPI_SMEM;
-  static constexpr int kStagesRaw = kAvail / kStage;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-  static constexpr int kSmemBytes = 1024 + kStages * kStage + kBarBytes + EPI_SMEM;
-  static_assert(kStages >= 2, "not enough shared memory for a 2-stage ring");
   static_assert(BN == 128 || BN == 256, "BN");
   static_assert(kAccBufs >= 2, "need two accumulator buffers");
 };
+
+// Host: shared-memory plan of one launch.  Returns false if nothing fits.
+struct GemmSmemPlan {
+  int stages = 0;
+  int a_res_bytes = 0;   // resident A block (ARES = 1), else 0
+  int stage_bytes = 0;
+  int total = 0;
+};
+template <int PREC, int BN, int CTAS, int ARES>
+inline bool plan_gemm_smem(int k_chunks, int epi_smem, GemmSmemPlan* out) {
+  using T = GemmTiles<PREC, BN, CTAS>;
+  using PT = PrecTraits<PREC>;
+  GemmSmemPlan p;
+  p.a_res_bytes = ARES ? PT::kPlanes * k_chunks * T::kATile : 0;
+  p.stage_bytes = PT::kPlanes * ((ARES ? 0 : T::kATile) + T::kBTile);
+  const int avail = GEMM_SMEM_MAX - 1024 /*align slack*/ - GEMM_BAR_BYTES - epi_smem - p.a_res_bytes;
+  if (avail < 2 * p.stage_bytes) return false;
+  p.stages = avail / p.stage_bytes;
+  if (p.stages > GEMM_MAX_STAGES) p.stages = GEMM_MAX_STAGES;
+  p.total = 1024 + p.a_res_bytes + p.stages * p.stage_bytes + GEMM_BAR_BYTES + epi_smem;
+  *out = p;
+  return true;
+}
 
 // Epilogue concept:
 //   struct Epi {
@@ -67,31 +90,42 @@ struct GemmLayout {
 //     static constexpr int kSmemBytes;     // CTA-shared scratch, 16-byte aligned
 //     __device__ Epi(const Params&, uint8_t* smem, int row_in_block);
 //     __device__ void begin_item(int m_row /*global A row of this thread*/, int split, int col_begin);
-//     __device__ void consume(int col0, const uint32_t (&acc)[32]);   // fp32 bits, columns col0..col0+31
+//     __device__ void begin_tile();
+//     // fp32 bits of columns col0..col0+31 of this thread's row; taddr = TMEM address of column col0
+//     // for this warp (a slow path may re-read single columns with tmem_ld1).  `pending` is the
+//     // register block of the NEXT chunk, whose tcgen05.ld may still be in flight: code that could
+//     // make the compiler move or spill registers (any slow path) must tmem_ld_wait(pending) first.
+//     __device__ void consume(int col0, const uint32_t (&acc)[32], uint32_t taddr, uint32_t (&pending)[32]);
 //     __device__ void end_item(int m_row, int split);
 //   };
 
-template <int PREC, int BN, int CTAS, class Epi>
+template <int PREC, int BN, int CTAS, int ARES, class Epi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                        const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                        GemmShape shape, typename Epi::Params ep) {
   using PT = PrecTraits<PREC>;
-  using L = GemmLayout<PREC, BN, CTAS, Epi::kSmemBytes>;
-  constexpr int STAGES = L::kStages;
-  constexpr int NBUF = L::kAccBufs;
+  using T = GemmTiles<PREC, BN, CTAS>;
+  constexpr int NBUF = T::kAccBufs;
+  constexpr int kStage = PT::kPlanes * ((ARES ? 0 : T::kATile) + T::kBTile);
+  constexpr int kBOff = ARES ? 0 : PT::kPlanes * T::kATile;  // offset of the B planes inside a stage
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage);
-  uint64_t* full_bar = bars;                    // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
-  uint64_t* acc_full = bars + 2 * STAGES;       // [NBUF]
-  uint64_t* acc_empty = bars + 2 * STAGES + NBUF;  // [NBUF]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NBUF);
-  uint8_t* epi_smem = smem + STAGES * L::kStage + L::kBarBytes;
+  const int STAGES = shape.stages;
+  const int a_res_bytes = ARES ? PT::kPlanes * shape.k_chunks * T::kATile : 0;
+  uint8_t* a_res = smem;                       // [plane][k_chunk][128 rows x 128 B]
+  uint8_t* stage_base = smem + a_res_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + STAGES * kStage);
+  uint64_t* full_bar = bars;                                   // [8]
+  uint64_t* empty_bar = bars + GEMM_MAX_STAGES;                // [8]
+  uint64_t* acc_full = bars + 2 * GEMM_MAX_STAGES;             // [NBUF]
+  uint64_t* acc_empty = acc_full + NBUF;                       // [NBUF]
+  uint64_t* a_full = acc_empty + NBUF;                         // [1]
+  uint64_t* a_empty = a_full + 1;                              // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+  uint8_t* epi_smem = reinterpret_cast<uint8_t*>(bars) + GEMM_BAR_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
@@ -102,13 +136,15 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], CTAS);   // one arrive(+tx) per producing CTA
+      mbar_init(&full_bar[s], 1);      // the leader's arrive.expect_tx; both CTAs' TMA bytes land on it
       mbar_init(&empty_bar[s], 1);     // one tcgen05.commit
     }
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(&acc_full[b], 1);                 // one tcgen05.commit
-      mbar_init(&acc_empty[b], GEMM_BM * CTAS);   // every epilogue thread of the unit
+      mbar_init(&acc_empty[b], 4 * CTAS);         // one arrive per epilogue warp of the unit
     }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
     fence_mbar_init();
   }
   if (warp == 4 && lane_id() == 0) {
@@ -131,38 +167,56 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
   if (warp == 4) {
     // ===================== TMA producer (one lane) =====================
     if (lane_id() == 0) {
-      uint32_t it = 0;
-      for (int item = unit; item < n_items; item += n_units) {
+      uint32_t it = 0, n_item = 0;
+      for (int item = unit; item < n_items; item += n_units, ++n_item) {
         const int split = item / shape.m_blocks;
         const int mb = item - split * shape.m_blocks;
         const int a_row = (mb * CTAS + (int)cta_rank) * GEMM_BM;
         const int t0 = split * shape.tiles_per_split;
         const int t1 = min(t0 + shape.tiles_per_split, shape.n_tiles);
+        if (ARES) {
+          // the previous item's MMAs must have finished reading the resident block
+          mbar_wait(a_empty, (n_item & 1u) ^ 1u);
+          // Only the leader arrives (with the byte count of BOTH CTAs).  The peer's TMA may complete_tx
+          // before that arrive: the phase cannot complete until the pending arrival is in.  A peer-side
+          // remote arrive would cost a cluster-scope release fence per stage, which serialises its TMAs.
+          if (leader) mbar_arrive_expect_tx(a_full, (uint32_t)a_res_bytes * (uint32_t)CTAS);
+          for (int kc = 0; kc < shape.k_chunks; ++kc) {
+            const int kx = kc * PT::kChunkElems;
+            uint8_t* dst = a_res + kc * T::kATile;
+            if (CTAS == 1) {
+              tma_load_2d(dst, &tm_a_hi, a_full, kx, a_row);
+              if (PT::kPlanes == 2) tma_load_2d(dst + shape.k_chunks * T::kATile, &tm_a_lo, a_full, kx, a_row);
+            } else {
+              tma_load_2d_pair(dst, &tm_a_hi, a_full, kx, a_row);
+              if (PT::kPlanes == 2) tma_load_2d_pair(dst + shape.k_chunks * T::kATile, &tm_a_lo, a_full, kx, a_row);
+            }
+          }
+        }
         for (int t = t0; t < t1; ++t) {
           const int b_row = t * BN + (int)cta_rank * (BN / CTAS);
           for (int kc = 0; kc < shape.k_chunks; ++kc, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(&empty_bar[s], ph ^ 1u);
-            uint8_t* st = stage_base + s * L::kStage;
+            uint8_t* st = stage_base + s * kStage;
             const int kx = kc * PT::kChunkElems;
             if (CTAS == 1) {
-              mbar_arrive_expect_tx(&full_bar[s], L::kStage);
-              tma_load_2d(st, &tm_a_hi, &full_bar[s], kx, a_row);
-              tma_load_2d(st + L::kATile * PT::kPlanes, &tm_b_hi, &full_bar[s], kx, b_row);
+              mbar_arrive_expect_tx(&full_bar[s], kStage);
+              if (!ARES) tma_load_2d(st, &tm_a_hi, &full_bar[s], kx, a_row);
+              tma_load_2d(st + kBOff, &tm_b_hi, &full_bar[s], kx, b_row);
               if (PT::kPlanes == 2) {
-                tma_load_2d(st + L::kATile, &tm_a_lo, &full_bar[s], kx, a_row);
-                tma_load_2d(st + L::kATile * 2 + L::kBTile, &tm_b_lo, &full_bar[s], kx, b_row);
+                if (!ARES) tma_load_2d(st + T::kATile, &tm_a_lo, &full_bar[s], kx, a_row);
+                tma_load_2d(st + kBOff + T::kBTile, &tm_b_lo, &full_bar[s], kx, b_row);
               }
             } else {
-              // Both CTAs' bytes are credited to the leader's barrier.
-              if (leader) mbar_arrive_expect_tx(&full_bar[s], L::kStage * 2);
-              else mbar_arrive_cluster(&full_bar[s], 0);
-              tma_load_2d_pair(st, &tm_a_hi, &full_bar[s], kx, a_row);
-              tma_load_2d_pair(st + L::kATile * PT::kPlanes, &tm_b_hi, &full_bar[s], kx, b_row);
+              // Both CTAs' bytes are credited to the leader's barrier (see a_full above).
+              if (leader) mbar_arrive_expect_tx(&full_bar[s], kStage * 2);
+              if (!ARES) tma_load_2d_pair(st, &tm_a_hi, &full_bar[s], kx, a_row);
+              tma_load_2d_pair(st + kBOff, &tm_b_hi, &full_bar[s], kx, b_row);
               if (PT::kPlanes == 2) {
-                tma_load_2d_pair(st + L::kATile, &tm_a_lo, &full_bar[s], kx, a_row);
-                tma_load_2d_pair(st + L::kATile * 2 + L::kBTile, &tm_b_lo, &full_bar[s], kx, b_row);
+                if (!ARES) tma_load_2d_pair(st + T::kATile, &tm_a_lo, &full_bar[s], kx, a_row);
+                tma_load_2d_pair(st + kBOff + T::kBTile, &tm_b_lo, &full_bar[s], kx, b_row);
               }
             }
           }
@@ -173,11 +227,15 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
     // ===================== MMA issuer (one lane of the leader CTA) =====================
     if (leader && lane_id() == 0) {
       constexpr uint32_t idesc = make_idesc(PT::kFmt, GEMM_BM * CTAS, BN);
-      uint32_t it = 0, tc = 0;
-      for (int item = unit; item < n_items; item += n_units) {
+      uint32_t it = 0, tc = 0, n_item = 0;
+      for (int item = unit; item < n_items; item += n_units, ++n_item) {
         const int split = item / shape.m_blocks;
         const int t0 = split * shape.tiles_per_split;
         const int t1 = min(t0 + shape.tiles_per_split, shape.n_tiles);
+        if (ARES) {
+          mbar_wait(a_full, n_item & 1u);
+          tc_fence_after_sync();
+        }
         for (int t = t0; t < t1; ++t, ++tc) {
           const int buf = tc % NBUF;
           const uint32_t aph = (tc / NBUF) & 1u;
@@ -189,15 +247,17 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(&full_bar[s], ph);
             tc_fence_after_sync();
-            const uint32_t st = smem_u32(stage_base + s * L::kStage);
-            const uint64_t a_hi = make_kmajor_desc<GEMM_SWZ>(st);
-            const uint64_t b_hi = make_kmajor_desc<GEMM_SWZ>(st + L::kATile * PT::kPlanes);
+            const uint32_t st = smem_u32(stage_base + s * kStage);
+            const uint32_t a_addr = ARES ? smem_u32(a_res + kc * T::kATile) : st;
+            const uint32_t a_lo_addr = ARES ? a_addr + (uint32_t)(shape.k_chunks * T::kATile) : st + T::kATile;
+            const uint64_t a_hi = make_kmajor_desc<GEMM_SWZ>(a_addr);
+            const uint64_t b_hi = make_kmajor_desc<GEMM_SWZ>(st + kBOff);
 #pragma unroll
             for (int ks = 0; ks < PT::kKSteps; ++ks) {
               const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes of K, in 16-byte units
               if (PT::kPlanes == 2) {
-                const uint64_t a_lo = make_kmajor_desc<GEMM_SWZ>(st + L::kATile);
-                const uint64_t b_lo = make_kmajor_desc<GEMM_SWZ>(st + L::kATile * 2 + L::kBTile);
+                const uint64_t a_lo = make_kmajor_desc<GEMM_SWZ>(a_lo_addr);
+                const uint64_t b_lo = make_kmajor_desc<GEMM_SWZ>(st + kBOff + T::kBTile);
                 // small cross terms first, dominant term last
                 tc_mma<CTAS, PT::kTf32>(d_tmem, a_lo + adv, b_hi + adv, idesc, (kc | ks) != 0);
                 tc_mma<CTAS, PT::kTf32>(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
@@ -210,6 +270,7 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
           }
           tc_commit<CTAS>(&acc_full[buf]);    // accumulator tile complete
         }
+        if (ARES) tc_commit<CTAS>(a_empty);   // resident A block reusable once the item's MMAs retire
       }
     }
   } else {
@@ -228,6 +289,7 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
       for (int t = t0; t < t1; ++t, ++tc) {
         const int buf = tc % NBUF;
         const uint32_t aph = (tc / NBUF) & 1u;
+        epi.begin_tile();
         mbar_wait(&acc_full[buf], aph);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * BN);
@@ -237,15 +299,18 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
         for (int c = 0; c < BN / 32; c += 2) {
           tmem_ld_wait(va);
           tmem_ld32(taddr + (uint32_t)((c + 1) * 32), vb);
-          epi.consume(t * BN + c * 32, va);
+          epi.consume(t * BN + c * 32, va, taddr + (uint32_t)(c * 32), vb);
           tmem_ld_wait(vb);
           if (c + 2 < BN / 32) tmem_ld32(taddr + (uint32_t)((c + 2) * 32), va);
-          epi.consume(t * BN + (c + 1) * 32, vb);
+          epi.consume(t * BN + (c + 1) * 32, vb, taddr + (uint32_t)((c + 1) * 32), va);
         }
-        // all of this thread's TMEM reads of `buf` have completed (wait::ld above)
+        // all of this warp's TMEM reads of `buf` have completed (wait::ld above)
         tc_fence_before_sync();
-        if (CTAS == 1 || leader) mbar_arrive(&acc_empty[buf]);
-        else mbar_arrive_cluster(&acc_empty[buf], 0);
+        __syncwarp();
+        if (lane_id() == 0) {
+          if (CTAS == 1 || leader) mbar_arrive(&acc_empty[buf]);
+          else mbar_arrive_cluster(&acc_empty[buf], 0);
+        }
       }
       epi.end_item(m_row, split);
     }
@@ -262,20 +327,25 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
 
 // Host-side launch of one instantiation.  maps = {A hi, A lo, B hi, B lo}; single-plane modes pass
 // the hi map twice.  n_units = persistent CTAs (CTAS == 1) or CTA pairs (CTAS == 2).
-template <int PREC, int BN, int CTAS, class Epi>
-int launch_nt_gemm(const CUtensorMap* maps, const GemmShape& shape, const typename Epi::Params& ep, int n_units,
+// shape.stages is filled in here from the shared-memory plan.
+template <int PREC, int BN, int CTAS, int ARES, class Epi>
+int launch_nt_gemm(const CUtensorMap* maps, GemmShape shape, const typename Epi::Params& ep, int n_units,
                    cudaStream_t stream) {
-  using L = GemmLayout<PREC, BN, CTAS, Epi::kSmemBytes>;
-  auto kern = nt_gemm_rowscan_kernel<PREC, BN, CTAS, Epi>;
+  GemmSmemPlan plan;
+  const bool fits = plan_gemm_smem<PREC, BN, CTAS, ARES>(shape.k_chunks, Epi::kSmemBytes, &plan);
+  DIF_REQUIRE(fits, DIF_ERR_CAPACITY, "nt_gemm: K = %d chunks does not fit the shared-memory plan (ARES=%d)",
+              shape.k_chunks, ARES);
+  shape.stages = plan.stages;
+  auto kern = nt_gemm_rowscan_kernel<PREC, BN, CTAS, ARES, Epi>;
   static bool configured = false;   // per instantiation
   if (!configured) {
-    DIF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmemBytes));
+    DIF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_MAX));
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(n_units * CTAS));
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = L::kSmemBytes;
+  cfg.dynamicSmemBytes = (size_t)plan.total;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -70,8 +70,9 @@ int dif_gallery_add_host(dif_gallery_t* g, const float* rows_host, const int64_t
 int dif_gallery_fill_synth(dif_gallery_t* g, uint64_t seed, int64_t row0, int64_t n, void* stream);
 int dif_gallery_set_id_base(dif_gallery_t* g, int64_t id_base); /* default ids = id_base + local row */
 int64_t dif_gallery_size(const dif_gallery_t* g);
-/* tuning / test knobs: "gemm_ctas" = 1 | 2 (CTA pair, default), "force_fallback" = 0 | 1 (send every
- * query through the exact brute-force path as well) */
+/* tuning / test knobs: "gemm_ctas" = 1 | 2 (CTA pair, default); "force_fallback" = 0 | 1 (send every
+ * query through the exact brute-force path as well); "resident_queries" = -1 auto | 0 | 1 (keep the
+ * query block resident in shared memory while gallery tiles stream); "splits" = 0 auto | n */
 int dif_gallery_set_option(dif_gallery_t* g, const char* name, int value);
 int dif_gallery_reset(dif_gallery_t* g);
 /* scores [Q*k] fp32, ids [Q*k] int64, rows [Q*k] int32 local row index (may be NULL).
@@ -82,8 +83,8 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
 int dif_gallery_search_host(dif_gallery_t* g, const float* queries_host, int n_queries, int k,
                             float* scores_host, int64_t* ids_host, int32_t* rows_host);
 /* counters of the last search: [0] queries that took the exact fallback, [1] kernels launched,
- * [2] candidate splits, [3] candidates per split */
-int dif_gallery_last_stats(const dif_gallery_t* g, int64_t out[4]);
+ * [2] candidate splits, [3] candidates per split, [4] 1 if the resident-query schedule ran, [5] reserved */
+int dif_gallery_last_stats(const dif_gallery_t* g, int64_t out[6]);
 /* duration in ms of the last search's tensor-core kernel (CUDA events on the launch stream);
  * only valid after the stream has been synchronised */
 int dif_gallery_last_kernel_ms(dif_gallery_t* g, float* ms);
@@ -100,9 +101,13 @@ int dif_topk_merge(const float* scores, const int64_t* grows, const int64_t* ids
 int dif_synth_fill(float* out, uint64_t seed, int64_t row0, const int64_t* rows_idx, int64_t n, int D, void* stream);
 
 /* diagnostic: C[M,N] (row-major, ldc = N) = A[M,K] * B[N,K]^T through the same tcgen05/TMA skeleton the
- * search and loss kernels use.  precision as above; ctas = 1 | 2.  Used by tests/test_gemm_gpu.py. */
+ * search and loss kernels use.  precision as above; ctas = 1 | 2 (+16: resident-A schedule).
+ * Used by tests/test_gemm_gpu.py. */
 int dif_debug_nt_gemm(const float* A, const float* B, int M, int N, int K, float* C, int precision, int ctas,
                       int n_splits, void* stream);
+
+/* diagnostic: average ms of the NT-GEMM main loop alone (checksum epilogue) on synthetic operands */
+int dif_debug_gemm_time(int M, int N, int K, int precision, int ctas, int n_splits, int iters, float* ms_out);
 
 /* ---- batch-hard / batch-all triplet losses ------------------------------------------------
  * deep_insight_face/common/losses.py:33-51 (BatchHardTripletLoss, cosine),
@@ -141,15 +146,27 @@ int dif_arcface(const float* X, const float* W, const int32_t* y, int B, int C, 
 
 /* ---- pair verification --------------------------------------------------------------------
  * deep_insight_face/evaluation/utility.py:52-66 `distance`: out [N]; metric 0 squared L2,
- * metric 1 arccos(cosine)/pi. */
-int dif_pair_distance(const float* e1, const float* e2, int64_t N, int D, int metric, float* out, void* stream);
+ * metric 1 arccos(cosine)/pi; any other metric fails with "Undefined distance metric %d" (utility.py:64).
+ * mean [D] (may be NULL) is subtracted from both rows first (utility.py:98-102,144-148 `subtract_mean`). */
+int dif_pair_distance(const float* e1, const float* e2, int64_t N, int D, int metric, const float* mean, float* out,
+                      void* stream);
 int dif_pair_distance_host(const float* e1_host, const float* e2_host, int64_t N, int D, int metric,
-                           float* out_host);
-/* deep_insight_face/evaluation/utility.py:36-49 `calculate_accuracy` / :69-77 `calculate_val_far`
- * for T thresholds in one pass: counts [T*4] int64 = tp, fp, tn, fn with predict = dist < thr
- * (strict, np.less); `select` (uint8 [N], may be NULL) restricts to a fold's train or test set. */
-int dif_threshold_sweep(const float* dist, const uint8_t* issame, const uint8_t* select, int64_t N,
-                        const float* thresholds, int T, int64_t* counts, void* stream);
+                           const float* mean_host, float* out_host);
+/* train-fold means of utility.py:98-102: folds are the contiguous KFold(shuffle=False) ranges
+ * [fold_begin[f], fold_begin[f+1]); mean [n_folds*D] row f = mean of both embedding sets over the rows
+ * NOT in fold f.  workspace: n_folds*D doubles. */
+int dif_fold_mean(const float* e1, const float* e2, const int64_t* fold_begin, int n_folds, int D, double* workspace,
+                  float* mean, void* stream);
+/* deep_insight_face/evaluation/utility.py:36-49 `calculate_accuracy` / :69-77 `calculate_val_far` for T
+ * thresholds and every fold in one pass: counts [n_folds*T*4] int64 = tp, fp, tn, fn over the pairs with
+ * fold[i] == f (fold NULL: one fold holding every pair), predict = (double)dist < thresholds[t]
+ * (strict, np.less against the float64 thresholds of np.arange).  ascending != 0 promises sorted
+ * thresholds (histogram + scan path; workspace n_folds*2*(T+1) u32); 0 takes the direct path. */
+int dif_threshold_sweep(const float* dist, const uint8_t* issame, const int32_t* fold, int64_t N, int n_folds,
+                        const double* thresholds, int T, int ascending, unsigned int* workspace, int64_t* counts,
+                        void* stream);
+int dif_threshold_sweep_host(const float* dist_host, const uint8_t* issame_host, const int32_t* fold_host, int64_t N,
+                             int n_folds, const double* thresholds_host, int T, int64_t* counts_host);
 
 #ifdef __cplusplus
 }

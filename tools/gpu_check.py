@@ -68,7 +68,7 @@ def stage_gemm(prec: int, ctas: int):
     print("gemm ok", json.dumps(res))
 
 
-def stage_search(prec: int, ctas: int, metric: int):
+def stage_search(prec: int, ctas: int, metric: int, resident: int = -1):
     import numpy as np
     import torch
 
@@ -83,6 +83,7 @@ def stage_search(prec: int, ctas: int, metric: int):
         q = rows[pick] + 0.3 * orc.synth_rows(33, 0, Q, D)
         g = Gallery(N, D, "cosine" if metric == 1 else "l2", prec)
         g.set_option("gemm_ctas", ctas)
+        g.set_option("resident_queries", resident)
         g.add(rows)
         s, ids, r = g.search(q, k, return_rows=True)
         st = g.last_stats()
@@ -105,7 +106,7 @@ def stage_search(prec: int, ctas: int, metric: int):
 STAGES = {
     "simt": lambda a: stage_simt(),
     "gemm": lambda a: stage_gemm(int(a[0]), int(a[1])),
-    "search": lambda a: stage_search(int(a[0]), int(a[1]), int(a[2])),
+    "search": lambda a: stage_search(*[int(x) for x in a]),
 }
 
 
@@ -115,14 +116,11 @@ def main():
         return
     os.makedirs(OUT, exist_ok=True)
     plan = [["simt"]]
-    for ctas in (1, 2):
-        for prec in (2, 1, 0):
-            plan.append(["gemm", str(prec), str(ctas)])
-    for ctas in (1, 2):
-        for prec in (2, 1, 0):
-            plan.append(["search", str(prec), str(ctas), "1"])
-    plan.append(["search", "0", "2", "0"])
-    plan.append(["search", "1", "1", "0"])
+    for prec, ctas in ((2, 1), (1, 2), (0, 2), (1, 18), (2, 18)):
+        plan.append(["gemm", str(prec), str(ctas)])
+    for prec, ctas, metric, res in ((0, 2, 1, -1), (1, 2, 1, -1), (2, 2, 1, -1), (1, 2, 0, -1), (2, 1, 1, -1),
+                                    (1, 2, 1, 0), (0, 2, 0, -1)):
+        plan.append(["search", str(prec), str(ctas), str(metric), str(res)])
     summary = {}
     for st in plan:
         name = "_".join(st)
