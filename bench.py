@@ -1,0 +1,344 @@
+"""Headline benchmark: 1:N gallery search queries/s (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c5] [--precision P]
+
+N = 1 : config C3 - 1M x 512 fp32 gallery, 4096 queries, top-10 cosine on one B200.
+N > 1 : the same global workload with the gallery rows sharded contiguously over N ranks
+        (strong scaling; one all-gather of the k candidates per query per rank + device merge).
+        `--workload c5` scales to the 100M x 512 / 65536-query configuration (rows = 12.5M x N).
+A step = one search of the whole query batch.  `value` times steps whose queries are already in
+HBM; `e2e` times the public host-facing call (numpy in, numpy out: pinned staging, H2D, search,
+exchange, merge, D2H).  One JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED_GALLERY = 3
+SEED_NOISE = 33
+WORKLOADS = {
+    # name: (rows, queries, dim, k)
+    "c3": (1_000_000, 4096, 512, 10),
+    "c5": (100_000_000, 65536, 512, 10),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override the global gallery rows")
+    ap.add_argument("--queries", type=int, default=0)
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "bf16", "tf32x1"])
+    ap.add_argument("--no-modes", action="store_true", help="skip the extra per-precision measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"bf16_tflops": float(d["bf16_tflops"]), "hbm_gbs": float(d["hbm_gbs"]), "source": "measured"}
+    return {"bf16_tflops": 1590.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+            }
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self._stop_evt.wait(0.02)
+        except Exception as e:  # NVML missing: report that instead of inventing numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except (ValueError, IndexError):
+            return local_rank
+    return local_rank
+
+
+def make_queries(lib, _ffi, torch, n_rows, Q, D, device):
+    """Noisy copies of Q distinct-ish gallery rows: every query has a true match (top-1 sanity check)."""
+    import numpy as np
+
+    rng = np.random.default_rng(12345)
+    pick = torch.from_numpy(rng.integers(0, n_rows, size=Q)).to(device)
+    base = torch.empty((Q, D), device=device)
+    noise = torch.empty((Q, D), device=device)
+    _ffi.check(lib.dif_synth_fill(_ffi.ptr(base), SEED_GALLERY, 0, _ffi.ptr(pick), Q, D, None))
+    _ffi.check(lib.dif_synth_fill(_ffi.ptr(noise), SEED_NOISE, 0, None, Q, D, None))
+    torch.cuda.synchronize()
+    return base + 0.3 * noise, pick
+
+
+def run_reference(args):
+    """The reference's CPU path for this metric: the oracle port (the reference has no 1:N routine and its TF
+    code cannot run here - SURVEY.md section 0), all host threads, a bounded query sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+
+    from oracle import c_oracle as orc
+
+    n_rows, Q, D, k = WORKLOADS[args.workload]
+    n_rows = args.rows or n_rows
+    threads = orc.num_threads()
+    sample_rows = min(n_rows, 1_000_000)
+    sample_q = 32
+    gal = orc.normalize_rows(orc.synth_rows(SEED_GALLERY, 0, sample_rows, D))
+    rng = np.random.default_rng(12345)
+    pick = rng.integers(0, sample_rows, size=sample_q)
+    q = orc.normalize_rows(gal[pick] + 0.3 * orc.synth_rows(SEED_NOISE, 0, sample_q, D))
+    for _ in range(max(1, min(args.warmup, 2))):
+        orc.gallery_search(gal, q, k, 1, normalize=False)
+    steps = max(1, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.gallery_search(gal, q, k, 1, normalize=False)
+    dt = (time.perf_counter() - t0) / steps
+    # queries/s against the FULL gallery: cost is linear in rows, the sample holds sample_rows of them
+    qps = sample_q / dt * (sample_rows / n_rows)
+    sample = (f"{sample_q} queries x {sample_rows} rows per step, {steps} steps, scaled linearly to {n_rows} rows; "
+              "oracle/dif_oracle.c (canonical fp32 brute force + top-k), OpenMP")
+    line = {
+        "impl": "reference", "metric": "gallery queries/s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"1:N gallery search, {n_rows} x {D} fp32 gallery, {Q} queries, top-{k} cosine"},
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from deep_insight_face_b200 import _ffi
+    from deep_insight_face_b200.gallery import ShardedGallery
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _ffi.init(local_rank)
+    lib = _ffi.load_library()
+
+    n_rows, Q, D, k = WORKLOADS[args.workload]
+    if args.workload == "c5":
+        n_rows = 12_500_000 * world  # rows per GPU of the 8-GPU 100M configuration
+    n_rows = args.rows or n_rows
+    Q = args.queries or Q
+    peaks = load_peaks()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def measure(precision: str, steps: int, warmup: int, full: bool):
+        """Returns a dict of timings for one precision mode."""
+        g = ShardedGallery(n_rows, D, "cosine", precision, device=local_rank)
+        g.fill_synthetic(SEED_GALLERY)
+        q_dev, pick = make_queries(lib, _ffi, torch, n_rows, Q, D, device)
+        out = {}
+        for _ in range(warmup):
+            scores, ids, _ = g.search(q_dev, k)
+        barrier()
+        sampler = ClockSampler(physical_gpu_index(local_rank)) if full and rank == 0 else None
+        if sampler:
+            sampler.start()
+        launches0 = _ffi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            scores, ids, _ = g.search(q_dev, k)
+        e1.record()
+        barrier()
+        if sampler:
+            out["clocks"] = sampler.stop()
+        out["launches"] = _ffi.launch_count() - launches0
+        ms = reduce_max(e0.elapsed_time(e1)) / steps
+        out["ms_per_step"] = ms
+        out["qps"] = Q / ms * 1e3
+        out["top1_recall"] = float((ids[:, 0] == pick).float().mean().item())
+        out["fallback_queries"] = g.local.last_stats()["fallback_queries"]
+        # dominant kernel: CUDA events recorded by the library around the tensor-core pass, on its launch stream
+        kms = []
+        for _ in range(max(3, min(steps, 10))):
+            g.search(q_dev, k)
+            torch.cuda.synchronize()
+            kms.append(g.local.last_kernel_ms())
+        out["kernel_ms"] = float(np.mean(kms))
+        if full:
+            # end to end through the host-facing call: numpy in -> numpy out
+            q_host = q_dev.cpu().numpy()
+            for _ in range(max(1, warmup)):
+                g.search_host(q_host, k)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                hs, hi = g.search_host(q_host, k)
+            torch.cuda.synchronize()
+            dt = reduce_max((time.perf_counter() - t0)) / steps
+            out["e2e_qps"] = Q / dt
+            out["e2e_ms"] = dt * 1e3
+            out["h2d"] = int(q_host.nbytes)
+            out["d2h"] = int(hs.nbytes + hi.nbytes)
+            out["e2e_same_ids"] = bool(np.array_equal(hi, ids.cpu().numpy()))
+        out["ids_sample"] = ids[:16].cpu().numpy()
+        out["q_sample"] = q_dev[:16].cpu().numpy()
+        g.close()
+        return out
+
+    main_res = measure(args.precision, args.steps, max(3, args.warmup), full=True)
+    modes = {}
+    if not args.no_modes and args.workload == "c3":
+        for p in ("bf16", "tf32x1", "tf32x3"):
+            if p == args.precision:
+                continue
+            r = measure(p, max(5, min(args.steps, 10)), 3, full=False)
+            modes[p] = {"value": r["qps"], "ms_per_step": r["ms_per_step"], "kernel_ms": r["kernel_ms"],
+                        "fallback_queries": r["fallback_queries"],
+                        "same_ids_as_headline": bool(np.array_equal(r["ids_sample"], main_res["ids_sample"]))}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    rows_local = (n_rows + world - 1) // world
+    alg_flops = 2.0 * Q * rows_local * D  # per launch of the tensor-core pass on one GPU
+    achieved = alg_flops / (main_res["kernel_ms"] * 1e-3) / 1e12
+    # TF32 is not in MEASURED_PEAKS.json: the TF32 peak is taken as measured bf16 / 2
+    tensor_peak = peaks["bf16_tflops"] if args.precision == "bf16" else peaks["bf16_tflops"] / 2.0
+    passes = 3 if args.precision == "tf32x3" else 1
+    roofline = {
+        "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
+        "traffic": None,
+        "kernel": "nt_gemm_rowscan_kernel<TopkEpi> (tcgen05/TMA GEMM + fused per-query top-k)",
+        "kernel_ms": main_res["kernel_ms"],
+        "peak_source": f"{peaks['source']} bf16 burst" + ("" if args.precision == "bf16" else " / 2 (TF32 not measured)"),
+        "tensor_passes_per_flop": passes, "hardware_frac": achieved * passes / tensor_peak,
+        "share_of_step": main_res["kernel_ms"] / main_res["ms_per_step"],
+    }
+
+    cpu_baseline = None
+    if not args.no_cpu and world == 1:
+        from oracle import c_oracle as orc
+
+        sample_q = 48
+        t0 = time.perf_counter()
+        gal = orc.normalize_rows(orc.synth_rows(SEED_GALLERY, 0, n_rows, D))
+        qn = orc.normalize_rows(main_res["q_sample"])
+        qrep = np.ascontiguousarray(np.tile(qn, (sample_q // 16, 1)))
+        t1 = time.perf_counter()
+        ws, wr = orc.gallery_search(gal, qrep, k, 1, normalize=False)
+        dt = time.perf_counter() - t1
+        ok = bool(np.array_equal(wr[:16], main_res["ids_sample"]))
+        cpu_baseline = {"value": sample_q / dt, "unit": "queries/s", "cores": orc.num_threads(), "kind": "port",
+                        "sample": f"{sample_q} of the {Q} queries against the full {n_rows}-row gallery "
+                                  f"(oracle/dif_oracle.c, OpenMP, {dt:.1f} s; gallery generation {t1 - t0:.1f} s untimed)",
+                        "ids_match_gpu": ok}
+
+    line = {
+        "metric": "gallery queries/s", "value": main_res["qps"], "unit": "queries/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": main_res["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": {"tf32x3": "f32 (3xTF32 tensor-core filter + canonical fp32 re-rank)",
+                  "bf16": "bf16 tensor-core filter + canonical fp32 re-rank (results identical to f32)",
+                  "tf32x1": "tf32 tensor-core filter + canonical fp32 re-rank (results identical to f32)"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": f"1:N gallery search, {n_rows} x {D} fp32 gallery, {Q} queries, top-{k} cosine",
+                   "precision": args.precision, "gallery_rows_per_gpu": rows_local, "parallelism": f"row-sharded x{world}",
+                   "l2": "inputs larger than L2 (gallery planes >= 2 GB per pass), no flush needed"},
+        "e2e": {"value": main_res["e2e_qps"], "unit": "queries/s", "h2d_bytes_per_step": main_res["h2d"],
+                "d2h_bytes_per_step": main_res["d2h"], "ms_per_step": main_res["e2e_ms"],
+                "same_ids_as_device_path": main_res["e2e_same_ids"]},
+        "gpu_launches": main_res["launches"],
+        "clocks": main_res.get("clocks"),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "top1_recall": main_res["top1_recall"],
+        "fallback_queries": main_res["fallback_queries"],
+        "modes": modes,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,17 @@
+"""deep_insight_face_b200 - the embedding-space distance path of sandyz1000/deep-insight-face on NVIDIA B200.
+
+Hand-written sm_100a kernels (tcgen05 / TMEM / TMA) behind a C ABI (include/dif_b200.h), bound with
+ctypes (_ffi.py) and exposed through the reference's own names:
+
+    common.losses        BatchHardTripletLoss, BatchHardTripletLossEuclidean, ...AutoAlpha, BatchAllTripletLoss
+    networks.triplet     triplet_loss
+    networks.siamese     euclidean_distance, contrastive_loss
+    networks.utils       distance, distance_to_proba, gaussian_kernel_dist_to_prob
+    evaluation.utility   distance, calculate_accuracy, calculate_val_far, calculate_roc, calculate_val, evaluate
+    api                  face_distance, compare_faces
+    predictions          TripletPrediction.verify
+    gallery              Gallery, ShardedGallery (1:N top-k search, new)
+
+There is no CPU fallback: importing is cheap, but any compute call needs libdif_b200.so and a B200.
+"""
+__version__ = "0.1.0"

@@ -22,7 +22,6 @@ PREC_TF32X1 = 2
 MAX_TOPK = 24
 LOSS_BH_COSINE = 0
 LOSS_BH_EUCLIDEAN = 1
-LOSS_BATCH_ALL = 2
 
 _PRECISIONS = {"tf32x3": PREC_TF32X3, "fp32": PREC_TF32X3, "bf16": PREC_BF16, "tf32": PREC_TF32X1,
                "tf32x1": PREC_TF32X1}
@@ -85,6 +84,7 @@ SIGNATURES = {
     "dif_debug_gemm_time": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_f32)]),
     "dif_batch_hard": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "dif_batch_hard_host": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "dif_labels_from_onehot": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "dif_triplet_apn": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "dif_euclidean_distance": (_i32, [_vp, _vp, _i32, _i32, _f32, _vp, _vp]),
     "dif_contrastive_loss": (_i32, [_vp, _vp, _i32, _f32, _vp, _vp, _vp]),

@@ -1,4 +1,4 @@
-"""In-tree build of libdif_b200.so (nvcc, sm_100a only) and of the CPU oracle used by the tests.
+"""In-tree build of libdif_b200.so (nvcc, sm_100a only).
 
 The shared objects stay next to their sources (git-ignored) so a `gpurun` snapshot carries them to
 the GPU box, where nothing is compiled.
@@ -16,8 +16,6 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libdif_b200.so")
-ORACLE_DIR = os.path.join(REPO_DIR, "oracle")
-ORACLE_LIB = os.path.join(ORACLE_DIR, "libdif_oracle.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -82,23 +80,5 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
-def build_oracle(force: bool = False) -> str:
-    """gcc build of oracle/dif_oracle.c (test infrastructure, never loaded by the package)."""
-    src = os.path.join(ORACLE_DIR, "dif_oracle.c")
-    stamp = os.path.join(ORACLE_DIR, ".stamp")
-    digest = _digest([src])
-    if not force and os.path.exists(ORACLE_LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
-        return ORACLE_LIB
-    cmd = ["gcc", "-O3", "-fopenmp", "-ffp-contract=off", "-mfma", "-mavx2", "-fPIC", "-shared",
-           "-fvisibility=hidden", "-o", ORACLE_LIB, src, "-lm"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"gcc failed for the oracle:\n{r.stdout}\n{r.stderr}")
-    with open(stamp, "w") as f:
-        f.write(digest)
-    return ORACLE_LIB
-
-
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
-    print(build_oracle(force="--force" in sys.argv))

@@ -1,0 +1,229 @@
+"""Drop-in for deep_insight_face/common/losses.py: the batch-hard triplet losses on B200 kernels.
+
+Same class names, constructor arguments, `call(labels, embeddings)` contract (one-hot labels, per-sample
+[B] result, reduction left to Keras) and `get_config` / `from_config` round trip as the reference
+(common/losses.py:5-30).  The arithmetic runs in libdif_b200.so (csrc/batch_hard.cu); there is no CPU path.
+
+    call(labels, embeddings)            per-sample loss; numpy in -> numpy out, torch-CUDA in -> differentiable
+                                        torch tensor out, TensorFlow in (when TF is installed) -> tf.custom_gradient
+    loss_and_grad(labels, embeddings)   (loss [B], d mean(loss) / d embeddings [B, D], info) in one fused call
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _ffi
+
+try:  # the reference subclasses tf.keras.losses.Loss; TensorFlow is optional here
+    import tensorflow as _tf  # type: ignore
+
+    _LossBase = _tf.keras.losses.Loss
+except Exception:  # pragma: no cover - TensorFlow is not installed in the build container
+    _tf = None
+
+    class _LossBase:  # the slice of the Keras Loss protocol the reference uses
+        def __init__(self, reduction="auto", name=None, **kwargs):
+            self.reduction = reduction
+            self.name = name or type(self).__name__
+
+        def __call__(self, y_true, y_pred, sample_weight=None):
+            per_sample = self.call(y_true, y_pred)
+            if sample_weight is not None:
+                per_sample = per_sample * sample_weight
+            return per_sample.mean()  # Keras AUTO / SUM_OVER_BATCH_SIZE
+
+        def get_config(self):
+            return {"reduction": self.reduction, "name": self.name}
+
+
+def _int_labels(labels):
+    """One-hot [B, C] (common/losses.py:35 argmax's it) or sparse int [B] labels -> host int32 [B]."""
+    lab = _ffi.host_array(labels, None)
+    if lab.ndim == 2:
+        lab = np.argmax(lab, axis=1)
+    return np.ascontiguousarray(lab, dtype=np.int32)
+
+
+def batch_hard(labels, embeddings, variant: int, alpha: float, dloss=None, want_grad: bool = True):
+    """Framework-neutral core.  Host arrays take dif_batch_hard_host (pinned staging, H2D, D2H); torch-CUDA
+    embeddings stay on the device.  Returns (loss, grad or None, info)."""
+    lib = _ffi.load_library()
+    if _ffi.is_device_tensor(embeddings):
+        import torch
+
+        emb = embeddings.detach().contiguous().float()
+        dev = emb.device
+        _ffi.init(dev.index or 0)
+        B, D = emb.shape
+        st = _ffi.current_stream_ptr(dev)
+        if _ffi.is_device_tensor(labels) and labels.dim() == 2:
+            oh = labels.detach().contiguous().float()
+            lab = torch.empty(B, dtype=torch.int32, device=dev)
+            _ffi.check(lib.dif_labels_from_onehot(_ffi.ptr(oh), B, oh.shape[1], _ffi.ptr(lab), st))
+        elif _ffi.is_device_tensor(labels):
+            lab = labels.detach().to(torch.int32).contiguous()
+        else:
+            lab = torch.from_numpy(_int_labels(labels)).to(dev)
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        pos = torch.empty(B, dtype=torch.int32, device=dev)
+        neg = torch.empty(B, dtype=torch.int32, device=dev)
+        stats = torch.empty(4, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(emb) if want_grad else None
+        dl = None if dloss is None else dloss.detach().contiguous().float()
+        _ffi.check(lib.dif_batch_hard(_ffi.ptr(emb), _ffi.ptr(lab), B, D, variant, float(alpha), _ffi.ptr(loss),
+                                      _ffi.ptr(pos), _ffi.ptr(neg), _ffi.ptr(stats), _ffi.ptr(dl), _ffi.ptr(grad),
+                                      _ffi.PREC_TF32X3, st))
+        return loss, grad, {"pos_idx": pos, "neg_idx": neg, "stats": stats}
+    _ffi.init(0)
+    emb = _ffi.host_array(embeddings, np.float32)
+    if emb.ndim != 2:
+        raise ValueError("embeddings must be [B, D]")
+    B, D = emb.shape
+    lab = _int_labels(labels)
+    if lab.shape != (B,):
+        raise ValueError(f"labels must be one-hot [B, C] or int [B]; got {lab.shape} for B={B}")
+    loss = np.empty(B, dtype=np.float32)
+    pos = np.empty(B, dtype=np.int32)
+    neg = np.empty(B, dtype=np.int32)
+    stats = np.empty(4, dtype=np.float32)
+    grad = np.empty((B, D), dtype=np.float32) if want_grad else None
+    dl = None if dloss is None else _ffi.host_array(dloss, np.float32, (B,))
+    _ffi.check(lib.dif_batch_hard_host(_ffi.ptr(emb), _ffi.ptr(lab), B, D, variant, float(alpha), _ffi.ptr(loss),
+                                       _ffi.ptr(pos), _ffi.ptr(neg), _ffi.ptr(stats), _ffi.ptr(dl), _ffi.ptr(grad),
+                                       _ffi.PREC_TF32X3))
+    return loss, grad, {"pos_idx": pos, "neg_idx": neg, "stats": stats}
+
+
+def _torch_function():
+    import torch
+
+    class _BatchHardFn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, emb, labels, variant, alpha):
+            loss, _, info = batch_hard(labels, emb, variant, alpha, want_grad=False)
+            ctx.save_for_backward(emb)
+            ctx.labels, ctx.variant, ctx.alpha = labels, variant, alpha
+            ctx.info = info
+            return loss
+
+        @staticmethod
+        def backward(ctx, dloss):
+            (emb,) = ctx.saved_tensors
+            _, grad, _ = batch_hard(ctx.labels, emb, ctx.variant, ctx.alpha, dloss=dloss, want_grad=True)
+            return grad, None, None, None
+
+    return _BatchHardFn
+
+
+class TripletLossWapper(_LossBase):
+    """common/losses.py:5-30 (the reference's spelling is kept)."""
+
+    _variant = None
+
+    def __init__(self, alpha=0.35, **kwargs):
+        super().__init__(**kwargs)
+        self.alpha = alpha
+        self.last_info = None
+
+    def __calculate_triplet_loss__(self, y_true, y_pred, alpha):
+        return None  # common/losses.py:17-18
+
+    def call(self, labels, embeddings):
+        return self.__calculate_triplet_loss__(labels, embeddings, self.alpha)
+
+    def get_config(self):
+        config = super().get_config()
+        config.update({"alpha": self.alpha})
+        return config
+
+    @classmethod
+    def from_config(cls, config):
+        return cls(**config)
+
+    # ---- shared implementation of the subclasses
+    def _dispatch(self, labels, embeddings, alpha):
+        if _tf is not None and isinstance(embeddings, (_tf.Tensor, _tf.Variable)):  # pragma: no cover
+            return self._tf_call(labels, embeddings, alpha)
+        if _ffi.is_device_tensor(embeddings):
+            out = _torch_function().apply(embeddings, labels, self._variant, float(alpha))
+            return out
+        loss, _, info = batch_hard(labels, embeddings, self._variant, alpha, want_grad=False)
+        self.last_info = info
+        return loss
+
+    def _tf_call(self, labels, embeddings, alpha):  # pragma: no cover - needs TensorFlow
+        variant = self._variant
+
+        @_tf.custom_gradient
+        def op(emb):
+            def fwd(e, l):
+                loss, _, _ = batch_hard(l, e, variant, alpha, want_grad=False)
+                return loss
+
+            loss = _tf.numpy_function(fwd, [emb, labels], _tf.float32)
+
+            def grad_fn(dloss):
+                def bwd(e, l, dl):
+                    _, g, _ = batch_hard(l, e, variant, alpha, dloss=dl, want_grad=True)
+                    return g
+
+                return _tf.numpy_function(bwd, [emb, labels, dloss], _tf.float32)
+
+            return loss, grad_fn
+
+        return op(embeddings)
+
+    def loss_and_grad(self, labels, embeddings, dloss=None):
+        """(loss [B], gradient of sum_i dloss_i * loss_i (default: mean) wrt embeddings, info) in one call."""
+        loss, grad, info = batch_hard(labels, embeddings, self._variant, self._current_alpha(), dloss=dloss)
+        self._after_step(info)
+        self.last_info = info
+        return loss, grad, info
+
+    def _current_alpha(self):
+        return self.alpha
+
+    def _after_step(self, info):
+        pass
+
+
+class BatchHardTripletLoss(TripletLossWapper):
+    """common/losses.py:33-51: cosine batch-hard, hard margin."""
+
+    _variant = _ffi.LOSS_BH_COSINE
+
+    def __calculate_triplet_loss__(self, labels, embeddings, alpha):
+        return self._dispatch(labels, embeddings, alpha)
+
+
+class BatchHardTripletLossEuclidean(TripletLossWapper):
+    """common/losses.py:54-85: squared-L2 batch-hard; the tf.print statistics are kept in `last_info['stats']`
+    = (mean(dists), mean(hardest_pos), mean(hardest_neg), max(dists))."""
+
+    _variant = _ffi.LOSS_BH_EUCLIDEAN
+
+    def __calculate_triplet_loss__(self, labels, embeddings, alpha):
+        return self._dispatch(labels, embeddings, alpha)
+
+
+class BatchHardTripletLossEuclideanAutoAlpha(TripletLossWapper):
+    """common/losses.py:88-128: the margin is the state `auto_alpha` (init 1, not trainable, not in get_config);
+    each call uses the PREVIOUS value (:112) and then sets auto_alpha = mean(dists) * alpha (:113)."""
+
+    _variant = _ffi.LOSS_BH_EUCLIDEAN
+
+    def __init__(self, alpha=0.1, init_auto_alpha=1, **kwargs):
+        super().__init__(alpha=alpha, **kwargs)
+        self.auto_alpha = float(init_auto_alpha)
+
+    def _current_alpha(self):
+        return self.auto_alpha
+
+    def _after_step(self, info):
+        self.auto_alpha = float(info["stats"][0]) * self.alpha
+
+    def __calculate_triplet_loss__(self, labels, embeddings, alpha):
+        loss, _, info = batch_hard(labels, embeddings, self._variant, self.auto_alpha, want_grad=False)
+        self._after_step(info)
+        self.last_info = info
+        return loss

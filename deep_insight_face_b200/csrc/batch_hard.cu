@@ -1,0 +1,617 @@
+// Batch-hard triplet losses, forward + backward, in canonical fp32 arithmetic.
+//   deep_insight_face/common/losses.py:33-51   BatchHardTripletLoss            (cosine,   DIF_LOSS_BH_COSINE)
+//   deep_insight_face/common/losses.py:54-85   BatchHardTripletLossEuclidean   (sq. L2,   DIF_LOSS_BH_EUCLIDEAN)
+//   deep_insight_face/common/losses.py:88-128  ...AutoAlpha                    (same kernel, alpha = state)
+//
+// Three launches per call, the B x B matrix never exists in memory:
+//   bh_mine_kernel   grid (row blocks x column splits).  A warp owns 8 anchors x 4 columns at a time: lane l
+//                    accumulates chain l (d = l, l+32, ...) of all 32 entries, a transposing butterfly hands
+//                    entry e to lane e with exactly the reduction tree of dif_canon.cuh, and the lane folds
+//                    the entry into the running masked min/max (value, first index, tie count) of its anchor.
+//                    Rows are normalised on the fly for the cosine variant (l2_normalize, losses.py:39).
+//   bh_merge_kernel  one block: merges the per-split records, global max / means (losses.py:70,72-80),
+//                    per-anchor loss, mined indices and gradient coefficients.
+//   bh_grad_kernel   one warp per row r: gathers  sum_j (G_rj + G_jr) * d(dist_rj)/d(x_r)  from the mined
+//                    columns of row r and from the rows that mined r (no atomics, fixed order), then the
+//                    l2_normalize backward.  Exact ties follow TensorFlow's reduce_min/max gradient: the
+//                    cotangent is split evenly over every tied position, filler positions included.
+#include <algorithm>
+
+#include "dif_canon.cuh"
+#include "dif_common.cuh"
+
+namespace dif {
+
+constexpr int BH_WARPS = 4;
+constexpr int BH_TI = 8;                      // anchors per warp
+constexpr int BH_TJ = 4;                      // columns per warp step
+constexpr int BH_RB = BH_WARPS * BH_TI;       // anchors per block
+constexpr int BH_CB = 32;                     // columns staged per tile
+constexpr int BH_MAX_KD = 16;                 // D <= 512
+
+struct BhRec {            // per (split, anchor)
+  float pos_val; int pos_idx; int pos_cnt;   // cosine: min over positives; euclid: max over positives
+  float neg_val; int neg_idx; int neg_cnt;   // cosine: max over negatives; euclid: min over negatives
+  float all_max; int all_idx; int all_cnt;   // max over every column (euclid filler, losses.py:70)
+  float row_sum; int n_pos; int pad;
+};
+
+struct BhRow {            // per anchor, written by bh_merge_kernel, read by bh_grad_kernel
+  float pos_val, neg_val;   // extreme over REAL positives / negatives
+  int pos_idx, neg_idx;     // first index, -1 if none
+  int pos_cnt, neg_cnt;     // real tie counts
+  float coef_pos, coef_neg; // dL/d(dist) applied to each tied real positive / negative column
+  float all_max; int all_idx; int all_cnt;
+  float coef_gmax;          // dL/d(dist) applied to every position holding the global max (euclid filler gradient)
+};
+
+template <bool MIN>
+__device__ __forceinline__ void fold(float v, int j, float& val, int& idx, int& cnt) {
+  if (MIN ? (v < val) : (v > val)) {
+    val = v;
+    idx = j;
+    cnt = 1;
+  } else if (v == val) {
+    ++cnt;
+    idx = (idx < 0 || j < idx) ? j : idx;
+  }
+}
+template <bool MIN>
+__device__ __forceinline__ void merge(float v, int j, int c, float& val, int& idx, int& cnt) {
+  if (c == 0) return;
+  if (cnt == 0 || (MIN ? (v < val) : (v > val))) {
+    val = v;
+    idx = j;
+    cnt = c;
+  } else if (v == val) {
+    cnt += c;
+    idx = j < idx ? j : idx;
+  }
+}
+
+// lane l holds chain-l partial sums of 32 entries in v[0..31]; returns the canonical total of entry `lane`.
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int e = 0; e < o; ++e) {
+      const float send = up ? v[e] : v[e + o];
+      const float keep = up ? v[e + o] : v[e];
+      v[e] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, o));
+    }
+  }
+  return v[0];
+}
+
+// Load `n` rows [row0, row0+n) of x into smem (zero beyond B); cosine: normalise in place; writes the
+// canonical sum of squares (euclid) or inverse norm (cosine) of each row to aux[n] in smem.
+template <bool COSINE>
+__device__ __forceinline__ void stage_rows(const float* __restrict__ x, int B, int D, int row0, int n, float* dst,
+                                           float* aux) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < n; r += BH_WARPS) {
+    const int gr = row0 + r;
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float t = gr < B ? x[(size_t)gr * D + d] : 0.f;
+      dst[r * D + d] = t;
+      acc = __fmaf_rn(t, t, acc);
+    }
+    const float ss = canon_tree(acc);
+    if (COSINE) {
+      const float inv = canon_inv_norm(ss);
+      for (int d = lane; d < D; d += 32) dst[r * D + d] = __fmul_rn(dst[r * D + d], inv);
+      if (lane == 0) aux[r] = inv;
+    } else {
+      if (lane == 0) aux[r] = ss;
+    }
+  }
+}
+
+template <bool COSINE>
+__global__ void __launch_bounds__(BH_WARPS * 32) bh_mine_kernel(const float* __restrict__ x,
+                                                                const int32_t* __restrict__ labels, int B, int D,
+                                                                int cols_per_split, BhRec* __restrict__ recs,
+                                                                float* __restrict__ row_aux) {
+  extern __shared__ float sm[];
+  float* sa = sm;                       // [BH_RB][D]
+  float* sb = sa + BH_RB * D;           // [BH_CB][D]
+  float* aux_a = sb + BH_CB * D;        // [BH_RB]
+  float* aux_b = aux_a + BH_RB;         // [BH_CB]
+  int* lab_b = reinterpret_cast<int*>(aux_b + BH_CB);  // [BH_CB]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * BH_RB;
+  const int split = blockIdx.y;
+  const int c_begin = split * cols_per_split, c_end = min(B, c_begin + cols_per_split);
+  const int kd = (D + 31) / 32;
+
+  stage_rows<COSINE>(x, B, D, row0, BH_RB, sa, aux_a);
+  __syncthreads();
+  if (split == 0 && threadIdx.x < BH_RB && row0 + threadIdx.x < B) row_aux[row0 + threadIdx.x] = aux_a[threadIdx.x];
+
+  const int my_i = warp * BH_TI + (lane >> 2);   // anchor (block-local) this lane reports on
+  const int gi = row0 + my_i;
+  const int my_lab = gi < B ? labels[gi] : -1;
+  const float my_aux = aux_a[my_i];
+
+  float pos_val = COSINE ? INFINITY : -INFINITY, neg_val = COSINE ? -INFINITY : INFINITY, all_max = -INFINITY;
+  int pos_idx = -1, neg_idx = -1, all_idx = -1, pos_cnt = 0, neg_cnt = 0, all_cnt = 0, n_pos = 0;
+  float row_sum = 0.f;
+
+  for (int c0 = c_begin; c0 < c_end; c0 += BH_CB) {
+    __syncthreads();   // previous tile fully consumed
+    stage_rows<COSINE>(x, B, D, c0, BH_CB, sb, aux_b);
+    if (threadIdx.x < BH_CB) lab_b[threadIdx.x] = (c0 + threadIdx.x < B) ? labels[c0 + threadIdx.x] : -2;
+    __syncthreads();
+    const int steps = min(BH_CB, c_end - c0);
+    for (int j0 = 0; j0 < steps; j0 += BH_TJ) {
+      float v[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) v[e] = 0.f;
+      for (int c = 0; c < kd; ++c) {
+        const int d = c * 32 + lane;
+        float a[BH_TI], b[BH_TJ];
+#pragma unroll
+        for (int i = 0; i < BH_TI; ++i) a[i] = d < D ? sa[(warp * BH_TI + i) * D + d] : 0.f;
+#pragma unroll
+        for (int j = 0; j < BH_TJ; ++j) b[j] = d < D ? sb[(j0 + j) * D + d] : 0.f;
+#pragma unroll
+        for (int i = 0; i < BH_TI; ++i)
+#pragma unroll
+          for (int j = 0; j < BH_TJ; ++j) v[i * BH_TJ + j] = __fmaf_rn(a[i], b[j], v[i * BH_TJ + j]);
+      }
+      const float dot = transpose_reduce32(v, lane);   // entry (lane >> 2, lane & 3)
+      const int jl = j0 + (lane & 3);
+      const int gj = c0 + jl;
+      if (gj < c_end && gi < B) {
+        const float dist = COSINE ? dot : __fsub_rn(__fadd_rn(my_aux, aux_b[jl]), __fmul_rn(2.f, dot));
+        row_sum += dist;
+        fold<false>(dist, gj, all_max, all_idx, all_cnt);
+        if (lab_b[jl] == my_lab) {
+          ++n_pos;
+          fold<COSINE>(dist, gj, pos_val, pos_idx, pos_cnt);
+        } else {
+          fold<!COSINE>(dist, gj, neg_val, neg_idx, neg_cnt);
+        }
+      }
+    }
+  }
+  // combine the 4 lanes of an anchor
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    const float pv = __shfl_xor_sync(0xffffffffu, pos_val, o);
+    const int pi = __shfl_xor_sync(0xffffffffu, pos_idx, o), pc = __shfl_xor_sync(0xffffffffu, pos_cnt, o);
+    const float nv = __shfl_xor_sync(0xffffffffu, neg_val, o);
+    const int ni = __shfl_xor_sync(0xffffffffu, neg_idx, o), nc = __shfl_xor_sync(0xffffffffu, neg_cnt, o);
+    const float av = __shfl_xor_sync(0xffffffffu, all_max, o);
+    const int ai = __shfl_xor_sync(0xffffffffu, all_idx, o), ac = __shfl_xor_sync(0xffffffffu, all_cnt, o);
+    merge<COSINE>(pv, pi, pc, pos_val, pos_idx, pos_cnt);
+    merge<!COSINE>(nv, ni, nc, neg_val, neg_idx, neg_cnt);
+    merge<false>(av, ai, ac, all_max, all_idx, all_cnt);
+    // fixed order: (lane0 + lane1) + (lane2 + lane3)
+    row_sum = __fadd_rn(row_sum, __shfl_xor_sync(0xffffffffu, row_sum, o));
+    n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
+  }
+  if ((lane & 3) == 0 && gi < B) {
+    BhRec r;
+    r.pos_val = pos_val; r.pos_idx = pos_idx; r.pos_cnt = pos_cnt;
+    r.neg_val = neg_val; r.neg_idx = neg_idx; r.neg_cnt = neg_cnt;
+    r.all_max = all_max; r.all_idx = all_idx; r.all_cnt = all_cnt;
+    r.row_sum = row_sum; r.n_pos = n_pos; r.pad = 0;
+    recs[(size_t)split * B + gi] = r;
+  }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+  return s;
+}
+
+// One block.  stats = {mean(dists), mean(hardest_pos), mean(hardest_neg), max(dists)}
+template <bool COSINE>
+__global__ void __launch_bounds__(1024) bh_merge_kernel(const BhRec* __restrict__ recs, int n_splits, int B,
+                                                        float alpha, const float* __restrict__ dloss,
+                                                        float* __restrict__ loss, int32_t* __restrict__ pos_idx_out,
+                                                        int32_t* __restrict__ neg_idx_out, float* __restrict__ stats,
+                                                        BhRow* __restrict__ rows) {
+  __shared__ double red[32];
+  __shared__ unsigned long long gmax_key;   // orderable(value) << 32 | ~first row
+  __shared__ int gmax_cnt_s;
+  if (threadIdx.x == 0) {
+    gmax_key = 0ull;
+    gmax_cnt_s = 0;
+  }
+  __syncthreads();
+  // phase 1: merge the splits of every anchor
+  double sum_d = 0.0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    BhRow r;
+    r.pos_val = COSINE ? INFINITY : -INFINITY; r.neg_val = COSINE ? -INFINITY : INFINITY; r.all_max = -INFINITY;
+    r.pos_idx = r.neg_idx = r.all_idx = -1;
+    r.pos_cnt = r.neg_cnt = r.all_cnt = 0;
+    r.coef_pos = r.coef_neg = r.coef_gmax = 0.f;
+    int n_pos = 0;
+    float rs = 0.f;
+    for (int s = 0; s < n_splits; ++s) {
+      const BhRec& q = recs[(size_t)s * B + i];
+      merge<COSINE>(q.pos_val, q.pos_idx, q.pos_cnt, r.pos_val, r.pos_idx, r.pos_cnt);
+      merge<!COSINE>(q.neg_val, q.neg_idx, q.neg_cnt, r.neg_val, r.neg_idx, r.neg_cnt);
+      merge<false>(q.all_max, q.all_idx, q.all_cnt, r.all_max, r.all_idx, r.all_cnt);
+      rs = __fadd_rn(rs, q.row_sum);
+      n_pos += q.n_pos;
+    }
+    r.coef_pos = __int_as_float(n_pos);   // parked here until phase 2
+    rows[i] = r;
+    sum_d += (double)rs;
+    if (r.all_cnt > 0) atomicMax(&gmax_key, ((unsigned long long)float_orderable(r.all_max) << 32) | (0xFFFFFFFFu - (unsigned)i));
+  }
+  const double tot_d = block_sum(sum_d, red);
+  __syncthreads();
+  const uint32_t gmax_o = (uint32_t)(gmax_key >> 32);
+  const float gmax = __uint_as_float((gmax_o & 0x80000000u) ? (gmax_o ^ 0x80000000u) : ~gmax_o);
+  for (int i = threadIdx.x; i < B; i += blockDim.x)
+    if (rows[i].all_max == gmax) atomicAdd(&gmax_cnt_s, rows[i].all_cnt);
+  __syncthreads();
+  const int gmax_cnt = gmax_cnt_s;
+
+  // phase 2: hardest values with fillers, loss, gradient coefficients
+  double sum_hp = 0.0, sum_hn = 0.0, gm_share = 0.0;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    BhRow r = rows[i];
+    const int n_pos = __float_as_int(r.coef_pos), n_non = B - n_pos;
+    // filler values: cosine where(pos, S, 1) / where(pos, -1, S); euclid where(pos, D, 0) / where(pos, gmax, D)
+    const float fill_p = COSINE ? 1.f : 0.f, fill_n = COSINE ? -1.f : gmax;
+    float hp = r.pos_val, hn = r.neg_val;
+    int tie_p = r.pos_cnt, tie_n = r.neg_cnt;
+    int pidx = r.pos_idx, nidx = r.neg_idx;
+    if (n_non > 0) {   // positive-side fillers sit in the non-positive columns
+      if (r.pos_cnt == 0 || (COSINE ? fill_p < hp : fill_p > hp)) { hp = fill_p; tie_p = n_non; pidx = -1; r.pos_cnt = 0; }
+      else if (fill_p == hp) tie_p += n_non;
+    }
+    if (n_pos > 0) {   // negative-side fillers sit in the positive columns
+      if (r.neg_cnt == 0 || (COSINE ? fill_n > hn : fill_n < hn)) { hn = fill_n; tie_n = n_pos; nidx = -1; r.neg_cnt = 0; }
+      else if (fill_n == hn) tie_n += n_pos;
+    }
+    const float basic = COSINE ? __fadd_rn(__fsub_rn(hn, hp), alpha) : __fsub_rn(__fadd_rn(hp, alpha), hn);
+    loss[i] = fmaxf(basic, 0.f);
+    if (pos_idx_out) pos_idx_out[i] = pidx;
+    if (neg_idx_out) neg_idx_out[i] = nidx;
+    sum_hp += (double)hp;
+    sum_hn += (double)hn;
+    // tf.maximum(basic, 0): the gradient goes to `basic` when basic >= 0
+    const float g = basic >= 0.f ? (dloss ? dloss[i] : 1.f / (float)B) : 0.f;
+    // d loss / d dist at each tied position: cosine  +g/tie_n (neg), -g/tie_p (pos); euclid  +g/tie_p (pos), -g/tie_n (neg)
+    r.coef_pos = r.pos_cnt > 0 ? (COSINE ? -g : g) / (float)tie_p : 0.f;
+    r.coef_neg = r.neg_cnt > 0 ? (COSINE ? g : -g) / (float)tie_n : 0.f;
+    r.pos_idx = pidx;
+    r.neg_idx = nidx;
+    if (!COSINE && n_pos > 0 && hn == gmax)   // share of the cotangent that lands on the max(dists) filler
+      gm_share += (double)(-g) * (double)n_pos / (double)tie_n;
+    rows[i] = r;
+  }
+  const double tot_hp = block_sum(sum_hp, red);
+  const double tot_hn = block_sum(sum_hn, red);
+  const double tot_gm = block_sum(gm_share, red);
+  if (threadIdx.x == 0) {
+    stats[0] = B > 0 ? (float)(tot_d / ((double)B * (double)B)) : 0.f;
+    stats[1] = B > 0 ? (float)(tot_hp / (double)B) : 0.f;
+    stats[2] = B > 0 ? (float)(tot_hn / (double)B) : 0.f;
+    stats[3] = gmax;
+  }
+  // every position holding the global max receives an equal part of gm_share
+  const float cg = (!COSINE && gmax_cnt > 0) ? (float)(tot_gm / (double)gmax_cnt) : 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) rows[i].coef_gmax = (rows[i].all_max == gmax) ? cg : 0.f;
+}
+
+// canonical dist(r, j) recomputed by one warp (tie resolution)
+template <bool COSINE>
+__device__ __forceinline__ float warp_dist(const float* __restrict__ x, const float* __restrict__ aux, int D, int r,
+                                           int j) {
+  const float* a = x + (size_t)r * D;
+  const float* b = x + (size_t)j * D;
+  float acc = 0.f;
+  if (COSINE) {
+    const float ia = aux[r], ib = aux[j];
+    for (int d = (int)(threadIdx.x & 31u); d < D; d += 32) acc = __fmaf_rn(__fmul_rn(a[d], ia), __fmul_rn(b[d], ib), acc);
+    return canon_tree(acc);
+  }
+  for (int d = (int)(threadIdx.x & 31u); d < D; d += 32) acc = __fmaf_rn(a[d], b[d], acc);
+  return __fsub_rn(__fadd_rn(aux[r], aux[j]), __fmul_rn(2.f, canon_tree(acc)));
+}
+
+// acc[c] += w * (value of row j at d = lane + 32c); cosine: the normalised row; euclid: (x_r - x_j) * 2
+template <bool COSINE>
+__device__ __forceinline__ void axpy_row(float (&acc)[BH_MAX_KD], float w, const float* __restrict__ x,
+                                         const float* __restrict__ aux, int D, int r, int j) {
+  const int lane = threadIdx.x & 31;
+  const float* b = x + (size_t)j * D;
+  const float* a = x + (size_t)r * D;
+  const float ib = COSINE ? aux[j] : 0.f;
+#pragma unroll
+  for (int c = 0; c < BH_MAX_KD; ++c) {
+    const int d = c * 32 + lane;
+    if (d < D) acc[c] += COSINE ? w * (b[d] * ib) : w * 2.f * (a[d] - b[d]);
+  }
+}
+
+template <bool COSINE>
+__global__ void __launch_bounds__(128) bh_grad_kernel(const float* __restrict__ x,
+                                                      const int32_t* __restrict__ labels, int B, int D,
+                                                      const float* __restrict__ aux,   // inv norm | sum of squares
+                                                      const BhRow* __restrict__ rows, float* __restrict__ demb) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= B) return;
+  float acc[BH_MAX_KD];
+#pragma unroll
+  for (int c = 0; c < BH_MAX_KD; ++c) acc[c] = 0.f;
+  const BhRow me = rows[r];
+  const int my_lab = labels[r];
+
+  // --- own row: tied real positive / negative columns
+  if (me.coef_pos != 0.f) {
+    if (me.pos_cnt == 1) axpy_row<COSINE>(acc, me.coef_pos, x, aux, D, r, me.pos_idx);
+    else
+      for (int j = 0; j < B; ++j)
+        if (labels[j] == my_lab && warp_dist<COSINE>(x, aux, D, r, j) == me.pos_val)
+          axpy_row<COSINE>(acc, me.coef_pos, x, aux, D, r, j);
+  }
+  if (me.coef_neg != 0.f) {
+    if (me.neg_cnt == 1) axpy_row<COSINE>(acc, me.coef_neg, x, aux, D, r, me.neg_idx);
+    else
+      for (int j = 0; j < B; ++j)
+        if (labels[j] != my_lab && warp_dist<COSINE>(x, aux, D, r, j) == me.neg_val)
+          axpy_row<COSINE>(acc, me.coef_neg, x, aux, D, r, j);
+  }
+  // --- rows that mined r
+  for (int j0 = 0; j0 < B; j0 += 32) {
+    const int j = j0 + lane;
+    float wp = 0.f, wn = 0.f;
+    bool tied_p = false, tied_n = false;
+    if (j < B) {
+      const BhRow o = rows[j];
+      if (o.coef_pos != 0.f) {
+        if (o.pos_cnt == 1) wp = (o.pos_idx == r) ? o.coef_pos : 0.f;
+        else tied_p = true;
+      }
+      if (o.coef_neg != 0.f) {
+        if (o.neg_cnt == 1) wn = (o.neg_idx == r) ? o.coef_neg : 0.f;
+        else tied_n = true;
+      }
+    }
+    unsigned hit = __ballot_sync(0xffffffffu, wp != 0.f || wn != 0.f || tied_p || tied_n);
+    while (hit) {
+      const int src = __ffs((int)hit) - 1;
+      hit &= hit - 1;
+      const int jj = j0 + src;
+      float w = __shfl_sync(0xffffffffu, wp + wn, src);
+      const bool tp = __shfl_sync(0xffffffffu, (int)tied_p, src) != 0, tn = __shfl_sync(0xffffffffu, (int)tied_n, src) != 0;
+      if (tp || tn) {
+        const BhRow o = rows[jj];
+        const float dv = warp_dist<COSINE>(x, aux, D, jj, r);
+        const bool same = labels[jj] == my_lab;
+        if (tp && same && dv == o.pos_val) w += o.coef_pos;
+        if (tn && !same && dv == o.neg_val) w += o.coef_neg;
+      }
+      // d dist(jj, r) / d x_r : cosine n_jj ; euclid 2 (x_r - x_jj)  -> same helper with roles (r, jj)
+      if (w != 0.f) axpy_row<COSINE>(acc, w, x, aux, D, r, jj);
+    }
+  }
+  // --- euclid: gradient through the max(dists) filler (both (r, j) and (j, r) hold the max)
+  if (!COSINE && me.coef_gmax != 0.f) {
+    if (me.all_cnt == 1) axpy_row<COSINE>(acc, 2.f * me.coef_gmax, x, aux, D, r, me.all_idx);
+    else
+      for (int j = 0; j < B; ++j)
+        if (warp_dist<COSINE>(x, aux, D, r, j) == me.all_max) axpy_row<COSINE>(acc, 2.f * me.coef_gmax, x, aux, D, r, j);
+  }
+  // --- write: cosine applies the l2_normalize backward  dx = inv * (dn - n * (n . dn))
+  if (COSINE) {
+    const float inv = aux[r];
+    const float* xr = x + (size_t)r * D;
+    float dotp = 0.f, ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < BH_MAX_KD; ++c) {
+      const int d = c * 32 + lane;
+      if (d < D) {
+        dotp += acc[c] * (xr[d] * inv);
+        ss += xr[d] * xr[d];
+      }
+    }
+    for (int o = 16; o >= 1; o >>= 1) {
+      dotp += __shfl_xor_sync(0xffffffffu, dotp, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    // below the epsilon, l2_normalize is x * rsqrt(eps): a plain scaling
+    const bool clamped = ss < kNormEps;
+#pragma unroll
+    for (int c = 0; c < BH_MAX_KD; ++c) {
+      const int d = c * 32 + lane;
+      if (d < D) demb[(size_t)r * D + d] = clamped ? inv * acc[c] : inv * (acc[c] - (xr[d] * inv) * dotp);
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < BH_MAX_KD; ++c) {
+      const int d = c * 32 + lane;
+      if (d < D) demb[(size_t)r * D + d] = acc[c];
+    }
+  }
+}
+
+// one-hot [B, C] -> int32 class ids (tf.argmax(labels, axis=1): first maximum), losses.py:35
+__global__ void argmax_rows_kernel(const float* __restrict__ onehot, int B, int C, int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= B) return;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = lane; c < C; c += 32) {
+    const float v = onehot[(size_t)r * C + c];
+    if (v > best || (v == best && c < bi)) {
+      best = v;
+      bi = c;
+    }
+  }
+  for (int o = 16; o >= 1; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  if (lane == 0) out[r] = bi == 0x7fffffff ? 0 : bi;
+}
+
+// workspace cache (per thread): split records, per-row info, row aux
+struct BhWorkspace {
+  BhRec* recs = nullptr;
+  size_t rec_cap = 0;
+  BhRow* rows = nullptr;
+  float* aux = nullptr;
+  size_t row_cap = 0;
+  int ensure(size_t n_rec, size_t n_rows) {
+    if (n_rec > rec_cap) {
+      cudaFree(recs);
+      recs = nullptr;
+      rec_cap = 0;
+      DIF_CUDA_OK(cudaMalloc((void**)&recs, n_rec * sizeof(BhRec)));
+      rec_cap = n_rec;
+    }
+    if (n_rows > row_cap) {
+      cudaFree(rows);
+      cudaFree(aux);
+      rows = nullptr;
+      aux = nullptr;
+      row_cap = 0;
+      DIF_CUDA_OK(cudaMalloc((void**)&rows, n_rows * sizeof(BhRow)));
+      DIF_CUDA_OK(cudaMalloc((void**)&aux, n_rows * sizeof(float)));
+      row_cap = n_rows;
+    }
+    return DIF_OK;
+  }
+};
+static thread_local BhWorkspace g_ws;
+
+struct BhHostStage {
+  void* h = nullptr;
+  void* d = nullptr;
+  size_t bytes = 0;
+  cudaStream_t st = nullptr;
+  int ensure(size_t need) {
+    if (!st) DIF_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    if (need <= bytes) return DIF_OK;
+    if (h) cudaFreeHost(h);
+    if (d) cudaFree(d);
+    h = d = nullptr;
+    bytes = 0;
+    DIF_CUDA_OK(cudaMallocHost(&h, need));
+    DIF_CUDA_OK(cudaMalloc(&d, need));
+    bytes = need;
+    return DIF_OK;
+  }
+};
+static thread_local BhHostStage g_bh_stage;
+
+template <bool COSINE>
+static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D, float alpha, float* loss,
+                          int32_t* pos_idx, int32_t* neg_idx, float* stats, const float* dloss, float* demb,
+                          cudaStream_t st) {
+  // column splits: enough blocks to cover the machine, at least one step of 4 columns each
+  const int row_blocks = (B + BH_RB - 1) / BH_RB;
+  const int sms = std::max(1, device_sm_count());
+  int splits = std::max(1, std::min((2 * sms + row_blocks - 1) / row_blocks, (B + BH_TJ - 1) / BH_TJ));
+  splits = std::min(splits, 64);
+  int cols = (B + splits - 1) / splits;
+  cols = (cols + BH_TJ - 1) / BH_TJ * BH_TJ;
+  splits = (B + cols - 1) / cols;
+  if (int rc = g_ws.ensure((size_t)splits * B, (size_t)B)) return rc;
+  const size_t smem = ((size_t)(BH_RB + BH_CB) * D + BH_RB + BH_CB) * sizeof(float) + BH_CB * sizeof(int);
+  static bool configured = false;
+  if (!configured) {
+    DIF_CUDA_OK(cudaFuncSetAttribute(bh_mine_kernel<COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  bh_mine_kernel<COSINE><<<dim3(row_blocks, splits), BH_WARPS * 32, smem, st>>>(emb, labels, B, D, cols, g_ws.recs, g_ws.aux);
+  DIF_LAUNCH_OK();
+  bh_merge_kernel<COSINE><<<1, 1024, 0, st>>>(g_ws.recs, splits, B, alpha, dloss, loss, pos_idx, neg_idx, stats, g_ws.rows);
+  DIF_LAUNCH_OK();
+  if (demb) {
+    bh_grad_kernel<COSINE><<<(B + 3) / 4, 128, 0, st>>>(emb, labels, B, D, g_ws.aux, g_ws.rows, demb);
+    DIF_LAUNCH_OK();
+  }
+  return DIF_OK;
+}
+
+}  // namespace dif
+
+using namespace dif;
+
+extern "C" {
+
+int dif_batch_hard(const float* emb, const int32_t* labels, int B, int D, int variant, float alpha, float* loss,
+                   int32_t* pos_idx, int32_t* neg_idx, float* stats, const float* dloss, float* demb, int precision,
+                   void* stream) {
+  DIF_REQUIRE(emb && labels && loss && stats, DIF_ERR_INVALID, "dif_batch_hard: null argument");
+  DIF_REQUIRE(B >= 1 && B <= 65536 && D >= 1 && D <= 32 * BH_MAX_KD, DIF_ERR_INVALID,
+              "dif_batch_hard: B %d (1..65536), D %d (1..%d)", B, D, 32 * BH_MAX_KD);
+  DIF_REQUIRE(variant == DIF_LOSS_BH_COSINE || variant == DIF_LOSS_BH_EUCLIDEAN, DIF_ERR_INVALID,
+              "dif_batch_hard: variant %d (batch-all is dif_batch_all)", variant);
+  DIF_REQUIRE(precision == DIF_PREC_TF32X3, DIF_ERR_INVALID,
+              "dif_batch_hard: only the fp32-exact path (precision 0) is implemented");
+  DIF_REQUIRE(device_sm_count() > 0, DIF_ERR_STATE, "dif_init has not succeeded on this process");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return variant == DIF_LOSS_BH_COSINE
+             ? run_batch_hard<true>(emb, labels, B, D, alpha, loss, pos_idx, neg_idx, stats, dloss, demb, st)
+             : run_batch_hard<false>(emb, labels, B, D, alpha, loss, pos_idx, neg_idx, stats, dloss, demb, st);
+}
+
+int dif_batch_hard_host(const float* emb_host, const int32_t* labels_host, int B, int D, int variant, float alpha,
+                        float* loss_host, int32_t* pos_idx_host, int32_t* neg_idx_host, float* stats_host,
+                        const float* dloss_host, float* demb_host, int precision) {
+  DIF_REQUIRE(emb_host && labels_host && loss_host && stats_host && B >= 1 && D >= 1, DIF_ERR_INVALID,
+              "dif_batch_hard_host: invalid argument");
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t eb = al((size_t)B * D * 4), lb = al((size_t)B * 4);
+  // input block: emb | labels | dloss ; output block: loss | pos | neg | stats | demb
+  const size_t in_bytes = eb + 2 * lb, out_bytes = 3 * lb + 256 + eb;
+  if (int rc = g_bh_stage.ensure(in_bytes + out_bytes)) return rc;
+  char* h = (char*)g_bh_stage.h;
+  char* d = (char*)g_bh_stage.d;
+  memcpy(h, emb_host, (size_t)B * D * 4);
+  memcpy(h + eb, labels_host, (size_t)B * 4);
+  if (dloss_host) memcpy(h + eb + lb, dloss_host, (size_t)B * 4);
+  cudaStream_t st = g_bh_stage.st;
+  DIF_CUDA_OK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st));
+  char* o = d + in_bytes;
+  if (int rc = dif_batch_hard((const float*)d, (const int32_t*)(d + eb), B, D, variant, alpha, (float*)o,
+                              (int32_t*)(o + lb), (int32_t*)(o + 2 * lb), (float*)(o + 3 * lb),
+                              dloss_host ? (const float*)(d + eb + lb) : nullptr,
+                              demb_host ? (float*)(o + 3 * lb + 256) : nullptr, precision, st))
+    return rc;
+  const size_t back = demb_host ? out_bytes : 3 * lb + 256;
+  DIF_CUDA_OK(cudaMemcpyAsync(h + in_bytes, o, back, cudaMemcpyDeviceToHost, st));
+  DIF_CUDA_OK(cudaStreamSynchronize(st));
+  char* ho = h + in_bytes;
+  memcpy(loss_host, ho, (size_t)B * 4);
+  if (pos_idx_host) memcpy(pos_idx_host, ho + lb, (size_t)B * 4);
+  if (neg_idx_host) memcpy(neg_idx_host, ho + 2 * lb, (size_t)B * 4);
+  memcpy(stats_host, ho + 3 * lb, 16);
+  if (demb_host) memcpy(demb_host, ho + 3 * lb + 256, (size_t)B * D * 4);
+  return DIF_OK;
+}
+
+int dif_labels_from_onehot(const float* onehot, int B, int C, int32_t* labels, void* stream) {
+  DIF_REQUIRE(onehot && labels && B >= 1 && C >= 1, DIF_ERR_INVALID, "dif_labels_from_onehot: invalid argument");
+  argmax_rows_kernel<<<(B + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(onehot, B, C, labels);
+  DIF_LAUNCH_OK();
+  return DIF_OK;
+}
+
+}  // extern "C"

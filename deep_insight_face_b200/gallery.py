@@ -196,6 +196,25 @@ class ShardedGallery:
         return merge_candidates(g_scores, g_rows, g_ids, self.metric)
 
 
+    def search_host(self, queries, k: int = 10):
+        """Host-facing call: numpy queries in, numpy (scores, ids) out.  One rank: the C-ABI host entry point
+        (pinned staging, H2D, search, D2H).  Several ranks: pinned H2D here, then search/exchange/merge, D2H."""
+        if self.world == 1:
+            return self.local.search(queries, k)
+        import torch
+
+        q = _ffi.host_array(queries, np.float32)
+        if getattr(self, "_pin", None) is None or self._pin.shape != q.shape:
+            self._pin = torch.empty(q.shape, dtype=torch.float32).pin_memory()
+        self._pin.numpy()[...] = q
+        qd = self._pin.to(f"cuda:{self.device}", non_blocking=True)
+        scores, ids, _ = self.search(qd, k)
+        return scores.cpu().numpy(), ids.cpu().numpy()
+
+    def close(self) -> None:
+        self.local.close()
+
+
 def exchange_candidates(scores, ids, grows, group=None):
     """All-gather the per-rank candidate lists: returns [world, Q, k] tensors (works on NCCL and gloo)."""
     import torch

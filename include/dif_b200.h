@@ -109,23 +109,26 @@ int dif_debug_nt_gemm(const float* A, const float* B, int M, int N, int K, float
 /* diagnostic: average ms of the NT-GEMM main loop alone (checksum epilogue) on synthetic operands */
 int dif_debug_gemm_time(int M, int N, int K, int precision, int ctas, int n_splits, int iters, float* ms_out);
 
-/* ---- batch-hard / batch-all triplet losses ------------------------------------------------
+/* ---- batch-hard triplet losses ------------------------------------------------------------
  * deep_insight_face/common/losses.py:33-51 (BatchHardTripletLoss, cosine),
  * :54-85 (BatchHardTripletLossEuclidean), :88-128 (...AutoAlpha: pass the current auto_alpha as
- * `alpha`; stats[0]*alpha_scale is the caller's next value), :131-148 (BatchAllTripletLoss).
- * labels are int32 class ids (argmax of the one-hot, losses.py:35).  Outputs:
- *   loss [B]; pos_idx/neg_idx [B] mined column (first index on ties, -1 if a filler won);
+ * `alpha`; the caller's next value is stats[0] * alpha_scale, losses.py:113).
+ * labels are int32 class ids (argmax of the one-hot, losses.py:35; see dif_labels_from_onehot).  Outputs:
+ *   loss [B]; pos_idx/neg_idx [B] mined column (first index on ties, -1 if a filler won; may be NULL);
  *   stats [4] = mean(dists), mean(hardest_pos), mean(hardest_neg), max(dists) (losses.py:72-80,70);
- *   demb [B*D] gradient of sum_i dloss[i]*loss[i] (dloss NULL -> 1/B each, Keras AUTO mean); NULL skips backward. */
+ *   demb [B*D] gradient of sum_i dloss[i]*loss[i] (dloss NULL -> 1/B each, Keras AUTO mean); NULL skips backward.
+ * Arithmetic is the canonical fp32 reduction of oracle/dif_oracle.c, so mined indices are reproducible
+ * bit for bit on the CPU; `precision` must be DIF_PREC_TF32X3 (fp32-exact). */
 #define DIF_LOSS_BH_COSINE 0
 #define DIF_LOSS_BH_EUCLIDEAN 1
-#define DIF_LOSS_BATCH_ALL 2
 int dif_batch_hard(const float* emb, const int32_t* labels, int B, int D, int variant, float alpha, float* loss,
                    int32_t* pos_idx, int32_t* neg_idx, float* stats, const float* dloss, float* demb,
                    int precision, void* stream);
 int dif_batch_hard_host(const float* emb_host, const int32_t* labels_host, int B, int D, int variant, float alpha,
                         float* loss_host, int32_t* pos_idx_host, int32_t* neg_idx_host, float* stats_host,
                         const float* dloss_host, float* demb_host, int precision);
+/* tf.argmax(labels, axis=1) of a one-hot [B, C] fp32 matrix (first maximum), losses.py:35 */
+int dif_labels_from_onehot(const float* onehot, int B, int C, int32_t* labels, void* stream);
 
 /* explicit-triplet loss on [B, 3D] rows (anchor|positive|negative):
  * deep_insight_face/networks/triplet.py:16-46 `triplet_loss`; loss [B]; dy [B*3D] optional (dloss NULL -> 1) */

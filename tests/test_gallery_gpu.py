@@ -1,0 +1,201 @@
+"""1:N gallery search through the C ABI against the CPU oracle: ids AND scores bit-exact in every tensor-core
+mode, ties to the lower row, ragged / short / empty inputs, the exact fallback, host and device entry points,
+and the multi-shard merge."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def make(orc, N, Q, D, seed=3):
+    rows = orc.synth_rows(seed, 0, N, D)
+    pick = np.random.default_rng(N + Q).integers(0, N, size=Q)
+    q = rows[pick] + 0.3 * orc.synth_rows(seed + 30, 0, Q, D)
+    return rows, q, pick
+
+
+def check(orc, g, rows, q, k, metric):
+    s, ids, r = g.search(q, k, return_rows=True)
+    ws, wr = orc.gallery_search(rows, q, k, metric)
+    assert np.array_equal(r.astype(np.int64), wr), "top-k rows differ from the oracle"
+    assert np.array_equal(s.view(np.uint32), ws.view(np.uint32)), "scores differ bitwise from the oracle"
+    return s, ids, r
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "bf16", "tf32x1"])
+@pytest.mark.parametrize("metric", ["cosine", "l2"])
+@pytest.mark.parametrize("N,Q,D,k", [(1000, 37, 64, 10), (20000, 300, 128, 10), (70001, 513, 512, 5), (300, 5, 96, 24)])
+def test_search_bit_exact(gpu, orc, precision, metric, N, Q, D, k):
+    from deep_insight_face_b200.gallery import Gallery
+
+    rows, q, pick = make(orc, N, Q, D)
+    m = 1 if metric == "cosine" else 0
+    with Gallery(N, D, metric, precision) as g:
+        g.add(rows)
+        _, _, r = check(orc, g, rows, q, k, m)
+        assert (r[:, 0] == pick).mean() > 0.99
+        assert g.last_stats()["fallback_queries"] <= max(2, Q // 50)
+
+
+@pytest.mark.parametrize("ctas,resident", [(1, 0), (2, 0), (2, 1)])
+def test_search_schedules_agree(gpu, orc, ctas, resident):
+    from deep_insight_face_b200.gallery import Gallery
+
+    rows, q, _ = make(orc, 30000, 260, 256)
+    with Gallery(30000, 256, "cosine", "bf16") as g:
+        g.set_option("gemm_ctas", ctas)
+        g.set_option("resident_queries", resident)
+        g.add(rows)
+        check(orc, g, rows, q, 10, 1)
+        assert g.last_stats()["resident_queries"] == (1 if (ctas == 2 and resident) else 0)
+
+
+def test_exact_fallback_path(gpu, orc):
+    from deep_insight_face_b200.gallery import Gallery
+
+    rows, q, _ = make(orc, 5000, 64, 128)
+    with Gallery(5000, 128, "cosine", "bf16") as g:
+        g.set_option("force_fallback", 1)
+        g.add(rows)
+        check(orc, g, rows, q, 10, 1)
+        assert g.last_stats()["fallback_queries"] == 64
+
+
+def test_ties_go_to_the_lower_row_and_short_gallery(gpu, orc):
+    from deep_insight_face_b200.gallery import Gallery
+
+    base = orc.synth_rows(1, 0, 3, 64)
+    rows = np.concatenate([base[:1]] * 4 + [base[1:]] + [base[:1]] * 2)   # rows 0-3 and 6-7 identical
+    with Gallery(16, 64, "cosine", "tf32x3") as g:
+        g.add(rows)
+        s, ids, r = check(orc, g, rows, base[:1], 12, 1)
+        assert r[0, :6].tolist() == [0, 1, 2, 3, 6, 7]
+        assert r[0, 8:].tolist() == [-1] * 4 and ids[0, 8:].tolist() == [-1] * 4
+
+
+def test_near_duplicates_flood_the_window(gpu, orc):
+    """Hundreds of rows inside the error window of the k-th best score: the window overflows or a split's list
+    saturates, the query is flagged and the exact scan answers - still bit-identical to the oracle."""
+    from deep_insight_face_b200.gallery import Gallery
+
+    D = 128
+    centre = orc.synth_rows(8, 0, 1, D)
+    near = centre + 1e-4 * orc.synth_rows(9, 0, 600, D)
+    rows = np.concatenate([orc.synth_rows(10, 0, 3000, D), near]).astype(np.float32)
+    with Gallery(rows.shape[0], D, "cosine", "bf16") as g:
+        g.add(rows)
+        check(orc, g, rows, centre, 10, 1)
+        assert g.last_stats()["fallback_queries"] == 1
+
+
+def test_ids_incremental_add_and_device_entry(gpu, orc):
+    import torch
+
+    from deep_insight_face_b200.gallery import Gallery
+
+    rows, q, _ = make(orc, 4000, 50, 128)
+    ids = (np.arange(4000, dtype=np.int64) * 7 + 100)
+    with Gallery(5000, 128, "cosine", "tf32x1") as g:
+        g.add(rows[:1500], ids[:1500])
+        g.add(torch.from_numpy(rows[1500:]).cuda(), torch.from_numpy(ids[1500:]).cuda())
+        assert len(g) == 4000
+        s, got_ids, r = g.search(q, 10, return_rows=True)
+        ws, wr = orc.gallery_search(rows, q, 10, 1)
+        assert np.array_equal(r.astype(np.int64), wr) and np.array_equal(got_ids, ids[wr])
+        sd, idd = g.search(torch.from_numpy(q).cuda(), 10)
+        assert np.array_equal(idd.cpu().numpy(), got_ids) and np.array_equal(sd.cpu().numpy(), s)
+        np.testing.assert_array_equal(g.rows(10, 5), orc.normalize_rows(rows[10:15]))
+        with pytest.raises(Exception):
+            g.add(rows[:2000])        # over capacity
+        with pytest.raises(Exception):
+            g.add(rows[:10])          # explicit ids were used before: they are required now
+
+
+def test_empty_gallery_and_bad_arguments(gpu, orc):
+    from deep_insight_face_b200 import _ffi
+    from deep_insight_face_b200.gallery import Gallery
+
+    with Gallery(100, 64, "cosine", "tf32x3") as g:
+        s, ids = g.search(orc.synth_rows(1, 0, 3, 64), 5)
+        assert (ids == -1).all() and (s == 0).all()
+        with pytest.raises(_ffi.DifError):
+            g.search(orc.synth_rows(1, 0, 3, 64), 25)   # k > DIF_MAX_TOPK
+        with pytest.raises(ValueError):
+            g.search(orc.synth_rows(1, 0, 3, 32), 5)
+    with pytest.raises(_ffi.DifError):
+        Gallery(100, 30, "cosine", "tf32x3")             # dim must be a multiple of 4 and >= 32
+
+
+def test_synthetic_fill_matches_oracle_generator(gpu, orc):
+    from deep_insight_face_b200.gallery import Gallery
+
+    with Gallery(3000, 128, "cosine", "bf16") as g:
+        g.fill_synthetic(3, 1000, 3000)
+        rows = orc.synth_rows(3, 1000, 3000, 128)
+        np.testing.assert_array_equal(g.rows(), orc.normalize_rows(rows))
+        q = rows[:40] + 0.3 * orc.synth_rows(33, 0, 40, 128)
+        check(orc, g, rows, q, 10, 1)
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_sharded_search_equals_single_gallery(gpu, orc, world):
+    """Emulates the ranks of ShardedGallery on one GPU: per-shard search with id_base, then the device merge."""
+    import torch
+
+    from deep_insight_face_b200.gallery import Gallery, merge_candidates, shard_range
+
+    N, Q, D, k = 10007, 120, 128, 10
+    rows, q, _ = make(orc, N, Q, D)
+    parts = []
+    for rank in range(world):
+        lo, hi = shard_range(N, rank, world)
+        with Gallery(hi - lo, D, "cosine", "bf16") as g:
+            g.set_id_base(lo)
+            g.add(rows[lo:hi])
+            s, ids, r = g.search(torch.from_numpy(q).cuda(), k, return_rows=True)
+            grow = torch.where(r >= 0, r.long() + lo, torch.full_like(ids, -1))
+            assert torch.equal(grow, ids)
+            parts.append((s, ids, grow))
+    gs = torch.stack([p[0] for p in parts])
+    gi = torch.stack([p[1] for p in parts])
+    gr = torch.stack([p[2] for p in parts])
+    s, ids, grows = merge_candidates(gs, gr, gi, 1)
+    ws, wr = orc.gallery_search(rows, q, k, 1)
+    assert np.array_equal(grows.cpu().numpy(), wr) and np.array_equal(ids.cpu().numpy(), wr)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), ws.view(np.uint32))
+
+
+def test_full_size_properties(gpu, orc):
+    """BASELINE config C3 (1M x 512, 4096 queries, top-10): properties that do not need the CPU to scan 4.2e12
+    products - planted matches come back first, scores are sorted, ids unique, three tensor-core modes agree
+    bit for bit, and a 24-query sample is checked against the oracle in full."""
+    import torch
+
+    from deep_insight_face_b200 import _ffi
+    from deep_insight_face_b200.gallery import Gallery
+
+    N, Q, D, k = 1_000_000, 4096, 512, 10
+    lib = _ffi.load_library()
+    pick = torch.from_numpy(np.random.default_rng(7).integers(0, N, size=Q)).cuda()
+    base = torch.empty((Q, D), device=gpu)
+    noise = torch.empty((Q, D), device=gpu)
+    _ffi.check(lib.dif_synth_fill(_ffi.ptr(base), 3, 0, _ffi.ptr(pick), Q, D, None))
+    _ffi.check(lib.dif_synth_fill(_ffi.ptr(noise), 33, 0, None, Q, D, None))
+    torch.cuda.synchronize()
+    q = base + 0.3 * noise
+    results = {}
+    for prec in ("bf16", "tf32x1", "tf32x3"):
+        with Gallery(N, D, "cosine", prec) as g:
+            g.fill_synthetic(3, 0, N)
+            s, ids = g.search(q, k)
+            results[prec] = (s.cpu().numpy(), ids.cpu().numpy())
+            assert g.last_stats()["fallback_queries"] <= 8
+    s, ids = results["tf32x3"]
+    for prec in ("bf16", "tf32x1"):
+        assert np.array_equal(results[prec][1], ids) and np.array_equal(results[prec][0], s)
+    assert (ids[:, 0] == pick.cpu().numpy()).all()
+    assert np.all(np.diff(s, axis=1) <= 0)
+    assert all(len(set(row)) == k for row in ids)
+    gal = orc.synth_rows(3, 0, N, D)
+    ws, wr = orc.gallery_search(gal, q[:24].cpu().numpy(), k, 1)
+    assert np.array_equal(wr, ids[:24]) and np.array_equal(ws.view(np.uint32), s[:24].view(np.uint32))

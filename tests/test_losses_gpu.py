@@ -1,0 +1,162 @@
+"""Batch-hard triplet losses (common/losses.py:33-128) and the row-wise losses through the C ABI against the
+numpy oracle: mined indices bit-exact (ties -> lower index), loss / gradient within 1e-4 relative
+(BASELINE.json), reference edge cases of SURVEY.md section 8c."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4  # BASELINE.json: loss, gradients and distances within 1e-4 relative in fp32
+
+
+def pk_batch(P, K, D, noise, seed=1, normalise=False):
+    rng = np.random.default_rng(seed)
+    cent = rng.standard_normal((P, D)).astype(np.float32)
+    emb = (np.repeat(cent, K, 0) + noise * rng.standard_normal((P * K, D))).astype(np.float32)
+    if normalise:
+        emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+    return emb, np.repeat(np.arange(P), K)
+
+
+def close(got, want, scale=None, rtol=RTOL):
+    scale = np.abs(want).max() if scale is None else scale
+    assert np.abs(np.asarray(got, dtype=np.float64) - want).max() <= rtol * max(scale, 1e-30), \
+        f"max err {np.abs(got - want).max()} vs scale {scale}"
+
+
+def run_case(cls, oracle_fn, emb, lab, alpha, onehot=True):
+    loss = cls(alpha=alpha)
+    labels = np.eye(lab.max() + 1, dtype=np.float32)[lab] if onehot else lab
+    got, grad, info = loss.loss_and_grad(labels, emb)
+    want = oracle_fn(lab, emb, alpha)
+    assert np.array_equal(info["pos_idx"], want["pos_idx"]), "mined positives differ"
+    assert np.array_equal(info["neg_idx"], want["neg_idx"]), "mined negatives differ"
+    close(got, want["loss"], scale=max(np.abs(want["loss"]).max(), np.abs(want["hardest_pos"]).max()))
+    close(grad, want["grad"])
+    close(info["stats"], want["stats"], scale=np.abs(want["stats"]).max())
+    return got, grad, info, want
+
+
+@pytest.mark.parametrize("P,K,D", [(18, 4, 128), (8, 4, 96), (33, 3, 100), (64, 4, 128), (256, 4, 128), (16, 2, 512)])
+@pytest.mark.parametrize("noise", [0.5, 1.5])
+def test_batch_hard_cosine(gpu, P, K, D, noise):
+    from deep_insight_face_b200.common.losses import BatchHardTripletLoss
+    from oracle import losses_oracle as lo
+
+    emb, lab = pk_batch(P, K, D, noise)
+    run_case(BatchHardTripletLoss, lo.batch_hard_cosine, emb, lab, 0.35)
+
+
+@pytest.mark.parametrize("P,K,D", [(18, 4, 128), (33, 3, 100), (256, 4, 128)])
+@pytest.mark.parametrize("alpha,normalise", [(0.35, True), (50.0, False)])
+def test_batch_hard_euclidean(gpu, P, K, D, alpha, normalise):
+    from deep_insight_face_b200.common.losses import BatchHardTripletLossEuclidean
+    from oracle import losses_oracle as lo
+
+    emb, lab = pk_batch(P, K, D, 1.5, normalise=normalise)
+    run_case(BatchHardTripletLossEuclidean, lo.batch_hard_euclidean, emb, lab, alpha)
+
+
+def test_batch_hard_large_batch_indices(gpu):
+    """B = 4096 (top of the BASELINE sweep): mined indices still bit-exact."""
+    from deep_insight_face_b200.common.losses import BatchHardTripletLoss, BatchHardTripletLossEuclidean
+    from oracle import losses_oracle as lo
+
+    emb, lab = pk_batch(1024, 4, 128, 1.0)
+    run_case(BatchHardTripletLoss, lo.batch_hard_cosine, emb, lab, 0.35, onehot=False)
+    run_case(BatchHardTripletLossEuclidean, lo.batch_hard_euclidean, emb, lab, 100.0, onehot=False)
+
+
+def test_edge_cases_single_sample_identity_and_single_identity(gpu):
+    from deep_insight_face_b200.common.losses import BatchHardTripletLoss, BatchHardTripletLossEuclidean
+    from oracle import losses_oracle as lo
+
+    emb, lab = pk_batch(10, 3, 64, 1.0)
+    lab = lab.copy()
+    lab[-1] = 99  # an identity with K = 1: its only positive is itself (filler 1.0 / 0 may win)
+    lab = np.unique(lab, return_inverse=True)[1]
+    run_case(BatchHardTripletLoss, lo.batch_hard_cosine, emb, lab, 0.35)
+    run_case(BatchHardTripletLossEuclidean, lo.batch_hard_euclidean, emb, lab, 10.0)
+    one = np.zeros(30, dtype=np.int64)   # one identity only: hardest negative is the filler (-1 / max(dists))
+    _, _, info, _ = run_case(BatchHardTripletLoss, lo.batch_hard_cosine, emb, one, 0.35)
+    assert (info["neg_idx"] == -1).all()
+    _, grad, info, want = run_case(BatchHardTripletLossEuclidean, lo.batch_hard_euclidean, emb, one, 0.35)
+    assert (info["neg_idx"] == -1).all() and np.abs(want["grad"]).max() > 0  # gradient flows through max(dists)
+
+
+def test_exact_ties_split_the_gradient(gpu):
+    from deep_insight_face_b200.common.losses import BatchHardTripletLoss, BatchHardTripletLossEuclidean
+    from oracle import losses_oracle as lo
+
+    rng = np.random.default_rng(2)
+    emb = rng.standard_normal((12, 32)).astype(np.float32)
+    emb[5] = emb[4]
+    emb[9] = emb[8]
+    emb[2] = 0.0      # a zero row: l2_normalize leaves it at 0
+    lab = np.repeat(np.arange(4), 3)
+    run_case(BatchHardTripletLoss, lo.batch_hard_cosine, emb, lab, 5.0)
+    run_case(BatchHardTripletLossEuclidean, lo.batch_hard_euclidean, emb, lab, 5.0)
+
+
+def test_keras_protocol_and_auto_alpha(gpu):
+    from deep_insight_face_b200.common.losses import (BatchHardTripletLoss, BatchHardTripletLossEuclideanAutoAlpha,
+                                                      TripletLossWapper)
+    from oracle import losses_oracle as lo
+
+    emb, lab = pk_batch(18, 4, 128, 1.5)
+    onehot = np.eye(18, dtype=np.float32)[lab]
+    loss = BatchHardTripletLoss(alpha=0.2)
+    cfg = loss.get_config()
+    assert cfg["alpha"] == 0.2
+    again = BatchHardTripletLoss.from_config(cfg)
+    per_sample = again.call(onehot, emb)
+    assert per_sample.shape == (72,)
+    close(per_sample, lo.batch_hard_cosine(lab, emb, 0.2)["loss"])
+    close(again(onehot, emb), lo.batch_hard_cosine(lab, emb, 0.2)["loss"].mean())   # Keras AUTO reduction
+    assert TripletLossWapper().call(onehot, emb) is None                              # losses.py:17-18
+    auto = BatchHardTripletLossEuclideanAutoAlpha(alpha=0.1, init_auto_alpha=1)
+    first = auto.call(onehot, emb)
+    want1 = lo.batch_hard_euclidean(lab, emb, 1.0)                                    # uses the PREVIOUS alpha (:112)
+    close(first, want1["loss"], scale=np.abs(want1["hardest_pos"]).max())
+    assert abs(auto.auto_alpha - want1["stats"][0] * 0.1) <= 1e-4 * want1["stats"][0]  # :113
+    second = auto.call(onehot, emb)
+    close(second, lo.batch_hard_euclidean(lab, emb, auto.auto_alpha)["loss"], scale=np.abs(want1["hardest_pos"]).max())
+    assert "auto_alpha" not in auto.get_config()
+
+
+def test_torch_autograd_bridge(gpu):
+    import torch
+
+    from deep_insight_face_b200.common.losses import BatchHardTripletLoss
+    from oracle import losses_oracle as lo
+
+    emb, lab = pk_batch(18, 4, 128, 1.5)
+    x = torch.from_numpy(emb).cuda().requires_grad_(True)
+    onehot = torch.from_numpy(np.eye(18, dtype=np.float32)[lab]).cuda()
+    per_sample = BatchHardTripletLoss().call(onehot, x)
+    per_sample.mean().backward()
+    want = lo.batch_hard_cosine(lab, emb, 0.35)
+    close(x.grad.cpu().numpy(), want["grad"])
+
+
+def test_explicit_triplet_siamese_and_contrastive(gpu):
+    from deep_insight_face_b200.networks.siamese import _accuracy, contrastive_loss, euclidean_distance
+    from deep_insight_face_b200.networks.triplet import triplet_loss
+    from oracle import losses_oracle as lo
+
+    rng = np.random.default_rng(3)
+    y = rng.standard_normal((50, 3 * 128)).astype(np.float32)
+    got, grad = triplet_loss(None, y, alpha=0.4, return_grad=True)
+    want = lo.triplet_apn(y, 0.4)
+    assert np.array_equal(got.view(np.uint32), want["loss"].view(np.uint32))   # canonical arithmetic: bit-exact
+    close(grad, want["grad"])
+    a, b = y[:, :128], y[:, 128:256]
+    d = euclidean_distance([a, b])
+    assert d.shape == (50, 1)
+    close(d, lo.euclidean_distance(a, b))
+    yt = (rng.random(50) > 0.5).astype(np.float32)
+    val, dd = contrastive_loss(yt, d / 10, return_grad=True)
+    wv, wd = lo.contrastive_loss(yt, d / 10)
+    assert abs(val - wv) <= RTOL * abs(wv)
+    close(dd, wd)
+    assert _accuracy(yt, d[:, 0] / 10, 0.5) == lo.siamese_accuracy(yt, d[:, 0] / 10, 0.5)
