@@ -88,8 +88,8 @@ SIGNATURES = {
     "dif_triplet_apn": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "dif_euclidean_distance": (_i32, [_vp, _vp, _i32, _i32, _f32, _vp, _vp]),
     "dif_contrastive_loss": (_i32, [_vp, _vp, _i32, _f32, _vp, _vp, _vp]),
-    "dif_arcface": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _i32, _vp]),
-    "dif_arcface_host": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _i32]),
+    "dif_arcface": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "dif_arcface_host": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp, _vp, _i32]),
     "dif_pair_distance": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "dif_pair_distance_host": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "dif_fold_mean": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),

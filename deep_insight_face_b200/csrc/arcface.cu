@@ -1,0 +1,394 @@
+// ArcFace additive-angular-margin logits + softmax cross-entropy, forward + backward.
+// ABSENT from the reference; specification in DESIGN.md and oracle/losses_oracle.py:arcface (arXiv 1801.07698):
+//   xh = l2_normalize(x), wh = l2_normalize(w), cos = clip(xh . wh, -1, 1)
+//   target logit s * phi(cos_y), phi = cos(theta + m) if cos_y > cos(pi - m) else cos_y - m sin(pi - m); others s * cos
+//   loss_b = logsumexp(logits_b) - logits_b[y_b];   dX, dW = gradients of sum_b dloss_b * loss_b (default 1/B)
+//
+// All three contractions run on the tcgen05/TMA NT-GEMM skeleton in 3xTF32 (fp32-exact to ~1e-6):
+//   1. arc_fwd     cos = xh wh^T with a fused epilogue: clip, margin on the target column, scale, online
+//                  softmax (running max / sum per class split) in registers; cos is also written out once
+//   2. arc_loss    merges the per-split (max, sum) pairs -> logZ, loss, d phi / d cos
+//   3. arc_dcos    p - onehot -> d cos, written as TF32 hi/lo planes in both orientations ([B,C] and [C,B])
+//   4. dxh = dcos wh        (NT GEMM over K = C, split-K planes summed in a fixed order)
+//      dwh = dcos^T xh      (NT GEMM over K = B)
+//   5. arc_norm_bwd  l2_normalize backward for X rows and W rows
+#include <algorithm>
+
+#include "prep_rows.cuh"
+#include "store_epi.cuh"
+
+namespace dif {
+
+constexpr int kArcBN = 256;
+constexpr float kLog2e = 1.4426950408889634f;
+
+struct ArcMargin {
+  float s, cos_m, sin_m, th, mm;
+};
+
+__device__ __forceinline__ float arc_phi(float ct, const ArcMargin& a) {
+  return ct > a.th ? ct * a.cos_m - sqrtf(fmaxf(1.f - ct * ct, 0.f)) * a.sin_m : ct - a.mm;
+}
+__device__ __forceinline__ float arc_dphi(float ct, const ArcMargin& a) {
+  if (!(ct > a.th)) return 1.f;
+  const float st = sqrtf(fmaxf(1.f - ct * ct, 0.f));
+  return a.cos_m + (st > 0.f ? ct / st : 0.f) * a.sin_m;
+}
+
+// Forward epilogue: thread = one sample, columns = classes.
+struct ArcFwdEpi {
+  struct Params {
+    float* cosbuf;          // [B][ldc] raw (unclipped) cosines
+    const int32_t* y;       // [B]
+    float2* part;           // [B][n_slots] (running max, running sum) in log2 units of the scaled logits
+    int B, C, ldc, n_slots;
+    ArcMargin mg;
+  };
+  static constexpr int kSmemBytes = 16;
+  const Params& p;
+  float* row_ptr;
+  float m2, l2;   // running max / sum of 2^(logit * log2e - m2)
+  int yb;
+  __device__ ArcFwdEpi(const Params& pp, uint8_t*, int) : p(pp), row_ptr(nullptr), m2(-INFINITY), l2(0.f), yb(-1) {}
+  __device__ void begin_item(int m, int, int) {
+    row_ptr = m < p.B ? p.cosbuf + (size_t)m * p.ldc : nullptr;
+    yb = m < p.B ? p.y[m] : -1;
+    m2 = -INFINITY;
+    l2 = 0.f;
+  }
+  __device__ void begin_tile() {}
+  __device__ void consume(int col0, const uint32_t (&acc)[32], uint32_t, uint32_t (&)[32]) {
+    if (!row_ptr) return;
+    float z[32];
+    const float k2 = p.mg.s * kLog2e;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float raw = __uint_as_float(acc[i]);
+      const float c = fminf(fmaxf(raw, -1.f), 1.f);
+      z[i] = (col0 + i < p.C) ? c * k2 : -INFINITY;
+    }
+    if (yb >= col0 && yb < col0 + 32) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i == yb) z[i] = arc_phi(fminf(fmaxf(__uint_as_float(acc[i]), -1.f), 1.f), p.mg) * k2;
+    }
+    if (col0 + 32 <= p.ldc) {
+      float4* dst = reinterpret_cast<float4*>(row_ptr + col0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_float4(__uint_as_float(acc[4 * i]), __uint_as_float(acc[4 * i + 1]), __uint_as_float(acc[4 * i + 2]),
+                             __uint_as_float(acc[4 * i + 3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < p.ldc) row_ptr[col0 + i] = __uint_as_float(acc[i]);
+    }
+    float mx = z[0];
+#pragma unroll
+    for (int i = 1; i < 32; ++i) mx = fmaxf(mx, z[i]);
+    if (mx == -INFINITY) return;
+    const float mn = fmaxf(m2, mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sum += exp2f(z[i] - mn);
+    l2 = l2 * exp2f(m2 - mn) + sum;
+    m2 = mn;
+  }
+  __device__ void end_item(int m, int slot) {
+    if (m < p.B) p.part[(size_t)m * p.n_slots + slot] = make_float2(m2, l2);
+  }
+};
+
+// one thread per sample: merge the split partials, loss, logZ (natural log units), target phi and d phi
+__global__ void arc_loss_kernel(const float2* __restrict__ part, int n_slots, const float* __restrict__ cosbuf, int ldc,
+                                const int32_t* __restrict__ y, int B, ArcMargin mg, float* __restrict__ loss,
+                                float* __restrict__ logz, float* __restrict__ dphi) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float m2 = -INFINITY, l2 = 0.f;
+  for (int s = 0; s < n_slots; ++s) {
+    const float2 q = part[(size_t)b * n_slots + s];
+    if (q.x == -INFINITY) continue;
+    const float mn = fmaxf(m2, q.x);
+    l2 = l2 * exp2f(m2 - mn) + q.y * exp2f(q.x - mn);
+    m2 = mn;
+  }
+  const float lz = (m2 + log2f(l2)) / kLog2e;
+  const float ct = fminf(fmaxf(cosbuf[(size_t)b * ldc + y[b]], -1.f), 1.f);
+  loss[b] = lz - mg.s * arc_phi(ct, mg);
+  logz[b] = lz;
+  dphi[b] = arc_dphi(ct, mg);
+}
+
+// d cos in both orientations as TF32 hi/lo planes.  Tile 32 samples x 32 classes per block (32 x 8 threads).
+__global__ void __launch_bounds__(256) arc_dcos_kernel(const float* __restrict__ cosbuf, int ldc,
+                                                       const int32_t* __restrict__ y, const float* __restrict__ logz,
+                                                       const float* __restrict__ dphi, const float* __restrict__ dloss,
+                                                       int B, int C, ArcMargin mg, float* __restrict__ d_hi,
+                                                       float* __restrict__ d_lo,    // [Bp][ldc]
+                                                       float* __restrict__ t_hi, float* __restrict__ t_lo, int ldt,
+                                                       int Cp) {                    // [Cp][ldt]
+  __shared__ float tile[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int b = blockIdx.y * 32 + r;
+    float v = 0.f;
+    if (b < B && c < C) {
+      const float raw = cosbuf[(size_t)b * ldc + c];
+      const float ct = fminf(fmaxf(raw, -1.f), 1.f);
+      const float g = dloss ? dloss[b] : 1.f / (float)B;
+      const bool tgt = (c == y[b]);
+      const float logit = mg.s * (tgt ? arc_phi(ct, mg) : ct);
+      const float pr = expf(logit - logz[b]);
+      v = mg.s * g * (pr - (tgt ? 1.f : 0.f)) * (tgt ? dphi[b] : 1.f);
+      if (raw < -1.f || raw > 1.f) v = 0.f;   // clip_by_value passes no gradient outside the bounds
+    }
+    tile[r][threadIdx.x] = v;
+    if (b < ((B + 3) & ~3) && c < ldc) {
+      const float hi = tf32_round(v);
+      d_hi[(size_t)b * ldc + c] = hi;
+      d_lo[(size_t)b * ldc + c] = __fsub_rn(v, hi);
+    }
+  }
+  __syncthreads();
+  const int b2 = blockIdx.y * 32 + threadIdx.x;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int c2 = blockIdx.x * 32 + r;
+    if (c2 < Cp && b2 < ldt) {
+      const float v = tile[threadIdx.x][r];
+      const float hi = tf32_round(v);
+      t_hi[(size_t)c2 * ldt + b2] = hi;
+      t_lo[(size_t)c2 * ldt + b2] = __fsub_rn(v, hi);
+    }
+  }
+}
+
+// src [R][Cc] (hi + lo planes) -> transposed TF32 hi/lo planes [Cc][ldt] (zero padded to ldt)
+__global__ void __launch_bounds__(256) transpose_planes_kernel(const float* __restrict__ s_hi,
+                                                               const float* __restrict__ s_lo, int R, int Cc,
+                                                               float* __restrict__ t_hi, float* __restrict__ t_lo,
+                                                               int ldt) {
+  __shared__ float th[32][33], tl[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int row = blockIdx.y * 32 + r;
+    const bool ok = row < R && c < Cc;
+    th[r][threadIdx.x] = ok ? s_hi[(size_t)row * Cc + c] : 0.f;
+    tl[r][threadIdx.x] = ok ? s_lo[(size_t)row * Cc + c] : 0.f;
+  }
+  __syncthreads();
+  const int row2 = blockIdx.y * 32 + threadIdx.x;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int c2 = blockIdx.x * 32 + r;
+    if (c2 < Cc && row2 < ldt) {
+      t_hi[(size_t)c2 * ldt + row2] = th[threadIdx.x][r];
+      t_lo[(size_t)c2 * ldt + row2] = tl[threadIdx.x][r];
+    }
+  }
+}
+
+// out_r = inv_r * (g_r - h_r (h_r . g_r)) with g = sum over `planes` partial planes, h = hi + lo normalised row;
+// rows whose squared norm was clamped (inv == 1e6) are a plain scaling.  One warp per row.
+__global__ void __launch_bounds__(256) arc_norm_bwd_kernel(const float* __restrict__ g, int planes, size_t plane_stride,
+                                                           const float* __restrict__ h_hi, const float* __restrict__ h_lo,
+                                                           const float* __restrict__ inv, int R, int D,
+                                                           float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  float dot = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    float a = 0.f;
+    for (int s = 0; s < planes; ++s) a += g[(size_t)s * plane_stride + (size_t)r * D + d];
+    dot += a * (h_hi[(size_t)r * D + d] + h_lo[(size_t)r * D + d]);
+  }
+  for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  const float iv = inv[r];
+  const bool clamped = iv >= 0.99e6f;   // 1 / sqrt(1e-12)
+  for (int d = lane; d < D; d += 32) {
+    float a = 0.f;
+    for (int s = 0; s < planes; ++s) a += g[(size_t)s * plane_stride + (size_t)r * D + d];
+    const float h = h_hi[(size_t)r * D + d] + h_lo[(size_t)r * D + d];
+    out[(size_t)r * D + d] = clamped ? iv * a : iv * (a - h * dot);
+  }
+}
+
+struct ArcWorkspace {
+  char* base = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return DIF_OK;
+    cudaFree(base);
+    base = nullptr;
+    bytes = 0;
+    DIF_CUDA_OK(cudaMalloc((void**)&base, need));
+    bytes = need;
+    return DIF_OK;
+  }
+};
+static thread_local ArcWorkspace g_arc;
+
+static int tmaps(CUtensorMap* maps, const float* a_hi, const float* a_lo, int M, const float* b_hi, const float* b_lo,
+                 int N, int K, int ldk) {
+  if (int rc = make_tmap_2d(&maps[0], a_hi, M, K, (uint64_t)ldk * 4, GEMM_BM, 32, 0)) return rc;
+  if (int rc = make_tmap_2d(&maps[1], a_lo, M, K, (uint64_t)ldk * 4, GEMM_BM, 32, 0)) return rc;
+  if (int rc = make_tmap_2d(&maps[2], b_hi, N, K, (uint64_t)ldk * 4, kArcBN, 32, 0)) return rc;
+  if (int rc = make_tmap_2d(&maps[3], b_lo, N, K, (uint64_t)ldk * 4, kArcBN, 32, 0)) return rc;
+  return DIF_OK;
+}
+
+}  // namespace dif
+
+using namespace dif;
+
+extern "C" int dif_arcface(const float* X, const float* W, const int32_t* y, int B, int C, int D, float s, float m,
+                           float* loss, const float* dloss, float* dX, float* dW, int precision, void* stream) {
+  DIF_REQUIRE(X && W && y && loss, DIF_ERR_INVALID, "dif_arcface: null argument");
+  DIF_REQUIRE(B >= 1 && C >= 2 && D >= 32 && D % 4 == 0 && D <= 4096, DIF_ERR_INVALID,
+              "dif_arcface: B %d, C %d, D %d (D a multiple of 4 in 32..4096)", B, C, D);
+  DIF_REQUIRE(precision == DIF_PREC_TF32X3, DIF_ERR_INVALID, "dif_arcface: only the fp32-exact path (precision 0) is implemented");
+  DIF_REQUIRE((dX == nullptr) == (dW == nullptr), DIF_ERR_INVALID, "dif_arcface: pass both dX and dW, or neither");
+  DIF_REQUIRE(device_sm_count() > 0, DIF_ERR_STATE, "dif_init has not succeeded on this process");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool bwd = dX != nullptr;
+  const int sms = device_sm_count();
+  const int Bp = (B + 3) & ~3, Cp = (C + 3) & ~3;
+  ArcMargin mg{s, cosf(m), sinf(m), cosf(3.14159265358979323846f - m), sinf(3.14159265358979323846f - m) * m};
+
+  // ---- GEMM shapes
+  GemmShape fwd{};
+  fwd.m_blocks = (B + GEMM_BM - 1) / GEMM_BM;
+  fwd.n_tiles = (C + kArcBN - 1) / kArcBN;
+  fwd.k_chunks = (D + 31) / 32;
+  fwd.n_splits = std::max(1, std::min(fwd.n_tiles, 2 * sms / std::max(1, fwd.m_blocks)));
+  fwd.tiles_per_split = (fwd.n_tiles + fwd.n_splits - 1) / fwd.n_splits;
+  fwd.n_splits = (fwd.n_tiles + fwd.tiles_per_split - 1) / fwd.tiles_per_split;
+  GemmShape gx{};   // dxh [B, D] = dcos [B, Cp] x whT [D, Cp]^T, split over K = classes
+  gx.m_blocks = fwd.m_blocks;
+  gx.n_tiles = (D + kArcBN - 1) / kArcBN;
+  gx.k_chunks = (Cp + 31) / 32;
+  gx.n_splits = gx.n_tiles;
+  gx.tiles_per_split = 1;
+  gx.k_splits = std::max(1, std::min(gx.k_chunks, sms / std::max(1, gx.m_blocks * gx.n_tiles)));
+  gx.chunks_per_ksplit = (gx.k_chunks + gx.k_splits - 1) / gx.k_splits;
+  gx.k_splits = (gx.k_chunks + gx.chunks_per_ksplit - 1) / gx.chunks_per_ksplit;
+  GemmShape gw{};   // dwh [C, D] = dcosT [Cp, Bp] x xhT [D, Bp]^T
+  gw.m_blocks = (C + GEMM_BM - 1) / GEMM_BM;
+  gw.n_tiles = gx.n_tiles;
+  gw.k_chunks = (Bp + 31) / 32;
+  gw.n_splits = gw.n_tiles;
+  gw.tiles_per_split = 1;
+
+  // ---- workspace carve-up (256-byte aligned pieces)
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return at;
+  };
+  const size_t o_xh = take((size_t)B * D * 4), o_xl = take((size_t)B * D * 4), o_xi = take((size_t)B * 4);
+  const size_t o_wh = take((size_t)C * D * 4), o_wl = take((size_t)C * D * 4), o_wi = take((size_t)C * 4);
+  const size_t o_cos = take((size_t)B * Cp * 4);
+  const size_t o_part = take((size_t)B * fwd.n_splits * 8);
+  const size_t o_logz = take((size_t)B * 4), o_dphi = take((size_t)B * 4);
+  size_t o_dh = 0, o_dl = 0, o_th = 0, o_tl = 0, o_wth = 0, o_wtl = 0, o_xth = 0, o_xtl = 0, o_gx = 0, o_gw = 0;
+  if (bwd) {
+    o_dh = take((size_t)Bp * Cp * 4); o_dl = take((size_t)Bp * Cp * 4);
+    o_th = take((size_t)Cp * Bp * 4); o_tl = take((size_t)Cp * Bp * 4);
+    o_wth = take((size_t)D * Cp * 4); o_wtl = take((size_t)D * Cp * 4);
+    o_xth = take((size_t)D * Bp * 4); o_xtl = take((size_t)D * Bp * 4);
+    o_gx = take((size_t)gx.k_splits * B * D * 4);
+    o_gw = take((size_t)C * D * 4);
+  }
+  if (int rc = g_arc.ensure(off)) return rc;
+  char* ws = g_arc.base;
+  auto F = [&](size_t o) { return reinterpret_cast<float*>(ws + o); };
+
+  // ---- 0. normalise + TF32 planes
+  PrepParams px{};
+  px.src = X; px.n = B; px.D = D; px.normalize = 1; px.split = 1;
+  px.p0 = F(o_xh); px.p1 = F(o_xl); px.inv = F(o_xi);
+  if (int rc = prep_launch(px, false, st)) return rc;
+  PrepParams pw = px;
+  pw.src = W; pw.n = C; pw.p0 = F(o_wh); pw.p1 = F(o_wl); pw.inv = F(o_wi);
+  if (int rc = prep_launch(pw, false, st)) return rc;
+
+  // ---- 1. forward GEMM + online softmax
+  CUtensorMap maps[4];
+  if (int rc = tmaps(maps, F(o_xh), F(o_xl), B, F(o_wh), F(o_wl), C, D, D)) return rc;
+  ArcFwdEpi::Params fp{F(o_cos), y, reinterpret_cast<float2*>(ws + o_part), B, C, Cp, fwd.n_splits, mg};
+  if (int rc = launch_nt_gemm<0, kArcBN, 1, 0, ArcFwdEpi>(maps, fwd, fp, sms, st)) return rc;
+  // ---- 2. loss
+  arc_loss_kernel<<<(B + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float2*>(ws + o_part), fwd.n_splits, F(o_cos), Cp,
+                                                  y, B, mg, loss, F(o_logz), F(o_dphi));
+  DIF_LAUNCH_OK();
+  if (!bwd) return DIF_OK;
+
+  // ---- 3. d cos planes (both orientations) and transposed operand planes
+  arc_dcos_kernel<<<dim3((Cp + 31) / 32, (Bp + 31) / 32), dim3(32, 8), 0, st>>>(
+      F(o_cos), Cp, y, F(o_logz), F(o_dphi), dloss, B, C, mg, F(o_dh), F(o_dl), F(o_th), F(o_tl), Bp, Cp);
+  DIF_LAUNCH_OK();
+  transpose_planes_kernel<<<dim3((D + 31) / 32, (C + 31) / 32), dim3(32, 8), 0, st>>>(F(o_wh), F(o_wl), C, D, F(o_wth),
+                                                                                    F(o_wtl), Cp);
+  DIF_LAUNCH_OK();
+  transpose_planes_kernel<<<dim3((D + 31) / 32, (B + 31) / 32), dim3(32, 8), 0, st>>>(F(o_xh), F(o_xl), B, D, F(o_xth),
+                                                                                    F(o_xtl), Bp);
+  DIF_LAUNCH_OK();
+  // ---- 4. dxh (split-K planes) and dwh
+  if (int rc = tmaps(maps, F(o_dh), F(o_dl), B, F(o_wth), F(o_wtl), D, Cp, Cp)) return rc;
+  StoreEpi::Params sx{F(o_gx), B, D, D, gx.n_splits, (size_t)B * D};
+  if (int rc = launch_nt_gemm<0, kArcBN, 1, 0, StoreEpi>(maps, gx, sx, sms, st)) return rc;
+  if (int rc = tmaps(maps, F(o_th), F(o_tl), C, F(o_xth), F(o_xtl), D, Bp, Bp)) return rc;
+  StoreEpi::Params sw{F(o_gw), C, D, D, gw.n_splits, 0};
+  if (int rc = launch_nt_gemm<0, kArcBN, 1, 0, StoreEpi>(maps, gw, sw, sms, st)) return rc;
+  // ---- 5. l2_normalize backward
+  arc_norm_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(F(o_gx), gx.k_splits, (size_t)B * D, F(o_xh), F(o_xl), F(o_xi), B, D, dX);
+  DIF_LAUNCH_OK();
+  arc_norm_bwd_kernel<<<(C + 7) / 8, 256, 0, st>>>(F(o_gw), 1, 0, F(o_wh), F(o_wl), F(o_wi), C, D, dW);
+  DIF_LAUNCH_OK();
+  return DIF_OK;
+}
+
+extern "C" int dif_arcface_host(const float* X_host, const float* W_host, const int32_t* y_host, int B, int C, int D,
+                                float s, float m, float* loss_host, const float* dloss_host, float* dX_host,
+                                float* dW_host, int precision) {
+  DIF_REQUIRE(X_host && W_host && y_host && loss_host && B >= 1 && C >= 2 && D >= 1, DIF_ERR_INVALID,
+              "dif_arcface_host: invalid argument");
+  static thread_local struct {
+    void* h = nullptr; void* d = nullptr; size_t bytes = 0; cudaStream_t st = nullptr;
+  } stage;
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t xb = al((size_t)B * D * 4), wb = al((size_t)C * D * 4), yb = al((size_t)B * 4);
+  const size_t in_bytes = xb + wb + 2 * yb, out_bytes = yb + xb + wb;
+  if (!stage.st) DIF_CUDA_OK(cudaStreamCreateWithFlags(&stage.st, cudaStreamNonBlocking));
+  if (in_bytes + out_bytes > stage.bytes) {
+    if (stage.h) cudaFreeHost(stage.h);
+    if (stage.d) cudaFree(stage.d);
+    stage.h = stage.d = nullptr;
+    stage.bytes = 0;
+    DIF_CUDA_OK(cudaMallocHost(&stage.h, in_bytes + out_bytes));
+    DIF_CUDA_OK(cudaMalloc(&stage.d, in_bytes + out_bytes));
+    stage.bytes = in_bytes + out_bytes;
+  }
+  char* h = (char*)stage.h;
+  char* d = (char*)stage.d;
+  memcpy(h, X_host, (size_t)B * D * 4);
+  memcpy(h + xb, W_host, (size_t)C * D * 4);
+  memcpy(h + xb + wb, y_host, (size_t)B * 4);
+  if (dloss_host) memcpy(h + xb + wb + yb, dloss_host, (size_t)B * 4);
+  DIF_CUDA_OK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, stage.st));
+  char* o = d + in_bytes;
+  const bool bwd = dX_host && dW_host;
+  if (int rc = dif_arcface((const float*)d, (const float*)(d + xb), (const int32_t*)(d + xb + wb), B, C, D, s, m, (float*)o,
+                           dloss_host ? (const float*)(d + xb + wb + yb) : nullptr, bwd ? (float*)(o + yb) : nullptr,
+                           bwd ? (float*)(o + yb + xb) : nullptr, precision, stage.st))
+    return rc;
+  DIF_CUDA_OK(cudaMemcpyAsync(h + in_bytes, o, bwd ? out_bytes : yb, cudaMemcpyDeviceToHost, stage.st));
+  DIF_CUDA_OK(cudaStreamSynchronize(stage.st));
+  memcpy(loss_host, h + in_bytes, (size_t)B * 4);
+  if (bwd) {
+    memcpy(dX_host, h + in_bytes + yb, (size_t)B * D * 4);
+    memcpy(dW_host, h + in_bytes + yb + xb, (size_t)C * D * 4);
+  }
+  return DIF_OK;
+}

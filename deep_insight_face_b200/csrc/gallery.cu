@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "gallery_epi.cuh"
+#include "prep_rows.cuh"
 
 namespace dif {
 
@@ -26,63 +27,6 @@ constexpr int kRerankThreads = 128;
 constexpr int kRerankCap = 256;     // candidates inside the 2*eps window before a query is flagged
 constexpr int kExactChunks = 64;    // row chunks per flagged query in the exact scan
 constexpr int kExactThreads = 256;
-
-// ------------------------------------------------------------------------------------------
-// K5: rows -> canonical planes.  One warp per row.
-//   SRC 0: rows read from `src`; SRC 1: synthetic rows (seed, row0 + r).
-//   p0/p1: fp32 planes (TF32x3: p0 = tf32(x), p1 = x - p0 exactly; otherwise p0 = x, p1 unused)
-//   pb   : bf16 plane (bf16 mode only);  sq[r] = canonical sum of squares of the STORED row
-//   gmax : running max of sq (orderable uint), may be NULL
-// ------------------------------------------------------------------------------------------
-struct PrepParams {
-  const float* src;
-  uint64_t seed;
-  int64_t row0;
-  int64_t n;
-  int D;
-  int normalize;
-  int split;  // 1: write hi/lo planes
-  float* p0;
-  float* p1;
-  __nv_bfloat16* pb;
-  float* sq;
-  unsigned int* gmax;
-};
-
-template <int SRC>
-__global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < p.n; r += warps) {
-    const float* s = SRC == 0 ? p.src + r * p.D : nullptr;
-    float acc = 0.f;
-    for (int d = lane; d < p.D; d += 32) {
-      const float x = SRC == 0 ? s[d] : synth_value(p.seed, (uint64_t)(p.row0 + r), (uint64_t)d, (uint64_t)p.D);
-      acc = __fmaf_rn(x, x, acc);
-    }
-    const float ss = canon_tree(acc);
-    const float inv = p.normalize ? canon_inv_norm(ss) : 1.0f;
-    float acc2 = 0.f;
-    for (int d = lane; d < p.D; d += 32) {
-      float x = SRC == 0 ? s[d] : synth_value(p.seed, (uint64_t)(p.row0 + r), (uint64_t)d, (uint64_t)p.D);
-      if (p.normalize) x = __fmul_rn(x, inv);
-      acc2 = __fmaf_rn(x, x, acc2);
-      if (p.split) {
-        const float hi = tf32_round(x);
-        p.p0[r * p.D + d] = hi;
-        p.p1[r * p.D + d] = __fsub_rn(x, hi);
-      } else {
-        p.p0[r * p.D + d] = x;
-      }
-      if (p.pb) p.pb[r * p.D + d] = __float2bfloat16_rn(x);
-    }
-    const float ss2 = canon_tree(acc2);
-    if (lane == 0) {
-      if (p.sq) p.sq[r] = ss2;
-      if (p.gmax) atomicMax(p.gmax, float_orderable(ss2));
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // Selection helpers on unique 64-bit keys held in shared memory.
@@ -414,17 +358,6 @@ namespace {
 template <class T>
 int dev_alloc(T** p, size_t n) {
   DIF_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
-  return DIF_OK;
-}
-
-int prep_launch(const PrepParams& pp, bool synth, cudaStream_t st) {
-  if (pp.n == 0) return DIF_OK;
-  const int warps_per_block = 8;
-  int64_t blocks = (pp.n + warps_per_block - 1) / warps_per_block;
-  blocks = std::min<int64_t>(blocks, 148 * 16);
-  if (synth) prep_rows_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(pp);
-  else prep_rows_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(pp);
-  DIF_LAUNCH_OK();
   return DIF_OK;
 }
 

@@ -4,28 +4,9 @@
 
 #include "dif_canon.cuh"
 #include "nt_gemm.cuh"
+#include "store_epi.cuh"
 
 namespace dif {
-
-struct StoreEpi {
-  struct Params {
-    float* C;
-    int M, N;
-  };
-  static constexpr int kSmemBytes = 16;
-  const Params& p;
-  int m_row;
-  __device__ StoreEpi(const Params& pp, uint8_t*, int) : p(pp), m_row(0) {}
-  __device__ void begin_item(int m, int, int) { m_row = m; }
-  __device__ void begin_tile() {}
-  __device__ void consume(int col0, const uint32_t (&acc)[32], uint32_t, uint32_t (&)[32]) {
-    if (m_row >= p.M) return;
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (col0 + i < p.N) p.C[(size_t)m_row * p.N + col0 + i] = __uint_as_float(acc[i]);
-  }
-  __device__ void end_item(int, int) {}
-};
 
 // Epilogue that only folds the tile into one checksum per row: isolates main-loop speed.
 struct SumEpi {
@@ -78,7 +59,7 @@ static int run_debug(const void* a0, const void* a1, const void* b0, const void*
   shape.n_splits = std::max(1, std::min(n_splits, shape.n_tiles));
   shape.tiles_per_split = (shape.n_tiles + shape.n_splits - 1) / shape.n_splits;
   shape.n_splits = (shape.n_tiles + shape.tiles_per_split - 1) / shape.tiles_per_split;
-  StoreEpi::Params ep{C, M, N};
+  StoreEpi::Params ep{C, M, N, N, shape.n_splits, 0};
   const int units = std::max(1, device_sm_count() / CTAS);
   if (ares) {
     if constexpr (PREC != 0 && CTAS == 2) return launch_nt_gemm<PREC, BN, CTAS, 1, StoreEpi>(maps, shape, ep, units, st);

@@ -49,6 +49,8 @@ struct GemmShape {
   int n_splits;         // B tile range is cut into n_splits pieces -> items = n_splits * m_blocks
   int tiles_per_split;  // ceil(n_tiles / n_splits)
   int stages;           // smem ring depth (host-computed from the shared-memory budget)
+  int k_splits;         // the K range is cut into k_splits pieces -> items *= k_splits (0/1: no split)
+  int chunks_per_ksplit;
 };
 
 template <int PREC, int BN, int CTAS>
@@ -89,6 +91,7 @@ inline bool plan_gemm_smem(int k_chunks, int epi_smem, GemmSmemPlan* out) {
 //     struct Params;                       // POD, passed by value to the kernel
 //     static constexpr int kSmemBytes;     // CTA-shared scratch, 16-byte aligned
 //     __device__ Epi(const Params&, uint8_t* smem, int row_in_block);
+//     // split = index of the (K split, B-tile range) slot of this item: k_split * n_splits + n_split
 //     __device__ void begin_item(int m_row /*global A row of this thread*/, int split, int col_begin);
 //     __device__ void begin_tile();
 //     // fp32 bits of columns col0..col0+31 of this thread's row; taddr = TMEM address of column col0
@@ -132,7 +135,8 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
   const bool leader = (cta_rank == 0);
   const int unit = (CTAS == 2) ? (blockIdx.x >> 1) : blockIdx.x;   // persistent work unit (CTA or pair)
   const int n_units = (CTAS == 2) ? (gridDim.x >> 1) : gridDim.x;
-  const int n_items = shape.n_splits * shape.m_blocks;
+  const int items_per_ks = shape.n_splits * shape.m_blocks;
+  const int n_items = items_per_ks * shape.k_splits;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -169,8 +173,11 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
     if (lane_id() == 0) {
       uint32_t it = 0, n_item = 0;
       for (int item = unit; item < n_items; item += n_units, ++n_item) {
-        const int split = item / shape.m_blocks;
-        const int mb = item - split * shape.m_blocks;
+        const int ks = item / items_per_ks;
+        const int rem = item - ks * items_per_ks;
+        const int split = rem / shape.m_blocks;
+        const int mb = rem - split * shape.m_blocks;
+        const int kc0 = ks * shape.chunks_per_ksplit, kc1 = min(shape.k_chunks, kc0 + shape.chunks_per_ksplit);
         const int a_row = (mb * CTAS + (int)cta_rank) * GEMM_BM;
         const int t0 = split * shape.tiles_per_split;
         const int t1 = min(t0 + shape.tiles_per_split, shape.n_tiles);
@@ -195,7 +202,7 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
         }
         for (int t = t0; t < t1; ++t) {
           const int b_row = t * BN + (int)cta_rank * (BN / CTAS);
-          for (int kc = 0; kc < shape.k_chunks; ++kc, ++it) {
+          for (int kc = kc0; kc < kc1; ++kc, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -229,7 +236,9 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
       constexpr uint32_t idesc = make_idesc(PT::kFmt, GEMM_BM * CTAS, BN);
       uint32_t it = 0, tc = 0, n_item = 0;
       for (int item = unit; item < n_items; item += n_units, ++n_item) {
-        const int split = item / shape.m_blocks;
+        const int ks = item / items_per_ks;
+        const int split = (item - ks * items_per_ks) / shape.m_blocks;
+        const int kc0 = ks * shape.chunks_per_ksplit, kc1 = min(shape.k_chunks, kc0 + shape.chunks_per_ksplit);
         const int t0 = split * shape.tiles_per_split;
         const int t1 = min(t0 + shape.tiles_per_split, shape.n_tiles);
         if (ARES) {
@@ -242,7 +251,7 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
           mbar_wait(&acc_empty[buf], aph ^ 1u);
           tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-          for (int kc = 0; kc < shape.k_chunks; ++kc, ++it) {
+          for (int kc = kc0; kc < kc1; ++kc, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(&full_bar[s], ph);
@@ -253,17 +262,17 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             const uint64_t a_hi = make_kmajor_desc<GEMM_SWZ>(a_addr);
             const uint64_t b_hi = make_kmajor_desc<GEMM_SWZ>(st + kBOff);
 #pragma unroll
-            for (int ks = 0; ks < PT::kKSteps; ++ks) {
-              const uint64_t adv = (uint64_t)(ks * 2);  // 32 bytes of K, in 16-byte units
+            for (int kstep = 0; kstep < PT::kKSteps; ++kstep) {
+              const uint64_t adv = (uint64_t)(kstep * 2);  // 32 bytes of K, in 16-byte units
               if (PT::kPlanes == 2) {
                 const uint64_t a_lo = make_kmajor_desc<GEMM_SWZ>(a_lo_addr);
                 const uint64_t b_lo = make_kmajor_desc<GEMM_SWZ>(st + kBOff + T::kBTile);
                 // small cross terms first, dominant term last
-                tc_mma<CTAS, PT::kTf32>(d_tmem, a_lo + adv, b_hi + adv, idesc, (kc | ks) != 0);
+                tc_mma<CTAS, PT::kTf32>(d_tmem, a_lo + adv, b_hi + adv, idesc, ((kc - kc0) | kstep) != 0);
                 tc_mma<CTAS, PT::kTf32>(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
                 tc_mma<CTAS, PT::kTf32>(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
               } else {
-                tc_mma<CTAS, PT::kTf32>(d_tmem, a_hi + adv, b_hi + adv, idesc, (kc | ks) != 0);
+                tc_mma<CTAS, PT::kTf32>(d_tmem, a_hi + adv, b_hi + adv, idesc, ((kc - kc0) | kstep) != 0);
               }
             }
             tc_commit<CTAS>(&empty_bar[s]);   // smem slot reusable once these MMAs retire
@@ -280,10 +289,12 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
     const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
     uint32_t tc = 0;
     for (int item = unit; item < n_items; item += n_units) {
-      const int split = item / shape.m_blocks;
-      const int mb = item - split * shape.m_blocks;
+      const int ks = item / items_per_ks;
+      const int rem = item - ks * items_per_ks;
+      const int split = rem / shape.m_blocks + ks * shape.n_splits;   // slot index: K split major
+      const int mb = rem % shape.m_blocks;
       const int m_row = (mb * CTAS + (int)cta_rank) * GEMM_BM + row;
-      const int t0 = split * shape.tiles_per_split;
+      const int t0 = (rem / shape.m_blocks) * shape.tiles_per_split;
       const int t1 = min(t0 + shape.tiles_per_split, shape.n_tiles);
       epi.begin_item(m_row, split, t0 * BN);
       for (int t = t0; t < t1; ++t, ++tc) {
@@ -336,6 +347,11 @@ int launch_nt_gemm(const CUtensorMap* maps, GemmShape shape, const typename Epi:
   DIF_REQUIRE(fits, DIF_ERR_CAPACITY, "nt_gemm: K = %d chunks does not fit the shared-memory plan (ARES=%d)",
               shape.k_chunks, ARES);
   shape.stages = plan.stages;
+  if (shape.k_splits <= 1) {
+    shape.k_splits = 1;
+    shape.chunks_per_ksplit = shape.k_chunks;
+  }
+  DIF_REQUIRE(!(ARES && shape.k_splits > 1), DIF_ERR_INVALID, "nt_gemm: the resident-A schedule does not split K");
   auto kern = nt_gemm_rowscan_kernel<PREC, BN, CTAS, ARES, Epi>;
   static bool configured = false;   // per instantiation
   if (!configured) {

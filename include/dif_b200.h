@@ -141,11 +141,16 @@ int dif_contrastive_loss(const float* y_true, const float* dist, int B, float ma
                          void* stream);
 
 /* ---- ArcFace additive-angular-margin logits + softmax cross-entropy ------------------------
- * Absent from the reference; spec in DESIGN.md (arXiv 1801.07698): logits = s*cos(theta + m*onehot)
- * over L2-normalised X [B,D] and W [C,D]; loss [B]; dX [B*D], dW [C*D] gradients of mean(loss)
- * (either may be NULL to skip the backward pass). */
+ * Absent from the reference; spec in DESIGN.md / oracle/losses_oracle.py:arcface (arXiv 1801.07698):
+ * logits = s*cos(theta + m*onehot) over L2-normalised X [B,D] and W [C,D] (easy-margin fallback past
+ * pi - m); loss [B] = per-sample cross-entropy; dX [B*D], dW [C*D] = gradients of sum_b dloss[b]*loss[b]
+ * (dloss NULL -> 1/B each); pass dX = dW = NULL to skip the backward pass.  precision must be
+ * DIF_PREC_TF32X3 (fp32-exact tensor-core path). */
 int dif_arcface(const float* X, const float* W, const int32_t* y, int B, int C, int D, float s, float m,
-                float* loss, float* dX, float* dW, int precision, void* stream);
+                float* loss, const float* dloss, float* dX, float* dW, int precision, void* stream);
+int dif_arcface_host(const float* X_host, const float* W_host, const int32_t* y_host, int B, int C, int D, float s,
+                     float m, float* loss_host, const float* dloss_host, float* dX_host, float* dW_host,
+                     int precision);
 
 /* ---- pair verification --------------------------------------------------------------------
  * deep_insight_face/evaluation/utility.py:52-66 `distance`: out [N]; metric 0 squared L2,

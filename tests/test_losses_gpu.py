@@ -32,7 +32,8 @@ def run_case(cls, oracle_fn, emb, lab, alpha, onehot=True):
     assert np.array_equal(info["pos_idx"], want["pos_idx"]), "mined positives differ"
     assert np.array_equal(info["neg_idx"], want["neg_idx"]), "mined negatives differ"
     close(got, want["loss"], scale=max(np.abs(want["loss"]).max(), np.abs(want["hardest_pos"]).max()))
-    close(grad, want["grad"])
+    # gradient scale floor: one active anchor moves its row by ~ |x| / B (exactly cancelling terms leave rounding noise)
+    close(grad, want["grad"], scale=max(np.abs(want["grad"]).max(), np.abs(emb).max() / emb.shape[0]))
     close(info["stats"], want["stats"], scale=np.abs(want["stats"]).max())
     return got, grad, info, want
 
@@ -80,7 +81,8 @@ def test_edge_cases_single_sample_identity_and_single_identity(gpu):
     one = np.zeros(30, dtype=np.int64)   # one identity only: hardest negative is the filler (-1 / max(dists))
     _, _, info, _ = run_case(BatchHardTripletLoss, lo.batch_hard_cosine, emb, one, 0.35)
     assert (info["neg_idx"] == -1).all()
-    _, grad, info, want = run_case(BatchHardTripletLossEuclidean, lo.batch_hard_euclidean, emb, one, 0.35)
+    run_case(BatchHardTripletLossEuclidean, lo.batch_hard_euclidean, emb, one, 0.35)
+    _, grad, info, want = run_case(BatchHardTripletLossEuclidean, lo.batch_hard_euclidean, emb, one, 500.0)
     assert (info["neg_idx"] == -1).all() and np.abs(want["grad"]).max() > 0  # gradient flows through max(dists)
 
 
