@@ -223,9 +223,10 @@ def exchange_candidates(scores, ids, grows, group=None):
     world = dist.get_world_size(group)
     out = []
     for t in (scores, ids, grows):
-        buf = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        # concatenation along dim 0 (the layout both NCCL and gloo accept), viewed as [world, Q, k]
+        buf = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(buf, t.contiguous(), group=group)
-        out.append(buf)
+        out.append(buf.view((world,) + tuple(t.shape)))
     return tuple(out)
 
 
