@@ -122,6 +122,64 @@ def make_queries(lib, _ffi, torch, n_rows, Q, D, device):
     return base + 0.3 * noise, pick
 
 
+def secondary_metrics(torch, device):
+    """The other configurations of BASELINE.json, reported beside the headline (not the bench contract's `value`):
+    C1 batch-hard triplet loss steps/s (B = 72, D = 128, fwd + bwd), the B = 4096 end of the C4 sweep, and
+    C2 ArcFace fwd + bwd (512 x 512, 10k classes).  Device-resident timing with CUDA events; `e2e` = host call."""
+    import numpy as np
+
+    from deep_insight_face_b200.arcface import arcface_loss
+    from deep_insight_face_b200.common.losses import BatchHardTripletLoss, batch_hard
+    from deep_insight_face_b200 import _ffi
+    from oracle import losses_oracle as lo
+
+    out = {}
+    rng = np.random.default_rng(1)
+
+    def timed(fn, iters, warm=5):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    for name, P, K, D, iters in (("c1_batch_hard_B72_D128", 18, 4, 128, 300), ("c4_batch_hard_B4096_D128", 1024, 4, 128, 30)):
+        cent = rng.standard_normal((P, D)).astype(np.float32)
+        emb = (np.repeat(cent, K, 0) + 1.0 * rng.standard_normal((P * K, D))).astype(np.float32)
+        lab = np.repeat(np.arange(P), K).astype(np.int32)
+        xd = torch.from_numpy(emb).to(device)
+        ld = torch.from_numpy(lab).to(device)
+        ms = timed(lambda: batch_hard(ld, xd, _ffi.LOSS_BH_COSINE, 0.35, want_grad=True), iters)
+        loss = BatchHardTripletLoss()
+        t0 = time.perf_counter()
+        n_host = max(10, iters // 3)
+        for _ in range(n_host):
+            loss.loss_and_grad(lab, emb)
+        host_ms = (time.perf_counter() - t0) / n_host * 1e3
+        t0 = time.perf_counter()
+        n_cpu = 20 if P * K <= 128 else 1
+        for _ in range(n_cpu):
+            lo.batch_hard_cosine(lab, emb, 0.35)
+        cpu_ms = (time.perf_counter() - t0) / n_cpu * 1e3
+        B = P * K
+        out[name] = {"steps_per_s": 1e3 / ms, "ms_per_step": ms, "e2e_steps_per_s": 1e3 / host_ms,
+                     "kernels_per_step": 3, "alg_gflop_fwd": 2.0 * B * B * D / 1e9,
+                     "cpu_oracle_steps_per_s": 1e3 / cpu_ms, "note": "fwd + bwd, canonical fp32 CUDA-core mining"}
+    B, C, D = 512, 10000, 512
+    X = torch.randn(B, D, device=device)
+    W = 0.01 * torch.randn(C, D, device=device)
+    y = torch.randint(0, C, (B,), device=device)
+    ms = timed(lambda: arcface_loss(X, W, y, 64.0, 0.5), 30)
+    out["c2_arcface_512x512x10000"] = {"steps_per_s": 1e3 / ms, "ms_per_step": ms, "alg_gflop": 6.0 * B * C * D / 1e9,
+                                       "alg_tflops": 6.0 * B * C * D / ms / 1e9, "note": "fwd + bwd, 3xTF32 tcgen05 GEMMs"}
+    return out
+
+
 def run_reference(args):
     """The reference's CPU path for this metric: the oracle port (the reference has no 1:N routine and its TF
     code cannot run here - SURVEY.md section 0), all host threads, a bounded query sample per step."""
@@ -130,28 +188,32 @@ def run_reference(args):
         return
     import numpy as np
 
+    from oracle import blas_baseline as bb
     from oracle import c_oracle as orc
 
     n_rows, Q, D, k = WORKLOADS[args.workload]
     n_rows = args.rows or n_rows
-    threads = orc.num_threads()
+    threads = bb.num_threads()
     sample_rows = min(n_rows, 1_000_000)
-    sample_q = 32
-    gal = orc.normalize_rows(orc.synth_rows(SEED_GALLERY, 0, sample_rows, D))
+    sample_q = min(Q, 1024)
+    raw = orc.synth_rows(SEED_GALLERY, 0, sample_rows, D)
     rng = np.random.default_rng(12345)
     pick = rng.integers(0, sample_rows, size=sample_q)
-    q = orc.normalize_rows(gal[pick] + 0.3 * orc.synth_rows(SEED_NOISE, 0, sample_q, D))
+    q = orc.normalize_rows(raw[pick] + 0.3 * orc.synth_rows(SEED_NOISE, 0, sample_q, D))
+    gal = orc.normalize_rows(raw)
+    del raw
     for _ in range(max(1, min(args.warmup, 2))):
-        orc.gallery_search(gal, q, k, 1, normalize=False)
+        bb.gallery_search_blas(gal, q[:64], k)
     steps = max(1, min(args.steps, 10))
     t0 = time.perf_counter()
     for _ in range(steps):
-        orc.gallery_search(gal, q, k, 1, normalize=False)
+        _, rows = bb.gallery_search_blas(gal, q, k)
     dt = (time.perf_counter() - t0) / steps
+    assert (rows[:, 0] == pick).mean() > 0.99
     # queries/s against the FULL gallery: cost is linear in rows, the sample holds sample_rows of them
     qps = sample_q / dt * (sample_rows / n_rows)
-    sample = (f"{sample_q} queries x {sample_rows} rows per step, {steps} steps, scaled linearly to {n_rows} rows; "
-              "oracle/dif_oracle.c (canonical fp32 brute force + top-k), OpenMP")
+    sample = (f"{sample_q} of the {Q} queries x {sample_rows} rows per step, {steps} steps, scaled linearly to {n_rows} rows; "
+              "oracle/blas_baseline.py (the reference's numpy/TF-CPU style: multithreaded sgemm + top-k)")
     line = {
         "impl": "reference", "metric": "gallery queries/s", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -278,6 +340,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    secondary = secondary_metrics(torch, device) if (world == 1 and not args.no_modes) else {}
 
     rows_local = (n_rows + world - 1) // world
     alg_flops = 2.0 * Q * rows_local * D  # per launch of the tensor-core pass on one GPU
@@ -297,20 +360,26 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu and world == 1:
+        from oracle import blas_baseline as bb
         from oracle import c_oracle as orc
 
-        sample_q = 48
         t0 = time.perf_counter()
         gal = orc.normalize_rows(orc.synth_rows(SEED_GALLERY, 0, n_rows, D))
         qn = orc.normalize_rows(main_res["q_sample"])
-        qrep = np.ascontiguousarray(np.tile(qn, (sample_q // 16, 1)))
         t1 = time.perf_counter()
-        ws, wr = orc.gallery_search(gal, qrep, k, 1, normalize=False)
-        dt = time.perf_counter() - t1
-        ok = bool(np.array_equal(wr[:16], main_res["ids_sample"]))
-        cpu_baseline = {"value": sample_q / dt, "unit": "queries/s", "cores": orc.num_threads(), "kind": "port",
-                        "sample": f"{sample_q} of the {Q} queries against the full {n_rows}-row gallery "
-                                  f"(oracle/dif_oracle.c, OpenMP, {dt:.1f} s; gallery generation {t1 - t0:.1f} s untimed)",
+        ws, wr = orc.gallery_search(gal, qn, k, 1, normalize=False)       # the checker: canonical oracle, 16 queries
+        ok = bool(np.array_equal(wr, main_res["ids_sample"]))
+        canon_qps = qn.shape[0] / (time.perf_counter() - t1)
+        sample_q = min(Q, 1024)
+        qs = np.ascontiguousarray(np.tile(qn, (sample_q // qn.shape[0], 1)))
+        bb.gallery_search_blas(gal, qs[:64], k)
+        t2 = time.perf_counter()
+        bb.gallery_search_blas(gal, qs, k)                                # the baseline: BLAS-speed CPU path
+        dt = time.perf_counter() - t2
+        cpu_baseline = {"value": sample_q / dt, "unit": "queries/s", "cores": bb.num_threads(), "kind": "port",
+                        "sample": f"{sample_q} queries against the full {n_rows}-row gallery, oracle/blas_baseline.py "
+                                  f"(multithreaded sgemm + top-k, {dt:.1f} s; gallery generation {t1 - t0:.1f} s untimed)",
+                        "canonical_oracle_qps": canon_qps, "canonical_oracle_threads": orc.num_threads(),
                         "ids_match_gpu": ok}
 
     line = {
@@ -334,6 +403,7 @@ def main():
         "top1_recall": main_res["top1_recall"],
         "fallback_queries": main_res["fallback_queries"],
         "modes": modes,
+        "secondary": secondary,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
