@@ -139,9 +139,12 @@ def check(rc: int) -> None:
 
 def init(device: int = 0) -> None:
     """Select `device`, verify it is sm_100 and create its context (idempotent per device)."""
+    device = int(device)
+    if device in _inited_devices:   # dif_init queries device properties (milliseconds): once per device is enough
+        return
     lib = load_library()
-    check(lib.dif_init(int(device)))
-    _inited_devices.add(int(device))
+    check(lib.dif_init(device))
+    _inited_devices.add(device)
 
 
 def launch_count() -> int:
