@@ -44,7 +44,7 @@ struct ArcFwdEpi {
     int B, C, ldc, n_slots;
     ArcMargin mg;
   };
-  static constexpr int kSmemBytes = 16;
+  static int smem_bytes(const Params&) { return 16; }
   const Params& p;
   float* row_ptr;
   float m2, l2;   // running max / sum of 2^(logit * log2e - m2)

@@ -337,6 +337,8 @@ struct dif_gallery {
   size_t cand_elems = 0;
   int* flagged = nullptr;  // [0] = count, [1..] = list
   unsigned int* bound = nullptr;  // [q_cap] shared per-query lower bound on the k-th best score
+  unsigned int* maxima = nullptr; // [splits][q_cap] best score of each split's list
+  size_t maxima_elems = 0;
   uint64_t* ex_keys = nullptr;
   size_t ex_elems = 0;
   // host staging for the *_host entry points
@@ -378,6 +380,14 @@ int ensure_query_ws(dif_gallery* g, int Q, int S, int kp) {
     DIF_CUDA_OK(cudaMemset(g->qsq, 0, (size_t)q_pad * 4));
     g->q_cap = q_pad;
   }
+  const size_t need_max = (size_t)g->q_cap * S;
+  if (need_max > g->maxima_elems) {
+    cudaFree(g->maxima);
+    g->maxima = nullptr;
+    g->maxima_elems = 0;
+    if (int rc = dev_alloc(&g->maxima, need_max)) return rc;
+    g->maxima_elems = need_max;
+  }
   const size_t need = (size_t)q_pad * S * kp;
   if (need > g->cand_elems) {
     cudaFree(g->cand);
@@ -390,9 +400,9 @@ int ensure_query_ws(dif_gallery* g, int Q, int S, int kp) {
 }
 
 // resident-A schedule whenever the query block (all of K) fits beside a >= 3-stage B ring
-bool ares_fits(int precision, int k_chunks) {
+bool ares_fits(int precision, int k_chunks, int kp) {
   GemmSmemPlan plan;
-  const int epi = TopkEpi<1>::kSmemBytes;
+  const int epi = TopkEpi<1>::smem_bytes_kp(kp);
   bool ok = false;
   if (precision == DIF_PREC_BF16) ok = plan_gemm_smem<1, kGalBN, 2, 1>(k_chunks, epi, &plan);
   else if (precision == DIF_PREC_TF32X1) ok = plan_gemm_smem<2, kGalBN, 2, 1>(k_chunks, epi, &plan);
@@ -441,7 +451,7 @@ void dif_gallery_destroy(dif_gallery_t* g) {
   if (!g) return;
   cudaFree(g->g0); cudaFree(g->g1); cudaFree(g->gb); cudaFree(g->gsq); cudaFree(g->gmax); cudaFree(g->ids);
   cudaFree(g->q0); cudaFree(g->q1); cudaFree(g->qb); cudaFree(g->qsq); cudaFree(g->cand); cudaFree(g->flagged);
-  cudaFree(g->bound); cudaFree(g->ex_keys); cudaFree(g->d_stage);
+  cudaFree(g->bound); cudaFree(g->maxima); cudaFree(g->ex_keys); cudaFree(g->d_stage);
   if (g->h_pin) cudaFreeHost(g->h_pin);
   if (g->own_stream) cudaStreamDestroy(g->own_stream);
   if (g->ev0) cudaEventDestroy(g->ev0);
@@ -626,8 +636,10 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
       if (int rc = make_tmap_2d(&maps[3], g->g1, g->size, D, (uint64_t)D * 4, kGalBN / ctas, bcols, 0)) return rc;
     }
     DIF_CUDA_OK(cudaMemsetAsync(g->bound, 0, (size_t)g->q_cap * sizeof(unsigned int), st));
-    TopkEpi<1>::Params ep{g->cand, g->gsq, g->bound, g->qsq, g->gmax, (int)g->size, splits, kp, mode_eps(g->precision)};
-    const int ares = ctas == 2 && g->opt_resident != 0 && ares_fits(g->precision, shape.k_chunks);
+    DIF_CUDA_OK(cudaMemsetAsync(g->maxima, 0, (size_t)g->q_cap * splits * sizeof(unsigned int), st));
+    TopkEpi<1>::Params ep{g->cand, g->gsq, g->bound, g->maxima, g->q_cap, k, g->qsq, g->gmax, (int)g->size, splits, kp,
+                          mode_eps(g->precision)};
+    const int ares = ctas == 2 && g->opt_resident != 0 && ares_fits(g->precision, shape.k_chunks, kp);
     g->stats[4] = ares;
     DIF_CUDA_OK(cudaEventRecord(g->ev0, st));
     const int rc = g->precision == DIF_PREC_TF32X3 ? launch_search_tf32x3(g->metric, ctas, ares, maps, shape, ep, units, st)

@@ -53,6 +53,9 @@ struct TopkEpi {
     uint64_t* cand;          // [rows padded][n_splits][kp]
     const float* gnorm;      // [n_rows padded to tile] canonical |g|^2 (METRIC 0)
     unsigned int* bound;     // [rows padded] shared lower bound on the k-th best score (orderable u32, 0 = none)
+    unsigned int* maxima;    // [n_splits][q_pad] best score seen so far by each split's list (orderable u32, 0 = none)
+    int q_pad;
+    int k;                   // result size: the k-th largest of the split maxima is a second lower bound
     const float* q_sq;       // [rows padded] canonical |q|^2 (METRIC 0 margin)
     const unsigned int* gmax;  // orderable max |g|^2
     int n_rows;
@@ -60,11 +63,18 @@ struct TopkEpi {
     int kp;
     float eps_rel;
   };
-  static constexpr int kSmemBytes = DIF_MAX_TOPK * GEMM_BM * 8;
+  // lists [kp][128] u64 + selection scratch [kp][128] f32
+  __host__ __device__ static int smem_bytes_kp(int kp) { return kp * GEMM_BM * 12; }
+  static int smem_bytes(const Params& pp) { return smem_bytes_kp(pp.kp); }
 
   const Params& p;
   uint64_t* keys;  // this thread's slot 0; slot s at keys[s * GEMM_BM]
+  float* sel;      // selection scratch, slot s at sel[s * GEMM_BM]
   unsigned int* my_bound;
+  unsigned int* my_max;    // this (split, query)'s cell of `maxima`
+  const unsigned int* max_col;  // maxima + m_row: stride q_pad between splits
+  float own_max;
+  int tiles_seen;
   float thr;      // drop threshold
   float own_min;  // minimum of the own list once it is full, else -inf
   float shared;   // last value read from the shared bound, minus margin
@@ -73,31 +83,81 @@ struct TopkEpi {
   int fill;
 
   __device__ TopkEpi(const Params& pp, uint8_t* smem, int row)
-      : p(pp), keys(reinterpret_cast<uint64_t*>(smem) + row), my_bound(nullptr), thr(-INFINITY), own_min(-INFINITY),
-        shared(-INFINITY), margin(0.f), min_slot(0), fill(0) {}
+      : p(pp), keys(reinterpret_cast<uint64_t*>(smem) + row),
+        sel(reinterpret_cast<float*>(smem + (size_t)pp.kp * GEMM_BM * 8) + row), my_bound(nullptr), my_max(nullptr),
+        max_col(nullptr), own_max(-INFINITY), tiles_seen(0), thr(-INFINITY), own_min(-INFINITY), shared(-INFINITY),
+        margin(0.f), min_slot(0), fill(0) {}
 
   __device__ __forceinline__ void refresh() {
     const unsigned int b = *reinterpret_cast<volatile unsigned int*>(my_bound);
-    shared = b ? orderable_to_float(b) - margin : -INFINITY;
+    shared = fmaxf(shared, b ? orderable_to_float(b) - margin : -INFINITY);
     thr = fmaxf(own_min, shared);
   }
+  // Second lower bound on the k-th best score: the maxima of k different splits are k different rows, so the
+  // k-th largest split maximum is reached by at least k rows.  Unlike a single list's minimum it tracks the
+  // k-th best of EVERYTHING scanned so far for this query, by any CTA.
+  __device__ __forceinline__ void refresh_maxima() {
+    const int k = p.k;
+    if (p.n_splits < k) return;
+    int n = 0, ms = 0;
+    float mn = INFINITY;
+    for (int s0 = 0; s0 < p.n_splits; s0 += 8) {
+      unsigned int o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)   // eight independent loads in flight
+        o[j] = (s0 + j < p.n_splits) ? *reinterpret_cast<const volatile unsigned int*>(max_col + (size_t)(s0 + j) * p.q_pad) : 0u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!o[j]) continue;
+        const float v = orderable_to_float(o[j]);
+        if (n < k) {
+          sel[n * GEMM_BM] = v;
+          if (v < mn) { mn = v; ms = n; }
+          ++n;
+        } else if (v > mn) {
+          sel[ms * GEMM_BM] = v;
+          mn = sel[0];
+          ms = 0;
+          for (int i = 1; i < k; ++i) {
+            const float w = sel[i * GEMM_BM];
+            if (w < mn) { mn = w; ms = i; }
+          }
+        }
+      }
+    }
+    if (n == k) shared = fmaxf(shared, mn - margin);
+  }
 
-  __device__ void begin_item(int m_row, int, int) {
+  __device__ void begin_item(int m_row, int split, int) {
     for (int s = 0; s < p.kp; ++s) keys[s * GEMM_BM] = 0ull;
     own_min = -INFINITY;
+    own_max = -INFINITY;
+    shared = -INFINITY;
     min_slot = 0;
     fill = 0;
+    tiles_seen = 0;
     my_bound = p.bound + m_row;
+    max_col = p.maxima + m_row;
+    my_max = p.maxima + (size_t)split * p.q_pad + m_row;
     const float eps = window_eps(METRIC, p.eps_rel, METRIC == 0 ? p.q_sq[m_row] : 1.f,
                                  METRIC == 0 ? orderable_to_float(*p.gmax) : 1.f);
     margin = 2.f * eps * 1.001f + 1e-30f;
     refresh();
   }
 
-  __device__ __forceinline__ void begin_tile() { refresh(); }
+  __device__ __forceinline__ void begin_tile() {
+    // the bound improves like log(columns seen): look at tiles 1, 2, 4, 8, 16, ... of the item
+    ++tiles_seen;
+    if ((tiles_seen & (tiles_seen - 1)) == 0) refresh_maxima();
+    refresh();
+  }
 
   __device__ __forceinline__ void insert(float v, int col) {
     const uint64_t key = make_key(v, (uint32_t)col);
+    if (v > own_max) {
+      own_max = v;
+      *reinterpret_cast<volatile unsigned int*>(my_max) = (unsigned int)(key >> 32);
+    }
     if (fill < p.kp) {
       keys[fill * GEMM_BM] = key;
       if (++fill < p.kp) return;
@@ -187,7 +247,7 @@ template <int PREC>
 int launch_search_prec(int metric, int ctas, int ares, const CUtensorMap* maps, const GemmShape& shape,
                        const TopkEpi<1>::Params& ep1, int n_units, cudaStream_t st) {
   // TopkEpi<0>::Params and TopkEpi<1>::Params have identical members
-  TopkEpi<0>::Params ep0{ep1.cand, ep1.gnorm, ep1.bound, ep1.q_sq, ep1.gmax, ep1.n_rows, ep1.n_splits, ep1.kp, ep1.eps_rel};
+  TopkEpi<0>::Params ep0{ep1.cand, ep1.gnorm, ep1.bound, ep1.maxima, ep1.q_pad, ep1.k, ep1.q_sq, ep1.gmax, ep1.n_rows, ep1.n_splits, ep1.kp, ep1.eps_rel};
   if (ctas == 2) {
     if (ares) {
       if constexpr (PREC != 0) {

@@ -13,7 +13,7 @@ struct SumEpi {
   struct Params {
     float* row_sum;  // [rows padded]
   };
-  static constexpr int kSmemBytes = 16;
+  static int smem_bytes(const Params&) { return 16; }
   const Params& p;
   float acc_sum;
   __device__ SumEpi(const Params& pp, uint8_t*, int) : p(pp), acc_sum(0.f) {}

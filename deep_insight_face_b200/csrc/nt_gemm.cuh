@@ -89,7 +89,7 @@ inline bool plan_gemm_smem(int k_chunks, int epi_smem, GemmSmemPlan* out) {
 // Epilogue concept:
 //   struct Epi {
 //     struct Params;                       // POD, passed by value to the kernel
-//     static constexpr int kSmemBytes;     // CTA-shared scratch, 16-byte aligned
+//     static int smem_bytes(const Params&); // host: CTA-shared scratch the epilogue needs, 16-byte multiple
 //     __device__ Epi(const Params&, uint8_t* smem, int row_in_block);
 //     // split = index of the (K split, B-tile range) slot of this item: k_split * n_splits + n_split
 //     __device__ void begin_item(int m_row /*global A row of this thread*/, int split, int col_begin);
@@ -320,7 +320,7 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
         __syncwarp();
         if (lane_id() == 0) {
           if (CTAS == 1 || leader) mbar_arrive(&acc_empty[buf]);
-          else mbar_arrive_cluster(&acc_empty[buf], 0);
+          else mbar_arrive_cluster_relaxed(&acc_empty[buf], 0);
         }
       }
       epi.end_item(m_row, split);
@@ -343,7 +343,7 @@ template <int PREC, int BN, int CTAS, int ARES, class Epi>
 int launch_nt_gemm(const CUtensorMap* maps, GemmShape shape, const typename Epi::Params& ep, int n_units,
                    cudaStream_t stream) {
   GemmSmemPlan plan;
-  const bool fits = plan_gemm_smem<PREC, BN, CTAS, ARES>(shape.k_chunks, Epi::kSmemBytes, &plan);
+  const bool fits = plan_gemm_smem<PREC, BN, CTAS, ARES>(shape.k_chunks, Epi::smem_bytes(ep), &plan);
   DIF_REQUIRE(fits, DIF_ERR_CAPACITY, "nt_gemm: K = %d chunks does not fit the shared-memory plan (ARES=%d)",
               shape.k_chunks, ARES);
   shape.stages = plan.stages;

@@ -13,7 +13,7 @@ struct StoreEpi {
     int n_splits;          // slots that belong to one K split (= shape.n_splits)
     size_t slot_stride;    // elements between K-split planes (0: single plane)
   };
-  static constexpr int kSmemBytes = 16;
+  static int smem_bytes(const Params&) { return 16; }
   const Params& p;
   float* row_ptr;
   __device__ StoreEpi(const Params& pp, uint8_t*, int) : p(pp), row_ptr(nullptr) {}
