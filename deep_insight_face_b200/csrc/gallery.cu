@@ -25,7 +25,8 @@ namespace dif {
 
 constexpr int kRerankThreads = 128;
 constexpr int kRerankCap = 256;     // candidates inside the 2*eps window before a query is flagged
-constexpr int kExactChunks = 64;    // row chunks per flagged query in the exact scan
+constexpr int kExactChunks = 256;   // row chunks per flagged query in the exact scan
+constexpr int kExactMaxFlagged = 2048;  // flagged queries the exact scan has workspace for (the rest is reported)
 constexpr int kExactThreads = 256;
 
 // ------------------------------------------------------------------------------------------
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
 __global__ void __launch_bounds__(kExactThreads) exact_scan_kernel(RerankParams p, uint64_t* ex_keys) {
   extern __shared__ float sm_q[];  // [D]
   __shared__ uint64_t lists[kExactThreads / 32][DIF_MAX_TOPK];
-  const int n_flag = *p.flagged_count;
+  const int n_flag = min(*p.flagged_count, kExactMaxFlagged);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int64_t chunk_rows = (p.n_rows + kExactChunks - 1) / kExactChunks;
   for (int item = blockIdx.x; item < n_flag * kExactChunks; item += gridDim.x) {
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(kExactThreads) exact_scan_kernel(RerankParams 
 
 __global__ void __launch_bounds__(kRerankThreads) exact_merge_kernel(RerankParams p, const uint64_t* ex_keys) {
   extern __shared__ uint64_t sm_keys[];
-  const int n_flag = *p.flagged_count;
+  const int n_flag = min(*p.flagged_count, kExactMaxFlagged);
   const int n = kExactChunks * p.k;
   for (int fi = blockIdx.x; fi < n_flag; fi += gridDim.x) {
     const int q = p.flagged_list[fi];
@@ -594,6 +595,10 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
   if (shape.n_tiles > 0) {
     const int rounds = std::max(1, std::min(8, (shape.n_tiles * shape.m_blocks) / (units * 8)));
     splits = std::max(1, (units * rounds + shape.m_blocks - 1) / shape.m_blocks);
+    // Each split keeps only k candidates: a split that scans a large share of the shard fills its list with
+    // rows inside the re-rank window and flags the query for the exact scan.  >= 32 splits keep every list's
+    // k-th best well below the window for the wide (bf16 / TF32) filters even at 10^7 rows per shard.
+    splits = std::max(splits, 32);
     splits = std::min(splits, shape.n_tiles);
     splits = std::min(splits, 512);
     if (g->opt_splits > 0) splits = std::min(g->opt_splits, shape.n_tiles);
@@ -685,7 +690,7 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
 
   // 4. exact path for flagged queries (grids sized for the hardware, work read from the device counter)
   if (g->size > 0) {
-    const size_t need = (size_t)g->q_cap * kExactChunks * k;
+    const size_t need = (size_t)std::min(g->q_cap, kExactMaxFlagged) * kExactChunks * k;
     if (need > g->ex_elems) {
       // allocated lazily but before it can be needed: the flagged count is only known on the device
       cudaFree(g->ex_keys);
@@ -696,7 +701,10 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
     }
     exact_scan_kernel<<<device_sm_count() * 4, kExactThreads, (size_t)D * 4, st>>>(rp, g->ex_keys);
     DIF_LAUNCH_OK();
-    exact_merge_kernel<<<device_sm_count() * 2, kRerankThreads, (size_t)kExactChunks * k * 8, st>>>(rp, g->ex_keys);
+    const size_t em_smem = (size_t)kExactChunks * k * 8;
+    if (em_smem > 40 * 1024)
+      DIF_CUDA_OK(cudaFuncSetAttribute(exact_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em_smem));
+    exact_merge_kernel<<<device_sm_count() * 2, kRerankThreads, em_smem, st>>>(rp, g->ex_keys);
     DIF_LAUNCH_OK();
   }
   g->stats[1] = dif_launch_count() - launches0;
@@ -725,6 +733,13 @@ int dif_gallery_search_host(dif_gallery_t* g, const float* queries_host, int n_q
   if (int rc = dif_gallery_search(g, (const float*)dp, n_queries, k, d_scores, d_ids, d_rows, st)) return rc;
   DIF_CUDA_OK(cudaMemcpyAsync(hp + qb_al, dp + qb_al, ob, cudaMemcpyDeviceToHost, st));
   DIF_CUDA_OK(cudaStreamSynchronize(st));
+  {
+    int n_flag = 0;
+    DIF_CUDA_OK(cudaMemcpy(&n_flag, g->flagged, sizeof(int), cudaMemcpyDeviceToHost));
+    DIF_REQUIRE(n_flag <= kExactMaxFlagged, DIF_ERR_CAPACITY,
+                "%d queries need the exact scan (limit %d): candidate lists saturated; use a finer filter precision",
+                n_flag, kExactMaxFlagged);
+  }
   memcpy(ids_host, hp + qb_al, nk * 8);
   memcpy(scores_host, hp + qb_al + nk * 8, nk * 4);
   if (rows_host) memcpy(rows_host, hp + qb_al + nk * 12, nk * 4);
@@ -740,7 +755,7 @@ int dif_gallery_last_stats(const dif_gallery_t* g, int64_t out[6]) {
   out[2] = g->stats[2];
   out[3] = g->stats[3];
   out[4] = g->stats[4];
-  out[5] = 0;
+  out[5] = n_flag > kExactMaxFlagged ? n_flag - kExactMaxFlagged : 0;   // flagged queries left with unverified results
   return DIF_OK;
 }
 
