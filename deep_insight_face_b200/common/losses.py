@@ -94,6 +94,60 @@ def batch_hard(labels, embeddings, variant: int, alpha: float, dloss=None, want_
     return loss, grad, {"pos_idx": pos, "neg_idx": neg, "stats": stats}
 
 
+class BatchHardStep:
+    """Preallocated, optionally CUDA-graphed batch-hard step for a fixed (B, D): the training-loop form.
+
+    The three kernels of a step take ~12 us on a B200 at B = 72; building five output tensors and a 14-argument
+    ctypes call per step costs more than that, so the buffers and the argument tuple are made once and a step is
+    one foreign call - or, with `graph=True`, one cudaGraphLaunch of the captured kernel sequence.
+
+        step = BatchHardStep(B, D, variant=LOSS_BH_COSINE, alpha=0.35, device="cuda:0", graph=True)
+        step.emb.copy_(embeddings); step.labels.copy_(int_labels)      # or write into them in place
+        step()                                                          # fills step.loss, step.grad, step.pos_idx, ...
+    """
+
+    def __init__(self, B: int, D: int, variant: int = _ffi.LOSS_BH_COSINE, alpha: float = 0.35, device="cuda:0",
+                 graph: bool = False, want_grad: bool = True):
+        import torch
+
+        dev = torch.device(device)
+        _ffi.init(dev.index or 0)
+        self._lib = _ffi.load_library()
+        self.B, self.D, self.variant, self.alpha = int(B), int(D), int(variant), float(alpha)
+        self.emb = torch.zeros((B, D), dtype=torch.float32, device=dev)
+        self.labels = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.loss = torch.empty(B, dtype=torch.float32, device=dev)
+        self.pos_idx = torch.empty(B, dtype=torch.int32, device=dev)
+        self.neg_idx = torch.empty(B, dtype=torch.int32, device=dev)
+        self.stats = torch.empty(4, dtype=torch.float32, device=dev)
+        self.grad = torch.empty((B, D), dtype=torch.float32, device=dev) if want_grad else None
+        self._dev = dev
+        self._graph = None
+        self._launch()                       # warm-up: sizes the library workspace outside any capture
+        torch.cuda.synchronize(dev)
+        if graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch()
+            self._graph = g
+
+    def _launch(self):
+        import torch
+
+        st = int(torch.cuda.current_stream(self._dev).cuda_stream)
+        _ffi.check(self._lib.dif_batch_hard(self.emb.data_ptr(), self.labels.data_ptr(), self.B, self.D, self.variant,
+                                            self.alpha, self.loss.data_ptr(), self.pos_idx.data_ptr(),
+                                            self.neg_idx.data_ptr(), self.stats.data_ptr(), None,
+                                            None if self.grad is None else self.grad.data_ptr(), _ffi.PREC_TF32X3, st))
+
+    def __call__(self):
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._launch()
+        return self.loss, self.grad
+
+
 def _torch_function():
     import torch
 
@@ -227,3 +281,63 @@ class BatchHardTripletLossEuclideanAutoAlpha(TripletLossWapper):
         self._after_step(info)
         self.last_info = info
         return loss
+
+
+def batch_all(labels, embeddings, alpha: float, dloss=None, want_grad: bool = True):
+    """Framework-neutral core of BatchAllTripletLoss (common/losses.py:131-148).  Returns (loss, grad or None)."""
+    import torch
+
+    lib = _ffi.load_library()
+    on_dev = _ffi.is_device_tensor(embeddings)
+    emb = embeddings.detach().contiguous().float() if on_dev else torch.from_numpy(
+        _ffi.host_array(embeddings, np.float32)).cuda()
+    dev = emb.device
+    _ffi.init(dev.index or 0)
+    B, D = emb.shape
+    st = _ffi.current_stream_ptr(dev)
+    if _ffi.is_device_tensor(labels) and labels.dim() == 2:
+        oh = labels.detach().contiguous().float()
+        lab = torch.empty(B, dtype=torch.int32, device=dev)
+        _ffi.check(lib.dif_labels_from_onehot(_ffi.ptr(oh), B, oh.shape[1], _ffi.ptr(lab), st))
+    elif _ffi.is_device_tensor(labels):
+        lab = labels.detach().to(torch.int32).contiguous()
+    else:
+        lab = torch.from_numpy(_int_labels(labels)).to(dev)
+    loss = torch.empty(B, dtype=torch.float32, device=dev)
+    grad = torch.empty_like(emb) if want_grad else None
+    dl = None
+    if dloss is not None:
+        dl = dloss.detach().contiguous().float() if _ffi.is_device_tensor(dloss) else torch.from_numpy(
+            _ffi.host_array(dloss, np.float32, (B,))).to(dev)
+    _ffi.check(lib.dif_batch_all(_ffi.ptr(emb), _ffi.ptr(lab), B, D, float(alpha), _ffi.ptr(loss), _ffi.ptr(dl),
+                                 _ffi.ptr(grad), st))
+    if on_dev:
+        return loss, grad
+    return loss.cpu().numpy(), (None if grad is None else grad.cpu().numpy())
+
+
+class BatchAllTripletLoss(TripletLossWapper):
+    """common/losses.py:131-148: cosine batch-all (mean positive distance + mean of the still-violating negatives)."""
+
+    def __calculate_triplet_loss__(self, labels, embeddings, alpha):
+        if _ffi.is_device_tensor(embeddings) and embeddings.requires_grad:
+            import torch
+
+            class _Fn(torch.autograd.Function):
+                @staticmethod
+                def forward(ctx, emb):
+                    loss, _ = batch_all(labels, emb, alpha, want_grad=False)
+                    ctx.save_for_backward(emb)
+                    return loss
+
+                @staticmethod
+                def backward(ctx, dloss):
+                    (emb,) = ctx.saved_tensors
+                    return batch_all(labels, emb, alpha, dloss=dloss, want_grad=True)[1]
+
+            return _Fn.apply(embeddings)
+        return batch_all(labels, embeddings, alpha, want_grad=False)[0]
+
+    def loss_and_grad(self, labels, embeddings, dloss=None):
+        loss, grad = batch_all(labels, embeddings, self.alpha, dloss=dloss, want_grad=True)
+        return loss, grad, {}

@@ -187,29 +187,53 @@ __global__ void __launch_bounds__(256) transpose_planes_kernel(const float* __re
   }
 }
 
-// out_r = inv_r * (g_r - h_r (h_r . g_r)) with g = sum over `planes` partial planes, h = hi + lo normalised row;
-// rows whose squared norm was clamped (inv == 1e6) are a plain scaling.  One warp per row.
+// out_r = inv_r * (g_r - h_r (h_r . g_r)) with g = sum over `planes` partial planes (fixed order), h = hi + lo
+// normalised row; rows whose squared norm was clamped (inv == 1e6) are a plain scaling.  One block per row,
+// one thread per 4 columns: every load is independent and coalesced (the planes are read exactly once).
 __global__ void __launch_bounds__(256) arc_norm_bwd_kernel(const float* __restrict__ g, int planes, size_t plane_stride,
                                                            const float* __restrict__ h_hi, const float* __restrict__ h_lo,
                                                            const float* __restrict__ inv, int R, int D,
                                                            float* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= R) return;
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  const size_t base = (size_t)r * D;
   float dot = 0.f;
-  for (int d = lane; d < D; d += 32) {
-    float a = 0.f;
-    for (int s = 0; s < planes; ++s) a += g[(size_t)s * plane_stride + (size_t)r * D + d];
-    dot += a * (h_hi[(size_t)r * D + d] + h_lo[(size_t)r * D + d]);
+  // D <= 4096 and D % 4 == 0: each thread owns up to 4 float4 groups, kept in registers between the passes
+  float4 a[4], h[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int d = (threadIdx.x + t * 256) * 4;
+    a[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    h[t] = a[t];
+    if (d < D) {
+      for (int s = 0; s < planes; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(g + (size_t)s * plane_stride + base + d);
+        a[t].x += v.x; a[t].y += v.y; a[t].z += v.z; a[t].w += v.w;
+      }
+      const float4 hh = *reinterpret_cast<const float4*>(h_hi + base + d);
+      const float4 hl = *reinterpret_cast<const float4*>(h_lo + base + d);
+      h[t] = make_float4(hh.x + hl.x, hh.y + hl.y, hh.z + hl.z, hh.w + hl.w);
+      dot += a[t].x * h[t].x + a[t].y * h[t].y + a[t].z * h[t].z + a[t].w * h[t].w;
+    }
   }
   for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  dot = 0.f;
+  for (int w = 0; w < 8; ++w) dot += red[w];
   const float iv = inv[r];
   const bool clamped = iv >= 0.99e6f;   // 1 / sqrt(1e-12)
-  for (int d = lane; d < D; d += 32) {
-    float a = 0.f;
-    for (int s = 0; s < planes; ++s) a += g[(size_t)s * plane_stride + (size_t)r * D + d];
-    const float h = h_hi[(size_t)r * D + d] + h_lo[(size_t)r * D + d];
-    out[(size_t)r * D + d] = clamped ? iv * a : iv * (a - h * dot);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int d = (threadIdx.x + t * 256) * 4;
+    if (d < D) {
+      float4 o4;
+      o4.x = clamped ? iv * a[t].x : iv * (a[t].x - h[t].x * dot);
+      o4.y = clamped ? iv * a[t].y : iv * (a[t].y - h[t].y * dot);
+      o4.z = clamped ? iv * a[t].z : iv * (a[t].z - h[t].z * dot);
+      o4.w = clamped ? iv * a[t].w : iv * (a[t].w - h[t].w * dot);
+      *reinterpret_cast<float4*>(out + base + d) = o4;
+    }
   }
 }
 
@@ -342,9 +366,9 @@ extern "C" int dif_arcface(const float* X, const float* W, const int32_t* y, int
   StoreEpi::Params sw{F(o_gw), C, D, D, gw.n_splits, 0};
   if (int rc = launch_nt_gemm<0, kArcBN, 1, 0, StoreEpi>(maps, gw, sw, sms, st)) return rc;
   // ---- 5. l2_normalize backward
-  arc_norm_bwd_kernel<<<(B + 7) / 8, 256, 0, st>>>(F(o_gx), gx.k_splits, (size_t)B * D, F(o_xh), F(o_xl), F(o_xi), B, D, dX);
+  arc_norm_bwd_kernel<<<B, 256, 0, st>>>(F(o_gx), gx.k_splits, (size_t)B * D, F(o_xh), F(o_xl), F(o_xi), B, D, dX);
   DIF_LAUNCH_OK();
-  arc_norm_bwd_kernel<<<(C + 7) / 8, 256, 0, st>>>(F(o_gw), 1, 0, F(o_wh), F(o_wl), F(o_wi), C, D, dW);
+  arc_norm_bwd_kernel<<<C, 256, 0, st>>>(F(o_gw), 1, 0, F(o_wh), F(o_wl), F(o_wi), C, D, dW);
   DIF_LAUNCH_OK();
   return DIF_OK;
 }

@@ -17,97 +17,9 @@
 //                    cotangent is split evenly over every tied position, filler positions included.
 #include <algorithm>
 
-#include "dif_canon.cuh"
-#include "dif_common.cuh"
+#include "bh_tile.cuh"
 
 namespace dif {
-
-constexpr int BH_WARPS = 4;
-constexpr int BH_TI = 8;                      // anchors per warp
-constexpr int BH_TJ = 4;                      // columns per warp step
-constexpr int BH_RB = BH_WARPS * BH_TI;       // anchors per block
-constexpr int BH_CB = 32;                     // columns staged per tile
-constexpr int BH_MAX_KD = 16;                 // D <= 512
-
-struct BhRec {            // per (split, anchor)
-  float pos_val; int pos_idx; int pos_cnt;   // cosine: min over positives; euclid: max over positives
-  float neg_val; int neg_idx; int neg_cnt;   // cosine: max over negatives; euclid: min over negatives
-  float all_max; int all_idx; int all_cnt;   // max over every column (euclid filler, losses.py:70)
-  float row_sum; int n_pos; int pad;
-};
-
-struct BhRow {            // per anchor, written by bh_merge_kernel, read by bh_grad_kernel
-  float pos_val, neg_val;   // extreme over REAL positives / negatives
-  int pos_idx, neg_idx;     // first index, -1 if none
-  int pos_cnt, neg_cnt;     // real tie counts
-  float coef_pos, coef_neg; // dL/d(dist) applied to each tied real positive / negative column
-  float all_max; int all_idx; int all_cnt;
-  float coef_gmax;          // dL/d(dist) applied to every position holding the global max (euclid filler gradient)
-};
-
-template <bool MIN>
-__device__ __forceinline__ void fold(float v, int j, float& val, int& idx, int& cnt) {
-  if (MIN ? (v < val) : (v > val)) {
-    val = v;
-    idx = j;
-    cnt = 1;
-  } else if (v == val) {
-    ++cnt;
-    idx = (idx < 0 || j < idx) ? j : idx;
-  }
-}
-template <bool MIN>
-__device__ __forceinline__ void merge(float v, int j, int c, float& val, int& idx, int& cnt) {
-  if (c == 0) return;
-  if (cnt == 0 || (MIN ? (v < val) : (v > val))) {
-    val = v;
-    idx = j;
-    cnt = c;
-  } else if (v == val) {
-    cnt += c;
-    idx = j < idx ? j : idx;
-  }
-}
-
-// lane l holds chain-l partial sums of 32 entries in v[0..31]; returns the canonical total of entry `lane`.
-__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int e = 0; e < o; ++e) {
-      const float send = up ? v[e] : v[e + o];
-      const float keep = up ? v[e + o] : v[e];
-      v[e] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, o));
-    }
-  }
-  return v[0];
-}
-
-// Load `n` rows [row0, row0+n) of x into smem (zero beyond B); cosine: normalise in place; writes the
-// canonical sum of squares (euclid) or inverse norm (cosine) of each row to aux[n] in smem.
-template <bool COSINE>
-__device__ __forceinline__ void stage_rows(const float* __restrict__ x, int B, int D, int row0, int n, float* dst,
-                                           float* aux) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < n; r += BH_WARPS) {
-    const int gr = row0 + r;
-    float acc = 0.f;
-    for (int d = lane; d < D; d += 32) {
-      const float t = gr < B ? x[(size_t)gr * D + d] : 0.f;
-      dst[r * D + d] = t;
-      acc = __fmaf_rn(t, t, acc);
-    }
-    const float ss = canon_tree(acc);
-    if (COSINE) {
-      const float inv = canon_inv_norm(ss);
-      for (int d = lane; d < D; d += 32) dst[r * D + d] = __fmul_rn(dst[r * D + d], inv);
-      if (lane == 0) aux[r] = inv;
-    } else {
-      if (lane == 0) aux[r] = ss;
-    }
-  }
-}
 
 template <bool COSINE>
 __global__ void __launch_bounds__(BH_WARPS * 32) bh_mine_kernel(const float* __restrict__ x,
@@ -138,7 +50,7 @@ __global__ void __launch_bounds__(BH_WARPS * 32) bh_mine_kernel(const float* __r
 
   float pos_val = COSINE ? INFINITY : -INFINITY, neg_val = COSINE ? -INFINITY : INFINITY, all_max = -INFINITY;
   int pos_idx = -1, neg_idx = -1, all_idx = -1, pos_cnt = 0, neg_cnt = 0, all_cnt = 0, n_pos = 0;
-  float row_sum = 0.f;
+  float row_sum = 0.f, pos_sum = 0.f;
 
   for (int c0 = c_begin; c0 < c_end; c0 += BH_CB) {
     __syncthreads();   // previous tile fully consumed
@@ -171,6 +83,7 @@ __global__ void __launch_bounds__(BH_WARPS * 32) bh_mine_kernel(const float* __r
         fold<false>(dist, gj, all_max, all_idx, all_cnt);
         if (lab_b[jl] == my_lab) {
           ++n_pos;
+          pos_sum += dist;
           fold<COSINE>(dist, gj, pos_val, pos_idx, pos_cnt);
         } else {
           fold<!COSINE>(dist, gj, neg_val, neg_idx, neg_cnt);
@@ -192,6 +105,7 @@ __global__ void __launch_bounds__(BH_WARPS * 32) bh_mine_kernel(const float* __r
     merge<false>(av, ai, ac, all_max, all_idx, all_cnt);
     // fixed order: (lane0 + lane1) + (lane2 + lane3)
     row_sum = __fadd_rn(row_sum, __shfl_xor_sync(0xffffffffu, row_sum, o));
+    pos_sum = __fadd_rn(pos_sum, __shfl_xor_sync(0xffffffffu, pos_sum, o));
     n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
   }
   if ((lane & 3) == 0 && gi < B) {
@@ -199,7 +113,7 @@ __global__ void __launch_bounds__(BH_WARPS * 32) bh_mine_kernel(const float* __r
     r.pos_val = pos_val; r.pos_idx = pos_idx; r.pos_cnt = pos_cnt;
     r.neg_val = neg_val; r.neg_idx = neg_idx; r.neg_cnt = neg_cnt;
     r.all_max = all_max; r.all_idx = all_idx; r.all_cnt = all_cnt;
-    r.row_sum = row_sum; r.n_pos = n_pos; r.pad = 0;
+    r.row_sum = row_sum; r.n_pos = n_pos; r.pos_sum = pos_sum;
     recs[(size_t)split * B + gi] = r;
   }
 }
@@ -526,7 +440,8 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
   // column splits: enough blocks to cover the machine, at least one step of 4 columns each
   const int row_blocks = (B + BH_RB - 1) / BH_RB;
   const int sms = std::max(1, device_sm_count());
-  int splits = std::max(1, std::min((2 * sms + row_blocks - 1) / row_blocks, (B + BH_TJ - 1) / BH_TJ));
+  // at least one full staged tile (32 columns) per split: finer splits only add staging and merge work
+  int splits = std::max(1, std::min((2 * sms + row_blocks - 1) / row_blocks, (B + BH_CB - 1) / BH_CB));
   splits = std::min(splits, 64);
   int cols = (B + splits - 1) / splits;
   cols = (cols + BH_TJ - 1) / BH_TJ * BH_TJ;
@@ -540,7 +455,8 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
   }
   bh_mine_kernel<COSINE><<<dim3(row_blocks, splits), BH_WARPS * 32, smem, st>>>(emb, labels, B, D, cols, g_ws.recs, g_ws.aux);
   DIF_LAUNCH_OK();
-  bh_merge_kernel<COSINE><<<1, 1024, 0, st>>>(g_ws.recs, splits, B, alpha, dloss, loss, pos_idx, neg_idx, stats, g_ws.rows);
+  const int merge_threads = std::min(1024, std::max(64, (B + 31) / 32 * 32));
+  bh_merge_kernel<COSINE><<<1, merge_threads, 0, st>>>(g_ws.recs, splits, B, alpha, dloss, loss, pos_idx, neg_idx, stats, g_ws.rows);
   DIF_LAUNCH_OK();
   if (demb) {
     bh_grad_kernel<COSINE><<<(B + 3) / 4, 128, 0, st>>>(emb, labels, B, D, g_ws.aux, g_ws.rows, demb);
@@ -548,6 +464,227 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
   }
   return DIF_OK;
 }
+
+
+// =============================================================================================
+// Batch-all triplet loss, deep_insight_face/common/losses.py:131-148 (cosine):
+//   pos_loss_i = sum_j (1 - where(pos, S, 1)) / n_pos_i;  hp_i = min_j where(pos, S, 1)
+//   valid_ij   = !pos_ij && (hp_i - S_ij < alpha);  neg_loss_i = sum_j where(valid, S, 0) / (n_valid_i + 1)
+// Pass 1 is bh_mine_kernel<true> (hp, n_pos, sum of positive similarities); pass 2 needs hp_i and counts the
+// valid negatives; the backward pass recomputes S tile by tile and accumulates (G + G^T) N in registers
+// (the `valid` mask is piecewise constant, so no gradient flows through hp).
+// =============================================================================================
+struct BaRow {
+  float hp;      // min over positives and the 1.0 fillers of the non-positive columns
+  float cp;      // dL/dS applied to every positive column of this anchor   (-g / n_pos)
+  float cn;      // dL/dS applied to every valid negative column            (+g / (n_valid + 1))
+  int n_pos;
+};
+
+__global__ void __launch_bounds__(256) ba_merge1_kernel(const BhRec* __restrict__ recs, int n_splits, int B,
+                                                        BaRow* __restrict__ rows, float* __restrict__ pos_loss) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  float hp = INFINITY, ps = 0.f;
+  int idx = -1, cnt = 0, n_pos = 0;
+  for (int s = 0; s < n_splits; ++s) {
+    const BhRec& q = recs[(size_t)s * B + i];
+    merge<true>(q.pos_val, q.pos_idx, q.pos_cnt, hp, idx, cnt);
+    ps = __fadd_rn(ps, q.pos_sum);
+    n_pos += q.n_pos;
+  }
+  if (n_pos < B) hp = fminf(hp, 1.f);
+  BaRow r;
+  r.hp = hp;
+  r.cp = r.cn = 0.f;
+  r.n_pos = n_pos;
+  rows[i] = r;
+  pos_loss[i] = ((float)n_pos - ps) / (float)n_pos;   // sum over positives of (1 - S)
+}
+
+__global__ void __launch_bounds__(BH_WARPS * 32) ba_valid_kernel(const float* __restrict__ x,
+                                                                 const int32_t* __restrict__ labels, int B, int D,
+                                                                 int cols_per_split, const BaRow* __restrict__ rows,
+                                                                 float alpha, float2* __restrict__ vrec) {
+  extern __shared__ float sm[];
+  float* sa = sm;
+  float* sb = sa + BH_RB * D;
+  float* aux_a = sb + BH_CB * D;
+  float* aux_b = aux_a + BH_RB;
+  int* lab_b = reinterpret_cast<int*>(aux_b + BH_CB);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * BH_RB, split = blockIdx.y;
+  const int c_begin = split * cols_per_split, c_end = min(B, c_begin + cols_per_split);
+  const int kd = (D + 31) / 32;
+  stage_rows<true>(x, B, D, row0, BH_RB, sa, aux_a);
+  __syncthreads();
+  const int gi = row0 + warp * BH_TI + (lane >> 2);
+  const int my_lab = gi < B ? labels[gi] : -1;
+  const float my_hp = gi < B ? rows[gi].hp : 0.f;
+  float sum_v = 0.f;
+  int n_v = 0;
+  for (int c0 = c_begin; c0 < c_end; c0 += BH_CB) {
+    __syncthreads();
+    stage_rows<true>(x, B, D, c0, BH_CB, sb, aux_b);
+    if (threadIdx.x < BH_CB) lab_b[threadIdx.x] = (c0 + threadIdx.x < B) ? labels[c0 + threadIdx.x] : -2;
+    __syncthreads();
+    const int steps = min(BH_CB, c_end - c0);
+    for (int j0 = 0; j0 < steps; j0 += BH_TJ) {
+      const float sim = tile_step_dot(sa, sb, D, kd, warp, lane, j0);
+      const int jl = j0 + (lane & 3), gj = c0 + jl;
+      if (gj < c_end && gi < B && lab_b[jl] != my_lab && __fsub_rn(my_hp, sim) < alpha) {
+        sum_v += sim;
+        ++n_v;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    sum_v = __fadd_rn(sum_v, __shfl_xor_sync(0xffffffffu, sum_v, o));
+    n_v += __shfl_xor_sync(0xffffffffu, n_v, o);
+  }
+  if ((lane & 3) == 0 && gi < B) vrec[(size_t)split * B + gi] = make_float2(sum_v, __int_as_float(n_v));
+}
+
+__global__ void __launch_bounds__(256) ba_merge2_kernel(const float2* __restrict__ vrec, int n_splits, int B,
+                                                        const float* __restrict__ pos_loss,
+                                                        const float* __restrict__ dloss, float* __restrict__ loss,
+                                                        BaRow* __restrict__ rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  float sv = 0.f;
+  int nv = 0;
+  for (int s = 0; s < n_splits; ++s) {
+    const float2 q = vrec[(size_t)s * B + i];
+    sv = __fadd_rn(sv, q.x);
+    nv += __float_as_int(q.y);
+  }
+  loss[i] = pos_loss[i] + sv / ((float)nv + 1.f);
+  const float g = dloss ? dloss[i] : 1.f / (float)B;
+  rows[i].cp = -g / (float)rows[i].n_pos;
+  rows[i].cn = g / ((float)nv + 1.f);
+}
+
+template <int KD>
+__global__ void __launch_bounds__(BH_WARPS * 32) ba_grad_kernel(const float* __restrict__ x,
+                                                                const int32_t* __restrict__ labels, int B, int D,
+                                                                const BaRow* __restrict__ rows, float alpha,
+                                                                float* __restrict__ demb) {
+  extern __shared__ float sm[];
+  float* sa = sm;
+  float* sb = sa + BH_RB * D;
+  float* aux_a = sb + BH_CB * D;
+  float* aux_b = aux_a + BH_RB;
+  int* lab_b = reinterpret_cast<int*>(aux_b + BH_CB);
+  float* hp_b = reinterpret_cast<float*>(lab_b + BH_CB);
+  float* cp_b = hp_b + BH_CB;
+  float* cn_b = cp_b + BH_CB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * BH_RB;
+  const int kd = (D + 31) / 32;
+  stage_rows<true>(x, B, D, row0, BH_RB, sa, aux_a);
+  __syncthreads();
+  const int gi = row0 + warp * BH_TI + (lane >> 2);
+  const int my_lab = gi < B ? labels[gi] : -1;
+  BaRow me;
+  me.hp = me.cp = me.cn = 0.f;
+  me.n_pos = 0;
+  if (gi < B) me = rows[gi];
+  float acc[BH_TI][KD];
+#pragma unroll
+  for (int i = 0; i < BH_TI; ++i)
+#pragma unroll
+    for (int c = 0; c < KD; ++c) acc[i][c] = 0.f;
+
+  for (int c0 = 0; c0 < B; c0 += BH_CB) {
+    __syncthreads();
+    stage_rows<true>(x, B, D, c0, BH_CB, sb, aux_b);
+    if (threadIdx.x < BH_CB) {
+      const int gj = c0 + threadIdx.x;
+      lab_b[threadIdx.x] = gj < B ? labels[gj] : -2;
+      hp_b[threadIdx.x] = gj < B ? rows[gj].hp : 0.f;
+      cp_b[threadIdx.x] = gj < B ? rows[gj].cp : 0.f;
+      cn_b[threadIdx.x] = gj < B ? rows[gj].cn : 0.f;
+    }
+    __syncthreads();
+    const int steps = min(BH_CB, B - c0);
+    for (int j0 = 0; j0 < steps; j0 += BH_TJ) {
+      const float sim = tile_step_dot(sa, sb, D, kd, warp, lane, j0);
+      const int jl = j0 + (lane & 3), gj = c0 + jl;
+      float w = 0.f;
+      if (gj < B && gi < B) {
+        if (lab_b[jl] == my_lab) {
+          w = me.cp + cp_b[jl];
+        } else {
+          if (__fsub_rn(me.hp, sim) < alpha) w += me.cn;          // j is a valid negative of anchor i
+          if (__fsub_rn(hp_b[jl], sim) < alpha) w += cn_b[jl];    // i is a valid negative of anchor j
+        }
+      }
+      // acc[i][:] += w(i, j) * n_j for the 32 entries of this step
+#pragma unroll
+      for (int j = 0; j < BH_TJ; ++j) {
+        float nb[KD];
+#pragma unroll
+        for (int c = 0; c < KD; ++c) {
+          const int d = c * 32 + lane;
+          nb[c] = (c < kd && d < D) ? sb[(j0 + j) * D + d] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < BH_TI; ++i) {
+          const float we = __shfl_sync(0xffffffffu, w, i * BH_TJ + j);
+#pragma unroll
+          for (int c = 0; c < KD; ++c) acc[i][c] = fmaf(we, nb[c], acc[i][c]);
+        }
+      }
+    }
+  }
+  // l2_normalize backward per anchor: dx = inv * (dn - n (n . dn))
+#pragma unroll
+  for (int i = 0; i < BH_TI; ++i) {
+    const int r = row0 + warp * BH_TI + i;
+    if (r >= B) continue;   // warp-uniform
+    const float* n = sa + (warp * BH_TI + i) * D;
+    float dotp = 0.f;
+#pragma unroll
+    for (int c = 0; c < KD; ++c) {
+      const int d = c * 32 + lane;
+      if (c < kd && d < D) dotp += acc[i][c] * n[d];
+    }
+    for (int o = 16; o >= 1; o >>= 1) dotp += __shfl_xor_sync(0xffffffffu, dotp, o);
+    const float inv = aux_a[warp * BH_TI + i];
+    const bool clamped = inv >= 0.99e6f;
+#pragma unroll
+    for (int c = 0; c < KD; ++c) {
+      const int d = c * 32 + lane;
+      if (c < kd && d < D) demb[(size_t)r * D + d] = clamped ? inv * acc[i][c] : inv * (acc[i][c] - n[d] * dotp);
+    }
+  }
+}
+
+struct BaWorkspace {
+  BaRow* rows = nullptr;
+  float* pos_loss = nullptr;
+  size_t row_cap = 0;
+  float2* vrec = nullptr;
+  size_t v_cap = 0;
+  int ensure(size_t n_rows, size_t n_v) {
+    if (n_rows > row_cap) {
+      cudaFree(rows); cudaFree(pos_loss);
+      rows = nullptr; pos_loss = nullptr; row_cap = 0;
+      DIF_CUDA_OK(cudaMalloc((void**)&rows, n_rows * sizeof(BaRow)));
+      DIF_CUDA_OK(cudaMalloc((void**)&pos_loss, n_rows * sizeof(float)));
+      row_cap = n_rows;
+    }
+    if (n_v > v_cap) {
+      cudaFree(vrec);
+      vrec = nullptr; v_cap = 0;
+      DIF_CUDA_OK(cudaMalloc((void**)&vrec, n_v * sizeof(float2)));
+      v_cap = n_v;
+    }
+    return DIF_OK;
+  }
+};
+static thread_local BaWorkspace g_ba;
 
 }  // namespace dif
 
@@ -604,6 +741,51 @@ int dif_batch_hard_host(const float* emb_host, const int32_t* labels_host, int B
   if (neg_idx_host) memcpy(neg_idx_host, ho + 2 * lb, (size_t)B * 4);
   memcpy(stats_host, ho + 3 * lb, 16);
   if (demb_host) memcpy(demb_host, ho + 3 * lb + 256, (size_t)B * D * 4);
+  return DIF_OK;
+}
+
+int dif_batch_all(const float* emb, const int32_t* labels, int B, int D, float alpha, float* loss, const float* dloss,
+                  float* demb, void* stream) {
+  DIF_REQUIRE(emb && labels && loss, DIF_ERR_INVALID, "dif_batch_all: null argument");
+  DIF_REQUIRE(B >= 1 && B <= 65536 && D >= 1 && D <= 32 * BH_MAX_KD, DIF_ERR_INVALID,
+              "dif_batch_all: B %d (1..65536), D %d (1..%d)", B, D, 32 * BH_MAX_KD);
+  DIF_REQUIRE(device_sm_count() > 0, DIF_ERR_STATE, "dif_init has not succeeded on this process");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int row_blocks = (B + BH_RB - 1) / BH_RB;
+  const int sms = std::max(1, device_sm_count());
+  // at least one full staged tile (32 columns) per split: finer splits only add staging and merge work
+  int splits = std::max(1, std::min((2 * sms + row_blocks - 1) / row_blocks, (B + BH_CB - 1) / BH_CB));
+  splits = std::min(splits, 64);
+  int cols = (B + splits - 1) / splits;
+  cols = (cols + BH_TJ - 1) / BH_TJ * BH_TJ;
+  splits = (B + cols - 1) / cols;
+  if (int rc = g_ws.ensure((size_t)splits * B, (size_t)B)) return rc;
+  if (int rc = g_ba.ensure((size_t)B, (size_t)splits * B)) return rc;
+  const size_t smem = ((size_t)(BH_RB + BH_CB) * D + BH_RB + BH_CB) * sizeof(float) + BH_CB * sizeof(int) + 3 * BH_CB * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    DIF_CUDA_OK(cudaFuncSetAttribute(bh_mine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DIF_CUDA_OK(cudaFuncSetAttribute(ba_valid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DIF_CUDA_OK(cudaFuncSetAttribute(ba_grad_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DIF_CUDA_OK(cudaFuncSetAttribute(ba_grad_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DIF_CUDA_OK(cudaFuncSetAttribute(ba_grad_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  bh_mine_kernel<true><<<dim3(row_blocks, splits), BH_WARPS * 32, smem, st>>>(emb, labels, B, D, cols, g_ws.recs, g_ws.aux);
+  DIF_LAUNCH_OK();
+  ba_merge1_kernel<<<(B + 255) / 256, 256, 0, st>>>(g_ws.recs, splits, B, g_ba.rows, g_ba.pos_loss);
+  DIF_LAUNCH_OK();
+  ba_valid_kernel<<<dim3(row_blocks, splits), BH_WARPS * 32, smem, st>>>(emb, labels, B, D, cols, g_ba.rows, alpha, g_ba.vrec);
+  DIF_LAUNCH_OK();
+  ba_merge2_kernel<<<(B + 255) / 256, 256, 0, st>>>(g_ba.vrec, splits, B, g_ba.pos_loss, dloss, loss, g_ba.rows);
+  DIF_LAUNCH_OK();
+  if (demb) {
+    const int kd = (D + 31) / 32;
+    if (kd <= 4) ba_grad_kernel<4><<<row_blocks, BH_WARPS * 32, smem, st>>>(emb, labels, B, D, g_ba.rows, alpha, demb);
+    else if (kd <= 8) ba_grad_kernel<8><<<row_blocks, BH_WARPS * 32, smem, st>>>(emb, labels, B, D, g_ba.rows, alpha, demb);
+    else ba_grad_kernel<16><<<row_blocks, BH_WARPS * 32, smem, st>>>(emb, labels, B, D, g_ba.rows, alpha, demb);
+    DIF_LAUNCH_OK();
+  }
   return DIF_OK;
 }
 

@@ -124,18 +124,29 @@ def batch_hard_euclidean(labels, emb, alpha=0.35, dloss=None):
     return _finish(loss, hp, hn, Dm, pos_idx, neg_idx, grad)
 
 
-def batch_all_cosine(labels, emb, alpha=0.35):
-    """common/losses.py:131-148 BatchAllTripletLoss (forward)."""
+def batch_all_cosine(labels, emb, alpha=0.35, dloss=None):
+    """common/losses.py:131-148 BatchAllTripletLoss.  The `valid` mask is piecewise constant, so the gradient is
+    -1/n_pos on the positive columns and +1/(n_valid + 1) on the valid negative columns (tf.where + reduce_sum)."""
     lab = _labels(labels)
-    S, _ = cosine_matrix(emb)
+    x = np.ascontiguousarray(emb, dtype=F32)
+    B = x.shape[0]
+    S, n = cosine_matrix(x)
     pos = lab[:, None] == lab[None, :]
     posv = np.where(pos, S, F32(1.0))
     pos_loss = (F32(1.0) - posv).sum(1) / pos.sum(1).astype(F32)        # :140-141
     hp = posv.min(1, keepdims=True)                                      # :142
     valid = ~pos & ((hp - S) < F32(alpha))                               # :144
     neg_loss = np.where(valid, S, F32(0.0)).sum(1) / (valid.sum(1).astype(F32) + F32(1.0))  # :145-147
+    g = (np.full(B, 1.0 / B) if dloss is None else np.asarray(dloss, dtype=np.float64))[:, None]
+    G = -g / pos.sum(1, keepdims=True) * pos + g / (valid.sum(1, keepdims=True) + 1.0) * valid
+    n64 = n.astype(np.float64)
+    dN = (G + G.T) @ n64
+    ss = (x.astype(np.float64) ** 2).sum(1)
+    inv = 1.0 / np.sqrt(np.maximum(ss, float(EPS)))
+    proj = dN - n64 * (n64 * dN).sum(1, keepdims=True)
+    grad = np.where((ss < float(EPS))[:, None], dN, proj) * inv[:, None]
     return {"loss": (pos_loss + neg_loss).astype(F32), "pos_loss": pos_loss, "neg_loss": neg_loss,
-            "valid_count": valid.sum(1)}
+            "valid_count": valid.sum(1), "grad": grad}
 
 
 def triplet_apn(y_pred, alpha=0.4, dloss=None):

@@ -162,3 +162,40 @@ def test_explicit_triplet_siamese_and_contrastive(gpu):
     assert abs(val - wv) <= RTOL * abs(wv)
     close(dd, wd)
     assert _accuracy(yt, d[:, 0] / 10, 0.5) == lo.siamese_accuracy(yt, d[:, 0] / 10, 0.5)
+
+
+@pytest.mark.parametrize("P,K,D", [(18, 4, 128), (33, 3, 100), (128, 4, 256), (16, 2, 512)])
+@pytest.mark.parametrize("noise,alpha", [(0.5, 0.35), (1.5, 0.2)])
+def test_batch_all(gpu, P, K, D, noise, alpha):
+    from deep_insight_face_b200.common.losses import BatchAllTripletLoss
+    from oracle import losses_oracle as lo
+
+    emb, lab = pk_batch(P, K, D, noise)
+    onehot = np.eye(P, dtype=np.float32)[lab]
+    loss = BatchAllTripletLoss(alpha=alpha)
+    got, grad, _ = loss.loss_and_grad(onehot, emb)
+    want = lo.batch_all_cosine(lab, emb, alpha)
+    close(got, want["loss"])
+    close(grad, want["grad"], scale=max(np.abs(want["grad"]).max(), np.abs(emb).max() / emb.shape[0] * 1e-2))
+    close(loss.call(onehot, emb), want["loss"])
+
+
+def test_batch_hard_step_graph(gpu):
+    import torch
+
+    from deep_insight_face_b200 import _ffi
+    from deep_insight_face_b200.common.losses import BatchHardStep
+    from oracle import losses_oracle as lo
+
+    emb, lab = pk_batch(18, 4, 128, 1.5)
+    want = lo.batch_hard_cosine(lab, emb, 0.35)
+    for graph in (False, True):
+        step = BatchHardStep(72, 128, _ffi.LOSS_BH_COSINE, 0.35, "cuda:0", graph=graph)
+        step.emb.copy_(torch.from_numpy(emb))
+        step.labels.copy_(torch.from_numpy(lab.astype(np.int32)))
+        for _ in range(3):
+            loss, grad = step()
+        torch.cuda.synchronize()
+        assert np.array_equal(step.pos_idx.cpu().numpy(), want["pos_idx"])
+        close(loss.cpu().numpy(), want["loss"])
+        close(grad.cpu().numpy(), want["grad"])
