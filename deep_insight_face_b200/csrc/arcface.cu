@@ -56,7 +56,7 @@ struct ArcFwdEpi {
     m2 = -INFINITY;
     l2 = 0.f;
   }
-  __device__ void begin_tile() {}
+  __device__ void begin_tile(int) {}
   __device__ void consume(int col0, const uint32_t (&acc)[32], uint32_t, uint32_t (&)[32]) {
     if (!row_ptr) return;
     float z[32];

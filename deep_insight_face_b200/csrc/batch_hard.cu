@@ -118,6 +118,17 @@ __global__ void __launch_bounds__(BH_WARPS * 32) bh_mine_kernel(const float* __r
   }
 }
 
+// compact per-anchor record for the "who mined me" scan: x = positive column (-1 none, -2 tied: see BhRow),
+// y = negative column, z / w = the two coefficients as float bits
+__device__ __forceinline__ int4 make_compact(const BhRow& r) {
+  int4 c;
+  c.x = r.coef_pos == 0.f ? -1 : (r.pos_cnt == 1 ? r.pos_idx : -2);
+  c.y = r.coef_neg == 0.f ? -1 : (r.neg_cnt == 1 ? r.neg_idx : -2);
+  c.z = __float_as_int(r.coef_pos);
+  c.w = __float_as_int(r.coef_neg);
+  return c;
+}
+
 __device__ __forceinline__ double block_sum(double v, double* red) {
   for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   __syncthreads();
@@ -134,7 +145,7 @@ __global__ void __launch_bounds__(1024) bh_merge_kernel(const BhRec* __restrict_
                                                         float alpha, const float* __restrict__ dloss,
                                                         float* __restrict__ loss, int32_t* __restrict__ pos_idx_out,
                                                         int32_t* __restrict__ neg_idx_out, float* __restrict__ stats,
-                                                        BhRow* __restrict__ rows) {
+                                                        BhRow* __restrict__ rows, int4* __restrict__ compact) {
   __shared__ double red[32];
   __shared__ unsigned long long gmax_key;   // orderable(value) << 32 | ~first row
   __shared__ int gmax_cnt_s;
@@ -221,7 +232,89 @@ __global__ void __launch_bounds__(1024) bh_merge_kernel(const BhRec* __restrict_
   }
   // every position holding the global max receives an equal part of gm_share
   const float cg = (!COSINE && gmax_cnt > 0) ? (float)(tot_gm / (double)gmax_cnt) : 0.f;
-  for (int i = threadIdx.x; i < B; i += blockDim.x) rows[i].coef_gmax = (rows[i].all_max == gmax) ? cg : 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    rows[i].coef_gmax = (rows[i].all_max == gmax) ? cg : 0.f;
+    compact[i] = make_compact(rows[i]);
+  }
+}
+
+// Multi-block form of the second half of bh_merge_kernel for the tensor-core path (one merged record per anchor,
+// max(dists) already reduced into gmax_key by the re-rank kernel).  Per-block partial sums go to `partials`
+// [gridDim.x][5] = {sum dists, sum hardest_pos, sum hardest_neg, filler share, positions holding the max};
+// bh_stats_kernel folds them in a fixed order.
+template <bool COSINE>
+__global__ void __launch_bounds__(256) bh_finalize_kernel(const BhRec* __restrict__ recs, int B, float alpha,
+                                                          const float* __restrict__ dloss,
+                                                          const unsigned long long* __restrict__ gmax_key,
+                                                          float* __restrict__ loss, int32_t* __restrict__ pos_idx_out,
+                                                          int32_t* __restrict__ neg_idx_out, BhRow* __restrict__ rows,
+                                                          int4* __restrict__ compact, double* __restrict__ partials) {
+  __shared__ double red[32];
+  const uint32_t gmax_o = (uint32_t)(*gmax_key >> 32);
+  const float gmax = __uint_as_float((gmax_o & 0x80000000u) ? (gmax_o ^ 0x80000000u) : ~gmax_o);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double s_d = 0.0, s_hp = 0.0, s_hn = 0.0, s_gm = 0.0, s_cnt = 0.0;
+  if (i < B) {
+    const BhRec q = recs[i];
+    BhRow r;
+    r.pos_val = q.pos_val; r.neg_val = q.neg_val; r.pos_idx = q.pos_idx; r.neg_idx = q.neg_idx;
+    r.pos_cnt = q.pos_cnt; r.neg_cnt = q.neg_cnt; r.all_max = q.all_max; r.all_idx = q.all_idx; r.all_cnt = q.all_cnt;
+    const int n_pos = q.n_pos, n_non = B - n_pos;
+    const float fill_p = COSINE ? 1.f : 0.f, fill_n = COSINE ? -1.f : gmax;
+    float hp = r.pos_val, hn = r.neg_val;
+    int tie_p = r.pos_cnt, tie_n = r.neg_cnt, pidx = r.pos_idx, nidx = r.neg_idx;
+    if (n_non > 0) {
+      if (r.pos_cnt == 0 || (COSINE ? fill_p < hp : fill_p > hp)) { hp = fill_p; tie_p = n_non; pidx = -1; r.pos_cnt = 0; }
+      else if (fill_p == hp) tie_p += n_non;
+    }
+    if (n_pos > 0) {
+      if (r.neg_cnt == 0 || (COSINE ? fill_n > hn : fill_n < hn)) { hn = fill_n; tie_n = n_pos; nidx = -1; r.neg_cnt = 0; }
+      else if (fill_n == hn) tie_n += n_pos;
+    }
+    const float basic = COSINE ? __fadd_rn(__fsub_rn(hn, hp), alpha) : __fsub_rn(__fadd_rn(hp, alpha), hn);
+    loss[i] = fmaxf(basic, 0.f);
+    if (pos_idx_out) pos_idx_out[i] = pidx;
+    if (neg_idx_out) neg_idx_out[i] = nidx;
+    const float g = basic >= 0.f ? (dloss ? dloss[i] : 1.f / (float)B) : 0.f;
+    r.coef_pos = r.pos_cnt > 0 ? (COSINE ? -g : g) / (float)tie_p : 0.f;
+    r.coef_neg = r.neg_cnt > 0 ? (COSINE ? g : -g) / (float)tie_n : 0.f;
+    r.pos_idx = pidx;
+    r.neg_idx = nidx;
+    r.coef_gmax = (!COSINE && r.all_max == gmax) ? 1.f : 0.f;   // flag: bh_grad_kernel substitutes the real share
+    rows[i] = r;
+    compact[i] = make_compact(r);
+    s_d = (double)q.row_sum;
+    s_hp = (double)hp;
+    s_hn = (double)hn;
+    if (!COSINE && n_pos > 0 && hn == gmax) s_gm = (double)(-g) * (double)n_pos / (double)tie_n;
+    if (r.all_max == gmax) s_cnt = (double)r.all_cnt;
+  }
+  const double t_d = block_sum(s_d, red), t_hp = block_sum(s_hp, red), t_hn = block_sum(s_hn, red);
+  const double t_gm = block_sum(s_gm, red), t_cnt = block_sum(s_cnt, red);
+  if (threadIdx.x == 0) {
+    double* o = partials + (size_t)blockIdx.x * 5;
+    o[0] = t_d; o[1] = t_hp; o[2] = t_hn; o[3] = t_gm; o[4] = t_cnt;
+  }
+}
+
+// one warp: partials -> stats [4] and the per-position share of the max(dists) filler gradient
+__global__ void bh_stats_kernel(const double* __restrict__ partials, int n_parts, int B,
+                                const unsigned long long* __restrict__ gmax_key, float* __restrict__ stats,
+                                float* __restrict__ cg_out) {
+  const int lane = threadIdx.x;
+  double t[5] = {0, 0, 0, 0, 0};
+  for (int p = lane; p < n_parts; p += 32)
+    for (int k = 0; k < 5; ++k) t[k] += partials[(size_t)p * 5 + k];
+  for (int o = 16; o >= 1; o >>= 1)
+    for (int k = 0; k < 5; ++k) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
+  if (lane == 0) {
+    const uint32_t gmax_o = (uint32_t)(*gmax_key >> 32);
+    stats[0] = (float)(t[0] / ((double)B * (double)B));
+    stats[1] = (float)(t[1] / (double)B);
+    stats[2] = (float)(t[2] / (double)B);
+    stats[3] = __uint_as_float((gmax_o & 0x80000000u) ? (gmax_o ^ 0x80000000u) : ~gmax_o);
+    *cg_out = t[4] > 0.0 ? (float)(t[3] / t[4]) : 0.f;
+  }
 }
 
 // canonical dist(r, j) recomputed by one warp (tie resolution)
@@ -255,69 +348,85 @@ __device__ __forceinline__ void axpy_row(float (&acc)[BH_MAX_KD], float w, const
   }
 }
 
+constexpr int BH_GRAD_WARPS = 8;
+constexpr int BH_GRAD_CHUNK = 1024;   // compact records staged per pass (16 KB)
+
 template <bool COSINE>
-__global__ void __launch_bounds__(128) bh_grad_kernel(const float* __restrict__ x,
-                                                      const int32_t* __restrict__ labels, int B, int D,
-                                                      const float* __restrict__ aux,   // inv norm | sum of squares
-                                                      const BhRow* __restrict__ rows, float* __restrict__ demb) {
+__global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_grad_kernel(const float* __restrict__ x,
+                                                                     const int32_t* __restrict__ labels, int B, int D,
+                                                                     const float* __restrict__ aux,   // inv norm | sum sq
+                                                                     const BhRow* __restrict__ rows,
+                                                                     const int4* __restrict__ compact,
+                                                                     const float* __restrict__ cg_dev,
+                                                                     float* __restrict__ demb) {
+  __shared__ int4 s_c[BH_GRAD_CHUNK];
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= B) return;
+  const int r = blockIdx.x * BH_GRAD_WARPS + (threadIdx.x >> 5);
+  const bool active = r < B;
   float acc[BH_MAX_KD];
 #pragma unroll
   for (int c = 0; c < BH_MAX_KD; ++c) acc[c] = 0.f;
-  const BhRow me = rows[r];
-  const int my_lab = labels[r];
+  BhRow me;
+  me.pos_val = me.neg_val = me.coef_pos = me.coef_neg = me.all_max = me.coef_gmax = 0.f;
+  me.pos_idx = me.neg_idx = me.all_idx = -1;
+  me.pos_cnt = me.neg_cnt = me.all_cnt = 0;
+  if (active) me = rows[r];
+  const int my_lab = active ? labels[r] : -1;
+  if (cg_dev) me.coef_gmax = me.coef_gmax != 0.f ? *cg_dev : 0.f;   // multi-block finalize leaves a flag here
 
   // --- own row: tied real positive / negative columns
-  if (me.coef_pos != 0.f) {
+  if (active && me.coef_pos != 0.f) {
     if (me.pos_cnt == 1) axpy_row<COSINE>(acc, me.coef_pos, x, aux, D, r, me.pos_idx);
     else
       for (int j = 0; j < B; ++j)
         if (labels[j] == my_lab && warp_dist<COSINE>(x, aux, D, r, j) == me.pos_val)
           axpy_row<COSINE>(acc, me.coef_pos, x, aux, D, r, j);
   }
-  if (me.coef_neg != 0.f) {
+  if (active && me.coef_neg != 0.f) {
     if (me.neg_cnt == 1) axpy_row<COSINE>(acc, me.coef_neg, x, aux, D, r, me.neg_idx);
     else
       for (int j = 0; j < B; ++j)
         if (labels[j] != my_lab && warp_dist<COSINE>(x, aux, D, r, j) == me.neg_val)
           axpy_row<COSINE>(acc, me.coef_neg, x, aux, D, r, j);
   }
-  // --- rows that mined r
-  for (int j0 = 0; j0 < B; j0 += 32) {
-    const int j = j0 + lane;
-    float wp = 0.f, wn = 0.f;
-    bool tied_p = false, tied_n = false;
-    if (j < B) {
-      const BhRow o = rows[j];
-      if (o.coef_pos != 0.f) {
-        if (o.pos_cnt == 1) wp = (o.pos_idx == r) ? o.coef_pos : 0.f;
-        else tied_p = true;
+  // --- rows that mined r: the block stages the compact records once and its 8 warps scan them
+  for (int chunk0 = 0; chunk0 < B; chunk0 += BH_GRAD_CHUNK) {
+    const int n_chunk = min(BH_GRAD_CHUNK, B - chunk0);
+    __syncthreads();
+    for (int t = threadIdx.x; t < n_chunk; t += blockDim.x) s_c[t] = compact[chunk0 + t];
+    __syncthreads();
+    if (!active) continue;
+    for (int j0 = 0; j0 < n_chunk; j0 += 32) {
+      const int jl = j0 + lane;
+      float w0 = 0.f;
+      bool tied_p = false, tied_n = false;
+      if (jl < n_chunk) {
+        const int4 c = s_c[jl];
+        if (c.x == r) w0 += __int_as_float(c.z);
+        if (c.y == r) w0 += __int_as_float(c.w);
+        tied_p = c.x == -2;
+        tied_n = c.y == -2;
       }
-      if (o.coef_neg != 0.f) {
-        if (o.neg_cnt == 1) wn = (o.neg_idx == r) ? o.coef_neg : 0.f;
-        else tied_n = true;
+      unsigned hit = __ballot_sync(0xffffffffu, w0 != 0.f || tied_p || tied_n);
+      while (hit) {
+        const int src = __ffs((int)hit) - 1;
+        hit &= hit - 1;
+        const int jj = chunk0 + j0 + src;
+        float w = __shfl_sync(0xffffffffu, w0, src);
+        const bool tp = __shfl_sync(0xffffffffu, (int)tied_p, src) != 0, tn = __shfl_sync(0xffffffffu, (int)tied_n, src) != 0;
+        if (tp || tn) {
+          const BhRow o = rows[jj];
+          const float dv = warp_dist<COSINE>(x, aux, D, jj, r);
+          const bool same = labels[jj] == my_lab;
+          if (tp && same && dv == o.pos_val) w += o.coef_pos;
+          if (tn && !same && dv == o.neg_val) w += o.coef_neg;
+        }
+        // d dist(jj, r) / d x_r : cosine n_jj ; euclid 2 (x_r - x_jj)  -> same helper with roles (r, jj)
+        if (w != 0.f) axpy_row<COSINE>(acc, w, x, aux, D, r, jj);
       }
-    }
-    unsigned hit = __ballot_sync(0xffffffffu, wp != 0.f || wn != 0.f || tied_p || tied_n);
-    while (hit) {
-      const int src = __ffs((int)hit) - 1;
-      hit &= hit - 1;
-      const int jj = j0 + src;
-      float w = __shfl_sync(0xffffffffu, wp + wn, src);
-      const bool tp = __shfl_sync(0xffffffffu, (int)tied_p, src) != 0, tn = __shfl_sync(0xffffffffu, (int)tied_n, src) != 0;
-      if (tp || tn) {
-        const BhRow o = rows[jj];
-        const float dv = warp_dist<COSINE>(x, aux, D, jj, r);
-        const bool same = labels[jj] == my_lab;
-        if (tp && same && dv == o.pos_val) w += o.coef_pos;
-        if (tn && !same && dv == o.neg_val) w += o.coef_neg;
-      }
-      // d dist(jj, r) / d x_r : cosine n_jj ; euclid 2 (x_r - x_jj)  -> same helper with roles (r, jj)
-      if (w != 0.f) axpy_row<COSINE>(acc, w, x, aux, D, r, jj);
     }
   }
+  if (!active) return;
   // --- euclid: gradient through the max(dists) filler (both (r, j) and (j, r) hold the max)
   if (!COSINE && me.coef_gmax != 0.f) {
     if (me.all_cnt == 1) axpy_row<COSINE>(acc, 2.f * me.coef_gmax, x, aux, D, r, me.all_idx);
@@ -389,6 +498,9 @@ struct BhWorkspace {
   size_t rec_cap = 0;
   BhRow* rows = nullptr;
   float* aux = nullptr;
+  int4* compact = nullptr;
+  double* partials = nullptr;              // [ceil(rows / 256)][5]
+  unsigned long long* gmax_key = nullptr;  // [1] + float cg right behind it
   size_t row_cap = 0;
   int ensure(size_t n_rec, size_t n_rows) {
     if (n_rec > rec_cap) {
@@ -401,11 +513,18 @@ struct BhWorkspace {
     if (n_rows > row_cap) {
       cudaFree(rows);
       cudaFree(aux);
+      cudaFree(compact);
+      cudaFree(partials);
       rows = nullptr;
       aux = nullptr;
+      compact = nullptr;
+      partials = nullptr;
       row_cap = 0;
       DIF_CUDA_OK(cudaMalloc((void**)&rows, n_rows * sizeof(BhRow)));
       DIF_CUDA_OK(cudaMalloc((void**)&aux, n_rows * sizeof(float)));
+      DIF_CUDA_OK(cudaMalloc((void**)&compact, n_rows * sizeof(int4)));
+      DIF_CUDA_OK(cudaMalloc((void**)&partials, ((n_rows + 255) / 256) * 5 * sizeof(double)));
+      if (!gmax_key) DIF_CUDA_OK(cudaMalloc((void**)&gmax_key, 16));
       row_cap = n_rows;
     }
     return DIF_OK;
@@ -433,6 +552,8 @@ struct BhHostStage {
 };
 static thread_local BhHostStage g_bh_stage;
 
+static int g_bh_force_path = 0;   // 0 auto, 1 CUDA-core miner, 2 tensor-core miner (tests)
+
 template <bool COSINE>
 static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D, float alpha, float* loss,
                           int32_t* pos_idx, int32_t* neg_idx, float* stats, const float* dloss, float* demb,
@@ -453,13 +574,31 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
     DIF_CUDA_OK(cudaFuncSetAttribute(bh_mine_kernel<COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  bh_mine_kernel<COSINE><<<dim3(row_blocks, splits), BH_WARPS * 32, smem, st>>>(emb, labels, B, D, cols, g_ws.recs, g_ws.aux);
-  DIF_LAUNCH_OK();
-  const int merge_threads = std::min(1024, std::max(64, (B + 31) / 32 * 32));
-  bh_merge_kernel<COSINE><<<1, merge_threads, 0, st>>>(g_ws.recs, splits, B, alpha, dloss, loss, pos_idx, neg_idx, stats, g_ws.rows);
-  DIF_LAUNCH_OK();
+  // large batches: tensor-core filter + canonical re-rank (bh_tc.cu), then a multi-block finalize
+  const bool tensor_path = (g_bh_force_path == 2 || (g_bh_force_path == 0 && B >= 512)) && D >= 32 && D % 4 == 0;
+  const float* cg_dev = nullptr;
+  if (tensor_path) {
+    DIF_CUDA_OK(cudaMemsetAsync(g_ws.gmax_key, 0, 16, st));
+    if (int rc = bh_mine_tensor<COSINE>(emb, labels, B, D, g_ws.recs, g_ws.aux, g_ws.gmax_key, st)) return rc;
+    const int fb = (B + 255) / 256;
+    bh_finalize_kernel<COSINE><<<fb, 256, 0, st>>>(g_ws.recs, B, alpha, dloss, g_ws.gmax_key, loss, pos_idx, neg_idx,
+                                                  g_ws.rows, g_ws.compact, g_ws.partials);
+    DIF_LAUNCH_OK();
+    float* cg = reinterpret_cast<float*>(g_ws.gmax_key + 1);
+    bh_stats_kernel<<<1, 32, 0, st>>>(g_ws.partials, fb, B, g_ws.gmax_key, stats, cg);
+    DIF_LAUNCH_OK();
+    cg_dev = cg;
+  } else {
+    bh_mine_kernel<COSINE><<<dim3(row_blocks, splits), BH_WARPS * 32, smem, st>>>(emb, labels, B, D, cols, g_ws.recs, g_ws.aux);
+    DIF_LAUNCH_OK();
+    const int merge_threads = std::min(1024, std::max(64, (B + 31) / 32 * 32));
+    bh_merge_kernel<COSINE><<<1, merge_threads, 0, st>>>(g_ws.recs, splits, B, alpha, dloss, loss, pos_idx, neg_idx, stats,
+                                                       g_ws.rows, g_ws.compact);
+    DIF_LAUNCH_OK();
+  }
   if (demb) {
-    bh_grad_kernel<COSINE><<<(B + 3) / 4, 128, 0, st>>>(emb, labels, B, D, g_ws.aux, g_ws.rows, demb);
+    bh_grad_kernel<COSINE><<<(B + BH_GRAD_WARPS - 1) / BH_GRAD_WARPS, BH_GRAD_WARPS * 32, 0, st>>>(
+        emb, labels, B, D, g_ws.aux, g_ws.rows, g_ws.compact, cg_dev, demb);
     DIF_LAUNCH_OK();
   }
   return DIF_OK;
@@ -786,6 +925,12 @@ int dif_batch_all(const float* emb, const int32_t* labels, int B, int D, float a
     else ba_grad_kernel<16><<<row_blocks, BH_WARPS * 32, smem, st>>>(emb, labels, B, D, g_ba.rows, alpha, demb);
     DIF_LAUNCH_OK();
   }
+  return DIF_OK;
+}
+
+int dif_batch_hard_set_path(int path) {
+  DIF_REQUIRE(path >= 0 && path <= 2, DIF_ERR_INVALID, "dif_batch_hard_set_path: 0 auto, 1 CUDA-core miner, 2 tensor-core miner");
+  g_bh_force_path = path;
   return DIF_OK;
 }
 

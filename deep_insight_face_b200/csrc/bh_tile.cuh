@@ -95,6 +95,12 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ x, int B, i
 }
 
 
+// Tensor-core miner (bh_tc.cu): writes ONE merged record per anchor (recs [B]) and aux [B] (inverse norm |
+// sum of squares) - the same data bh_mine_kernel + the split merge produce, bit for bit.
+template <bool COSINE>
+int bh_mine_tensor(const float* emb, const int32_t* labels, int B, int D, BhRec* recs, float* aux,
+                   unsigned long long* gmax_key, cudaStream_t st);
+
 // One warp step: canonical dot products of anchors (warp*8 .. +7) with columns (j0 .. j0+3) of the staged
 // tiles; returns the value of entry (lane >> 2, lane & 3).
 __device__ __forceinline__ float tile_step_dot(const float* __restrict__ sa, const float* __restrict__ sb, int D, int kd,

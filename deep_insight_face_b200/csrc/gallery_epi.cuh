@@ -145,7 +145,7 @@ struct TopkEpi {
     refresh();
   }
 
-  __device__ __forceinline__ void begin_tile() {
+  __device__ __forceinline__ void begin_tile(int) {
     // the bound improves like log(columns seen): look at tiles 1, 2, 4, 8, 16, ... of the item
     ++tiles_seen;
     if ((tiles_seen & (tiles_seen - 1)) == 0) refresh_maxima();

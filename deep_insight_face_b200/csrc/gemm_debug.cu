@@ -18,7 +18,7 @@ struct SumEpi {
   float acc_sum;
   __device__ SumEpi(const Params& pp, uint8_t*, int) : p(pp), acc_sum(0.f) {}
   __device__ void begin_item(int, int, int) { acc_sum = 0.f; }
-  __device__ void begin_tile() {}
+  __device__ void begin_tile(int) {}
   __device__ void consume(int, const uint32_t (&acc)[32], uint32_t, uint32_t (&)[32]) {
     float m = __uint_as_float(acc[0]);
 #pragma unroll

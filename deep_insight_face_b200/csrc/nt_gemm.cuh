@@ -93,7 +93,7 @@ inline bool plan_gemm_smem(int k_chunks, int epi_smem, GemmSmemPlan* out) {
 //     __device__ Epi(const Params&, uint8_t* smem, int row_in_block);
 //     // split = index of the (K split, B-tile range) slot of this item: k_split * n_splits + n_split
 //     __device__ void begin_item(int m_row /*global A row of this thread*/, int split, int col_begin);
-//     __device__ void begin_tile();
+//     __device__ void begin_tile(int col_begin);   // called by all 128 epilogue threads before the tile is ready
 //     // fp32 bits of columns col0..col0+31 of this thread's row; taddr = TMEM address of column col0
 //     // for this warp (a slow path may re-read single columns with tmem_ld1).  `pending` is the
 //     // register block of the NEXT chunk, whose tcgen05.ld may still be in flight: code that could
@@ -300,7 +300,7 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
       for (int t = t0; t < t1; ++t, ++tc) {
         const int buf = tc % NBUF;
         const uint32_t aph = (tc / NBUF) & 1u;
-        epi.begin_tile();
+        epi.begin_tile(t * BN);
         mbar_wait(&acc_full[buf], aph);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * BN);

@@ -20,7 +20,7 @@ struct StoreEpi {
   __device__ void begin_item(int m, int slot, int) {
     row_ptr = m < p.M ? p.C + (size_t)(slot / p.n_splits) * p.slot_stride + (size_t)m * p.ldc : nullptr;
   }
-  __device__ void begin_tile() {}
+  __device__ void begin_tile(int) {}
   __device__ void consume(int col0, const uint32_t (&acc)[32], uint32_t, uint32_t (&)[32]) {
     if (!row_ptr) return;
     if (col0 + 32 <= p.N && (p.ldc & 3) == 0) {

@@ -199,3 +199,43 @@ def test_batch_hard_step_graph(gpu):
         assert np.array_equal(step.pos_idx.cpu().numpy(), want["pos_idx"])
         close(loss.cpu().numpy(), want["loss"])
         close(grad.cpu().numpy(), want["grad"])
+
+
+@pytest.fixture
+def tensor_path(lib):
+    from deep_insight_face_b200 import _ffi
+
+    _ffi.check(lib.dif_batch_hard_set_path(2))
+    yield
+    _ffi.check(lib.dif_batch_hard_set_path(0))
+
+
+@pytest.mark.parametrize("P,K,D", [(18, 4, 128), (33, 3, 100), (130, 4, 64), (256, 4, 128), (100, 5, 512)])
+@pytest.mark.parametrize("variant", ["cosine", "euclid"])
+def test_tensor_core_miner_matches_oracle(gpu, tensor_path, P, K, D, variant):
+    """The tcgen05 filter + canonical re-rank path (default for B >= 512), forced on at every size."""
+    from deep_insight_face_b200.common.losses import BatchHardTripletLoss, BatchHardTripletLossEuclidean
+    from oracle import losses_oracle as lo
+
+    emb, lab = pk_batch(P, K, D, 1.0)
+    if variant == "cosine":
+        run_case(BatchHardTripletLoss, lo.batch_hard_cosine, emb, lab, 0.35, onehot=False)
+    else:
+        run_case(BatchHardTripletLossEuclidean, lo.batch_hard_euclidean, emb, lab, 0.3 * D, onehot=False)
+
+
+def test_tensor_core_miner_ties_and_single_identity(gpu, tensor_path):
+    from deep_insight_face_b200.common.losses import BatchHardTripletLoss, BatchHardTripletLossEuclidean
+    from oracle import losses_oracle as lo
+
+    rng = np.random.default_rng(2)
+    emb = rng.standard_normal((48, 64)).astype(np.float32)
+    for a, b in ((5, 4), (9, 8), (10, 8), (11, 8), (12, 8), (13, 8)):   # six copies of row 8: overflows a 4-slot list
+        emb[a] = emb[b]
+    emb[2] = 0.0
+    lab = np.repeat(np.arange(6), 8)
+    run_case(BatchHardTripletLoss, lo.batch_hard_cosine, emb, lab, 5.0, onehot=False)
+    run_case(BatchHardTripletLossEuclidean, lo.batch_hard_euclidean, emb, lab, 5.0, onehot=False)
+    one = np.zeros(48, dtype=np.int64)
+    run_case(BatchHardTripletLoss, lo.batch_hard_cosine, emb, one, 0.35, onehot=False)
+    run_case(BatchHardTripletLossEuclidean, lo.batch_hard_euclidean, emb, one, 500.0, onehot=False)
