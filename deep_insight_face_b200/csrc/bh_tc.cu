@@ -97,41 +97,65 @@ struct MineEpi {
     return COSINE ? a : __fsub_rn(__fadd_rn(my_sq, s_sq[jl]), __fmul_rn(2.f, a));
   }
 
-  __device__ __forceinline__ void consume(int col0, const uint32_t (&acc)[32], uint32_t, uint32_t (&pending)[32]) {
-    const bool row_ok = my_row < p.B;
+  // One chunk of 32 columns.  Fast path (branch-free): masked running extremes of the chunk and one test against
+  // the worst kept candidate of each class; only if some lane beats a threshold does the warp build per-element
+  // hit masks and insert.  CHECK = the chunk straddles the end of the batch (columns >= B are TMA zero fill).
+  template <bool CHECK>
+  __device__ __forceinline__ void consume_impl(int col0, const uint32_t (&acc)[32], uint32_t (&pending)[32]) {
     const int base = col0 - tile0;
-    // thresholds: the current worst kept candidate of each class
-    const bool p_open = pi[kMineM - 1] < 0, n_open = ni[kMineM - 1] < 0, a_open = ai[kMineM - 1] < 0;
-    const float p_thr = pv[kMineM - 1], n_thr = nv[kMineM - 1], a_thr = av[kMineM - 1];
+    const float kWorstP = COSINE ? INFINITY : -INFINITY, kWorstN = COSINE ? -INFINITY : INFINITY;
+    // an open list accepts anything: its threshold is the worst possible value
+    const float p_thr = pi[kMineM - 1] < 0 ? kWorstP : pv[kMineM - 1];
+    const float n_thr = ni[kMineM - 1] < 0 ? kWorstN : nv[kMineM - 1];
+    const float a_thr = ai[kMineM - 1] < 0 ? -INFINITY : av[kMineM - 1];
     float dv[32];
-    uint32_t mask = 0;
+    float m_pos = kWorstP, m_neg = kWorstN, m_all = -INFINITY, rs = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       dv[i] = dist_of(acc[i], base + i);
-      if (row_ok && col0 + i < p.B) {
-        row_sum += dv[i];
-        const bool same = s_lab[base + i] == my_lab;
-        n_pos += same ? 1 : 0;
-        bool hit = same ? (p_open || better<COSINE>(dv[i], p_thr)) : (n_open || better<!COSINE>(dv[i], n_thr));
-        if (!COSINE) hit = hit || a_open || dv[i] > a_thr;
-        else av[0] = fmaxf(av[0], dv[i]);   // cosine: running row maximum for the max(dists) statistic
-        mask |= hit ? (1u << i) : 0u;
-      }
+      const bool valid = !CHECK || (col0 + i < p.B);
+      const bool same = s_lab[base + i] == my_lab;
+      const float vp = (valid && same) ? dv[i] : kWorstP;
+      const float vn = (valid && !same) ? dv[i] : kWorstN;
+      m_pos = COSINE ? fminf(m_pos, vp) : fmaxf(m_pos, vp);
+      m_neg = COSINE ? fmaxf(m_neg, vn) : fminf(m_neg, vn);
+      m_all = fmaxf(m_all, valid ? dv[i] : -INFINITY);
+      rs += valid ? dv[i] : 0.f;
     }
-    if (__any_sync(0xffffffffu, mask != 0u)) {
+    row_sum += rs;
+    if (COSINE) av[0] = fmaxf(av[0], m_all);   // running row maximum for the max(dists) statistic
+    const bool lane_hit = better<COSINE>(m_pos, p_thr) || better<!COSINE>(m_neg, n_thr) || (!COSINE && m_all > a_thr);
+    if (__any_sync(0xffffffffu, lane_hit)) {
       tmem_ld_wait(pending);   // warp-uniform: no tcgen05.ld in flight while registers are shuffled below
-      while (mask) {           // per-lane loop, no collectives inside
-        const int i = __ffs((int)mask) - 1;
-        mask &= mask - 1;
-        float d = 0.f;         // registers cannot be indexed dynamically: select chain
+      if (lane_hit) {
+        uint32_t mask = 0;
 #pragma unroll
-        for (int t = 0; t < 32; ++t) d = (t == i) ? dv[t] : d;
-        const int j = col0 + i;
-        if (s_lab[base + i] == my_lab) cand_insert<COSINE>(pv, pi, d, j);
-        else cand_insert<!COSINE>(nv, ni, d, j);
-        if (!COSINE) cand_insert<false>(av, ai, d, j);
+        for (int i = 0; i < 32; ++i) {
+          const bool valid = !CHECK || (col0 + i < p.B);
+          const bool same = s_lab[base + i] == my_lab;
+          bool hit = same ? better<COSINE>(dv[i], p_thr) : better<!COSINE>(dv[i], n_thr);
+          if (!COSINE) hit = hit || dv[i] > a_thr;
+          mask |= (valid && hit) ? (1u << i) : 0u;
+        }
+        while (mask) {           // per-lane loop, no collectives inside
+          const int i = __ffs((int)mask) - 1;
+          mask &= mask - 1;
+          float d = 0.f;         // registers cannot be indexed dynamically: select chain
+#pragma unroll
+          for (int t = 0; t < 32; ++t) d = (t == i) ? dv[t] : d;
+          const int j = col0 + i;
+          if (s_lab[base + i] == my_lab) cand_insert<COSINE>(pv, pi, d, j);
+          else cand_insert<!COSINE>(nv, ni, d, j);
+          if (!COSINE) cand_insert<false>(av, ai, d, j);
+        }
       }
     }
+  }
+
+  __device__ __forceinline__ void consume(int col0, const uint32_t (&acc)[32], uint32_t, uint32_t (&pending)[32]) {
+    if (col0 >= p.B) return;                       // warp-uniform: the whole chunk is zero fill
+    if (col0 + 32 <= p.B) consume_impl<false>(col0, acc, pending);
+    else consume_impl<true>(col0, acc, pending);
   }
 
   __device__ void end_item(int m_row, int slot) {
@@ -144,7 +168,7 @@ struct MineEpi {
       c.av[s] = av[s]; c.ai[s] = ai[s];
     }
     c.row_sum = row_sum;
-    c.n_pos = n_pos;
+    c.n_pos = 0;   // counted by the re-rank kernel
     p.cand[(size_t)slot * p.B + m_row] = c;
   }
 };
@@ -266,10 +290,12 @@ __global__ void __launch_bounds__(128) bh_rerank_kernel(const BhCand* __restrict
     }
   }
   float rs = 0.f;
-  int np_ = 0;
-  for (int s = 0; s < n_slots; ++s) {
-    rs += cand[(size_t)s * B + r].row_sum;
-    np_ += cand[(size_t)s * B + r].n_pos;
+  for (int s = 0; s < n_slots; ++s) rs += cand[(size_t)s * B + r].row_sum;
+  int np_ = 0;   // positives of this anchor (itself included): label matches over the batch
+  {
+    const int my_l = labels[r];
+    for (int j = lane; j < B; j += 32) np_ += labels[j] == my_l ? 1 : 0;
+    for (int o = 16; o >= 1; o >>= 1) np_ += __shfl_xor_sync(0xffffffffu, np_, o);
   }
   rec.row_sum = rs;
   rec.n_pos = np_;
