@@ -149,6 +149,7 @@ def secondary_metrics(torch, device):
         return e0.elapsed_time(e1) / iters
 
     for name, P, K, D, iters in (("c1_batch_hard_B72_D128", 18, 4, 128, 300), ("c4_batch_hard_B4096_D128", 1024, 4, 128, 30)):
+        B = P * K
         cent = rng.standard_normal((P, D)).astype(np.float32)
         emb = (np.repeat(cent, K, 0) + 1.0 * rng.standard_normal((P * K, D))).astype(np.float32)
         lab = np.repeat(np.arange(P), K).astype(np.int32)
@@ -172,12 +173,13 @@ def secondary_metrics(torch, device):
         for _ in range(n_cpu):
             lo.batch_hard_cosine(lab, emb, 0.35)
         cpu_ms = (time.perf_counter() - t0) / n_cpu * 1e3
-        B = P * K
         out[name] = {"steps_per_s": 1e3 / ms, "ms_per_step": ms, "ungraphed_call_steps_per_s": 1e3 / ms_call,
                      "e2e_steps_per_s": 1e3 / host_ms,
-                     "kernels_per_step": 3, "alg_gflop_fwd": 2.0 * B * B * D / 1e9,
-                     "cpu_oracle_steps_per_s": 1e3 / cpu_ms, "note": "fwd + bwd, canonical fp32 CUDA-core mining; steps_per_s = CUDA-graphed BatchHardStep, "
-                             "e2e = numpy in/out through dif_batch_hard_host"}
+                     "path": "tcgen05 3xTF32 filter + canonical re-rank (6 kernels)" if B >= 512 else
+                             "canonical fp32 CUDA-core miner (3 kernels)",
+                     "alg_gflop_fwd": 2.0 * B * B * D / 1e9,
+                     "cpu_oracle_steps_per_s": 1e3 / cpu_ms, "note": "fwd + bwd; steps_per_s = CUDA-graphed BatchHardStep, e2e = numpy in/out through "
+                             "dif_batch_hard_host"}
     B, C, D = 512, 10000, 512
     X = torch.randn(B, D, device=device)
     W = 0.01 * torch.randn(C, D, device=device)
