@@ -358,9 +358,15 @@ def main():
     # TF32 is not in MEASURED_PEAKS.json: the TF32 peak is taken as measured bf16 / 2
     tensor_peak = peaks["bf16_tflops"] if args.precision == "bf16" else peaks["bf16_tflops"] / 2.0
     passes = 3 if args.precision == "tf32x3" else 1
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` captures of this exact
+    # workload (profiles/r01_ncu_search_*_c3*.md: dram__bytes_read.sum + dram__bytes_write.sum); other shapes: null
+    ncu_traffic = {"tf32x3": 5.725465e9 + 16.753408e6, "bf16": 1.258923e9 + 16.037376e6}
+    traffic = ncu_traffic.get(args.precision) if (args.workload == "c3" and world == 1 and not args.rows
+                                                  and not args.queries) else None
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
-        "traffic": None,
+        "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
+        "algorithmic_bytes": float(rows_local) * D * (2 if args.precision == "bf16" else (8 if args.precision == "tf32x3" else 4)),
         "kernel": "nt_gemm_rowscan_kernel<TopkEpi> (tcgen05/TMA GEMM + fused per-query top-k)",
         "kernel_ms": main_res["kernel_ms"],
         "peak_source": f"{peaks['source']} bf16 burst" + ("" if args.precision == "bf16" else " / 2 (TF32 not measured)"),
