@@ -354,6 +354,7 @@ struct dif_gallery {
   int opt_force_fallback = 0;
   int opt_resident = -1;   // -1 auto, 0 never, 1 whenever it fits
   int opt_splits = 0;      // 0 auto
+  int opt_l2_prefetch = 0;   // measured: no gain at C3 (tiles are L2 hits already), so off by default
 };
 
 namespace {
@@ -469,6 +470,8 @@ int dif_gallery_set_option(dif_gallery_t* g, const char* name, int value) {
     g->opt_force_fallback = value != 0;
   } else if (!strcmp(name, "resident_queries")) {
     g->opt_resident = value < 0 ? -1 : (value != 0);
+  } else if (!strcmp(name, "l2_prefetch")) {
+    g->opt_l2_prefetch = value != 0;
   } else if (!strcmp(name, "splits")) {
     g->opt_splits = value < 0 ? 0 : value;
   } else {
@@ -603,6 +606,7 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
     splits = std::min(splits, 512);
     if (g->opt_splits > 0) splits = std::min(g->opt_splits, shape.n_tiles);
   }
+  shape.l2_prefetch = g->opt_l2_prefetch;
   shape.n_splits = splits;
   shape.tiles_per_split = shape.n_tiles > 0 ? (shape.n_tiles + splits - 1) / splits : 0;
   if (shape.tiles_per_split > 0) shape.n_splits = splits = (shape.n_tiles + shape.tiles_per_split - 1) / shape.tiles_per_split;

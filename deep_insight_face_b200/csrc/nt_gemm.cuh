@@ -51,6 +51,7 @@ struct GemmShape {
   int stages;           // smem ring depth (host-computed from the shared-memory budget)
   int k_splits;         // the K range is cut into k_splits pieces -> items *= k_splits (0/1: no split)
   int chunks_per_ksplit;
+  int l2_prefetch;      // 1: the producer prefetches B tiles into L2 two tiles ahead
 };
 
 template <int PREC, int BN, int CTAS>
@@ -202,6 +203,15 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
         }
         for (int t = t0; t < t1; ++t) {
           const int b_row = t * BN + (int)cta_rank * (BN / CTAS);
+          // warm L2 with this CTA's rows of the B tile two tiles ahead: the ring only buffers ~1.3 us of MMA work,
+          // less than a DRAM round trip under load, so first-touch tiles would otherwise stall the tensor pipe
+          if (shape.l2_prefetch && t + 2 < t1) {
+            const int p_row = (t + 2) * BN + (int)cta_rank * (BN / CTAS);
+            for (int kc = kc0; kc < kc1; ++kc) {
+              tma_prefetch_l2_2d(&tm_b_hi, kc * PT::kChunkElems, p_row);
+              if (PT::kPlanes == 2) tma_prefetch_l2_2d(&tm_b_lo, kc * PT::kChunkElems, p_row);
+            }
+          }
           for (int kc = kc0; kc < kc1; ++kc, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;

@@ -72,7 +72,8 @@ int dif_gallery_set_id_base(dif_gallery_t* g, int64_t id_base); /* default ids =
 int64_t dif_gallery_size(const dif_gallery_t* g);
 /* tuning / test knobs: "gemm_ctas" = 1 | 2 (CTA pair, default); "force_fallback" = 0 | 1 (send every
  * query through the exact brute-force path as well); "resident_queries" = -1 auto | 0 | 1 (keep the
- * query block resident in shared memory while gallery tiles stream); "splits" = 0 auto | n */
+ * query block resident in shared memory while gallery tiles stream); "splits" = 0 auto | n;
+ * "l2_prefetch" = 0 | 1 (producer prefetches gallery tiles into L2 two tiles ahead; off by default) */
 int dif_gallery_set_option(dif_gallery_t* g, const char* name, int value);
 int dif_gallery_reset(dif_gallery_t* g);
 /* scores [Q*k] fp32, ids [Q*k] int64, rows [Q*k] int32 local row index (may be NULL).
