@@ -140,12 +140,13 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 }
 
 // One block.  stats = {mean(dists), mean(hardest_pos), mean(hardest_neg), max(dists)}
+// Body shared by bh_merge_kernel (one block) and the fused small-batch kernel (every block redoes it into its own
+// shared memory; `write_out` selects the block that also writes loss / indices / statistics).
 template <bool COSINE>
-__global__ void __launch_bounds__(1024) bh_merge_kernel(const BhRec* __restrict__ recs, int n_splits, int B,
-                                                        float alpha, const float* __restrict__ dloss,
-                                                        float* __restrict__ loss, int32_t* __restrict__ pos_idx_out,
-                                                        int32_t* __restrict__ neg_idx_out, float* __restrict__ stats,
-                                                        BhRow* __restrict__ rows, int4* __restrict__ compact) {
+__device__ __forceinline__ void bh_merge_body(const BhRec* __restrict__ recs, int n_splits, int B, float alpha,
+                                              const float* __restrict__ dloss, float* __restrict__ loss,
+                                              int32_t* __restrict__ pos_idx_out, int32_t* __restrict__ neg_idx_out,
+                                              float* __restrict__ stats, BhRow* rows, int4* compact, bool write_out) {
   __shared__ double red[32];
   __shared__ unsigned long long gmax_key;   // orderable(value) << 32 | ~first row
   __shared__ int gmax_cnt_s;
@@ -205,9 +206,11 @@ __global__ void __launch_bounds__(1024) bh_merge_kernel(const BhRec* __restrict_
       else if (fill_n == hn) tie_n += n_pos;
     }
     const float basic = COSINE ? __fadd_rn(__fsub_rn(hn, hp), alpha) : __fsub_rn(__fadd_rn(hp, alpha), hn);
-    loss[i] = fmaxf(basic, 0.f);
-    if (pos_idx_out) pos_idx_out[i] = pidx;
-    if (neg_idx_out) neg_idx_out[i] = nidx;
+    if (write_out) {
+      loss[i] = fmaxf(basic, 0.f);
+      if (pos_idx_out) pos_idx_out[i] = pidx;
+      if (neg_idx_out) neg_idx_out[i] = nidx;
+    }
     sum_hp += (double)hp;
     sum_hn += (double)hn;
     // tf.maximum(basic, 0): the gradient goes to `basic` when basic >= 0
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(1024) bh_merge_kernel(const BhRec* __restrict_
   const double tot_hp = block_sum(sum_hp, red);
   const double tot_hn = block_sum(sum_hn, red);
   const double tot_gm = block_sum(gm_share, red);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && write_out) {
     stats[0] = B > 0 ? (float)(tot_d / ((double)B * (double)B)) : 0.f;
     stats[1] = B > 0 ? (float)(tot_hp / (double)B) : 0.f;
     stats[2] = B > 0 ? (float)(tot_hn / (double)B) : 0.f;
@@ -236,6 +239,15 @@ __global__ void __launch_bounds__(1024) bh_merge_kernel(const BhRec* __restrict_
     rows[i].coef_gmax = (rows[i].all_max == gmax) ? cg : 0.f;
     compact[i] = make_compact(rows[i]);
   }
+}
+
+template <bool COSINE>
+__global__ void __launch_bounds__(1024) bh_merge_kernel(const BhRec* __restrict__ recs, int n_splits, int B,
+                                                        float alpha, const float* __restrict__ dloss,
+                                                        float* __restrict__ loss, int32_t* __restrict__ pos_idx_out,
+                                                        int32_t* __restrict__ neg_idx_out, float* __restrict__ stats,
+                                                        BhRow* __restrict__ rows, int4* __restrict__ compact) {
+  bh_merge_body<COSINE>(recs, n_splits, B, alpha, dloss, loss, pos_idx_out, neg_idx_out, stats, rows, compact, true);
 }
 
 // Multi-block form of the second half of bh_merge_kernel for the tensor-core path (one merged record per anchor,
@@ -352,13 +364,10 @@ constexpr int BH_GRAD_WARPS = 8;
 constexpr int BH_GRAD_CHUNK = 1024;   // compact records staged per pass (16 KB)
 
 template <bool COSINE>
-__global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_grad_kernel(const float* __restrict__ x,
-                                                                     const int32_t* __restrict__ labels, int B, int D,
-                                                                     const float* __restrict__ aux,   // inv norm | sum sq
-                                                                     const BhRow* __restrict__ rows,
-                                                                     const int4* __restrict__ compact,
-                                                                     const float* __restrict__ cg_dev,
-                                                                     float* __restrict__ demb) {
+__device__ __forceinline__ void bh_grad_body(const float* __restrict__ x, const int32_t* __restrict__ labels, int B, int D,
+                                             const float* __restrict__ aux,   // inv norm | sum sq
+                                             const BhRow* rows, const int4* compact, const float* __restrict__ cg_dev,
+                                             float* __restrict__ demb) {
   __shared__ int4 s_c[BH_GRAD_CHUNK];
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * BH_GRAD_WARPS + (threadIdx.x >> 5);
@@ -465,6 +474,35 @@ __global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_grad_kernel(const float
       if (d < D) demb[(size_t)r * D + d] = acc[c];
     }
   }
+}
+
+template <bool COSINE>
+__global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_grad_kernel(const float* __restrict__ x,
+                                                                     const int32_t* __restrict__ labels, int B, int D,
+                                                                     const float* __restrict__ aux,
+                                                                     const BhRow* __restrict__ rows,
+                                                                     const int4* __restrict__ compact,
+                                                                     const float* __restrict__ cg_dev,
+                                                                     float* __restrict__ demb) {
+  bh_grad_body<COSINE>(x, labels, B, D, aux, rows, compact, cg_dev, demb);
+}
+
+// Small batches (B <= 256): merge + gradient in one launch.  Every block redoes the (tiny) merge of all anchors
+// into its own shared memory and then runs the gradient gather for its 8 rows; block 0 also writes the loss,
+// the mined indices and the statistics.  Saves one launch and the one-block merge kernel on the C1-size step.
+constexpr int BH_FUSED_MAX_B = 256;
+template <bool COSINE>
+__global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_merge_grad_kernel(
+    const BhRec* __restrict__ recs, int n_splits, const float* __restrict__ x, const int32_t* __restrict__ labels, int B,
+    int D, float alpha, const float* __restrict__ dloss, const float* __restrict__ aux, float* __restrict__ loss,
+    int32_t* __restrict__ pos_idx_out, int32_t* __restrict__ neg_idx_out, float* __restrict__ stats,
+    float* __restrict__ demb) {
+  __shared__ BhRow s_rows[BH_FUSED_MAX_B];
+  __shared__ int4 s_compact[BH_FUSED_MAX_B];
+  bh_merge_body<COSINE>(recs, n_splits, B, alpha, dloss, loss, pos_idx_out, neg_idx_out, stats, s_rows, s_compact,
+                        blockIdx.x == 0);
+  __syncthreads();
+  bh_grad_body<COSINE>(x, labels, B, D, aux, s_rows, s_compact, nullptr, demb);
 }
 
 // one-hot [B, C] -> int32 class ids (tf.argmax(labels, axis=1): first maximum), losses.py:35
@@ -591,6 +629,12 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
   } else {
     bh_mine_kernel<COSINE><<<dim3(row_blocks, splits), BH_WARPS * 32, smem, st>>>(emb, labels, B, D, cols, g_ws.recs, g_ws.aux);
     DIF_LAUNCH_OK();
+    if (demb && B <= BH_FUSED_MAX_B) {
+      bh_merge_grad_kernel<COSINE><<<(B + BH_GRAD_WARPS - 1) / BH_GRAD_WARPS, BH_GRAD_WARPS * 32, 0, st>>>(
+          g_ws.recs, splits, emb, labels, B, D, alpha, dloss, g_ws.aux, loss, pos_idx, neg_idx, stats, demb);
+      DIF_LAUNCH_OK();
+      return DIF_OK;
+    }
     const int merge_threads = std::min(1024, std::max(64, (B + 31) / 32 * 32));
     bh_merge_kernel<COSINE><<<1, merge_threads, 0, st>>>(g_ws.recs, splits, B, alpha, dloss, loss, pos_idx, neg_idx, stats,
                                                        g_ws.rows, g_ws.compact);
