@@ -122,7 +122,7 @@ def pair_distance(e1, e2, metric: int) -> np.ndarray:
 def threshold_sweep(dist, issame, thresholds, select=None) -> np.ndarray:
     d = _f32(dist)
     s = np.ascontiguousarray(issame, dtype=np.uint8)
-    t = _f32(thresholds)
+    t = np.ascontiguousarray(np.atleast_1d(np.asarray(thresholds, dtype=np.float64)))
     sel = None if select is None else np.ascontiguousarray(select, dtype=np.uint8)
     out = np.empty((t.shape[0], 4), dtype=np.int64)
     lib().dif_or_threshold_sweep(d.ctypes.data, s.ctypes.data, None if sel is None else sel.ctypes.data, d.shape[0],

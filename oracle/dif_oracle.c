@@ -207,14 +207,17 @@ EXPORT void dif_or_pair_distance(const float* e1, const float* e2, int64_t n, in
   }
 }
 
-/* utility.py:36-49 / :69-77 for T thresholds: counts[t] = {tp, fp, tn, fn}, predict = dist < thr */
+/* utility.py:36-49 / :69-77 for T thresholds: counts[t] = {tp, fp, tn, fn}, predict = dist < thr.
+ * np.less(dist, threshold) compares the float32 distances with the FLOAT64 thresholds of np.arange: the
+ * comparison is done in double (a distance that equals a threshold after rounding to float32 can still be
+ * strictly below the float64 threshold). */
 EXPORT void dif_or_threshold_sweep(const float* dist, const uint8_t* issame, const uint8_t* select, int64_t n,
-                                   const float* thr, int T, int64_t* counts) {
+                                   const double* thr, int T, int64_t* counts) {
   for (int t = 0; t < T; ++t) {
     int64_t tp = 0, fp = 0, tn = 0, fn = 0;
     for (int64_t i = 0; i < n; ++i) {
       if (select && !select[i]) continue;
-      const int pred = dist[i] < thr[t];
+      const int pred = (double)dist[i] < thr[t];
       const int same = issame[i] != 0;
       tp += pred && same;
       fp += pred && !same;
