@@ -728,9 +728,16 @@ int dif_gallery_search_host(dif_gallery_t* g, const float* queries_host, int n_q
   if (int rc = ensure_stage(g, qb_al + ob + 256)) return rc;
   char* hp = (char*)g->h_pin;
   char* dp = (char*)g->d_stage;
-  memcpy(hp, queries_host, qb);
   cudaStream_t st = g->own_stream;
-  DIF_CUDA_OK(cudaMemcpyAsync(dp, hp, qb, cudaMemcpyHostToDevice, st));
+  {
+    // staged in 1 MB pieces so the DMA of piece i overlaps the host memcpy of piece i + 1
+    const size_t piece = (size_t)1 << 20;
+    for (size_t off = 0; off < qb; off += piece) {
+      const size_t n = std::min(piece, qb - off);
+      memcpy(hp + off, (const char*)queries_host + off, n);
+      DIF_CUDA_OK(cudaMemcpyAsync(dp + off, hp + off, n, cudaMemcpyHostToDevice, st));
+    }
+  }
   int64_t* d_ids = (int64_t*)(dp + qb_al);
   float* d_scores = (float*)(dp + qb_al + nk * 8);
   int32_t* d_rows = (int32_t*)(dp + qb_al + nk * 12);
