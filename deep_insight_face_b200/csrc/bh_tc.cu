@@ -52,18 +52,21 @@ struct MineEpi {
     const float* sq;         // [B] canonical sum of squares (euclid)
     int B;
   };
-  static int smem_bytes(const Params&) { return kMineBN * 8; }   // labels + sq of the current tile
+  // labels + sq of the current tile, then a [32][128] scratch the insert path indexes dynamically
+  static int smem_bytes(const Params&) { return kMineBN * 8 + 32 * GEMM_BM * 4; }
 
   const Params& p;
   int* s_lab;
   float* s_sq;
+  float* s_dv;   // this thread's column of the scratch: element i at s_dv[i * GEMM_BM]
   float pv[kMineM], nv[kMineM], av[kMineM];
   int pi[kMineM], ni[kMineM], ai[kMineM];
   float row_sum, my_sq;
   int n_pos, my_lab, my_row, tile0;
 
   __device__ MineEpi(const Params& pp, uint8_t* smem, int)
-      : p(pp), s_lab(reinterpret_cast<int*>(smem)), s_sq(reinterpret_cast<float*>(smem) + kMineBN), row_sum(0.f),
+      : p(pp), s_lab(reinterpret_cast<int*>(smem)), s_sq(reinterpret_cast<float*>(smem) + kMineBN),
+        s_dv(reinterpret_cast<float*>(smem) + 2 * kMineBN + (threadIdx.x & (GEMM_BM - 1))), row_sum(0.f),
         my_sq(0.f), n_pos(0), my_lab(-1), my_row(0), tile0(0) {}
 
   __device__ void begin_item(int m_row, int, int) {
@@ -136,13 +139,12 @@ struct MineEpi {
           bool hit = same ? better<COSINE>(dv[i], p_thr) : better<!COSINE>(dv[i], n_thr);
           if (!COSINE) hit = hit || dv[i] > a_thr;
           mask |= (valid && hit) ? (1u << i) : 0u;
+          s_dv[i * GEMM_BM] = dv[i];     // registers cannot be indexed dynamically: park the chunk in smem
         }
         while (mask) {           // per-lane loop, no collectives inside
           const int i = __ffs((int)mask) - 1;
           mask &= mask - 1;
-          float d = 0.f;         // registers cannot be indexed dynamically: select chain
-#pragma unroll
-          for (int t = 0; t < 32; ++t) d = (t == i) ? dv[t] : d;
+          const float d = s_dv[i * GEMM_BM];
           const int j = col0 + i;
           if (s_lab[base + i] == my_lab) cand_insert<COSINE>(pv, pi, d, j);
           else cand_insert<!COSINE>(nv, ni, d, j);
