@@ -180,6 +180,23 @@ def secondary_metrics(torch, device):
                      "alg_gflop_fwd": 2.0 * B * B * D / 1e9,
                      "cpu_oracle_steps_per_s": 1e3 / cpu_ms, "note": "fwd + bwd; steps_per_s = CUDA-graphed BatchHardStep, e2e = numpy in/out through "
                              "dif_batch_hard_host"}
+    # C4: verification sweep, 6000 LFW-style pairs, 10 folds, 400 + 4000 thresholds (evaluation/utility.py:10-33)
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from synth import pairs as synth_pairs
+
+    from deep_insight_face_b200.evaluation import utility as U
+
+    emb_p, issame = synth_pairs(44, 6000, 128)
+    U.evaluate(emb_p, issame)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        res = U.evaluate(emb_p, issame)
+    ver_ms = (time.perf_counter() - t0) / 5 * 1e3
+    out["c4_verification_6000_pairs"] = {
+        "evaluate_ms": ver_ms, "evaluations_per_s": 1e3 / ver_ms, "accuracy_mean": float(np.mean(res[2])),
+        "note": "evaluate(): pair distances + k-fold ROC (400 thresholds) + VAL@FAR (4000 thresholds), host buffers in, "
+                "one histogram pass per distance vector; the reference's calculate_roc alone took 0.43-0.50 s on "
+                "8 cores in the build container (SURVEY.md section 6)"}
     B, C, D = 512, 10000, 512
     X = torch.randn(B, D, device=device)
     W = 0.01 * torch.randn(C, D, device=device)
