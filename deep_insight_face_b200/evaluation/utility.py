@@ -100,6 +100,18 @@ def calculate_accuracy(threshold, dist, actual_issame, display_cm=False):
     return _acc_from_counts(*c, np.size(dist))
 
 
+def _rates_from_counts(c):
+    """Vectorised utility.py:43-45,73-77 over a [T, 4] count block: (tpr, fpr, acc) as float64 arrays.  The same
+    IEEE divisions as the scalar formulas, so the values are bit-identical to the reference's python floats."""
+    c = np.asarray(c, dtype=np.float64)
+    tp, fp, tn, fn = c[:, 0], c[:, 1], c[:, 2], c[:, 3]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        tpr = np.where(tp + fn == 0, 0.0, tp / (tp + fn))
+        fpr = np.where(fp + tn == 0, 0.0, fp / (fp + tn))
+        acc = (tp + tn) / (tp + fp + tn + fn)
+    return tpr, fpr, acc
+
+
 def _val_far_from_counts(tp, fp, tn, fn):
     """utility.py:73-77."""
     n_same, n_diff = int(tp + fn), int(fp + tn)
@@ -157,14 +169,10 @@ def calculate_roc(thresholds, embeddings1, embeddings2, actual_issame, nrof_fold
         counts = shared
         test = counts[fold_idx]                       # [T, 4]
         train = counts.sum(axis=0) - test             # exact integer arithmetic
-        n_train = int(train[0].sum())
         n_test = int(test[0].sum())
-        acc_train = np.zeros((nrof_thresholds))
-        for t in range(nrof_thresholds):
-            acc_train[t] = float(train[t, 0] + train[t, 2]) / n_train
+        _, _, acc_train = _rates_from_counts(train)
         best_threshold_index = np.argmax(acc_train)   # utility.py:159, first maximum
-        for t in range(nrof_thresholds):
-            tprs[fold_idx, t], fprs[fold_idx, t], _, _ = _acc_from_counts(*test[t], n_test)
+        tprs[fold_idx], fprs[fold_idx], _ = _rates_from_counts(test)
         _, _, accuracy[fold_idx], f1scores[fold_idx] = _acc_from_counts(*test[best_threshold_index], n_test)
     tpr = np.mean(tprs, 0)
     fpr = np.mean(fprs, 0)
@@ -196,9 +204,7 @@ def calculate_val(thresholds, embeddings1, embeddings2, actual_issame, far_targe
         if subtract_mean or shared is None:
             shared = threshold_counts(dists[fold_idx], actual_issame[:nrof_pairs], thresholds, fold, nrof_folds)
         train = shared.sum(axis=0) - shared[fold_idx]
-        far_train = np.zeros(nrof_thresholds)
-        for t in range(nrof_thresholds):
-            _, far_train[t] = _val_far_from_counts(*train[t])
+        _, far_train, _ = _rates_from_counts(train)   # far = fp / n_diff, utility.py:76-77
         if np.max(far_train) >= far_target:
             threshold = _interp_threshold(far_train, thresholds, far_target)
         else:
