@@ -54,6 +54,54 @@ def arcface_loss(X, W, y, s: float = 64.0, m: float = 0.5, dloss=None, want_grad
     return (loss, dX, dW) if want_grad else loss
 
 
+class ArcFaceStep:
+    """Preallocated, optionally CUDA-graphed ArcFace fwd + bwd for fixed (B, C, D): the training-loop form.
+
+    One step is 13 kernel launches and a dozen tensor-map encodes; with `graph=True` they are captured once and
+    replayed with a single cudaGraphLaunch.  Write into `X`, `W`, `y` in place, call the step, read `loss`, `dX`, `dW`.
+    """
+
+    def __init__(self, B: int, C: int, D: int, s: float = 64.0, m: float = 0.5, device="cuda:0", graph: bool = False):
+        import torch
+
+        dev = torch.device(device)
+        _ffi.init(dev.index or 0)
+        self._lib = _ffi.load_library()
+        self.B, self.C, self.D, self.s, self.m = int(B), int(C), int(D), float(s), float(m)
+        self.X = torch.zeros((B, D), dtype=torch.float32, device=dev)
+        self.W = torch.zeros((C, D), dtype=torch.float32, device=dev)
+        self.y = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.loss = torch.empty(B, dtype=torch.float32, device=dev)
+        self.dX = torch.empty_like(self.X)
+        self.dW = torch.empty_like(self.W)
+        self._dev = dev
+        self._graph = None
+        self.X.normal_()
+        self.W.normal_()
+        self._launch()                      # warm-up: sizes the library workspace outside any capture
+        torch.cuda.synchronize(dev)
+        if graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch()
+            self._graph = g
+
+    def _launch(self):
+        import torch
+
+        st = int(torch.cuda.current_stream(self._dev).cuda_stream)
+        _ffi.check(self._lib.dif_arcface(self.X.data_ptr(), self.W.data_ptr(), self.y.data_ptr(), self.B, self.C, self.D,
+                                         self.s, self.m, self.loss.data_ptr(), None, self.dX.data_ptr(),
+                                         self.dW.data_ptr(), _ffi.PREC_TF32X3, st))
+
+    def __call__(self):
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._launch()
+        return self.loss, self.dX, self.dW
+
+
 class ArcFaceLoss:
     """Keras-style callable: `loss(y_true, y_pred)` with y_pred = embeddings and the class centres held here."""
 

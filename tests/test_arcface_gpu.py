@@ -52,3 +52,23 @@ def test_arcface_device_entry_and_dloss(gpu):
     head = ArcFaceLoss(W, 30.0, 0.35)
     onehot = np.eye(500, dtype=np.float32)[y]
     assert abs(head(onehot, X) - want["loss"].mean()) <= RTOL * want["loss"].mean()
+
+
+def test_arcface_step_graph(gpu):
+    import torch
+
+    from deep_insight_face_b200.arcface import ArcFaceStep
+    from oracle import losses_oracle as lo
+
+    X, W, y = data(64, 300, 64)
+    want = lo.arcface(X, W, y, 64.0, 0.5)
+    for graph in (False, True):
+        step = ArcFaceStep(64, 300, 64, 64.0, 0.5, "cuda:0", graph=graph)
+        step.X.copy_(torch.from_numpy(X))
+        step.W.copy_(torch.from_numpy(W))
+        step.y.copy_(torch.from_numpy(y.astype(np.int32)))
+        for _ in range(3):
+            loss, dX, dW = step()
+        torch.cuda.synchronize()
+        assert np.abs(loss.cpu().numpy() - want["loss"]).max() <= RTOL * np.abs(want["loss"]).max()
+        assert np.abs(dW.cpu().numpy() - want["dW"]).max() <= RTOL * np.abs(want["dW"]).max()
