@@ -22,6 +22,7 @@ PREC_TF32X1 = 2
 MAX_TOPK = 24
 LOSS_BH_COSINE = 0
 LOSS_BH_EUCLIDEAN = 1
+LOSS_SOFT_MARGIN = 4
 
 _PRECISIONS = {"tf32x3": PREC_TF32X3, "fp32": PREC_TF32X3, "bf16": PREC_BF16, "tf32": PREC_TF32X1,
                "tf32x1": PREC_TF32X1}

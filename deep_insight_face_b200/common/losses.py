@@ -174,9 +174,12 @@ class TripletLossWapper(_LossBase):
 
     _variant = None
 
-    def __init__(self, alpha=0.35, **kwargs):
+    def __init__(self, alpha=0.35, soft=False, **kwargs):
         super().__init__(**kwargs)
         self.alpha = alpha
+        # soft=True: log(1 + exp(.)) margin of arXiv 1703.07737 eq. 4 instead of the reference's hard margin
+        # (an extension - the reference only has max(. + alpha, 0), common/losses.py:51,85)
+        self.soft = bool(soft)
         self.last_info = None
 
     def __calculate_triplet_loss__(self, y_true, y_pred, alpha):
@@ -188,6 +191,8 @@ class TripletLossWapper(_LossBase):
     def get_config(self):
         config = super().get_config()
         config.update({"alpha": self.alpha})
+        if self.soft:
+            config["soft"] = True
         return config
 
     @classmethod
@@ -199,14 +204,14 @@ class TripletLossWapper(_LossBase):
         if _tf is not None and isinstance(embeddings, (_tf.Tensor, _tf.Variable)):  # pragma: no cover
             return self._tf_call(labels, embeddings, alpha)
         if _ffi.is_device_tensor(embeddings):
-            out = _torch_function().apply(embeddings, labels, self._variant, float(alpha))
+            out = _torch_function().apply(embeddings, labels, self._code(), float(alpha))
             return out
-        loss, _, info = batch_hard(labels, embeddings, self._variant, alpha, want_grad=False)
+        loss, _, info = batch_hard(labels, embeddings, self._code(), alpha, want_grad=False)
         self.last_info = info
         return loss
 
     def _tf_call(self, labels, embeddings, alpha):  # pragma: no cover - needs TensorFlow
-        variant = self._variant
+        variant = self._code()
 
         @_tf.custom_gradient
         def op(emb):
@@ -229,10 +234,13 @@ class TripletLossWapper(_LossBase):
 
     def loss_and_grad(self, labels, embeddings, dloss=None):
         """(loss [B], gradient of sum_i dloss_i * loss_i (default: mean) wrt embeddings, info) in one call."""
-        loss, grad, info = batch_hard(labels, embeddings, self._variant, self._current_alpha(), dloss=dloss)
+        loss, grad, info = batch_hard(labels, embeddings, self._code(), self._current_alpha(), dloss=dloss)
         self._after_step(info)
         self.last_info = info
         return loss, grad, info
+
+    def _code(self):
+        return self._variant | (_ffi.LOSS_SOFT_MARGIN if self.soft else 0)
 
     def _current_alpha(self):
         return self.alpha
@@ -277,7 +285,7 @@ class BatchHardTripletLossEuclideanAutoAlpha(TripletLossWapper):
         self.auto_alpha = float(info["stats"][0]) * self.alpha
 
     def __calculate_triplet_loss__(self, labels, embeddings, alpha):
-        loss, _, info = batch_hard(labels, embeddings, self._variant, self.auto_alpha, want_grad=False)
+        loss, _, info = batch_hard(labels, embeddings, self._code(), self.auto_alpha, want_grad=False)
         self._after_step(info)
         self.last_info = info
         return loss

@@ -140,10 +140,24 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 }
 
 // One block.  stats = {mean(dists), mean(hardest_pos), mean(hardest_neg), max(dists)}
+// Per-anchor loss and cotangent scale from the hardest positive / negative (x = hn - hp for cosine similarities,
+// hp - hn for distances).  Hard margin (the reference, losses.py:47-51,81-85): max(x + alpha, 0), gradient 1 when
+// x + alpha >= 0 (tf.maximum).  Soft margin (arXiv 1703.07737 eq. 4, not in the reference): log(1 + exp(x)),
+// gradient sigmoid(x).  `basic` is the reference's own expression so the hard loss keeps its fp32 rounding.
+__device__ __forceinline__ void bh_loss_rule(float basic, float x, int soft, float dl, float& loss, float& g) {
+  if (!soft) {
+    loss = fmaxf(basic, 0.f);
+    g = basic >= 0.f ? dl : 0.f;
+  } else {
+    loss = x > 0.f ? x + log1pf(expf(-x)) : log1pf(expf(x));
+    g = dl / (1.f + expf(-x));
+  }
+}
+
 // Body shared by bh_merge_kernel (one block) and the fused small-batch kernel (every block redoes it into its own
 // shared memory; `write_out` selects the block that also writes loss / indices / statistics).
 template <bool COSINE>
-__device__ __forceinline__ void bh_merge_body(const BhRec* __restrict__ recs, int n_splits, int B, float alpha,
+__device__ __forceinline__ void bh_merge_body(const BhRec* __restrict__ recs, int n_splits, int B, float alpha, int soft,
                                               const float* __restrict__ dloss, float* __restrict__ loss,
                                               int32_t* __restrict__ pos_idx_out, int32_t* __restrict__ neg_idx_out,
                                               float* __restrict__ stats, BhRow* rows, int4* compact, bool write_out) {
@@ -206,15 +220,15 @@ __device__ __forceinline__ void bh_merge_body(const BhRec* __restrict__ recs, in
       else if (fill_n == hn) tie_n += n_pos;
     }
     const float basic = COSINE ? __fadd_rn(__fsub_rn(hn, hp), alpha) : __fsub_rn(__fadd_rn(hp, alpha), hn);
+    float li, g;
+    bh_loss_rule(basic, COSINE ? hn - hp : hp - hn, soft, dloss ? dloss[i] : 1.f / (float)B, li, g);
     if (write_out) {
-      loss[i] = fmaxf(basic, 0.f);
+      loss[i] = li;
       if (pos_idx_out) pos_idx_out[i] = pidx;
       if (neg_idx_out) neg_idx_out[i] = nidx;
     }
     sum_hp += (double)hp;
     sum_hn += (double)hn;
-    // tf.maximum(basic, 0): the gradient goes to `basic` when basic >= 0
-    const float g = basic >= 0.f ? (dloss ? dloss[i] : 1.f / (float)B) : 0.f;
     // d loss / d dist at each tied position: cosine  +g/tie_n (neg), -g/tie_p (pos); euclid  +g/tie_p (pos), -g/tie_n (neg)
     r.coef_pos = r.pos_cnt > 0 ? (COSINE ? -g : g) / (float)tie_p : 0.f;
     r.coef_neg = r.neg_cnt > 0 ? (COSINE ? g : -g) / (float)tie_n : 0.f;
@@ -243,11 +257,11 @@ __device__ __forceinline__ void bh_merge_body(const BhRec* __restrict__ recs, in
 
 template <bool COSINE>
 __global__ void __launch_bounds__(1024) bh_merge_kernel(const BhRec* __restrict__ recs, int n_splits, int B,
-                                                        float alpha, const float* __restrict__ dloss,
+                                                        float alpha, int soft, const float* __restrict__ dloss,
                                                         float* __restrict__ loss, int32_t* __restrict__ pos_idx_out,
                                                         int32_t* __restrict__ neg_idx_out, float* __restrict__ stats,
                                                         BhRow* __restrict__ rows, int4* __restrict__ compact) {
-  bh_merge_body<COSINE>(recs, n_splits, B, alpha, dloss, loss, pos_idx_out, neg_idx_out, stats, rows, compact, true);
+  bh_merge_body<COSINE>(recs, n_splits, B, alpha, soft, dloss, loss, pos_idx_out, neg_idx_out, stats, rows, compact, true);
 }
 
 // Multi-block form of the second half of bh_merge_kernel for the tensor-core path (one merged record per anchor,
@@ -255,7 +269,7 @@ __global__ void __launch_bounds__(1024) bh_merge_kernel(const BhRec* __restrict_
 // [gridDim.x][5] = {sum dists, sum hardest_pos, sum hardest_neg, filler share, positions holding the max};
 // bh_stats_kernel folds them in a fixed order.
 template <bool COSINE>
-__global__ void __launch_bounds__(256) bh_finalize_kernel(const BhRec* __restrict__ recs, int B, float alpha,
+__global__ void __launch_bounds__(256) bh_finalize_kernel(const BhRec* __restrict__ recs, int B, float alpha, int soft,
                                                           const float* __restrict__ dloss,
                                                           const unsigned long long* __restrict__ gmax_key,
                                                           float* __restrict__ loss, int32_t* __restrict__ pos_idx_out,
@@ -284,10 +298,11 @@ __global__ void __launch_bounds__(256) bh_finalize_kernel(const BhRec* __restric
       else if (fill_n == hn) tie_n += n_pos;
     }
     const float basic = COSINE ? __fadd_rn(__fsub_rn(hn, hp), alpha) : __fsub_rn(__fadd_rn(hp, alpha), hn);
-    loss[i] = fmaxf(basic, 0.f);
+    float li, g;
+    bh_loss_rule(basic, COSINE ? hn - hp : hp - hn, soft, dloss ? dloss[i] : 1.f / (float)B, li, g);
+    loss[i] = li;
     if (pos_idx_out) pos_idx_out[i] = pidx;
     if (neg_idx_out) neg_idx_out[i] = nidx;
-    const float g = basic >= 0.f ? (dloss ? dloss[i] : 1.f / (float)B) : 0.f;
     r.coef_pos = r.pos_cnt > 0 ? (COSINE ? -g : g) / (float)tie_p : 0.f;
     r.coef_neg = r.neg_cnt > 0 ? (COSINE ? g : -g) / (float)tie_n : 0.f;
     r.pos_idx = pidx;
@@ -494,12 +509,12 @@ constexpr int BH_FUSED_MAX_B = 256;
 template <bool COSINE>
 __global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_merge_grad_kernel(
     const BhRec* __restrict__ recs, int n_splits, const float* __restrict__ x, const int32_t* __restrict__ labels, int B,
-    int D, float alpha, const float* __restrict__ dloss, const float* __restrict__ aux, float* __restrict__ loss,
+    int D, float alpha, int soft, const float* __restrict__ dloss, const float* __restrict__ aux, float* __restrict__ loss,
     int32_t* __restrict__ pos_idx_out, int32_t* __restrict__ neg_idx_out, float* __restrict__ stats,
     float* __restrict__ demb) {
   __shared__ BhRow s_rows[BH_FUSED_MAX_B];
   __shared__ int4 s_compact[BH_FUSED_MAX_B];
-  bh_merge_body<COSINE>(recs, n_splits, B, alpha, dloss, loss, pos_idx_out, neg_idx_out, stats, s_rows, s_compact,
+  bh_merge_body<COSINE>(recs, n_splits, B, alpha, soft, dloss, loss, pos_idx_out, neg_idx_out, stats, s_rows, s_compact,
                         blockIdx.x == 0);
   __syncthreads();
   bh_grad_body<COSINE>(x, labels, B, D, aux, s_rows, s_compact, nullptr, demb);
@@ -593,7 +608,7 @@ static thread_local BhHostStage g_bh_stage;
 static int g_bh_force_path = 0;   // 0 auto, 1 CUDA-core miner, 2 tensor-core miner (tests)
 
 template <bool COSINE>
-static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D, float alpha, float* loss,
+static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D, float alpha, int soft, float* loss,
                           int32_t* pos_idx, int32_t* neg_idx, float* stats, const float* dloss, float* demb,
                           cudaStream_t st) {
   // column splits: enough blocks to cover the machine, at least one step of 4 columns each
@@ -619,7 +634,7 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
     DIF_CUDA_OK(cudaMemsetAsync(g_ws.gmax_key, 0, 16, st));
     if (int rc = bh_mine_tensor<COSINE>(emb, labels, B, D, g_ws.recs, g_ws.aux, g_ws.gmax_key, st)) return rc;
     const int fb = (B + 255) / 256;
-    bh_finalize_kernel<COSINE><<<fb, 256, 0, st>>>(g_ws.recs, B, alpha, dloss, g_ws.gmax_key, loss, pos_idx, neg_idx,
+    bh_finalize_kernel<COSINE><<<fb, 256, 0, st>>>(g_ws.recs, B, alpha, soft, dloss, g_ws.gmax_key, loss, pos_idx, neg_idx,
                                                   g_ws.rows, g_ws.compact, g_ws.partials);
     DIF_LAUNCH_OK();
     float* cg = reinterpret_cast<float*>(g_ws.gmax_key + 1);
@@ -631,12 +646,12 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
     DIF_LAUNCH_OK();
     if (demb && B <= BH_FUSED_MAX_B) {
       bh_merge_grad_kernel<COSINE><<<(B + BH_GRAD_WARPS - 1) / BH_GRAD_WARPS, BH_GRAD_WARPS * 32, 0, st>>>(
-          g_ws.recs, splits, emb, labels, B, D, alpha, dloss, g_ws.aux, loss, pos_idx, neg_idx, stats, demb);
+          g_ws.recs, splits, emb, labels, B, D, alpha, soft, dloss, g_ws.aux, loss, pos_idx, neg_idx, stats, demb);
       DIF_LAUNCH_OK();
       return DIF_OK;
     }
     const int merge_threads = std::min(1024, std::max(64, (B + 31) / 32 * 32));
-    bh_merge_kernel<COSINE><<<1, merge_threads, 0, st>>>(g_ws.recs, splits, B, alpha, dloss, loss, pos_idx, neg_idx, stats,
+    bh_merge_kernel<COSINE><<<1, merge_threads, 0, st>>>(g_ws.recs, splits, B, alpha, soft, dloss, loss, pos_idx, neg_idx, stats,
                                                        g_ws.rows, g_ws.compact);
     DIF_LAUNCH_OK();
   }
@@ -881,6 +896,8 @@ int dif_batch_hard(const float* emb, const int32_t* labels, int B, int D, int va
   DIF_REQUIRE(emb && labels && loss && stats, DIF_ERR_INVALID, "dif_batch_hard: null argument");
   DIF_REQUIRE(B >= 1 && B <= 65536 && D >= 1 && D <= 32 * BH_MAX_KD, DIF_ERR_INVALID,
               "dif_batch_hard: B %d (1..65536), D %d (1..%d)", B, D, 32 * BH_MAX_KD);
+  const int soft = (variant & DIF_LOSS_SOFT_MARGIN) ? 1 : 0;
+  variant &= ~DIF_LOSS_SOFT_MARGIN;
   DIF_REQUIRE(variant == DIF_LOSS_BH_COSINE || variant == DIF_LOSS_BH_EUCLIDEAN, DIF_ERR_INVALID,
               "dif_batch_hard: variant %d (batch-all is dif_batch_all)", variant);
   DIF_REQUIRE(precision == DIF_PREC_TF32X3, DIF_ERR_INVALID,
@@ -888,8 +905,8 @@ int dif_batch_hard(const float* emb, const int32_t* labels, int B, int D, int va
   DIF_REQUIRE(device_sm_count() > 0, DIF_ERR_STATE, "dif_init has not succeeded on this process");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return variant == DIF_LOSS_BH_COSINE
-             ? run_batch_hard<true>(emb, labels, B, D, alpha, loss, pos_idx, neg_idx, stats, dloss, demb, st)
-             : run_batch_hard<false>(emb, labels, B, D, alpha, loss, pos_idx, neg_idx, stats, dloss, demb, st);
+             ? run_batch_hard<true>(emb, labels, B, D, alpha, soft, loss, pos_idx, neg_idx, stats, dloss, demb, st)
+             : run_batch_hard<false>(emb, labels, B, D, alpha, soft, loss, pos_idx, neg_idx, stats, dloss, demb, st);
 }
 
 int dif_batch_hard_host(const float* emb_host, const int32_t* labels_host, int B, int D, int variant, float alpha,

@@ -123,6 +123,9 @@ int dif_debug_gemm_time(int M, int N, int K, int precision, int ctas, int n_spli
  * bit for bit on the CPU; `precision` must be DIF_PREC_TF32X3 (fp32-exact). */
 #define DIF_LOSS_BH_COSINE 0
 #define DIF_LOSS_BH_EUCLIDEAN 1
+/* OR into `variant`: soft margin log(1 + exp(hn - hp | hp - hn)) of arXiv 1703.07737 eq. 4 instead of the
+ * reference's hard margin max(. + alpha, 0); alpha is ignored.  Not in the reference. */
+#define DIF_LOSS_SOFT_MARGIN 4
 int dif_batch_hard(const float* emb, const int32_t* labels, int B, int D, int variant, float alpha, float* loss,
                    int32_t* pos_idx, int32_t* neg_idx, float* stats, const float* dloss, float* demb,
                    int precision, void* stream);

@@ -56,7 +56,17 @@ def _finish(loss, hp, hn, dists, pos_idx, neg_idx, grad, extra=None):
     return out
 
 
-def batch_hard_cosine(labels, emb, alpha=0.35, dloss=None):
+def _margin(basic, x, soft, B, dloss):
+    """Hard margin of the reference (max(basic, 0), gradient where basic >= 0) or the soft margin
+    log(1 + exp(x)) of arXiv 1703.07737 eq. 4 (extension, gradient sigmoid(x))."""
+    dl = (1.0 / B) if dloss is None else np.asarray(dloss, dtype=np.float64)
+    if not soft:
+        return np.maximum(basic, F32(0.0)), np.where(basic >= 0, dl, 0.0)
+    x64 = x.astype(np.float64)
+    return np.logaddexp(0.0, x64).astype(F32), dl / (1.0 + np.exp(-x64))
+
+
+def batch_hard_cosine(labels, emb, alpha=0.35, dloss=None, soft=False):
     """common/losses.py:33-51 BatchHardTripletLoss."""
     lab = _labels(labels)
     x = np.ascontiguousarray(emb, dtype=F32)
@@ -68,13 +78,12 @@ def batch_hard_cosine(labels, emb, alpha=0.35, dloss=None):
     negv = np.where(pos, F32(-1.0), S)                                   # :45
     hn = negv.max(axis=1)                                                # :46
     basic = (hn - hp) + F32(alpha)                                       # :47
-    loss = np.maximum(basic, F32(0.0))                                   # :51
+    loss, g = _margin(basic, hn - hp, soft, B, dloss)                    # :51
     pos_idx = np.full(B, -1, dtype=np.int64)
     neg_idx = np.full(B, -1, dtype=np.int64)
     for i in range(B):
         pos_idx[i] = _first_index(pos[i] & (S[i] == hp[i]))             # -1 when the filler (1.0) wins strictly
         neg_idx[i] = _first_index(~pos[i] & (S[i] == hn[i]))
-    g = np.where(basic >= 0, (1.0 / B) if dloss is None else np.asarray(dloss, dtype=np.float64), 0.0)
     tied_p = posv == hp[:, None]
     tied_n = negv == hn[:, None]
     G = np.zeros((B, B), dtype=np.float64)
@@ -89,7 +98,7 @@ def batch_hard_cosine(labels, emb, alpha=0.35, dloss=None):
     return _finish(loss, hp, hn, S, pos_idx, neg_idx, grad.astype(np.float64))
 
 
-def batch_hard_euclidean(labels, emb, alpha=0.35, dloss=None):
+def batch_hard_euclidean(labels, emb, alpha=0.35, dloss=None, soft=False):
     """common/losses.py:54-85 BatchHardTripletLossEuclidean (and :88-128 with alpha = auto_alpha)."""
     lab = _labels(labels)
     x = np.ascontiguousarray(emb, dtype=F32)
@@ -102,13 +111,12 @@ def batch_hard_euclidean(labels, emb, alpha=0.35, dloss=None):
     negv = np.where(pos, gmax, Dm)                                       # :70
     hn = negv.min(axis=1)                                                # :71
     basic = (hp + F32(alpha)) - hn                                       # :81
-    loss = np.maximum(basic, F32(0.0))                                   # :85
+    loss, g = _margin(basic, hp - hn, soft, B, dloss)                    # :85
     pos_idx = np.full(B, -1, dtype=np.int64)
     neg_idx = np.full(B, -1, dtype=np.int64)
     for i in range(B):
         pos_idx[i] = _first_index(pos[i] & (Dm[i] == hp[i]))            # -1 when the filler (0) wins strictly
         neg_idx[i] = _first_index(~pos[i] & (Dm[i] == hn[i]))           # -1 when only the max(dists) filler is left
-    g = np.where(basic >= 0, (1.0 / B) if dloss is None else np.asarray(dloss, dtype=np.float64), 0.0)
     tied_p = posv == hp[:, None]
     tied_n = negv == hn[:, None]
     G = np.zeros((B, B), dtype=np.float64)

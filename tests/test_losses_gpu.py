@@ -239,3 +239,20 @@ def test_tensor_core_miner_ties_and_single_identity(gpu, tensor_path):
     one = np.zeros(48, dtype=np.int64)
     run_case(BatchHardTripletLoss, lo.batch_hard_cosine, emb, one, 0.35, onehot=False)
     run_case(BatchHardTripletLossEuclidean, lo.batch_hard_euclidean, emb, one, 500.0, onehot=False)
+
+
+@pytest.mark.parametrize("P,K,D", [(18, 4, 128), (256, 4, 128)])
+def test_soft_margin_extension(gpu, P, K, D):
+    """log(1 + exp(.)) margin of arXiv 1703.07737 (not in the reference; oracle = this build's restatement)."""
+    from deep_insight_face_b200.common.losses import BatchHardTripletLoss, BatchHardTripletLossEuclidean
+    from oracle import losses_oracle as lo
+
+    emb, lab = pk_batch(P, K, D, 1.0, normalise=True)
+    for cls, fn in ((BatchHardTripletLoss, lo.batch_hard_cosine), (BatchHardTripletLossEuclidean, lo.batch_hard_euclidean)):
+        loss = cls(soft=True)
+        got, grad, info = loss.loss_and_grad(lab, emb)
+        want = fn(lab, emb, soft=True)
+        assert np.array_equal(info["pos_idx"], want["pos_idx"]) and np.array_equal(info["neg_idx"], want["neg_idx"])
+        close(got, want["loss"])
+        close(grad, want["grad"])
+        assert (got > 0).all() and cls.from_config(loss.get_config()).soft
