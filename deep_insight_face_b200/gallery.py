@@ -177,11 +177,13 @@ class ShardedGallery:
         self.local = Gallery(max(1, self.row_hi - self.row_lo), dim, metric, precision, device)
         self.local.set_id_base(self.row_lo)
         self.device = device
+        self._explicit_ids = False
 
     def fill_synthetic(self, seed: int) -> None:
         self.local.fill_synthetic(seed, self.row_lo, self.row_hi - self.row_lo)
 
     def add_local(self, rows, ids=None) -> None:
+        self._explicit_ids = self._explicit_ids or ids is not None
         self.local.add(rows, ids)
 
     def search(self, queries, k: int = 10):
@@ -189,10 +191,17 @@ class ShardedGallery:
         import torch
 
         scores, ids, rows = self.local.search(queries, k, return_rows=True)
+        if not self._explicit_ids:
+            # ids = id_base + row with id_base = row_lo: the id IS the global row (-1 in empty slots), so two
+            # all-gathers (scores, ids) carry everything the merge needs
+            if self.world == 1:
+                return scores, ids, ids
+            g_scores, g_ids = exchange_candidates(scores, ids, group=self.group)
+            return merge_candidates(g_scores, g_ids, g_ids, self.metric)
         grows = torch.where(rows >= 0, rows.to(torch.int64) + self.row_lo, torch.full_like(ids, -1))
         if self.world == 1:
             return scores, ids, grows
-        g_scores, g_ids, g_rows = exchange_candidates(scores, ids, grows, self.group)
+        g_scores, g_ids, g_rows = exchange_candidates(scores, ids, grows, group=self.group)
         return merge_candidates(g_scores, g_rows, g_ids, self.metric)
 
 
@@ -215,14 +224,14 @@ class ShardedGallery:
         self.local.close()
 
 
-def exchange_candidates(scores, ids, grows, group=None):
-    """All-gather the per-rank candidate lists: returns [world, Q, k] tensors (works on NCCL and gloo)."""
+def exchange_candidates(*tensors, group=None):
+    """All-gather the per-rank candidate lists: returns one [world, Q, k] tensor per input (NCCL and gloo)."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     out = []
-    for t in (scores, ids, grows):
+    for t in tensors:
         # concatenation along dim 0 (the layout both NCCL and gloo accept), viewed as [world, Q, k]
         buf = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(buf, t.contiguous(), group=group)
