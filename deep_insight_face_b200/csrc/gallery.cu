@@ -26,7 +26,7 @@ namespace dif {
 constexpr int kRerankThreads = 128;
 constexpr int kRerankCap = 256;     // candidates inside the 2*eps window before a query is flagged
 constexpr int kExactChunks = 256;   // row chunks per flagged query in the exact scan
-constexpr int kExactMaxFlagged = 2048;  // flagged queries the exact scan has workspace for (the rest is reported)
+constexpr int kExactMaxFlagged = 2048;  // flagged queries one exact-scan round has workspace for (rounds cover the rest)
 constexpr int kExactThreads = 256;
 
 // ------------------------------------------------------------------------------------------
@@ -180,15 +180,15 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
 
 // Exact scan of flagged queries: work item = (flagged index, row chunk); 8 warps interleave rows,
 // each keeps a top-k list in shared memory; the block merges and writes k canonical keys.
-__global__ void __launch_bounds__(kExactThreads) exact_scan_kernel(RerankParams p, uint64_t* ex_keys) {
+__global__ void __launch_bounds__(kExactThreads) exact_scan_kernel(RerankParams p, uint64_t* ex_keys, int flag_base) {
   extern __shared__ float sm_q[];  // [D]
   __shared__ uint64_t lists[kExactThreads / 32][DIF_MAX_TOPK];
-  const int n_flag = min(*p.flagged_count, kExactMaxFlagged);
+  const int n_flag = max(0, min(*p.flagged_count - flag_base, kExactMaxFlagged));   // this round's share
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int64_t chunk_rows = (p.n_rows + kExactChunks - 1) / kExactChunks;
   for (int item = blockIdx.x; item < n_flag * kExactChunks; item += gridDim.x) {
     const int fi = item / kExactChunks, chunk = item - fi * kExactChunks;
-    const int q = p.flagged_list[fi];
+    const int q = p.flagged_list[flag_base + fi];
     __syncthreads();
     for (int d = threadIdx.x; d < p.D; d += blockDim.x)
       sm_q[d] = p.q1 ? __fadd_rn(p.q0[(size_t)q * p.D + d], p.q1[(size_t)q * p.D + d]) : p.q0[(size_t)q * p.D + d];
@@ -236,12 +236,13 @@ __global__ void __launch_bounds__(kExactThreads) exact_scan_kernel(RerankParams 
   }
 }
 
-__global__ void __launch_bounds__(kRerankThreads) exact_merge_kernel(RerankParams p, const uint64_t* ex_keys) {
+__global__ void __launch_bounds__(kRerankThreads) exact_merge_kernel(RerankParams p, const uint64_t* ex_keys,
+                                                                     int flag_base) {
   extern __shared__ uint64_t sm_keys[];
-  const int n_flag = min(*p.flagged_count, kExactMaxFlagged);
+  const int n_flag = max(0, min(*p.flagged_count - flag_base, kExactMaxFlagged));
   const int n = kExactChunks * p.k;
   for (int fi = blockIdx.x; fi < n_flag; fi += gridDim.x) {
-    const int q = p.flagged_list[fi];
+    const int q = p.flagged_list[flag_base + fi];
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) sm_keys[i] = ex_keys[(size_t)fi * n + i];
     __syncthreads();
@@ -703,13 +704,17 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
       if (int rc = dev_alloc(&g->ex_keys, need)) return rc;
       g->ex_elems = need;
     }
-    exact_scan_kernel<<<device_sm_count() * 4, kExactThreads, (size_t)D * 4, st>>>(rp, g->ex_keys);
-    DIF_LAUNCH_OK();
     const size_t em_smem = (size_t)kExactChunks * k * 8;
     if (em_smem > 40 * 1024)
       DIF_CUDA_OK(cudaFuncSetAttribute(exact_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)em_smem));
-    exact_merge_kernel<<<device_sm_count() * 2, kRerankThreads, em_smem, st>>>(rp, g->ex_keys);
-    DIF_LAUNCH_OK();
+    // the flagged count lives on the device: launch enough rounds of (scan, merge) to cover every query; a round
+    // whose share is empty returns at once
+    for (int base = 0; base < n_queries; base += kExactMaxFlagged) {
+      exact_scan_kernel<<<device_sm_count() * 4, kExactThreads, (size_t)D * 4, st>>>(rp, g->ex_keys, base);
+      DIF_LAUNCH_OK();
+      exact_merge_kernel<<<device_sm_count() * 2, kRerankThreads, em_smem, st>>>(rp, g->ex_keys, base);
+      DIF_LAUNCH_OK();
+    }
   }
   g->stats[1] = dif_launch_count() - launches0;
   g->stats[2] = splits;
@@ -744,13 +749,7 @@ int dif_gallery_search_host(dif_gallery_t* g, const float* queries_host, int n_q
   if (int rc = dif_gallery_search(g, (const float*)dp, n_queries, k, d_scores, d_ids, d_rows, st)) return rc;
   DIF_CUDA_OK(cudaMemcpyAsync(hp + qb_al, dp + qb_al, ob, cudaMemcpyDeviceToHost, st));
   DIF_CUDA_OK(cudaStreamSynchronize(st));
-  {
-    int n_flag = 0;
-    DIF_CUDA_OK(cudaMemcpy(&n_flag, g->flagged, sizeof(int), cudaMemcpyDeviceToHost));
-    DIF_REQUIRE(n_flag <= kExactMaxFlagged, DIF_ERR_CAPACITY,
-                "%d queries need the exact scan (limit %d): candidate lists saturated; use a finer filter precision",
-                n_flag, kExactMaxFlagged);
-  }
+
   memcpy(ids_host, hp + qb_al, nk * 8);
   memcpy(scores_host, hp + qb_al + nk * 8, nk * 4);
   if (rows_host) memcpy(rows_host, hp + qb_al + nk * 12, nk * 4);
@@ -766,7 +765,7 @@ int dif_gallery_last_stats(const dif_gallery_t* g, int64_t out[6]) {
   out[2] = g->stats[2];
   out[3] = g->stats[3];
   out[4] = g->stats[4];
-  out[5] = n_flag > kExactMaxFlagged ? n_flag - kExactMaxFlagged : 0;   // flagged queries left with unverified results
+  out[5] = 0;   // (reserved; every flagged query is verified by the exact scan rounds)
   return DIF_OK;
 }
 

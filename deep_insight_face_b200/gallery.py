@@ -140,7 +140,7 @@ class Gallery:
         out = (C.c_int64 * 6)()
         _ffi.check(self._lib.dif_gallery_last_stats(self._h, out))
         return {"fallback_queries": int(out[0]), "kernels": int(out[1]), "splits": int(out[2]),
-                "candidates_per_split": int(out[3]), "resident_queries": int(out[4]), "unverified_queries": int(out[5])}
+                "candidates_per_split": int(out[3]), "resident_queries": int(out[4])}
 
     def last_kernel_ms(self) -> float:
         ms = C.c_float()

@@ -85,7 +85,7 @@ int dif_gallery_search_host(dif_gallery_t* g, const float* queries_host, int n_q
                             float* scores_host, int64_t* ids_host, int32_t* rows_host);
 /* counters of the last search: [0] queries that took the exact fallback, [1] kernels launched,
  * [2] candidate splits, [3] candidates per split, [4] 1 if the resident-query schedule ran,
- * [5] flagged queries beyond the exact scan's workspace (their results are unverified; the _host call fails) */
+ * [5] reserved (0) */
 int dif_gallery_last_stats(const dif_gallery_t* g, int64_t out[6]);
 /* duration in ms of the last search's tensor-core kernel (CUDA events on the launch stream);
  * only valid after the stream has been synchronised */

@@ -62,6 +62,18 @@ def test_exact_fallback_path(gpu, orc):
         assert g.last_stats()["fallback_queries"] == 64
 
 
+def test_exact_scan_rounds_cover_thousands_of_flagged_queries(gpu, orc):
+    """More flagged queries than one exact-scan round has workspace for (2048): the rounds cover them all."""
+    from deep_insight_face_b200.gallery import Gallery
+
+    rows, q, _ = make(orc, 3000, 2500, 64)
+    with Gallery(3000, 64, "l2", "bf16") as g:
+        g.set_option("force_fallback", 1)
+        g.add(rows)
+        check(orc, g, rows, q, 10, 0)
+        assert g.last_stats()["fallback_queries"] == 2500
+
+
 def test_ties_go_to_the_lower_row_and_short_gallery(gpu, orc):
     from deep_insight_face_b200.gallery import Gallery
 
