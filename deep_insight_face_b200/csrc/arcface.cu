@@ -20,6 +20,7 @@
 namespace dif {
 
 constexpr int kArcBN = 256;
+constexpr int kArcCtas = 2;   // CTA pairs: 64 KB stages -> a 3-deep ring instead of 2 (the 1-CTA 3xTF32 loop was TMA-latency bound)
 constexpr float kLog2e = 1.4426950408889634f;
 
 struct ArcMargin {
@@ -188,24 +189,28 @@ __global__ void __launch_bounds__(256) transpose_planes_kernel(const float* __re
 }
 
 // out_r = inv_r * (g_r - h_r (h_r . g_r)) with g = sum over `planes` partial planes (fixed order), h = hi + lo
-// normalised row; rows whose squared norm was clamped (inv == 1e6) are a plain scaling.  One block per row,
-// one thread per 4 columns: every load is independent and coalesced (the planes are read exactly once).
+// normalised row; rows whose squared norm was clamped (inv == 1e6) are a plain scaling.  TPR threads own one row
+// (TPR = 32: a warp per row, 8 rows per block, D <= 512; TPR = 256: a block per row, D <= 4096), one float4 group
+// per thread and pass: every load is independent and coalesced and the planes are read exactly once.
+template <int TPR>
 __global__ void __launch_bounds__(256) arc_norm_bwd_kernel(const float* __restrict__ g, int planes, size_t plane_stride,
                                                            const float* __restrict__ h_hi, const float* __restrict__ h_lo,
                                                            const float* __restrict__ inv, int R, int D,
                                                            float* __restrict__ out) {
   __shared__ float red[8];
-  const int r = blockIdx.x;
+  constexpr int kRows = 256 / TPR;
+  const int r = blockIdx.x * kRows + (int)threadIdx.x / TPR;
+  const int lane = (int)threadIdx.x % TPR;
+  const bool live = r < R;
   const size_t base = (size_t)r * D;
   float dot = 0.f;
-  // D <= 4096 and D % 4 == 0: each thread owns up to 4 float4 groups, kept in registers between the passes
   float4 a[4], h[4];
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    const int d = (threadIdx.x + t * 256) * 4;
+    const int d = (lane + t * TPR) * 4;
     a[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     h[t] = a[t];
-    if (d < D) {
+    if (live && d < D) {
       for (int s = 0; s < planes; ++s) {
         const float4 v = *reinterpret_cast<const float4*>(g + (size_t)s * plane_stride + base + d);
         a[t].x += v.x; a[t].y += v.y; a[t].z += v.z; a[t].w += v.w;
@@ -217,15 +222,18 @@ __global__ void __launch_bounds__(256) arc_norm_bwd_kernel(const float* __restri
     }
   }
   for (int o = 16; o >= 1; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
-  __syncthreads();
-  dot = 0.f;
-  for (int w = 0; w < 8; ++w) dot += red[w];
+  if (TPR > 32) {
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    dot = 0.f;
+    for (int w = 0; w < 8; ++w) dot += red[w];
+  }
+  if (!live) return;
   const float iv = inv[r];
   const bool clamped = iv >= 0.99e6f;   // 1 / sqrt(1e-12)
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
-    const int d = (threadIdx.x + t * 256) * 4;
+    const int d = (lane + t * TPR) * 4;
     if (d < D) {
       float4 o4;
       o4.x = clamped ? iv * a[t].x : iv * (a[t].x - h[t].x * dot);
@@ -235,6 +243,14 @@ __global__ void __launch_bounds__(256) arc_norm_bwd_kernel(const float* __restri
       *reinterpret_cast<float4*>(out + base + d) = o4;
     }
   }
+}
+
+static void launch_norm_bwd(const float* g, int planes, size_t plane_stride, const float* h_hi, const float* h_lo,
+                            const float* inv, int R, int D, float* out, cudaStream_t st) {
+  if (D <= 512)
+    arc_norm_bwd_kernel<32><<<(R + 7) / 8, 256, 0, st>>>(g, planes, plane_stride, h_hi, h_lo, inv, R, D, out);
+  else
+    arc_norm_bwd_kernel<256><<<R, 256, 0, st>>>(g, planes, plane_stride, h_hi, h_lo, inv, R, D, out);
 }
 
 struct ArcWorkspace {
@@ -256,8 +272,8 @@ static int tmaps(CUtensorMap* maps, const float* a_hi, const float* a_lo, int M,
                  int N, int K, int ldk) {
   if (int rc = make_tmap_2d(&maps[0], a_hi, M, K, (uint64_t)ldk * 4, GEMM_BM, 32, 0)) return rc;
   if (int rc = make_tmap_2d(&maps[1], a_lo, M, K, (uint64_t)ldk * 4, GEMM_BM, 32, 0)) return rc;
-  if (int rc = make_tmap_2d(&maps[2], b_hi, N, K, (uint64_t)ldk * 4, kArcBN, 32, 0)) return rc;
-  if (int rc = make_tmap_2d(&maps[3], b_lo, N, K, (uint64_t)ldk * 4, kArcBN, 32, 0)) return rc;
+  if (int rc = make_tmap_2d(&maps[2], b_hi, N, K, (uint64_t)ldk * 4, kArcBN / kArcCtas, 32, 0)) return rc;
+  if (int rc = make_tmap_2d(&maps[3], b_lo, N, K, (uint64_t)ldk * 4, kArcBN / kArcCtas, 32, 0)) return rc;
   return DIF_OK;
 }
 
@@ -281,10 +297,11 @@ extern "C" int dif_arcface(const float* X, const float* W, const int32_t* y, int
 
   // ---- GEMM shapes
   GemmShape fwd{};
-  fwd.m_blocks = (B + GEMM_BM - 1) / GEMM_BM;
+  const int bm = GEMM_BM * kArcCtas, units = std::max(1, sms / kArcCtas);
+  fwd.m_blocks = (B + bm - 1) / bm;
   fwd.n_tiles = (C + kArcBN - 1) / kArcBN;
   fwd.k_chunks = (D + 31) / 32;
-  fwd.n_splits = std::max(1, std::min(fwd.n_tiles, 2 * sms / std::max(1, fwd.m_blocks)));
+  fwd.n_splits = std::max(1, std::min(fwd.n_tiles, 2 * units / std::max(1, fwd.m_blocks)));
   fwd.tiles_per_split = (fwd.n_tiles + fwd.n_splits - 1) / fwd.n_splits;
   fwd.n_splits = (fwd.n_tiles + fwd.tiles_per_split - 1) / fwd.tiles_per_split;
   GemmShape gx{};   // dxh [B, D] = dcos [B, Cp] x whT [D, Cp]^T, split over K = classes
@@ -293,11 +310,11 @@ extern "C" int dif_arcface(const float* X, const float* W, const int32_t* y, int
   gx.k_chunks = (Cp + 31) / 32;
   gx.n_splits = gx.n_tiles;
   gx.tiles_per_split = 1;
-  gx.k_splits = std::max(1, std::min(gx.k_chunks, sms / std::max(1, gx.m_blocks * gx.n_tiles)));
+  gx.k_splits = std::max(1, std::min(gx.k_chunks, units / std::max(1, gx.m_blocks * gx.n_tiles)));
   gx.chunks_per_ksplit = (gx.k_chunks + gx.k_splits - 1) / gx.k_splits;
   gx.k_splits = (gx.k_chunks + gx.chunks_per_ksplit - 1) / gx.chunks_per_ksplit;
   GemmShape gw{};   // dwh [C, D] = dcosT [Cp, Bp] x xhT [D, Bp]^T
-  gw.m_blocks = (C + GEMM_BM - 1) / GEMM_BM;
+  gw.m_blocks = (C + bm - 1) / bm;
   gw.n_tiles = gx.n_tiles;
   gw.k_chunks = (Bp + 31) / 32;
   gw.n_splits = gw.n_tiles;
@@ -341,7 +358,7 @@ extern "C" int dif_arcface(const float* X, const float* W, const int32_t* y, int
   CUtensorMap maps[4];
   if (int rc = tmaps(maps, F(o_xh), F(o_xl), B, F(o_wh), F(o_wl), C, D, D)) return rc;
   ArcFwdEpi::Params fp{F(o_cos), y, reinterpret_cast<float2*>(ws + o_part), B, C, Cp, fwd.n_splits, mg};
-  if (int rc = launch_nt_gemm<0, kArcBN, 1, 0, ArcFwdEpi>(maps, fwd, fp, sms, st)) return rc;
+  if (int rc = launch_nt_gemm<0, kArcBN, kArcCtas, 0, ArcFwdEpi>(maps, fwd, fp, units, st)) return rc;
   // ---- 2. loss
   arc_loss_kernel<<<(B + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float2*>(ws + o_part), fwd.n_splits, F(o_cos), Cp,
                                                   y, B, mg, loss, F(o_logz), F(o_dphi));
@@ -361,14 +378,14 @@ extern "C" int dif_arcface(const float* X, const float* W, const int32_t* y, int
   // ---- 4. dxh (split-K planes) and dwh
   if (int rc = tmaps(maps, F(o_dh), F(o_dl), B, F(o_wth), F(o_wtl), D, Cp, Cp)) return rc;
   StoreEpi::Params sx{F(o_gx), B, D, D, gx.n_splits, (size_t)B * D};
-  if (int rc = launch_nt_gemm<0, kArcBN, 1, 0, StoreEpi>(maps, gx, sx, sms, st)) return rc;
+  if (int rc = launch_nt_gemm<0, kArcBN, kArcCtas, 0, StoreEpi>(maps, gx, sx, units, st)) return rc;
   if (int rc = tmaps(maps, F(o_th), F(o_tl), C, F(o_xth), F(o_xtl), D, Bp, Bp)) return rc;
   StoreEpi::Params sw{F(o_gw), C, D, D, gw.n_splits, 0};
-  if (int rc = launch_nt_gemm<0, kArcBN, 1, 0, StoreEpi>(maps, gw, sw, sms, st)) return rc;
+  if (int rc = launch_nt_gemm<0, kArcBN, kArcCtas, 0, StoreEpi>(maps, gw, sw, units, st)) return rc;
   // ---- 5. l2_normalize backward
-  arc_norm_bwd_kernel<<<B, 256, 0, st>>>(F(o_gx), gx.k_splits, (size_t)B * D, F(o_xh), F(o_xl), F(o_xi), B, D, dX);
+  launch_norm_bwd(F(o_gx), gx.k_splits, (size_t)B * D, F(o_xh), F(o_xl), F(o_xi), B, D, dX, st);
   DIF_LAUNCH_OK();
-  arc_norm_bwd_kernel<<<C, 256, 0, st>>>(F(o_gw), 1, 0, F(o_wh), F(o_wl), F(o_wi), C, D, dW);
+  launch_norm_bwd(F(o_gw), 1, 0, F(o_wh), F(o_wl), F(o_wi), C, D, dW, st);
   DIF_LAUNCH_OK();
   return DIF_OK;
 }
