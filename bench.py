@@ -180,6 +180,19 @@ def secondary_metrics(torch, device):
                      "alg_gflop_fwd": 2.0 * B * B * D / 1e9,
                      "cpu_oracle_steps_per_s": 1e3 / cpu_ms, "note": "fwd + bwd; steps_per_s = CUDA-graphed BatchHardStep, e2e = numpy in/out through "
                              "dif_batch_hard_host"}
+    # a8: the tensorflow_addons losses the reference compiles its triplet models with (networks/triplet.py:196,209,211)
+    from deep_insight_face_b200.common.tfa_losses import TFA_HARD, TFA_SEMIHARD, tfa_triplet
+
+    for name, P, K, D, iters in (("tfa_triplet_B72_D128", 18, 4, 128, 200), ("tfa_triplet_B4096_D128", 1024, 4, 128, 20)):
+        cent = 0.05 * rng.standard_normal((P, D)).astype(np.float32)
+        emb = (np.repeat(cent, K, 0) + 0.5 * rng.standard_normal((P * K, D))).astype(np.float32)
+        xd = torch.from_numpy(emb).to(device)
+        ld = torch.from_numpy(np.repeat(np.arange(P), K).astype(np.int32)).to(device)
+        ms_h = timed(lambda: tfa_triplet(ld, xd, TFA_HARD, 1.0), iters)
+        ms_s = timed(lambda: tfa_triplet(ld, xd, TFA_SEMIHARD, 1.0), iters)
+        out[name] = {"hard_steps_per_s": 1e3 / ms_h, "semihard_steps_per_s": 1e3 / ms_s, "hard_ms": ms_h, "semihard_ms": ms_s,
+                     "note": "fwd + bwd, device tensors in/out, 5 kernels: canonical fp32 B x B matrix (CUDA cores), "
+                             "row kernel, finalize, fold, sparse gradient"}
     # C4: verification sweep, 6000 LFW-style pairs, 10 folds, 400 + 4000 thresholds (evaluation/utility.py:10-33)
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     from synth import pairs as synth_pairs

@@ -4,6 +4,7 @@ Hand-written sm_100a kernels (tcgen05 / TMEM / TMA) behind a C ABI (include/dif_
 ctypes (_ffi.py) and exposed through the reference's own names:
 
     common.losses        BatchHardTripletLoss, BatchHardTripletLossEuclidean, ...AutoAlpha, BatchAllTripletLoss
+    common.tfa_losses    TripletHardLoss, TripletSemiHardLoss (the tfa.losses the reference compiles with)
     networks.triplet     triplet_loss
     networks.siamese     euclidean_distance, contrastive_loss
     networks.utils       distance, distance_to_proba, gaussian_kernel_dist_to_prob

@@ -87,6 +87,7 @@ SIGNATURES = {
     "dif_batch_hard_host": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
     "dif_batch_hard_set_path": (_i32, [_i32]),
     "dif_batch_all": (_i32, [_vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
+    "dif_tfa_triplet": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _f32, _vp, _vp]),
     "dif_labels_from_onehot": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "dif_triplet_apn": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "dif_euclidean_distance": (_i32, [_vp, _vp, _i32, _i32, _f32, _vp, _vp]),

@@ -1,0 +1,148 @@
+"""Drop-ins for the two tensorflow_addons losses the reference trains its triplet models with:
+`tfa.losses.TripletHardLoss()` (deep_insight_face/networks/triplet.py:196,211) and
+`tfa.losses.TripletSemiHardLoss()` (:209), both with their defaults and sparse integer labels
+(`class_mode='sparse'`, training/triplet.py:72).
+
+Same constructor arguments as tfa (margin=1.0, soft=False, distance_metric="L2" | "squared-L2") and the same
+result: a SCALAR (tfa reduces inside the loss).  The arithmetic runs in libdif_b200.so (csrc/tfa_triplet.cu);
+there is no CPU path.  distance_metric="angular" and callables are not implemented (the reference never passes them).
+
+    loss(y_true, y_pred)                numpy in -> python float; torch-CUDA in -> differentiable 0-d tensor
+    loss.loss_and_grad(y_true, y_pred)  (loss, d loss / d y_pred [B, D], info) in one fused call
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _ffi
+from .losses import _LossBase
+
+TFA_HARD, TFA_SEMIHARD, TFA_SOFT, TFA_SQUARED = 0, 1, 4, 8
+
+
+def _metric_flag(distance_metric) -> int:
+    if distance_metric == "L2":
+        return 0
+    if distance_metric == "squared-L2":
+        return TFA_SQUARED
+    raise NotImplementedError(f"distance_metric {distance_metric!r}: only 'L2' and 'squared-L2' run on the GPU path")
+
+
+def tfa_triplet(labels, embeddings, kind: int, margin: float = 1.0, dloss: float = 1.0, want_grad: bool = True,
+                want_indices: bool = True):
+    """Framework-neutral core.  Returns (loss, grad or None, info); device tensors in -> device tensors out."""
+    import torch
+
+    lib = _ffi.load_library()
+    on_dev = _ffi.is_device_tensor(embeddings)
+    emb = embeddings.detach().contiguous().float() if on_dev else torch.from_numpy(
+        _ffi.host_array(embeddings, np.float32)).cuda()
+    if emb.dim() != 2:
+        raise ValueError("embeddings must be [B, D]")
+    dev = emb.device
+    _ffi.init(dev.index or 0)
+    B, D = emb.shape
+    st = _ffi.current_stream_ptr(dev)
+    if _ffi.is_device_tensor(labels):
+        lab = labels.detach().reshape(-1).to(torch.int32).contiguous()
+    else:
+        lab_np = np.asarray(_ffi.host_array(labels, None))
+        if lab_np.ndim == 2 and lab_np.shape[1] == 1:   # tfa reshapes [B] or [B, 1] to a column
+            lab_np = lab_np.reshape(-1)
+        if lab_np.ndim != 1:
+            raise ValueError("labels must be sparse integer class ids [B] (tfa convention), not one-hot")
+        lab = torch.from_numpy(np.ascontiguousarray(lab_np, dtype=np.int32)).to(dev)
+    if lab.shape != (B,):
+        raise ValueError(f"labels must be sparse int [B] (or [B, 1]); got {tuple(lab.shape)} for B={B}")
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    hard = (kind & 3) == TFA_HARD
+    pos = torch.empty(B, dtype=torch.int32, device=dev) if (hard and want_indices) else None
+    neg = torch.empty(B, dtype=torch.int32, device=dev) if (hard and want_indices) else None
+    grad = torch.empty_like(emb) if want_grad else None
+    _ffi.check(lib.dif_tfa_triplet(_ffi.ptr(emb), _ffi.ptr(lab), B, D, int(kind), float(margin), _ffi.ptr(loss),
+                                   _ffi.ptr(pos), _ffi.ptr(neg), float(dloss), _ffi.ptr(grad), st))
+    info = {} if pos is None else {"pos_idx": pos, "neg_idx": neg}
+    if on_dev:
+        return loss[0], grad, info
+    info = {k: v.cpu().numpy() for k, v in info.items()}
+    return float(loss.cpu()[0]), (None if grad is None else grad.cpu().numpy()), info
+
+
+class _TfaTripletBase(_LossBase):
+    _kind = TFA_HARD
+
+    def __init__(self, margin=1.0, distance_metric="L2", name=None, **kwargs):
+        super().__init__(name=name, **kwargs)
+        self.margin = margin
+        self.distance_metric = distance_metric
+        self._flag = _metric_flag(distance_metric)
+        self.last_info = None
+
+    def _code(self) -> int:
+        return self._kind | self._flag
+
+    def call(self, y_true, y_pred):
+        if _ffi.is_device_tensor(y_pred) and y_pred.requires_grad:
+            import torch
+
+            code, margin = self._code(), self.margin
+
+            class _Fn(torch.autograd.Function):
+                @staticmethod
+                def forward(ctx, emb):
+                    loss, _, _ = tfa_triplet(y_true, emb, code, margin, want_grad=False, want_indices=False)
+                    ctx.save_for_backward(emb)
+                    return loss
+
+                @staticmethod
+                def backward(ctx, dloss):
+                    (emb,) = ctx.saved_tensors
+                    return tfa_triplet(y_true, emb, code, margin, dloss=float(dloss), want_indices=False)[1]
+
+            return _Fn.apply(y_pred)
+        loss, _, info = tfa_triplet(y_true, y_pred, self._code(), self.margin, want_grad=False)
+        self.last_info = info
+        return loss
+
+    def __call__(self, y_true, y_pred, sample_weight=None):
+        return self.call(y_true, y_pred)   # already a scalar, as in tfa
+
+    def loss_and_grad(self, y_true, y_pred, dloss: float = 1.0):
+        loss, grad, info = tfa_triplet(y_true, y_pred, self._code(), self.margin, dloss=dloss)
+        self.last_info = info
+        return loss, grad, info
+
+    def get_config(self):
+        config = super().get_config()
+        config.update({"margin": self.margin, "distance_metric": self.distance_metric})
+        return config
+
+    @classmethod
+    def from_config(cls, config):
+        return cls(**config)
+
+
+class TripletHardLoss(_TfaTripletBase):
+    """tfa.losses.TripletHardLoss(margin=1.0, soft=False, distance_metric="L2"): mean over anchors of
+    max(hardest positive - hardest negative + margin, 0), or log1p(exp(.)) when soft."""
+
+    _kind = TFA_HARD
+
+    def __init__(self, margin=1.0, soft=False, distance_metric="L2", name=None, **kwargs):
+        super().__init__(margin=margin, distance_metric=distance_metric, name=name, **kwargs)
+        self.soft = bool(soft)
+
+    def _code(self) -> int:
+        return super()._code() | (TFA_SOFT if self.soft else 0)
+
+    def get_config(self):
+        config = super().get_config()
+        config["soft"] = self.soft
+        return config
+
+
+class TripletSemiHardLoss(_TfaTripletBase):
+    """tfa.losses.TripletSemiHardLoss(margin=1.0, distance_metric="L2"): for every positive pair the closest
+    negative farther than the positive (else the farthest negative); sum of the hinges / number of pairs."""
+
+    _kind = TFA_SEMIHARD

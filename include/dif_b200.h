@@ -139,6 +139,19 @@ int dif_batch_hard_set_path(int path);
  * demb [B*D] gradient of sum_i dloss[i]*loss[i] (dloss NULL -> 1/B each; demb NULL skips the backward pass). */
 int dif_batch_all(const float* emb, const int32_t* labels, int B, int D, float alpha, float* loss, const float* dloss,
                   float* demb, void* stream);
+/* tensorflow_addons TripletHardLoss / TripletSemiHardLoss with their defaults, the third-party losses of
+ * deep_insight_face/networks/triplet.py:196,209,211 (arithmetic of tensorflow_addons/losses/triplet.py and
+ * metric_learning.py, not in the reference tree).  labels [B] sparse int32; kind = DIF_TFA_HARD | DIF_TFA_SEMIHARD,
+ * optionally | DIF_TFA_SOFT (hard only: log1p(exp(hp - hn))) | DIF_TFA_SQUARED (distance_metric "squared-L2",
+ * default "L2").  loss [1] scalar (mean over anchors | sum over positive pairs / their number, NaN when there
+ * is none, as in tfa); pos_idx / neg_idx [B] optional, hard only: mined columns, first index on ties, -1 if the
+ * anchor has no positive / negative; demb [B*D] optional = dloss * d loss / d emb.  B <= 8192, D <= 512. */
+#define DIF_TFA_HARD 0
+#define DIF_TFA_SEMIHARD 1
+#define DIF_TFA_SOFT 4
+#define DIF_TFA_SQUARED 8
+int dif_tfa_triplet(const float* emb, const int32_t* labels, int B, int D, int kind, float margin, float* loss,
+                    int32_t* pos_idx, int32_t* neg_idx, float dloss, float* demb, void* stream);
 /* tf.argmax(labels, axis=1) of a one-hot [B, C] fp32 matrix (first maximum), losses.py:35 */
 int dif_labels_from_onehot(const float* onehot, int B, int C, int32_t* labels, void* stream);
 
