@@ -1,9 +1,11 @@
 """Host-side callers either side of the loss: the PK batch sampler of
 deep_insight_face/datagen/generator.py:15-41 and the LFW-style pairs.txt writer of
-scripts/generate_pairs.py:60-76.  Pure index / text logic - nothing here touches the GPU."""
+scripts/generate_pairs.py:60-76 and the pickled verification `.bin` of scripts/raw_img_tf.py:77-86.
+Pure index / text logic - nothing here touches the GPU."""
 from __future__ import annotations
 
 import io
+import pickle
 from typing import List, Sequence, Tuple
 
 import numpy as np
@@ -64,3 +66,22 @@ def write_pairs_to_file(fname: str, match_folds: List[List[Match]], mismatch_fol
 def pairs_issame(pairs) -> np.ndarray:
     """issame flag of each pairs.txt row (3 fields = same person, 4 = different; evaluation/utility.py:228-236)."""
     return np.array([len(p) == 3 for p in pairs], dtype=bool)
+
+
+def write_test_bin(fname: str, encoded_images: Sequence[bytes], issame_list: Sequence[bool]) -> None:
+    """scripts/raw_img_tf.py:77-86: the verification `.bin` is `pickle.dump([encoded_jpegs, issame_list])` with
+    two images per pair in pairs.txt order (get_paths order).  Encoding the JPEGs is the caller's business."""
+    if len(encoded_images) != 2 * len(issame_list):
+        raise ValueError("%d images for %d pairs: expected two per pair" % (len(encoded_images), len(issame_list)))
+    with open(fname, "wb") as f:
+        pickle.dump([list(encoded_images), [bool(s) for s in issame_list]], f)
+
+
+def read_test_bin(fname: str):
+    """Inverse of write_test_bin -> (encoded_images, issame bool array).  The embeddings of image 2i and 2i+1 are
+    what evaluation.utility.evaluate expects at rows 2i and 2i+1 (evaluation/utility.py:18-19)."""
+    with open(fname, "rb") as f:
+        images, issame = pickle.load(f, encoding="bytes")
+    if len(images) != 2 * len(issame):
+        raise ValueError("%s: %d images for %d pairs" % (fname, len(images), len(issame)))
+    return list(images), np.asarray(issame, dtype=bool)

@@ -10,6 +10,7 @@ the reference whenever the distances are.
 from __future__ import annotations
 
 import math
+import os
 
 import numpy as np
 
@@ -241,3 +242,41 @@ def read_pairs(pairs_filename):
         for line in f.readlines()[1:]:
             pairs.append(line.strip().split())
     return pairs
+
+
+def add_extension(path):
+    """utility.py:247-253: the image behind an LFW stem is a .jpg or a .png; anything else is an error."""
+    for ext in (".jpg", ".png"):
+        if os.path.exists(path + ext):
+            return path + ext
+    raise RuntimeError('No file "%s" with extension png or jpg.' % path)
+
+
+def get_paths(lfw_dir, pairs):
+    """utility.py:222-244: expand pairs.txt rows into a flat [path0, path1, ...] list and the issame flags.
+    A 3-field row is (name, i, j) of one person, a 4-field row (name1, i, name2, j) of two; images are
+    `<dir>/<name>/<name>_%04d.{jpg,png}`.  Rows whose images are missing are skipped and counted, as in the
+    reference (which, however, raises from add_extension before it can skip: here a missing stem skips too)."""
+    path_list, issame_list, skipped = [], [], 0
+
+    def stem(name, idx):
+        return os.path.join(lfw_dir, name, "%s_%04d" % (name, int(idx)))
+
+    for pair in pairs:
+        if len(pair) == 3:
+            stems, same = (stem(pair[0], pair[1]), stem(pair[0], pair[2])), True
+        elif len(pair) == 4:
+            stems, same = (stem(pair[0], pair[1]), stem(pair[2], pair[3])), False
+        else:
+            skipped += 1
+            continue
+        try:
+            found = [add_extension(s) for s in stems]
+        except RuntimeError:
+            skipped += 1
+            continue
+        path_list += found
+        issame_list.append(same)
+    if skipped > 0:
+        print('Skipped %d image pairs' % skipped)
+    return path_list, issame_list

@@ -1,5 +1,6 @@
 """Host-side helpers around the hot path: PK sampler, label layout, pairs.txt round trip."""
 import numpy as np
+import pytest
 
 from deep_insight_face_b200 import datagen
 
@@ -24,3 +25,27 @@ def test_pairs_file_round_trip(tmp_path):
     # the reader half lives with the evaluators (reference: evaluation/utility.py:256-262); no GPU needed for it
     pairs = [ln.split("\t") for ln in lines[1:]]
     assert datagen.pairs_issame(pairs).tolist() == [True, True, False, True, False, False]
+
+
+def test_get_paths_and_test_bin_round_trip(tmp_path):
+    """pairs.txt rows -> image paths (evaluation/utility.py:222-253) -> pickled .bin (scripts/raw_img_tf.py:77-86)."""
+    from deep_insight_face_b200 import datagen
+    from deep_insight_face_b200.evaluation import utility as U
+
+    for name, idx, ext in (("ann", 1, ".jpg"), ("ann", 2, ".png"), ("bob", 1, ".jpg")):
+        d = tmp_path / name
+        d.mkdir(exist_ok=True)
+        (d / ("%s_%04d%s" % (name, idx, ext))).write_bytes(b"img-%s-%d" % (name.encode(), idx))
+    pairs = [["ann", "1", "2"], ["ann", "2", "bob", "1"], ["ann", "1", "9"], ["bob", "1", "cat", "1"]]
+    paths, issame = U.get_paths(str(tmp_path), pairs)
+    assert issame == [True, False] and len(paths) == 4
+    assert paths[0].endswith("ann_0001.jpg") and paths[1].endswith("ann_0002.png") and paths[3].endswith("bob_0001.jpg")
+    with pytest.raises(RuntimeError):
+        U.add_extension(str(tmp_path / "ann" / "ann_0009"))
+    blobs = [open(p, "rb").read() for p in paths]
+    fname = str(tmp_path / "test.bin")
+    datagen.write_test_bin(fname, blobs, issame)
+    got, same = datagen.read_test_bin(fname)
+    assert got == blobs and same.tolist() == issame
+    with pytest.raises(ValueError):
+        datagen.write_test_bin(fname, blobs[:3], issame)
