@@ -10,7 +10,7 @@ ctypes (_ffi.py) and exposed through the reference's own names:
     networks.utils       distance, distance_to_proba, gaussian_kernel_dist_to_prob
     evaluation.utility   distance, calculate_accuracy, calculate_val_far, calculate_roc, calculate_val, evaluate
     api                  face_distance, compare_faces
-    predictions          TripletPrediction.verify
+    predictions          TripletPrediction.verify, SiamesePrediction.verify
     gallery              Gallery, ShardedGallery (1:N top-k search, new)
 
 There is no CPU fallback: importing is cheap, but any compute call needs libdif_b200.so and a B200.

@@ -71,6 +71,8 @@ SIGNATURES = {
     "dif_gallery_add_host": (_i32, [_vp, _vp, _vp, _i64]),
     "dif_gallery_fill_synth": (_i32, [_vp, _u64, _i64, _i64, _vp]),
     "dif_gallery_set_id_base": (_i32, [_vp, _i64]),
+    "dif_gallery_remove": (_i32, [_vp, _vp, _i64, _vp]),
+    "dif_gallery_get_ids": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "dif_gallery_size": (_i64, [_vp]),
     "dif_gallery_set_option": (_i32, [_vp, C.c_char_p, _i32]),
     "dif_gallery_reset": (_i32, [_vp]),

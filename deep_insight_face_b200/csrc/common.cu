@@ -12,6 +12,7 @@ namespace dif {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 static int g_sm_count = 0;
+static int g_device = -1;   // the one device this process is bound to (dif_init)
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -74,6 +75,8 @@ int dif_init(int device) {
     return DIF_ERR_NO_DEVICE;
   }
   DIF_REQUIRE(device >= 0 && device < n, DIF_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+  DIF_REQUIRE(dif::g_device < 0 || dif::g_device == device, DIF_ERR_STATE,
+              "this process is bound to device %d (one process per GPU); dif_init(%d) refused", dif::g_device, device);
   DIF_CUDA_OK(cudaSetDevice(device));
   cudaDeviceProp prop;
   DIF_CUDA_OK(cudaGetDeviceProperties(&prop, device));
@@ -81,6 +84,7 @@ int dif_init(int device) {
               "device %d is sm_%d%d; libdif_b200 is built for sm_100a (B200) only", device, prop.major, prop.minor);
   dif::g_sm_count = prop.multiProcessorCount;
   DIF_CUDA_OK(cudaFree(0));
+  dif::g_device = device;
   return DIF_OK;
 }
 

@@ -314,6 +314,33 @@ __global__ void gather_rows_kernel(const float* p0, const float* p1, int64_t row
 // ==========================================================================================
 using namespace dif;
 
+namespace dif {
+__global__ void iota_ids_kernel(int64_t* ids, int64_t n, int64_t base) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) ids[i] = base + i;
+}
+
+// Order-preserving delete, one chunk: every kept row r of [r_begin, r_end) goes to stage row
+// r - (#removed rows below r) - new_begin.  One warp per row, rows are `words` 4-byte words.
+__global__ void __launch_bounds__(256) compact_rows_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ stage,
+                                                           int words, const int64_t* __restrict__ removed, int64_t n_removed,
+                                                           int64_t r_begin, int64_t r_end, int64_t new_begin) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), stride = (int64_t)gridDim.x * 8;
+  for (int64_t r = r_begin + warp0; r < r_end; r += stride) {
+    int64_t lo = 0, hi = n_removed;   // first index with removed[idx] >= r
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (removed[mid] < r) lo = mid + 1;
+      else hi = mid;
+    }
+    if (lo < n_removed && removed[lo] == r) continue;
+    const uint32_t* s = src + (size_t)r * words;
+    uint32_t* d = stage + (size_t)(r - lo - new_begin) * words;
+    for (int w = lane; w < words; w += 32) d[w] = s[w];
+  }
+}
+}  // namespace dif
+
 struct dif_gallery {
   int device = 0;
   int64_t capacity = 0;
@@ -556,6 +583,69 @@ int dif_gallery_add_host(dif_gallery_t* g, const float* rows_host, const int64_t
                                 ids_host ? (const int64_t*)((char*)g->d_stage + rb) : nullptr, m, g->own_stream))
       return rc;
     DIF_CUDA_OK(cudaStreamSynchronize(g->own_stream));
+  }
+  return DIF_OK;
+}
+
+int dif_gallery_remove(dif_gallery_t* g, const int64_t* rows_host, int64_t n, void* stream) {
+  DIF_REQUIRE(g && (rows_host || n == 0) && n >= 0, DIF_ERR_INVALID, "dif_gallery_remove: invalid argument");
+  if (n == 0) return DIF_OK;
+  for (int64_t i = 0; i < n; ++i)
+    DIF_REQUIRE(rows_host[i] >= 0 && rows_host[i] < g->size && (i == 0 || rows_host[i] > rows_host[i - 1]), DIF_ERR_INVALID,
+                "dif_gallery_remove: rows must be strictly ascending and below the gallery size %lld (entry %lld = %lld)",
+                (long long)g->size, (long long)i, (long long)rows_host[i]);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t* removed = nullptr;
+  DIF_CUDA_OK(cudaMalloc((void**)&removed, (size_t)n * 8));
+  struct Free {
+    void* p;
+    ~Free() { cudaFree(p); }
+  } guard{removed};
+  DIF_CUDA_OK(cudaMemcpyAsync(removed, rows_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  if (!g->has_ids) {   // ids were the row numbers: make them explicit before rows move
+    if (!g->ids) DIF_CUDA_OK(cudaMalloc((void**)&g->ids, (size_t)g->capacity * 8));
+    iota_ids_kernel<<<(unsigned)std::min<int64_t>((g->size + 255) / 256, 148 * 8), 256, 0, st>>>(g->ids, g->size, g->id_base);
+    DIF_LAUNCH_OK();
+    g->has_ids = true;
+  }
+  const int64_t first = rows_host[0];
+  const int64_t chunk = std::max<int64_t>(1, (int64_t)(32u << 20) / (g->D * 4));
+  if (int rc = ensure_stage(g, (size_t)chunk * g->D * 4)) return rc;
+  struct Arr {
+    void* base;
+    int words;   // 4-byte words per row
+  } arrs[5] = {{g->g0, g->D}, {g->g1, g->D}, {g->gb, g->D / 2}, {g->gsq, 1}, {g->ids, 2}};
+  for (const Arr& a : arrs) {
+    if (!a.base) continue;
+    for (int64_t r0 = first; r0 < g->size; r0 += chunk) {
+      const int64_t r1 = std::min(g->size, r0 + chunk);
+      const int64_t before = std::lower_bound(rows_host, rows_host + n, r0) - rows_host;
+      const int64_t inside = (std::lower_bound(rows_host, rows_host + n, r1) - rows_host) - before;
+      const int64_t kept = (r1 - r0) - inside, new_begin = r0 - before;
+      if (kept == 0) continue;
+      compact_rows_kernel<<<(unsigned)std::min<int64_t>((r1 - r0 + 7) / 8, 148 * 16), 256, 0, st>>>(
+          (const uint32_t*)a.base, (uint32_t*)g->d_stage, a.words, removed, n, r0, r1, new_begin);
+      DIF_LAUNCH_OK();
+      // the destination ends at or before r1: it may overlap this chunk's (already staged) source, never a later one
+      DIF_CUDA_OK(cudaMemcpyAsync((char*)a.base + (size_t)new_begin * a.words * 4, g->d_stage, (size_t)kept * a.words * 4,
+                                  cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  DIF_CUDA_OK(cudaMemsetAsync(g->gsq + (g->size - n), 0, (size_t)n * 4, st));
+  DIF_CUDA_OK(cudaStreamSynchronize(st));   // `removed` is freed on return
+  g->size -= n;
+  return DIF_OK;
+}
+
+int dif_gallery_get_ids(dif_gallery_t* g, int64_t row0, int64_t n, int64_t* out, void* stream) {
+  DIF_REQUIRE(g && out && row0 >= 0 && n >= 0 && row0 + n <= g->size, DIF_ERR_INVALID, "dif_gallery_get_ids: range");
+  if (n == 0) return DIF_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g->has_ids) {
+    DIF_CUDA_OK(cudaMemcpyAsync(out, g->ids + row0, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+  } else {
+    iota_ids_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(out, n, g->id_base + row0);
+    DIF_LAUNCH_OK();
   }
   return DIF_OK;
 }

@@ -92,6 +92,29 @@ class Gallery:
     def reset(self) -> None:
         _ffi.check(self._lib.dif_gallery_reset(self._h))
 
+    def ids(self, row0: int = 0, n: int | None = None) -> np.ndarray:
+        """ids of the stored rows (explicit ids, or id_base + row) as a host int64 array."""
+        import torch
+
+        n = len(self) - row0 if n is None else n
+        out = torch.empty(n, dtype=torch.int64, device=f"cuda:{self.device}")
+        _ffi.check(self._lib.dif_gallery_get_ids(self._h, int(row0), int(n), _ffi.ptr(out),
+                                                 _ffi.current_stream_ptr(out.device)))
+        return out.cpu().numpy()
+
+    def remove(self, ids=None, rows=None) -> int:
+        """Delete identities by id (every row carrying one of `ids`) or by row number; the remaining rows keep
+        their order and ids.  Returns the number of rows removed.  (The persistent index of SURVEY 8f row 4,
+        replacing the python dict of predictions.py:112.)"""
+        if (ids is None) == (rows is None):
+            raise ValueError("pass exactly one of ids / rows")
+        if ids is not None:
+            rows = np.flatnonzero(np.isin(self.ids(), np.asarray(ids, dtype=np.int64).reshape(-1)))
+        rows = np.unique(np.asarray(rows, dtype=np.int64).reshape(-1))
+        if rows.size:
+            _ffi.check(self._lib.dif_gallery_remove(self._h, _ffi.ptr(rows), int(rows.size), None))
+        return int(rows.size)
+
     def rows(self, row0: int = 0, n: int | None = None) -> np.ndarray:
         """Canonical stored rows (normalised for cosine) as a host array."""
         import torch

@@ -46,7 +46,10 @@ extern "C" {
 #define DIF_MAX_TOPK 24
 
 /* ---- library ------------------------------------------------------------------------------ */
-int dif_init(int device);             /* selects the device, checks it is sm_100, warms the context */
+/* Selects the device, checks it is sm_100, warms the context.  One process drives ONE GPU (the multi-GPU model
+ * is one process per GPU over torch.distributed): the library's workspaces and kernel attributes belong to the
+ * device of the first successful call; a later call naming another device fails with DIF_ERR_STATE. */
+int dif_init(int device);
 const char* dif_last_error(void);
 int dif_sync(void* stream);
 const char* dif_version(void);
@@ -69,6 +72,13 @@ int dif_gallery_add_host(dif_gallery_t* g, const float* rows_host, const int64_t
 /* rows [row0, row0+n) of the synthetic gallery of oracle/dif_oracle.c:dif_synth_value (seed, dim) */
 int dif_gallery_fill_synth(dif_gallery_t* g, uint64_t seed, int64_t row0, int64_t n, void* stream);
 int dif_gallery_set_id_base(dif_gallery_t* g, int64_t id_base); /* default ids = id_base + local row */
+/* Incremental delete (the persistent identity index replacing the python dict of
+ * deep_insight_face/predictions.py:112).  rows_host: n strictly ascending row numbers; the remaining rows keep
+ * their order (so "ties -> lower row" still means "earlier enrolled") and their ids - default ids (id_base + row)
+ * are frozen into explicit ids first, after which dif_gallery_add needs ids too.  Synchronises the stream. */
+int dif_gallery_remove(dif_gallery_t* g, const int64_t* rows_host, int64_t n, void* stream);
+/* ids of rows [row0, row0+n) into a DEVICE buffer */
+int dif_gallery_get_ids(dif_gallery_t* g, int64_t row0, int64_t n, int64_t* out, void* stream);
 int64_t dif_gallery_size(const dif_gallery_t* g);
 /* tuning / test knobs: "gemm_ctas" = 1 | 2 (CTA pair, default); "force_fallback" = 0 | 1 (send every
  * query through the exact brute-force path as well); "resident_queries" = -1 auto | 0 | 1 (keep the

@@ -212,3 +212,40 @@ def test_full_size_properties(gpu, orc):
     gal = orc.synth_rows(3, 0, N, D)
     ws, wr = orc.gallery_search(gal, q[:24].cpu().numpy(), k, 1)
     assert np.array_equal(wr, ids[:24]) and np.array_equal(ws.view(np.uint32), s[:24].view(np.uint32))
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("explicit_ids", [False, True])
+def test_incremental_remove_keeps_order_and_ids(gpu, orc, precision, explicit_ids):
+    """Delete rows from a live gallery: the survivors keep their order and ids, and the search
+    equals the oracle on the surviving rows; rows can be enrolled again afterwards."""
+    from deep_insight_face_b200.gallery import Gallery
+
+    N, Q, D, k = 90001, 200, 128, 10     # > one 32 MB compaction chunk (65536 rows of 128 floats)
+    rows, q, _ = make(orc, N, Q, D)
+    rng = np.random.default_rng(9)
+    ids = (rng.permutation(N).astype(np.int64) + 5_000_000) if explicit_ids else None
+    gone = np.unique(np.concatenate([rng.integers(0, N, size=300), np.arange(70000, 70050), [0, N - 1]]))
+    keep = np.setdiff1d(np.arange(N), gone)
+    with Gallery(N, D, "cosine", precision) as g:
+        g.add(rows, ids)
+        if not explicit_ids:
+            g.set_id_base(1000)
+        want_ids = ids if explicit_ids else np.arange(N, dtype=np.int64) + 1000
+        if explicit_ids:
+            assert g.remove(ids=want_ids[gone]) == gone.size
+        else:
+            assert g.remove(rows=gone) == gone.size
+        assert len(g) == keep.size
+        assert np.array_equal(g.ids(), want_ids[keep])
+        assert np.array_equal(g.rows(), orc.normalize_rows(rows[keep]))
+        s, got_ids, r = check(orc, g, rows[keep], q, k, 1)
+        assert np.array_equal(got_ids, want_ids[keep][r])
+        # enrol new rows behind the survivors
+        extra = orc.synth_rows(77, 0, 40, D)
+        g.add(extra, np.arange(40, dtype=np.int64) + 9_000_000)
+        allrows = np.concatenate([rows[keep], extra])
+        _, got_ids, r = check(orc, g, allrows, np.concatenate([q[:20], extra[:5]]), k, 1)
+        assert (got_ids[20:, 0] == np.arange(5) + 9_000_000).all()
+        with pytest.raises(RuntimeError):
+            g.remove(rows=[len(g)])
