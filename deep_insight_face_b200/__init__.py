@@ -7,6 +7,7 @@ ctypes (_ffi.py) and exposed through the reference's own names:
     common.tfa_losses    TripletHardLoss, TripletSemiHardLoss (the tfa.losses the reference compiles with)
     networks.triplet     triplet_loss
     networks.siamese     euclidean_distance, contrastive_loss
+    networks.head        l2_normalize (the embedding head's Lambda)
     networks.utils       distance, distance_to_proba, gaussian_kernel_dist_to_prob
     evaluation.utility   distance, calculate_accuracy, calculate_val_far, calculate_roc, calculate_val, evaluate
     api                  face_distance, compare_faces

@@ -91,6 +91,8 @@ SIGNATURES = {
     "dif_batch_all": (_i32, [_vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "dif_tfa_triplet": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _f32, _vp, _vp]),
     "dif_labels_from_onehot": (_i32, [_vp, _i32, _i32, _vp, _vp]),
+    "dif_l2_normalize": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp]),
+    "dif_l2_normalize_bwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "dif_triplet_apn": (_i32, [_vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "dif_euclidean_distance": (_i32, [_vp, _vp, _i32, _i32, _f32, _vp, _vp]),
     "dif_contrastive_loss": (_i32, [_vp, _vp, _i32, _f32, _vp, _vp, _vp]),

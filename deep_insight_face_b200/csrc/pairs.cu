@@ -291,7 +291,60 @@ static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 using namespace dif;
 
+// ---------------------------------------------------------------------------------------------
+// Embedding head: tf.nn.l2_normalize(x, axis=1) = x * rsqrt(max(sum x^2, 1e-12))
+// (deep_insight_face/networks/inceptionv3.py:305, networks/triplet.py:138) and its backward
+// dx = inv * (g - y (y . g)), a plain scaling where the squared norm was clamped.  One warp per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2_normalize_kernel(const float* __restrict__ x, int64_t n, int D,
+                                                           float* __restrict__ y, float* __restrict__ inv_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * 8;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += warps) {
+    const float* s = x + r * D;
+    float acc = 0.f;
+    for (int d = lane; d < D; d += 32) acc = __fmaf_rn(s[d], s[d], acc);
+    const float inv = canon_inv_norm(canon_tree(acc));
+    for (int d = lane; d < D; d += 32) y[r * D + d] = __fmul_rn(s[d], inv);
+    if (lane == 0 && inv_out) inv_out[r] = inv;
+  }
+}
+
+__global__ void __launch_bounds__(256) l2_normalize_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                                               const float* __restrict__ inv, int64_t n, int D,
+                                                               float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * 8;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += warps) {
+    const float dot = canon_dot_warp(g + r * D, y + r * D, D);
+    const float iv = inv[r];
+    const bool clamped = iv >= 0.99e6f;   // 1 / sqrt(1e-12): max() passed no gradient to the norm
+    for (int d = lane; d < D; d += 32) {
+      const float gv = g[r * D + d];
+      dx[r * D + d] = clamped ? iv * gv : iv * (gv - y[r * D + d] * dot);
+    }
+  }
+}
+
 extern "C" {
+
+int dif_l2_normalize(const float* x, int64_t n, int D, float* y, float* inv_norm, void* stream) {
+  DIF_REQUIRE(x && y && n >= 0 && D >= 1, DIF_ERR_INVALID, "dif_l2_normalize: invalid argument");
+  if (n == 0) return DIF_OK;
+  l2_normalize_kernel<<<(unsigned)std::min<int64_t>((n + 7) / 8, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, n, D, y, inv_norm);
+  DIF_LAUNCH_OK();
+  return DIF_OK;
+}
+
+int dif_l2_normalize_bwd(const float* g, const float* y, const float* inv_norm, int64_t n, int D, float* dx, void* stream) {
+  DIF_REQUIRE(g && y && inv_norm && dx && n >= 0 && D >= 1, DIF_ERR_INVALID, "dif_l2_normalize_bwd: invalid argument");
+  if (n == 0) return DIF_OK;
+  l2_normalize_bwd_kernel<<<(unsigned)std::min<int64_t>((n + 7) / 8, 148 * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      g, y, inv_norm, n, D, dx);
+  DIF_LAUNCH_OK();
+  return DIF_OK;
+}
 
 int dif_pair_distance(const float* e1, const float* e2, int64_t N, int D, int metric, const float* mean, float* out,
                       void* stream) {

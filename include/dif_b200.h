@@ -165,6 +165,12 @@ int dif_tfa_triplet(const float* emb, const int32_t* labels, int B, int D, int k
 /* tf.argmax(labels, axis=1) of a one-hot [B, C] fp32 matrix (first maximum), losses.py:35 */
 int dif_labels_from_onehot(const float* onehot, int B, int C, int32_t* labels, void* stream);
 
+/* Embedding head: tf.nn.l2_normalize(x, axis=1) of deep_insight_face/networks/inceptionv3.py:305
+ * and networks/triplet.py:138, y = x * rsqrt(max(sum x^2, 1e-12)) in the canonical fp32 arithmetic; inv_norm [n]
+ * optional.  Backward: dx = inv * (g - y (y . g)) (a plain scaling for rows whose squared norm was clamped). */
+int dif_l2_normalize(const float* x, int64_t n, int D, float* y, float* inv_norm, void* stream);
+int dif_l2_normalize_bwd(const float* g, const float* y, const float* inv_norm, int64_t n, int D, float* dx, void* stream);
+
 /* explicit-triplet loss on [B, 3D] rows (anchor|positive|negative):
  * deep_insight_face/networks/triplet.py:16-46 `triplet_loss`; loss [B]; dy [B*3D] optional (dloss NULL -> 1) */
 int dif_triplet_apn(const float* y_pred, int B, int D, float alpha, float* loss, const float* dloss, float* dy,
