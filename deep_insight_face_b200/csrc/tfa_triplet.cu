@@ -21,7 +21,7 @@ namespace dif {
 
 constexpr int TFA_THREADS = 128;
 constexpr int TFA_WARPS = TFA_THREADS / 32;
-constexpr int TFA_MAX_B = 8192;
+constexpr int TFA_MAX_B = 8192;   // row kernel smem: 11 B per column (90 KB), u16 column ids
 
 // ---------------------------------------------------------------- K1: P = tfa pairwise_distance(emb)
 __global__ void __launch_bounds__(BH_WARPS * 32) tfa_pdist_kernel(const float* __restrict__ x, int B, int D,
@@ -188,9 +188,32 @@ __global__ void __launch_bounds__(TFA_THREADS) tfa_row_kernel(const float* __res
     if (sflag[j] == 2) fold<false>(srow[j], j, in_v, in_i, in_c);
   block_extreme<false>(in_v, in_i, in_c, s_v, s_i, s_c);
   const float inside = in_c > 0 ? in_v : 0.f;                // negatives_inside (row minimum 0 as filler)
+  // ordered list of this anchor's positives (ascending column), built chunk by chunk with warp ballots
+  unsigned short* spos = reinterpret_cast<unsigned short*>(sflag + ((B + 1) & ~1));   // [n_pos] <= [B]
+  {
+    const int lane = t & 31, warp = t >> 5;
+    int filled = 0;
+    for (int c0 = 0; c0 < B; c0 += TFA_THREADS) {
+      const int j = c0 + t;
+      const bool is_pos = j < B && sflag[j] == 1;
+      const unsigned m = __ballot_sync(0xffffffffu, is_pos);
+      __syncthreads();
+      if (lane == 0) s_c[warp] = __popc(m);
+      __syncthreads();
+      int base = filled, total = 0;
+#pragma unroll
+      for (int w = 0; w < TFA_WARPS; ++w) {
+        if (w < warp) base += s_c[w];
+        total += s_c[w];
+      }
+      if (is_pos) spos[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;
+      filled += total;
+    }
+    __syncthreads();
+  }
   double loss_sum = 0.0;
-  for (int a = 0; a < B; ++a) {
-    if (sflag[a] != 1) continue;                             // block-uniform
+  for (int ia = 0; ia < n_pos; ++ia) {
+    const int a = spos[ia];
     const float pa = srow[a];
     float out_v = INFINITY;
     int out_i = -1, out_c = 0, n_mask_t = 0;
@@ -405,7 +428,7 @@ extern "C" int dif_tfa_triplet(const float* emb, const int32_t* labels, int B, i
   tfa_pdist_kernel<<<dim3(row_blocks, splits), BH_WARPS * 32, smem1, st>>>(emb, B, D, cols, squared, g_tfa.P, ldp);
   DIF_LAUNCH_OK();
   // K2
-  const size_t smem2 = (size_t)B * 9 + 16;
+  const size_t smem2 = (size_t)B * 11 + 32;   // row, coefficient row (fp32), flags (u8), positives list (u16)
   float* cf = demb ? g_tfa.Cf : nullptr;
   if (base == DIF_TFA_HARD)
     tfa_row_kernel<DIF_TFA_HARD><<<B, TFA_THREADS, smem2, st>>>(g_tfa.P, ldp, labels, B, margin, soft, g_tfa.rows, pos_idx,
