@@ -52,22 +52,27 @@ struct MineEpi {
     const float* sq;         // [B] canonical sum of squares (euclid)
     int B;
   };
-  // labels + sq of the current tile, then a [32][128] scratch the insert path indexes dynamically
-  static int smem_bytes(const Params&) { return kMineBN * 8 + 32 * GEMM_BM * 4; }
+  // two warps per TMEM lane quarter: the epilogue (about 37 instructions per column) is latency bound with one
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kEpiThreads = kEpiWarps * 32;
+  // labels + sq of the current tile, then a [16][256] scratch the insert path indexes dynamically (half a chunk
+  // at a time: a [32][256] scratch would leave no room for two 96 KB operand stages)
+  static int smem_bytes(const Params&) { return kMineBN * 8 + 16 * kEpiThreads * 4; }
 
   const Params& p;
   int* s_lab;
   float* s_sq;
-  float* s_dv;   // this thread's column of the scratch: element i at s_dv[i * GEMM_BM]
+  float* s_dv;   // this thread's column of the scratch: element i at s_dv[i * kEpiThreads]
+  int e_tid;     // index among the 256 epilogue threads: half * 128 + row
   float pv[kMineM], nv[kMineM], av[kMineM];
   int pi[kMineM], ni[kMineM], ai[kMineM];
   float row_sum, my_sq;
   int n_pos, my_lab, my_row, tile0;
 
-  __device__ MineEpi(const Params& pp, uint8_t* smem, int)
+  __device__ MineEpi(const Params& pp, uint8_t* smem, int row, int half)
       : p(pp), s_lab(reinterpret_cast<int*>(smem)), s_sq(reinterpret_cast<float*>(smem) + kMineBN),
-        s_dv(reinterpret_cast<float*>(smem) + 2 * kMineBN + (threadIdx.x & (GEMM_BM - 1))), row_sum(0.f),
-        my_sq(0.f), n_pos(0), my_lab(-1), my_row(0), tile0(0) {}
+        s_dv(reinterpret_cast<float*>(smem) + 2 * kMineBN + half * GEMM_BM + row), e_tid(half * GEMM_BM + row),
+        row_sum(0.f), my_sq(0.f), n_pos(0), my_lab(-1), my_row(0), tile0(0) {}
 
   __device__ void begin_item(int m_row, int, int) {
     my_row = m_row;
@@ -83,16 +88,16 @@ struct MineEpi {
     n_pos = 0;
   }
 
-  // all 128 epilogue threads: stage the tile's labels (and squared norms) in shared memory
+  // all 256 epilogue threads: stage the tile's labels (and squared norms) in shared memory
   __device__ void begin_tile(int col_begin) {
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // the previous tile's readers are done
-    for (int i = threadIdx.x; i < kMineBN; i += GEMM_BM) {
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the previous tile's readers are done
+    for (int i = e_tid; i < kMineBN; i += kEpiThreads) {
       const int j = col_begin + i;
       s_lab[i] = j < p.B ? p.labels[j] : -2;
       if (!COSINE) s_sq[i] = j < p.B ? p.sq[j] : 0.f;
     }
     tile0 = col_begin;
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
   }
 
   __device__ __forceinline__ float dist_of(uint32_t acc_bits, int jl) const {
@@ -100,53 +105,50 @@ struct MineEpi {
     return COSINE ? a : __fsub_rn(__fadd_rn(my_sq, s_sq[jl]), __fmul_rn(2.f, a));
   }
 
-  // One chunk of 32 columns.  Fast path (branch-free): masked running extremes of the chunk and one test against
-  // the worst kept candidate of each class; only if some lane beats a threshold does the warp build per-element
-  // hit masks and insert.  CHECK = the chunk straddles the end of the batch (columns >= B are TMA zero fill).
+  // One chunk of 32 columns.  Branch-free pass: every column is tested against the worst kept candidate of its
+  // class (a signed compare: x = -d where smaller is better) and sets a bit of the lane's hit mask; only lanes
+  // with hits park the chunk in smem (registers cannot be indexed dynamically) and insert.  With 32 anchors in
+  // lockstep and lists that restart every work item some lane hits in most chunks, so the hit path has to be
+  // cheap: no second pass over the chunk.  CHECK = the chunk straddles the end of the batch (TMA zero fill).
   template <bool CHECK>
   __device__ __forceinline__ void consume_impl(int col0, const uint32_t (&acc)[32], uint32_t (&pending)[32]) {
     const int base = col0 - tile0;
-    const float kWorstP = COSINE ? INFINITY : -INFINITY, kWorstN = COSINE ? -INFINITY : INFINITY;
-    // an open list accepts anything: its threshold is the worst possible value
-    const float p_thr = pi[kMineM - 1] < 0 ? kWorstP : pv[kMineM - 1];
-    const float n_thr = ni[kMineM - 1] < 0 ? kWorstN : nv[kMineM - 1];
-    const float a_thr = ai[kMineM - 1] < 0 ? -INFINITY : av[kMineM - 1];
+    constexpr float kSgnN = COSINE ? 1.f : -1.f;           // negatives: cosine keeps the largest, euclid the smallest
+    // an open list accepts anything
+    const float tp = pi[kMineM - 1] < 0 ? -INFINITY : -kSgnN * pv[kMineM - 1];
+    const float tn = ni[kMineM - 1] < 0 ? -INFINITY : kSgnN * nv[kMineM - 1];
+    const float ta = ai[kMineM - 1] < 0 ? -INFINITY : av[kMineM - 1];
     float dv[32];
-    float m_pos = kWorstP, m_neg = kWorstN, m_all = -INFINITY, rs = 0.f;
+    float m_all = -INFINITY, rs = 0.f;
+    uint32_t mask = 0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       dv[i] = dist_of(acc[i], base + i);
       const bool valid = !CHECK || (col0 + i < p.B);
       const bool same = s_lab[base + i] == my_lab;
-      const float vp = (valid && same) ? dv[i] : kWorstP;
-      const float vn = (valid && !same) ? dv[i] : kWorstN;
-      m_pos = COSINE ? fminf(m_pos, vp) : fmaxf(m_pos, vp);
-      m_neg = COSINE ? fmaxf(m_neg, vn) : fminf(m_neg, vn);
-      m_all = fmaxf(m_all, valid ? dv[i] : -INFINITY);
+      const float sx = kSgnN * dv[i];
+      bool hit = (same ? -sx : sx) > (same ? tp : tn);
+      if (!COSINE) hit = hit || dv[i] > ta;
+      mask |= (valid && hit) ? (1u << i) : 0u;
+      if (COSINE) m_all = fmaxf(m_all, valid ? dv[i] : -INFINITY);
       rs += valid ? dv[i] : 0.f;
     }
     row_sum += rs;
     if (COSINE) av[0] = fmaxf(av[0], m_all);   // running row maximum for the max(dists) statistic
-    const bool lane_hit = better<COSINE>(m_pos, p_thr) || better<!COSINE>(m_neg, n_thr) || (!COSINE && m_all > a_thr);
-    if (__any_sync(0xffffffffu, lane_hit)) {
+    if (__any_sync(0xffffffffu, mask != 0u)) {
       tmem_ld_wait(pending);   // warp-uniform: no tcgen05.ld in flight while registers are shuffled below
-      if (lane_hit) {
-        uint32_t mask = 0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const bool valid = !CHECK || (col0 + i < p.B);
-          const bool same = s_lab[base + i] == my_lab;
-          bool hit = same ? better<COSINE>(dv[i], p_thr) : better<!COSINE>(dv[i], n_thr);
-          if (!COSINE) hit = hit || dv[i] > a_thr;
-          mask |= (valid && hit) ? (1u << i) : 0u;
-          s_dv[i * GEMM_BM] = dv[i];     // registers cannot be indexed dynamically: park the chunk in smem
-        }
-        while (mask) {           // per-lane loop, no collectives inside
-          const int i = __ffs((int)mask) - 1;
-          mask &= mask - 1;
-          const float d = s_dv[i * GEMM_BM];
-          const int j = col0 + i;
-          if (s_lab[base + i] == my_lab) cand_insert<COSINE>(pv, pi, d, j);
+      for (int h = 0; h < 2; ++h) {
+        uint32_t m16 = (mask >> (16 * h)) & 0xFFFFu;
+        if (!m16) continue;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s_dv[i * kEpiThreads] = dv[16 * h + i];
+        while (m16) {          // per-lane loop, no collectives inside
+          const int i = __ffs((int)m16) - 1;
+          m16 &= m16 - 1;
+          const float d = s_dv[i * kEpiThreads];
+          const int j = col0 + 16 * h + i;
+          if (s_lab[base + 16 * h + i] == my_lab) cand_insert<COSINE>(pv, pi, d, j);
           else cand_insert<!COSINE>(nv, ni, d, j);
           if (!COSINE) cand_insert<false>(av, ai, d, j);
         }
@@ -355,7 +357,8 @@ int bh_mine_tensor(const float* emb, const int32_t* labels, int B, int D, BhRec*
   shape.n_splits = std::max(1, std::min(shape.n_tiles, (2 * sms + shape.m_blocks - 1) / shape.m_blocks));
   shape.tiles_per_split = (shape.n_tiles + shape.n_splits - 1) / shape.n_splits;
   shape.n_splits = (shape.n_tiles + shape.tiles_per_split - 1) / shape.tiles_per_split;
-  if (int rc = g_tc.ensure((size_t)B * D, (size_t)shape.n_splits * B)) return rc;
+  const int n_slots = 2 * shape.n_splits;   // one candidate record per (column range, epilogue half)
+  if (int rc = g_tc.ensure((size_t)B * D, (size_t)n_slots * B)) return rc;
   DIF_CUDA_OK(cudaMemsetAsync(g_tc.gmax, 0, 4, st));
   PrepParams pp{};
   pp.src = emb; pp.n = B; pp.D = D; pp.normalize = COSINE ? 1 : 0; pp.split = 1;
@@ -369,7 +372,7 @@ int bh_mine_tensor(const float* emb, const int32_t* labels, int B, int D, BhRec*
   if (int rc = make_tmap_2d(&maps[3], g_tc.lo, B, D, (uint64_t)D * 4, kMineBN, 32, 0)) return rc;
   typename MineEpi<COSINE>::Params ep{g_tc.cand, labels, aux, B};
   if (int rc = launch_nt_gemm<0, kMineBN, 1, 0, MineEpi<COSINE>>(maps, shape, ep, sms, st)) return rc;
-  bh_rerank_kernel<COSINE><<<(B + 3) / 4, 128, 0, st>>>(g_tc.cand, shape.n_splits, emb, labels, aux, g_tc.gmax, B, D, recs, gmax_key);
+  bh_rerank_kernel<COSINE><<<(B + 3) / 4, 128, 0, st>>>(g_tc.cand, n_slots, emb, labels, aux, g_tc.gmax, B, D, recs, gmax_key);
   DIF_LAUNCH_OK();
   return DIF_OK;
 }

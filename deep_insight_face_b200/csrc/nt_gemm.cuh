@@ -20,13 +20,15 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "dif_common.cuh"
 #include "dif_ptx.cuh"
 
 namespace dif {
 
 constexpr int GEMM_BM = 128;          // A rows per CTA == epilogue threads == TMEM lanes
-constexpr int GEMM_THREADS = 192;     // 4 epilogue warps + producer + MMA
+constexpr int GEMM_THREADS = 192;     // 4 epilogue warps + producer + MMA (8 epilogue warps: 320, see EpiWarps)
 constexpr int GEMM_SWZ = 128;         // bytes of K per smem row (SWIZZLE_128B)
 constexpr int GEMM_SMEM_MAX = 232448; // 227 KB opt-in limit per CTA
 constexpr int GEMM_MAX_STAGES = 8;
@@ -94,7 +96,7 @@ inline bool plan_gemm_smem(int k_chunks, int epi_smem, GemmSmemPlan* out) {
 //     __device__ Epi(const Params&, uint8_t* smem, int row_in_block);
 //     // split = index of the (K split, B-tile range) slot of this item: k_split * n_splits + n_split
 //     __device__ void begin_item(int m_row /*global A row of this thread*/, int split, int col_begin);
-//     __device__ void begin_tile(int col_begin);   // called by all 128 epilogue threads before the tile is ready
+//     __device__ void begin_tile(int col_begin);   // called by all epilogue threads (128, or 256 with kEpiWarps = 8) before the tile is ready
 //     // fp32 bits of columns col0..col0+31 of this thread's row; taddr = TMEM address of column col0
 //     // for this warp (a slow path may re-read single columns with tmem_ld1).  `pending` is the
 //     // register block of the NEXT chunk, whose tcgen05.ld may still be in flight: code that could
@@ -103,14 +105,36 @@ inline bool plan_gemm_smem(int k_chunks, int epi_smem, GemmSmemPlan* out) {
 //     __device__ void end_item(int m_row, int split);
 //   };
 
+// An epilogue that declares `static constexpr int kEpiWarps = 8` gets TWO warps per TMEM lane quarter (warps 0-3
+// and 6-9): both own the same 32 rows and each consumes half of a tile's column chunks, so a latency-bound
+// epilogue has two warps per scheduler to hide behind.  Such an Epi is constructed with (params, smem, row, half)
+// and is handed the slot index 2 * slot + half: its per-row results are per (slot, half), merged downstream.
+template <class E, class = void>
+struct EpiWarps {
+  static constexpr int value = 4;
+};
+template <class E>
+struct EpiWarps<E, std::void_t<decltype(E::kEpiWarps)>> {
+  static constexpr int value = E::kEpiWarps;
+};
+template <class Epi, int EW>
+__device__ __forceinline__ Epi make_epi(const typename Epi::Params& p, uint8_t* smem, int row, int half) {
+  if constexpr (EW == 8) return Epi(p, smem, row, half);
+  else return Epi(p, smem, row);
+}
+
 template <int PREC, int BN, int CTAS, int ARES, class Epi>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__((2 + EpiWarps<Epi>::value) * 32, 1)
 nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                        const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                        GemmShape shape, typename Epi::Params ep) {
   using PT = PrecTraits<PREC>;
   using T = GemmTiles<PREC, BN, CTAS>;
   constexpr int NBUF = T::kAccBufs;
+  constexpr int EW = EpiWarps<Epi>::value;
+  static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
+  constexpr int CPW = (BN / 32) / (EW / 4);   // 32-column chunks of a tile per epilogue warp
+  static_assert(CPW >= 2 && CPW % 2 == 0, "the chunk loop is unrolled by two");
   constexpr int kStage = PT::kPlanes * ((ARES ? 0 : T::kATile) + T::kBTile);
   constexpr int kBOff = ARES ? 0 : PT::kPlanes * T::kATile;  // offset of the B planes inside a stage
 
@@ -146,7 +170,7 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
     }
     for (int b = 0; b < NBUF; ++b) {
       mbar_init(&acc_full[b], 1);                 // one tcgen05.commit
-      mbar_init(&acc_empty[b], 4 * CTAS);         // one arrive per epilogue warp of the unit
+      mbar_init(&acc_empty[b], EW * CTAS);        // one arrive per epilogue warp of the unit
     }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
@@ -293,15 +317,19 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
       }
     }
   } else {
-    // ===================== epilogue warps 0..3 =====================
-    const int row = threadIdx.x;  // 0..127 == TMEM lane
-    Epi epi(ep, epi_smem, row);
-    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    // ===================== epilogue warps 0..3 (and 6..9 when EW == 8) =====================
+    const int quarter = warp & 3;                      // the TMEM lane quarter a warp may read is warp id % 4
+    const int half = (EW == 8 && warp >= 6) ? 1 : 0;   // which half of every tile's chunks this warp consumes
+    const int row = quarter * 32 + (int)lane_id();     // 0..127 == TMEM lane
+    Epi epi = make_epi<Epi, EW>(ep, epi_smem, row, half);
+    const uint32_t lane_base = ((uint32_t)(quarter * 32)) << 16;
+    const int cb = half * CPW;
     uint32_t tc = 0;
     for (int item = unit; item < n_items; item += n_units) {
       const int ks = item / items_per_ks;
       const int rem = item - ks * items_per_ks;
-      const int split = rem / shape.m_blocks + ks * shape.n_splits;   // slot index: K split major
+      const int slot = rem / shape.m_blocks + ks * shape.n_splits;    // slot index: K split major
+      const int split = EW == 8 ? 2 * slot + half : slot;
       const int mb = rem % shape.m_blocks;
       const int m_row = (mb * CTAS + (int)cta_rank) * GEMM_BM + row;
       const int t0 = (rem / shape.m_blocks) * shape.tiles_per_split;
@@ -315,14 +343,14 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * BN);
         uint32_t va[32], vb[32];
-        tmem_ld32(taddr, va);
+        tmem_ld32(taddr + (uint32_t)(cb * 32), va);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; c += 2) {
+        for (int c = cb; c < cb + CPW; c += 2) {
           tmem_ld_wait(va);
           tmem_ld32(taddr + (uint32_t)((c + 1) * 32), vb);
           epi.consume(t * BN + c * 32, va, taddr + (uint32_t)(c * 32), vb);
           tmem_ld_wait(vb);
-          if (c + 2 < BN / 32) tmem_ld32(taddr + (uint32_t)((c + 2) * 32), va);
+          if (c + 2 < cb + CPW) tmem_ld32(taddr + (uint32_t)((c + 2) * 32), va);
           epi.consume(t * BN + (c + 1) * 32, vb, taddr + (uint32_t)((c + 1) * 32), va);
         }
         // all of this warp's TMEM reads of `buf` have completed (wait::ld above)
@@ -370,7 +398,7 @@ int launch_nt_gemm(const CUtensorMap* maps, GemmShape shape, const typename Epi:
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(n_units * CTAS));
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3((2 + EpiWarps<Epi>::value) * 32);
   cfg.dynamicSmemBytes = (size_t)plan.total;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
