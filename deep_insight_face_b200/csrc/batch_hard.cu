@@ -325,10 +325,10 @@ __global__ void __launch_bounds__(256) bh_finalize_kernel(const BhRec* __restric
 }
 
 // one warp: partials -> stats [4] and the per-position share of the max(dists) filler gradient
-__global__ void bh_stats_kernel(const double* __restrict__ partials, int n_parts, int B,
-                                const unsigned long long* __restrict__ gmax_key, float* __restrict__ stats,
-                                float* __restrict__ cg_out) {
-  const int lane = threadIdx.x;
+__device__ __forceinline__ void bh_stats_body(const double* __restrict__ partials, int n_parts, int B,
+                                              const unsigned long long* __restrict__ gmax_key, float* __restrict__ stats,
+                                              float* __restrict__ cg_out) {
+  const int lane = threadIdx.x & 31;
   double t[5] = {0, 0, 0, 0, 0};
   for (int p = lane; p < n_parts; p += 32)
     for (int k = 0; k < 5; ++k) t[k] += partials[(size_t)p * 5 + k];
@@ -342,6 +342,100 @@ __global__ void bh_stats_kernel(const double* __restrict__ partials, int n_parts
     stats[3] = __uint_as_float((gmax_o & 0x80000000u) ? (gmax_o ^ 0x80000000u) : ~gmax_o);
     *cg_out = t[4] > 0.0 ? (float)(t[3] / t[4]) : 0.f;
   }
+}
+
+__global__ void bh_stats_kernel(const double* __restrict__ partials, int n_parts, int B,
+                                const unsigned long long* __restrict__ gmax_key, float* __restrict__ stats,
+                                float* __restrict__ cg_out) {
+  bh_stats_body(partials, n_parts, B, gmax_key, stats, cg_out);
+}
+
+// Statistics (warp 0) + the inverse of the mining relation for the gradient gather, one block:
+//   off [B+1], csr [off[B]] : the anchors whose (untied) mined positive or negative is row r, CSR by r.  Counts,
+//                             the exclusive scan and the cursors live in shared memory, so nothing persists
+//                             between steps; entries of one row land in atomic (arbitrary) order and the gradient
+//                             warp walks them in ascending anchor order, which keeps the sums reproducible.
+//   tied [n_tied]           : anchors whose extreme is tied (compact x / y == -2), ascending (ordered compaction).
+constexpr int BH_INV_THREADS = 1024;
+constexpr int BH_INV_MAX_B = 8192;
+__global__ void __launch_bounds__(BH_INV_THREADS) bh_stats_inverse_kernel(
+    const double* __restrict__ partials, int n_parts, int B, const unsigned long long* __restrict__ gmax_key,
+    float* __restrict__ stats, float* __restrict__ cg_out, const int4* __restrict__ compact, int* __restrict__ off,
+    int* __restrict__ csr, int* __restrict__ tied, int* __restrict__ n_tied_out) {
+  extern __shared__ int s_inv[];
+  int* s_off = s_inv;            // [B + 1] counts, then exclusive offsets
+  int* s_cur = s_inv + B + 1;    // [B] fill cursors
+  __shared__ int s_warp[BH_INV_THREADS / 32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (warp == 0) bh_stats_body(partials, n_parts, B, gmax_key, stats, cg_out);
+  for (int i = t; i <= B; i += BH_INV_THREADS) {
+    s_off[i] = 0;
+    if (i < B) s_cur[i] = 0;
+  }
+  __syncthreads();
+  for (int a = t; a < B; a += BH_INV_THREADS) {
+    const int4 c = compact[a];
+    if (c.x >= 0) atomicAdd(&s_off[c.x], 1);
+    if (c.y >= 0) atomicAdd(&s_off[c.y], 1);
+  }
+  __syncthreads();
+  // exclusive scan: a contiguous run per thread, then a two-level scan of the run totals
+  const int per = (B + BH_INV_THREADS - 1) / BH_INV_THREADS;
+  const int r0 = min(B, t * per), r1 = min(B, r0 + per);
+  int run = 0;
+  for (int i = r0; i < r1; ++i) run += s_off[i];
+  int incl = run;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += v;
+    }
+    s_warp[lane] = w;   // inclusive totals of the warps
+  }
+  __syncthreads();
+  int base = (warp > 0 ? s_warp[warp - 1] : 0) + incl - run;
+  for (int i = r0; i < r1; ++i) {
+    const int d = s_off[i];
+    s_off[i] = base;
+    base += d;
+  }
+  if (t == BH_INV_THREADS - 1) s_off[B] = s_warp[BH_INV_THREADS / 32 - 1];
+  __syncthreads();
+  for (int i = t; i <= B; i += BH_INV_THREADS) off[i] = s_off[i];
+  for (int a = t; a < B; a += BH_INV_THREADS) {
+    const int4 c = compact[a];
+    if (c.x >= 0) csr[s_off[c.x] + atomicAdd(&s_cur[c.x], 1)] = a;
+    if (c.y >= 0) csr[s_off[c.y] + atomicAdd(&s_cur[c.y], 1)] = a;
+  }
+  // tied anchors, ascending
+  int filled = 0;
+  for (int a0 = 0; a0 < B; a0 += BH_INV_THREADS) {
+    const int a = a0 + t;
+    bool is_tied = false;
+    if (a < B) {
+      const int4 c = compact[a];
+      is_tied = c.x == -2 || c.y == -2;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, is_tied);
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = filled, total = 0;
+    for (int w = 0; w < BH_INV_THREADS / 32; ++w) {
+      if (w < warp) before += s_warp[w];
+      total += s_warp[w];
+    }
+    if (is_tied) tied[before + __popc(m & ((1u << lane) - 1u))] = a;
+    filled += total;
+  }
+  if (t == 0) *n_tied_out = filled;
 }
 
 // canonical dist(r, j) recomputed by one warp (tie resolution)
@@ -378,12 +472,17 @@ __device__ __forceinline__ void axpy_row(float (&acc)[BH_MAX_KD], float w, const
 constexpr int BH_GRAD_WARPS = 8;
 constexpr int BH_GRAD_CHUNK = 1024;   // compact records staged per pass (16 KB)
 
-template <bool COSINE>
+// CSR = false: every block stages the compact records of all anchors and its warps scan them (O(B) per row);
+// CSR = true : the rows that mined r come from the inverse lists of bh_stats_inverse_kernel (O(in-degree) per row).
+// Both visit the contributing anchors in ascending order, so the two variants give bit-identical gradients.
+template <bool COSINE, bool CSR>
 __device__ __forceinline__ void bh_grad_body(const float* __restrict__ x, const int32_t* __restrict__ labels, int B, int D,
                                              const float* __restrict__ aux,   // inv norm | sum sq
                                              const BhRow* rows, const int4* compact, const float* __restrict__ cg_dev,
-                                             float* __restrict__ demb) {
-  __shared__ int4 s_c[BH_GRAD_CHUNK];
+                                             float* __restrict__ demb, const int* __restrict__ off = nullptr,
+                                             const int* __restrict__ csr = nullptr, const int* __restrict__ tied = nullptr,
+                                             const int* __restrict__ n_tied_ptr = nullptr) {
+  __shared__ int4 s_c[CSR ? 1 : BH_GRAD_CHUNK];
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * BH_GRAD_WARPS + (threadIdx.x >> 5);
   const bool active = r < B;
@@ -413,6 +512,39 @@ __device__ __forceinline__ void bh_grad_body(const float* __restrict__ x, const 
         if (labels[j] != my_lab && warp_dist<COSINE>(x, aux, D, r, j) == me.neg_val)
           axpy_row<COSINE>(acc, me.coef_neg, x, aux, D, r, j);
   }
+  if (CSR) {
+    // --- rows that mined r, from the inverse lists, merged with the (usually empty) tied list in ascending order
+    if (active) {
+      const int beg = off[r], end = off[r + 1], n_tied = *n_tied_ptr;
+      const int mine = beg + lane < end ? csr[beg + lane] : 0x7fffffff;   // lists of <= 32 entries stay in registers
+      int last = -1, ti = 0;
+      while (true) {
+        int nc = mine > last ? mine : 0x7fffffff;
+        for (int t = beg + 32 + lane; t < end; t += 32) {
+          const int a = csr[t];
+          if (a > last && a < nc) nc = a;
+        }
+        for (int o = 16; o >= 1; o >>= 1) nc = min(nc, __shfl_xor_sync(0xffffffffu, nc, o));
+        const int nt = ti < n_tied ? tied[ti] : 0x7fffffff;
+        const int jj = min(nc, nt);
+        if (jj == 0x7fffffff) break;
+        const int4 c = compact[jj];
+        float w = 0.f;
+        if (c.x == r) w += __int_as_float(c.z);
+        if (c.y == r) w += __int_as_float(c.w);
+        if (jj == nt) {
+          ++ti;
+          const BhRow o = rows[jj];
+          const float dv = warp_dist<COSINE>(x, aux, D, jj, r);
+          const bool same = labels[jj] == my_lab;
+          if (c.x == -2 && same && dv == o.pos_val) w += o.coef_pos;
+          if (c.y == -2 && !same && dv == o.neg_val) w += o.coef_neg;
+        }
+        if (w != 0.f) axpy_row<COSINE>(acc, w, x, aux, D, r, jj);
+        last = jj;
+      }
+    }
+  } else
   // --- rows that mined r: the block stages the compact records once and its 8 warps scan them
   for (int chunk0 = 0; chunk0 < B; chunk0 += BH_GRAD_CHUNK) {
     const int n_chunk = min(BH_GRAD_CHUNK, B - chunk0);
@@ -499,7 +631,16 @@ __global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_grad_kernel(const float
                                                                      const int4* __restrict__ compact,
                                                                      const float* __restrict__ cg_dev,
                                                                      float* __restrict__ demb) {
-  bh_grad_body<COSINE>(x, labels, B, D, aux, rows, compact, cg_dev, demb);
+  bh_grad_body<COSINE, false>(x, labels, B, D, aux, rows, compact, cg_dev, demb);
+}
+
+template <bool COSINE>
+__global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_grad_csr_kernel(
+    const float* __restrict__ x, const int32_t* __restrict__ labels, int B, int D, const float* __restrict__ aux,
+    const BhRow* __restrict__ rows, const int4* __restrict__ compact, const float* __restrict__ cg_dev,
+    float* __restrict__ demb, const int* __restrict__ off, const int* __restrict__ csr, const int* __restrict__ tied,
+    const int* __restrict__ n_tied) {
+  bh_grad_body<COSINE, true>(x, labels, B, D, aux, rows, compact, cg_dev, demb, off, csr, tied, n_tied);
 }
 
 // Small batches (B <= 256): merge + gradient in one launch.  Every block redoes the (tiny) merge of all anchors
@@ -517,7 +658,7 @@ __global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_merge_grad_kernel(
   bh_merge_body<COSINE>(recs, n_splits, B, alpha, soft, dloss, loss, pos_idx_out, neg_idx_out, stats, s_rows, s_compact,
                         blockIdx.x == 0);
   __syncthreads();
-  bh_grad_body<COSINE>(x, labels, B, D, aux, s_rows, s_compact, nullptr, demb);
+  bh_grad_body<COSINE, false>(x, labels, B, D, aux, s_rows, s_compact, nullptr, demb);
 }
 
 // one-hot [B, C] -> int32 class ids (tf.argmax(labels, axis=1): first maximum), losses.py:35
@@ -553,6 +694,7 @@ struct BhWorkspace {
   float* aux = nullptr;
   int4* compact = nullptr;
   double* partials = nullptr;              // [ceil(rows / 256)][5]
+  int* inv = nullptr;                      // off [rows + 1] | csr [2 rows] | tied [rows] | n_tied [1]
   unsigned long long* gmax_key = nullptr;  // [1] + float cg right behind it
   size_t row_cap = 0;
   int ensure(size_t n_rec, size_t n_rows) {
@@ -568,6 +710,8 @@ struct BhWorkspace {
       cudaFree(aux);
       cudaFree(compact);
       cudaFree(partials);
+      cudaFree(inv);
+      inv = nullptr;
       rows = nullptr;
       aux = nullptr;
       compact = nullptr;
@@ -577,6 +721,7 @@ struct BhWorkspace {
       DIF_CUDA_OK(cudaMalloc((void**)&aux, n_rows * sizeof(float)));
       DIF_CUDA_OK(cudaMalloc((void**)&compact, n_rows * sizeof(int4)));
       DIF_CUDA_OK(cudaMalloc((void**)&partials, ((n_rows + 255) / 256) * 5 * sizeof(double)));
+      DIF_CUDA_OK(cudaMalloc((void**)&inv, (4 * n_rows + 2) * sizeof(int)));
       if (!gmax_key) DIF_CUDA_OK(cudaMalloc((void**)&gmax_key, 16));
       row_cap = n_rows;
     }
@@ -638,9 +783,29 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
                                                   g_ws.rows, g_ws.compact, g_ws.partials);
     DIF_LAUNCH_OK();
     float* cg = reinterpret_cast<float*>(g_ws.gmax_key + 1);
+    cg_dev = cg;
+    if (demb && B <= BH_INV_MAX_B) {
+      // statistics + inverse mining lists in one block, then the O(in-degree) gradient gather
+      static bool inv_configured = false;
+      if (!inv_configured) {
+        DIF_CUDA_OK(cudaFuncSetAttribute(bh_stats_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (2 * BH_INV_MAX_B + 1) * (int)sizeof(int)));
+        inv_configured = true;
+      }
+      int* off = g_ws.inv;
+      int* csr = off + B + 1;
+      int* tied = csr + 2 * (size_t)B;
+      int* n_tied = tied + B;
+      bh_stats_inverse_kernel<<<1, BH_INV_THREADS, (2 * (size_t)B + 1) * sizeof(int), st>>>(
+          g_ws.partials, fb, B, g_ws.gmax_key, stats, cg, g_ws.compact, off, csr, tied, n_tied);
+      DIF_LAUNCH_OK();
+      bh_grad_csr_kernel<COSINE><<<(B + BH_GRAD_WARPS - 1) / BH_GRAD_WARPS, BH_GRAD_WARPS * 32, 0, st>>>(
+          emb, labels, B, D, g_ws.aux, g_ws.rows, g_ws.compact, cg_dev, demb, off, csr, tied, n_tied);
+      DIF_LAUNCH_OK();
+      return DIF_OK;
+    }
     bh_stats_kernel<<<1, 32, 0, st>>>(g_ws.partials, fb, B, g_ws.gmax_key, stats, cg);
     DIF_LAUNCH_OK();
-    cg_dev = cg;
   } else {
     bh_mine_kernel<COSINE><<<dim3(row_blocks, splits), BH_WARPS * 32, smem, st>>>(emb, labels, B, D, cols, g_ws.recs, g_ws.aux);
     DIF_LAUNCH_OK();
