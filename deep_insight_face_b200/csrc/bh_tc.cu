@@ -50,6 +50,7 @@ struct MineEpi {
     BhCand* cand;            // [n_slots][B]
     const int32_t* labels;   // [B]
     const float* sq;         // [B] canonical sum of squares (euclid)
+    const unsigned int* gmax_sq;   // orderable max of sq (euclid): scales the error window like bh_rerank_kernel
     int B;
   };
   // two warps per TMEM lane quarter: the epilogue (about 37 instructions per column) is latency bound with one
@@ -66,18 +67,27 @@ struct MineEpi {
   int e_tid;     // index among the 256 epilogue threads: half * 128 + row
   float pv[kMineM], nv[kMineM], av[kMineM];
   int pi[kMineM], ni[kMineM], ai[kMineM];
-  float row_sum, my_sq;
+  float row_sum, my_sq, win;
   int n_pos, my_lab, my_row, tile0;
 
   __device__ MineEpi(const Params& pp, uint8_t* smem, int row, int half)
       : p(pp), s_lab(reinterpret_cast<int*>(smem)), s_sq(reinterpret_cast<float*>(smem) + kMineBN),
         s_dv(reinterpret_cast<float*>(smem) + 2 * kMineBN + half * GEMM_BM + row), e_tid(half * GEMM_BM + row),
-        row_sum(0.f), my_sq(0.f), n_pos(0), my_lab(-1), my_row(0), tile0(0) {}
+        row_sum(0.f), my_sq(0.f), win(0.f), n_pos(0), my_lab(-1), my_row(0), tile0(0) {}
 
   __device__ void begin_item(int m_row, int, int) {
     my_row = m_row;
     my_lab = m_row < p.B ? p.labels[m_row] : -1;
     my_sq = (!COSINE && m_row < p.B) ? p.sq[m_row] : 0.f;
+    // A candidate only matters if it lies inside the re-rank window (2 eps of bh_rerank_kernel) of the row's best:
+    // accepting "better than the 4th kept OR within `win` of the best kept" keeps every such candidate (or fills
+    // the list inside the window, which the re-rank detects) and cuts the insert traffic roughly threefold.
+    if (COSINE) {
+      win = 4.1e-5f;
+    } else {
+      const uint32_t o = *p.gmax_sq;
+      win = 4.1e-5f * (my_sq + __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o));
+    }
 #pragma unroll
     for (int s = 0; s < kMineM; ++s) {
       pv[s] = nv[s] = av[s] = 0.f;
@@ -115,9 +125,12 @@ struct MineEpi {
     const int base = col0 - tile0;
     constexpr float kSgnN = COSINE ? 1.f : -1.f;           // negatives: cosine keeps the largest, euclid the smallest
     // an open list accepts anything
-    const float tp = pi[kMineM - 1] < 0 ? -INFINITY : -kSgnN * pv[kMineM - 1];
-    const float tn = ni[kMineM - 1] < 0 ? -INFINITY : kSgnN * nv[kMineM - 1];
-    const float ta = ai[kMineM - 1] < 0 ? -INFINITY : av[kMineM - 1];
+    // (signed space: larger is better) the worst kept candidate, raised to best - win once a best exists
+    const float tp = fmaxf(pi[kMineM - 1] < 0 ? -INFINITY : -kSgnN * pv[kMineM - 1],
+                           pi[0] < 0 ? -INFINITY : -kSgnN * pv[0] - win);
+    const float tn = fmaxf(ni[kMineM - 1] < 0 ? -INFINITY : kSgnN * nv[kMineM - 1],
+                           ni[0] < 0 ? -INFINITY : kSgnN * nv[0] - win);
+    const float ta = fmaxf(ai[kMineM - 1] < 0 ? -INFINITY : av[kMineM - 1], ai[0] < 0 ? -INFINITY : av[0] - win);
     float dv[32];
     float m_all = -INFINITY, rs = 0.f;
     uint32_t mask = 0;
@@ -370,7 +383,7 @@ int bh_mine_tensor(const float* emb, const int32_t* labels, int B, int D, BhRec*
   if (int rc = make_tmap_2d(&maps[1], g_tc.lo, B, D, (uint64_t)D * 4, GEMM_BM, 32, 0)) return rc;
   if (int rc = make_tmap_2d(&maps[2], g_tc.hi, B, D, (uint64_t)D * 4, kMineBN, 32, 0)) return rc;
   if (int rc = make_tmap_2d(&maps[3], g_tc.lo, B, D, (uint64_t)D * 4, kMineBN, 32, 0)) return rc;
-  typename MineEpi<COSINE>::Params ep{g_tc.cand, labels, aux, B};
+  typename MineEpi<COSINE>::Params ep{g_tc.cand, labels, aux, g_tc.gmax, B};
   if (int rc = launch_nt_gemm<0, kMineBN, 1, 0, MineEpi<COSINE>>(maps, shape, ep, sms, st)) return rc;
   bh_rerank_kernel<COSINE><<<(B + 3) / 4, 128, 0, st>>>(g_tc.cand, n_slots, emb, labels, aux, g_tc.gmax, B, D, recs, gmax_key);
   DIF_LAUNCH_OK();
