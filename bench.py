@@ -175,7 +175,7 @@ def secondary_metrics(torch, device):
         cpu_ms = (time.perf_counter() - t0) / n_cpu * 1e3
         out[name] = {"steps_per_s": 1e3 / ms, "ms_per_step": ms, "ungraphed_call_steps_per_s": 1e3 / ms_call,
                      "e2e_steps_per_s": 1e3 / host_ms,
-                     "path": "tcgen05 3xTF32 filter + canonical re-rank (6 kernels)" if B >= 512 else
+                     "path": "tcgen05 3xTF32 filter (8 epilogue warps) + canonical re-rank + inverse-list gradient (6 kernels)" if B >= 512 else
                              "canonical fp32 CUDA-core miner (3 kernels)",
                      "alg_gflop_fwd": 2.0 * B * B * D / 1e9,
                      "cpu_oracle_steps_per_s": 1e3 / cpu_ms, "note": "fwd + bwd; steps_per_s = CUDA-graphed BatchHardStep, e2e = numpy in/out through "
