@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override the global gallery rows")
     ap.add_argument("--queries", type=int, default=0)
-    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "bf16", "tf32x1"])
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "bf16", "tf32x1", "bf16x3"])
     ap.add_argument("--no-modes", action="store_true", help="skip the extra per-precision measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     return ap.parse_args()
@@ -381,7 +381,7 @@ def main():
     main_res = measure(args.precision, args.steps, max(3, args.warmup), full=True)
     modes = {}
     if not args.no_modes and args.workload == "c3":
-        for p in ("bf16", "tf32x1", "tf32x3"):
+        for p in ("bf16", "tf32x1", "bf16x3", "tf32x3"):
             if p == args.precision:
                 continue
             r = measure(p, max(5, min(args.steps, 10)), 3, full=False)
@@ -399,8 +399,9 @@ def main():
     alg_flops = 2.0 * Q * rows_local * D  # per launch of the tensor-core pass on one GPU
     achieved = alg_flops / (main_res["kernel_ms"] * 1e-3) / 1e12
     # TF32 is not in MEASURED_PEAKS.json: the TF32 peak is taken as measured bf16 / 2
-    tensor_peak = peaks["bf16_tflops"] if args.precision == "bf16" else peaks["bf16_tflops"] / 2.0
-    passes = 3 if args.precision == "tf32x3" else 1
+    on_bf16_pipe = args.precision in ("bf16", "bf16x3")
+    tensor_peak = peaks["bf16_tflops"] if on_bf16_pipe else peaks["bf16_tflops"] / 2.0
+    passes = 3 if args.precision in ("tf32x3", "bf16x3") else 1
     # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` captures of this exact
     # workload (profiles/r01_ncu_search_*_c3*.md: dram__bytes_read.sum + dram__bytes_write.sum); other shapes: null
     ncu_traffic = {"tf32x3": 5.725465e9 + 16.753408e6, "bf16": 1.258923e9 + 16.037376e6}
@@ -409,10 +410,10 @@ def main():
     roofline = {
         "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": achieved / tensor_peak,
         "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write)",
-        "algorithmic_bytes": float(rows_local) * D * (2 if args.precision == "bf16" else (8 if args.precision == "tf32x3" else 4)),
+        "algorithmic_bytes": float(rows_local) * D * {"bf16": 2, "tf32x3": 8, "tf32x1": 4, "bf16x3": 4}[args.precision],
         "kernel": "nt_gemm_rowscan_kernel<TopkEpi> (tcgen05/TMA GEMM + fused per-query top-k)",
         "kernel_ms": main_res["kernel_ms"],
-        "peak_source": f"{peaks['source']} bf16 burst" + ("" if args.precision == "bf16" else " / 2 (TF32 not measured)"),
+        "peak_source": f"{peaks['source']} bf16 burst" + ("" if on_bf16_pipe else " / 2 (TF32 not measured)"),
         "tensor_passes_per_flop": passes, "hardware_frac": achieved * passes / tensor_peak,
         "share_of_step": main_res["kernel_ms"] / main_res["ms_per_step"],
     }
@@ -447,7 +448,8 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": {"tf32x3": "f32 (3xTF32 tensor-core filter + canonical fp32 re-rank)",
                   "bf16": "bf16 tensor-core filter + canonical fp32 re-rank (results identical to f32)",
-                  "tf32x1": "tf32 tensor-core filter + canonical fp32 re-rank (results identical to f32)"}[args.precision],
+                  "tf32x1": "tf32 tensor-core filter + canonical fp32 re-rank (results identical to f32)",
+                  "bf16x3": "f32 (3xBF16 tensor-core filter: x = b0 + b1, three bf16 products + canonical fp32 re-rank)"}[args.precision],
         "data": "synthetic",
         "config": {"workload": f"1:N gallery search, {n_rows} x {D} fp32 gallery, {Q} queries, top-{k} cosine",
                    "precision": args.precision, "gallery_rows_per_gpu": rows_local, "parallelism": f"row-sharded x{world}",

@@ -19,13 +19,14 @@ METRIC_COSINE = 1
 PREC_TF32X3 = 0
 PREC_BF16 = 1
 PREC_TF32X1 = 2
+PREC_BF16X3 = 3
 MAX_TOPK = 24
 LOSS_BH_COSINE = 0
 LOSS_BH_EUCLIDEAN = 1
 LOSS_SOFT_MARGIN = 4
 
 _PRECISIONS = {"tf32x3": PREC_TF32X3, "fp32": PREC_TF32X3, "bf16": PREC_BF16, "tf32": PREC_TF32X1,
-               "tf32x1": PREC_TF32X1}
+               "tf32x1": PREC_TF32X1, "bf16x3": PREC_BF16X3}
 _METRICS = {"cosine": METRIC_COSINE, "cos": METRIC_COSINE, "l2": METRIC_SQL2, "sql2": METRIC_SQL2,
             "euclidean": METRIC_SQL2}
 

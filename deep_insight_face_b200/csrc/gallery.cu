@@ -353,6 +353,7 @@ struct dif_gallery {
   float* g0 = nullptr;
   float* g1 = nullptr;
   __nv_bfloat16* gb = nullptr;
+  __nv_bfloat16* gb1 = nullptr;   // second bf16 plane (3xBF16)
   float* gsq = nullptr;  // [capacity + kGalBN]
   unsigned int* gmax = nullptr;
   int64_t* ids = nullptr;
@@ -361,6 +362,7 @@ struct dif_gallery {
   float* q0 = nullptr;
   float* q1 = nullptr;
   __nv_bfloat16* qb = nullptr;
+  __nv_bfloat16* qb1 = nullptr;
   float* qsq = nullptr;
   uint64_t* cand = nullptr;
   size_t cand_elems = 0;
@@ -396,14 +398,16 @@ int dev_alloc(T** p, size_t n) {
 int ensure_query_ws(dif_gallery* g, int Q, int S, int kp) {
   const int q_pad = (int)round_up(Q, GEMM_BM * 2);
   if (q_pad > g->q_cap) {
-    cudaFree(g->q0); cudaFree(g->q1); cudaFree(g->qb); cudaFree(g->qsq); cudaFree(g->flagged); cudaFree(g->bound);
-    g->q0 = g->q1 = nullptr; g->qb = nullptr; g->qsq = nullptr; g->flagged = nullptr; g->bound = nullptr;
+    cudaFree(g->q0); cudaFree(g->q1); cudaFree(g->qb); cudaFree(g->qb1); cudaFree(g->qsq); cudaFree(g->flagged); cudaFree(g->bound);
+    g->q0 = g->q1 = nullptr; g->qb = g->qb1 = nullptr; g->qsq = nullptr; g->flagged = nullptr; g->bound = nullptr;
     g->q_cap = 0;
     if (int rc = dev_alloc(&g->q0, (size_t)q_pad * g->D)) return rc;
     if (g->precision == DIF_PREC_TF32X3)
       if (int rc = dev_alloc(&g->q1, (size_t)q_pad * g->D)) return rc;
-    if (g->precision == DIF_PREC_BF16)
+    if (g->precision == DIF_PREC_BF16 || g->precision == DIF_PREC_BF16X3)
       if (int rc = dev_alloc(&g->qb, (size_t)q_pad * g->D)) return rc;
+    if (g->precision == DIF_PREC_BF16X3)
+      if (int rc = dev_alloc(&g->qb1, (size_t)q_pad * g->D)) return rc;
     if (int rc = dev_alloc(&g->qsq, (size_t)q_pad)) return rc;
     if (int rc = dev_alloc(&g->flagged, (size_t)q_pad + 1)) return rc;
     if (int rc = dev_alloc(&g->bound, (size_t)q_pad)) return rc;
@@ -446,8 +450,8 @@ extern "C" {
 dif_gallery_t* dif_gallery_create(int device, int64_t capacity_rows, int dim, int metric, int precision) {
   if (dif_init(device) != DIF_OK) return nullptr;
   if (capacity_rows <= 0 || capacity_rows >= (int64_t)0x7FFFFF00 || dim < 32 || dim % 4 != 0 || dim > 8192 ||
-      (metric != DIF_METRIC_SQL2 && metric != DIF_METRIC_COSINE) || precision < 0 || precision > 2 ||
-      (precision == DIF_PREC_BF16 && (dim % 8 != 0 || dim < 64))) {
+      (metric != DIF_METRIC_SQL2 && metric != DIF_METRIC_COSINE) || precision < 0 || precision > 3 ||
+      ((precision == DIF_PREC_BF16 || precision == DIF_PREC_BF16X3) && (dim % 8 != 0 || dim < 64))) {
     set_error("dif_gallery_create: invalid argument (capacity %lld, dim %d (multiple of 4 and >= 32; of 8 and >= 64 for "
               "bf16), metric %d, precision %d)", (long long)capacity_rows, dim, metric, precision);
     return nullptr;
@@ -462,7 +466,8 @@ dif_gallery_t* dif_gallery_create(int device, int64_t capacity_rows, int dim, in
   const size_t elems = (size_t)capacity_rows * dim;
   bool ok = cudaMalloc((void**)&g->g0, elems * 4) == cudaSuccess;
   if (ok && precision == DIF_PREC_TF32X3) ok = cudaMalloc((void**)&g->g1, elems * 4) == cudaSuccess;
-  if (ok && precision == DIF_PREC_BF16) ok = cudaMalloc((void**)&g->gb, elems * 2) == cudaSuccess;
+  if (ok && (precision == DIF_PREC_BF16 || precision == DIF_PREC_BF16X3)) ok = cudaMalloc((void**)&g->gb, elems * 2) == cudaSuccess;
+  if (ok && precision == DIF_PREC_BF16X3) ok = cudaMalloc((void**)&g->gb1, elems * 2) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&g->gsq, ((size_t)capacity_rows + kGalBN) * 4) == cudaSuccess;
   ok = ok && cudaMalloc((void**)&g->gmax, 4) == cudaSuccess;
   ok = ok && cudaMemset(g->gsq, 0, ((size_t)capacity_rows + kGalBN) * 4) == cudaSuccess;
@@ -479,8 +484,8 @@ dif_gallery_t* dif_gallery_create(int device, int64_t capacity_rows, int dim, in
 
 void dif_gallery_destroy(dif_gallery_t* g) {
   if (!g) return;
-  cudaFree(g->g0); cudaFree(g->g1); cudaFree(g->gb); cudaFree(g->gsq); cudaFree(g->gmax); cudaFree(g->ids);
-  cudaFree(g->q0); cudaFree(g->q1); cudaFree(g->qb); cudaFree(g->qsq); cudaFree(g->cand); cudaFree(g->flagged);
+  cudaFree(g->g0); cudaFree(g->g1); cudaFree(g->gb); cudaFree(g->gb1); cudaFree(g->gsq); cudaFree(g->gmax); cudaFree(g->ids);
+  cudaFree(g->q0); cudaFree(g->q1); cudaFree(g->qb); cudaFree(g->qb1); cudaFree(g->qsq); cudaFree(g->cand); cudaFree(g->flagged);
   cudaFree(g->bound); cudaFree(g->maxima); cudaFree(g->ex_keys); cudaFree(g->d_stage);
   if (g->h_pin) cudaFreeHost(g->h_pin);
   if (g->own_stream) cudaStreamDestroy(g->own_stream);
@@ -526,6 +531,7 @@ static int gallery_append(dif_gallery_t* g, const float* rows, bool synth, uint6
   pp.p0 = g->g0 + (size_t)g->size * g->D;
   pp.p1 = g->g1 ? g->g1 + (size_t)g->size * g->D : nullptr;
   pp.pb = g->gb ? g->gb + (size_t)g->size * g->D : nullptr;
+  pp.pb1 = g->gb1 ? g->gb1 + (size_t)g->size * g->D : nullptr;
   pp.sq = g->gsq + g->size;
   pp.gmax = g->gmax;
   if (int rc = prep_launch(pp, synth, st)) return rc;
@@ -614,7 +620,7 @@ int dif_gallery_remove(dif_gallery_t* g, const int64_t* rows_host, int64_t n, vo
   struct Arr {
     void* base;
     int words;   // 4-byte words per row
-  } arrs[5] = {{g->g0, g->D}, {g->g1, g->D}, {g->gb, g->D / 2}, {g->gsq, 1}, {g->ids, 2}};
+  } arrs[6] = {{g->g0, g->D}, {g->g1, g->D}, {g->gb, g->D / 2}, {g->gb1, g->D / 2}, {g->gsq, 1}, {g->ids, 2}};
   for (const Arr& a : arrs) {
     if (!a.base) continue;
     for (int64_t r0 = first; r0 < g->size; r0 += chunk) {
@@ -682,7 +688,8 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
   GemmShape shape{};
   shape.m_blocks = (n_queries + GEMM_BM * ctas - 1) / (GEMM_BM * ctas);
   shape.n_tiles = (int)((g->size + kGalBN - 1) / kGalBN);
-  const int chunk = g->precision == DIF_PREC_BF16 ? 64 : 32;
+  const bool bf = g->precision == DIF_PREC_BF16 || g->precision == DIF_PREC_BF16X3;
+  const int chunk = bf ? 64 : 32;
   shape.k_chunks = (D + chunk - 1) / chunk;
   const int units = std::max(1, device_sm_count() / ctas);
   int splits = 1;
@@ -714,6 +721,7 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
   pp.p0 = g->q0;
   pp.p1 = g->q1;
   pp.pb = g->qb;
+  pp.pb1 = g->qb1;
   pp.sq = g->qsq;
   pp.gmax = nullptr;
   if (int rc = prep_launch(pp, false, st)) return rc;
@@ -722,7 +730,6 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
   // 2. tensor-core filter
   if (shape.n_tiles > 0) {
     CUtensorMap maps[4];
-    const bool bf = g->precision == DIF_PREC_BF16;
     const void* a0 = bf ? (const void*)g->qb : (const void*)g->q0;
     const void* b0 = bf ? (const void*)g->gb : (const void*)g->g0;
     const int esz = bf ? 2 : 4;
@@ -734,6 +741,9 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
     if (g->precision == DIF_PREC_TF32X3) {
       if (int rc = make_tmap_2d(&maps[1], g->q1, n_queries, D, (uint64_t)D * 4, GEMM_BM, bcols, 0)) return rc;
       if (int rc = make_tmap_2d(&maps[3], g->g1, g->size, D, (uint64_t)D * 4, kGalBN / ctas, bcols, 0)) return rc;
+    } else if (g->precision == DIF_PREC_BF16X3) {
+      if (int rc = make_tmap_2d(&maps[1], g->qb1, n_queries, D, (uint64_t)D * 2, GEMM_BM, bcols, 1)) return rc;
+      if (int rc = make_tmap_2d(&maps[3], g->gb1, g->size, D, (uint64_t)D * 2, kGalBN / ctas, bcols, 1)) return rc;
     }
     DIF_CUDA_OK(cudaMemsetAsync(g->bound, 0, (size_t)g->q_cap * sizeof(unsigned int), st));
     DIF_CUDA_OK(cudaMemsetAsync(g->maxima, 0, (size_t)g->q_cap * splits * sizeof(unsigned int), st));
@@ -744,6 +754,7 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
     DIF_CUDA_OK(cudaEventRecord(g->ev0, st));
     const int rc = g->precision == DIF_PREC_TF32X3 ? launch_search_tf32x3(g->metric, ctas, ares, maps, shape, ep, units, st)
                    : g->precision == DIF_PREC_BF16 ? launch_search_bf16(g->metric, ctas, ares, maps, shape, ep, units, st)
+                   : g->precision == DIF_PREC_BF16X3 ? launch_search_bf16x3(g->metric, ctas, 0, maps, shape, ep, units, st)
                                                    : launch_search_tf32x1(g->metric, ctas, ares, maps, shape, ep, units, st);
     if (rc) return rc;
     DIF_CUDA_OK(cudaEventRecord(g->ev1, st));

@@ -12,7 +12,9 @@ constexpr int kGalBN = 256;
 //   3xTF32: dropped lo*lo terms + truncation of lo (2^-20) + <= 3*D/8 fp32 accumulations
 //   1xTF32: operand truncation 2 * 2^-10;   bf16: operand rounding 2 * 2^-9
 __host__ __device__ inline float mode_eps(int precision) {
-  return precision == DIF_PREC_TF32X3 ? 1.0e-4f : (precision == DIF_PREC_BF16 ? 5.0e-3f : 2.5e-3f);
+  // 3xBF16: |x - b0 - b1| <= 2^-18 |x|, so the three dropped terms stay below 1.1e-5 of sum |a||b| (9x margin)
+  return (precision == DIF_PREC_TF32X3 || precision == DIF_PREC_BF16X3) ? 1.0e-4f
+                                                                          : (precision == DIF_PREC_BF16 ? 5.0e-3f : 2.5e-3f);
 }
 
 // Half-width of the window around the k-th best approximate score inside which a row can still
@@ -242,6 +244,8 @@ int launch_search_bf16(int metric, int ctas, int ares, const CUtensorMap* maps, 
                        const TopkEpi<1>::Params& ep, int n_units, cudaStream_t st);
 int launch_search_tf32x1(int metric, int ctas, int ares, const CUtensorMap* maps, const GemmShape& shape,
                          const TopkEpi<1>::Params& ep, int n_units, cudaStream_t st);
+int launch_search_bf16x3(int metric, int ctas, int ares, const CUtensorMap* maps, const GemmShape& shape,
+                         const TopkEpi<1>::Params& ep, int n_units, cudaStream_t st);
 
 template <int PREC>
 int launch_search_prec(int metric, int ctas, int ares, const CUtensorMap* maps, const GemmShape& shape,
@@ -250,7 +254,7 @@ int launch_search_prec(int metric, int ctas, int ares, const CUtensorMap* maps, 
   TopkEpi<0>::Params ep0{ep1.cand, ep1.gnorm, ep1.bound, ep1.maxima, ep1.q_pad, ep1.k, ep1.q_sq, ep1.gmax, ep1.n_rows, ep1.n_splits, ep1.kp, ep1.eps_rel};
   if (ctas == 2) {
     if (ares) {
-      if constexpr (PREC != 0) {
+      if constexpr (PREC == 1 || PREC == 2) {   // the two-plane modes cannot keep a query block resident
         return metric == 1 ? launch_nt_gemm<PREC, kGalBN, 2, 1, TopkEpi<1>>(maps, shape, ep1, n_units, st)
                            : launch_nt_gemm<PREC, kGalBN, 2, 1, TopkEpi<0>>(maps, shape, ep0, n_units, st);
       }

@@ -8,6 +8,8 @@
 //   0  3xTF32: A = Ahi + Alo, B = Bhi + Blo pre-split into TF32 planes; Alo*Bhi + Ahi*Blo + Ahi*Bhi
 //   1  bf16  : single bf16 plane per operand
 //   2  1xTF32: fp32 storage read as TF32 by the tensor cores
+//   3  3xBF16: A = A0 + A1, B = B0 + B1 pre-split into bf16 planes (x - bf16(x) rounded to bf16 again);
+//              A1*B0 + A0*B1 + A0*B0 - the mode-0 schedule on the bf16 pipe (twice the MMA rate)
 //
 // Structure: persistent CTAs (or cta_group::2 CTA pairs), 6 warps: warps 0-3 epilogue (TMEM lane
 // quarter = warp index), warp 4 TMA producer, warp 5 TMEM allocator + single-thread MMA issuer.
@@ -36,9 +38,9 @@ constexpr int GEMM_BAR_BYTES = 1024;
 
 template <int PREC>
 struct PrecTraits {
-  static constexpr bool kTf32 = (PREC != 1);
+  static constexpr bool kTf32 = (PREC == 0 || PREC == 2);
   static constexpr int kElemBytes = kTf32 ? 4 : 2;
-  static constexpr int kPlanes = (PREC == 0) ? 2 : 1;
+  static constexpr int kPlanes = (PREC == 0 || PREC == 3) ? 2 : 1;
   static constexpr int kChunkElems = GEMM_SWZ / kElemBytes;  // K elements per chunk
   static constexpr int kKSteps = GEMM_SWZ / 32;               // MMAs (per product) per chunk: 32 B of K each
   static constexpr uint32_t kFmt = kTf32 ? 2u : 1u;

@@ -12,7 +12,8 @@ namespace dif {
 // K5: rows -> canonical planes.  One warp per row.
 //   SRC 0: rows read from `src`; SRC 1: synthetic rows (seed, row0 + r).
 //   p0/p1: fp32 planes (TF32x3: p0 = tf32(x), p1 = x - p0 exactly; otherwise p0 = x, p1 unused)
-//   pb   : bf16 plane (bf16 mode only);  sq[r] = canonical sum of squares of the STORED row
+//   pb   : bf16 plane (bf16 modes);  pb1: second bf16 plane, bf16(x - pb) (3xBF16 mode)
+//   sq[r] = canonical sum of squares of the STORED row
 //   gmax : running max of sq (orderable uint), may be NULL
 // ------------------------------------------------------------------------------------------
 struct PrepParams {
@@ -26,6 +27,7 @@ struct PrepParams {
   float* p0;
   float* p1;
   __nv_bfloat16* pb;
+  __nv_bfloat16* pb1;
   float* sq;
   unsigned int* gmax;
   float* inv;   // inverse norm applied to each row (normalize), may be NULL
@@ -56,7 +58,11 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(PrepParams p) {
       } else {
         p.p0[r * p.D + d] = x;
       }
-      if (p.pb) p.pb[r * p.D + d] = __float2bfloat16_rn(x);
+      if (p.pb) {
+        const __nv_bfloat16 b0 = __float2bfloat16_rn(x);
+        p.pb[r * p.D + d] = b0;
+        if (p.pb1) p.pb1[r * p.D + d] = __float2bfloat16_rn(__fsub_rn(x, __bfloat162float(b0)));
+      }
     }
     const float ss2 = canon_tree(acc2);
     if (lane == 0) {

@@ -19,7 +19,7 @@ from . import _ffi
 class Gallery:
     """Device-resident embedding index on one B200.
 
-    precision: "tf32x3" (fp32-exact tensor-core filter), "bf16", "tf32" - see include/dif_b200.h.
+    precision: "tf32x3" (fp32-exact tensor-core filter), "bf16x3", "bf16", "tf32" - see include/dif_b200.h.
     """
 
     def __init__(self, capacity: int, dim: int, metric="cosine", precision="tf32x3", device: int = 0):

@@ -42,6 +42,8 @@ extern "C" {
 #define DIF_PREC_TF32X3 0 /* fp32-exact: hi/lo TF32 planes, 3 tensor-core products per term (default) */
 #define DIF_PREC_BF16 1   /* bf16 operands, fp32 accumulate (reported separately) */
 #define DIF_PREC_TF32X1 2 /* fp32 storage read as TF32 by the tensor cores, one product per term */
+#define DIF_PREC_BF16X3 3 /* x = b0 + b1 in bf16; b1*b0 + b0*b1 + b0*b0, fp32 accumulate: error <= 1.1e-5 of sum |a||b|,
+                           * the 3xTF32 scheme on the bf16 pipe at half its cost (gallery filter only) */
 
 #define DIF_MAX_TOPK 24
 

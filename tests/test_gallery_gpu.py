@@ -22,7 +22,7 @@ def check(orc, g, rows, q, k, metric):
     return s, ids, r
 
 
-@pytest.mark.parametrize("precision", ["tf32x3", "bf16", "tf32x1"])
+@pytest.mark.parametrize("precision", ["tf32x3", "bf16", "tf32x1", "bf16x3"])
 @pytest.mark.parametrize("metric", ["cosine", "l2"])
 @pytest.mark.parametrize("N,Q,D,k", [(1000, 37, 64, 10), (20000, 300, 128, 10), (70001, 513, 512, 5), (300, 5, 96, 24)])
 def test_search_bit_exact(gpu, orc, precision, metric, N, Q, D, k):
@@ -197,14 +197,14 @@ def test_full_size_properties(gpu, orc):
     torch.cuda.synchronize()
     q = base + 0.3 * noise
     results = {}
-    for prec in ("bf16", "tf32x1", "tf32x3"):
+    for prec in ("bf16", "tf32x1", "bf16x3", "tf32x3"):
         with Gallery(N, D, "cosine", prec) as g:
             g.fill_synthetic(3, 0, N)
             s, ids = g.search(q, k)
             results[prec] = (s.cpu().numpy(), ids.cpu().numpy())
             assert g.last_stats()["fallback_queries"] <= 8
     s, ids = results["tf32x3"]
-    for prec in ("bf16", "tf32x1"):
+    for prec in ("bf16", "tf32x1", "bf16x3"):
         assert np.array_equal(results[prec][1], ids) and np.array_equal(results[prec][0], s)
     assert (ids[:, 0] == pick.cpu().numpy()).all()
     assert np.all(np.diff(s, axis=1) <= 0)
@@ -214,7 +214,7 @@ def test_full_size_properties(gpu, orc):
     assert np.array_equal(wr, ids[:24]) and np.array_equal(ws.view(np.uint32), s[:24].view(np.uint32))
 
 
-@pytest.mark.parametrize("precision", ["tf32x3", "bf16"])
+@pytest.mark.parametrize("precision", ["tf32x3", "bf16", "bf16x3"])
 @pytest.mark.parametrize("explicit_ids", [False, True])
 def test_incremental_remove_keeps_order_and_ids(gpu, orc, precision, explicit_ids):
     """Delete rows from a live gallery: the survivors keep their order and ids, and the search
