@@ -404,7 +404,8 @@ def main():
     passes = 3 if args.precision in ("tf32x3", "bf16x3") else 1
     # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` captures of this exact
     # workload (profiles/r01_ncu_search_*_c3*.md: dram__bytes_read.sum + dram__bytes_write.sum); other shapes: null
-    ncu_traffic = {"tf32x3": 5.725465e9 + 16.753408e6, "bf16": 1.258923e9 + 16.037376e6}
+    ncu_traffic = {"tf32x3": 5.725465e9 + 16.753408e6, "bf16": 1.258923e9 + 16.037376e6,
+                   "bf16x3": 3.806807e9 + 18.018560e6}
     traffic = ncu_traffic.get(args.precision) if (args.workload == "c3" and world == 1 and not args.rows
                                                   and not args.queries) else None
     roofline = {
