@@ -11,7 +11,8 @@ import numpy as np
 from . import _ffi
 
 
-def arcface_loss(X, W, y, s: float = 64.0, m: float = 0.5, dloss=None, want_grad: bool = True):
+def arcface_loss(X, W, y, s: float = 64.0, m: float = 0.5, dloss=None, want_grad: bool = True,
+                 precision="tf32x3"):
     """Per-sample loss [B] and (optionally) dX [B, D], dW [C, D] = gradients of mean(loss) (or of sum dloss * loss).
 
     numpy / torch-CPU inputs take the host entry point (pinned staging, H2D, D2H); torch-CUDA inputs stay on
@@ -32,7 +33,7 @@ def arcface_loss(X, W, y, s: float = 64.0, m: float = 0.5, dloss=None, want_grad
         dW = torch.empty_like(w) if want_grad else None
         dl = None if dloss is None else dloss.detach().contiguous().float()
         _ffi.check(lib.dif_arcface(_ffi.ptr(x), _ffi.ptr(w), _ffi.ptr(yy), B, C, D, float(s), float(m), _ffi.ptr(loss),
-                                   _ffi.ptr(dl), _ffi.ptr(dX), _ffi.ptr(dW), _ffi.PREC_TF32X3,
+                                   _ffi.ptr(dl), _ffi.ptr(dX), _ffi.ptr(dW), _ffi.precision_code(precision),
                                    _ffi.current_stream_ptr(x.device)))
         return (loss, dX, dW) if want_grad else loss
     _ffi.init(0)
@@ -50,7 +51,7 @@ def arcface_loss(X, W, y, s: float = 64.0, m: float = 0.5, dloss=None, want_grad
     dW = np.empty_like(w) if want_grad else None
     dl = None if dloss is None else _ffi.host_array(dloss, np.float32, (B,))
     _ffi.check(lib.dif_arcface_host(_ffi.ptr(x), _ffi.ptr(w), _ffi.ptr(yy), B, C, D, float(s), float(m), _ffi.ptr(loss),
-                                    _ffi.ptr(dl), _ffi.ptr(dX), _ffi.ptr(dW), _ffi.PREC_TF32X3))
+                                    _ffi.ptr(dl), _ffi.ptr(dX), _ffi.ptr(dW), _ffi.precision_code(precision)))
     return (loss, dX, dW) if want_grad else loss
 
 
@@ -61,7 +62,9 @@ class ArcFaceStep:
     replayed with a single cudaGraphLaunch.  Write into `X`, `W`, `y` in place, call the step, read `loss`, `dX`, `dW`.
     """
 
-    def __init__(self, B: int, C: int, D: int, s: float = 64.0, m: float = 0.5, device="cuda:0", graph: bool = False):
+    def __init__(self, B: int, C: int, D: int, s: float = 64.0, m: float = 0.5, device="cuda:0", graph: bool = False,
+                 precision="tf32x3"):
+        self.precision = _ffi.precision_code(precision)
         import torch
 
         dev = torch.device(device)
@@ -92,7 +95,7 @@ class ArcFaceStep:
         st = int(torch.cuda.current_stream(self._dev).cuda_stream)
         _ffi.check(self._lib.dif_arcface(self.X.data_ptr(), self.W.data_ptr(), self.y.data_ptr(), self.B, self.C, self.D,
                                          self.s, self.m, self.loss.data_ptr(), None, self.dX.data_ptr(),
-                                         self.dW.data_ptr(), _ffi.PREC_TF32X3, st))
+                                         self.dW.data_ptr(), self.precision, st))
 
     def __call__(self):
         if self._graph is not None:

@@ -121,14 +121,27 @@ __global__ void arc_loss_kernel(const float2* __restrict__ part, int n_slots, co
   dphi[b] = arc_dphi(ct, mg);
 }
 
-// d cos in both orientations as TF32 hi/lo planes.  Tile 32 samples x 32 classes per block (32 x 8 threads).
+// Operand planes: T = float -> TF32 hi + exact residual lo (mode 0); T = bf16 -> b0 = bf16(v), b1 = bf16(v - b0) (mode 3)
+__device__ __forceinline__ void split_store(float v, float* hi, float* lo, size_t i) {
+  const float h = tf32_round(v);
+  hi[i] = h;
+  lo[i] = __fsub_rn(v, h);
+}
+__device__ __forceinline__ void split_store(float v, __nv_bfloat16* p0, __nv_bfloat16* p1, size_t i) {
+  const __nv_bfloat16 b0 = __float2bfloat16_rn(v);
+  p0[i] = b0;
+  p1[i] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(b0)));
+}
+
+// d cos in both orientations as operand planes.  Tile 32 samples x 32 classes per block (32 x 8 threads).
+template <class T>
 __global__ void __launch_bounds__(256) arc_dcos_kernel(const float* __restrict__ cosbuf, int ldc,
                                                        const int32_t* __restrict__ y, const float* __restrict__ logz,
                                                        const float* __restrict__ dphi, const float* __restrict__ dloss,
-                                                       int B, int C, ArcMargin mg, float* __restrict__ d_hi,
-                                                       float* __restrict__ d_lo,    // [Bp][ldc]
-                                                       float* __restrict__ t_hi, float* __restrict__ t_lo, int ldt,
-                                                       int Cp) {                    // [Cp][ldt]
+                                                       int B, int C, ArcMargin mg, T* __restrict__ d_hi,
+                                                       T* __restrict__ d_lo,    // [Bp][ldc]
+                                                       T* __restrict__ t_hi, T* __restrict__ t_lo, int ldt,
+                                                       int Cp, int Bp) {            // [Cp][ldt]
   __shared__ float tile[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   for (int r = threadIdx.y; r < 32; r += 8) {
@@ -145,37 +158,30 @@ __global__ void __launch_bounds__(256) arc_dcos_kernel(const float* __restrict__
       if (raw < -1.f || raw > 1.f) v = 0.f;   // clip_by_value passes no gradient outside the bounds
     }
     tile[r][threadIdx.x] = v;
-    if (b < ((B + 3) & ~3) && c < ldc) {
-      const float hi = tf32_round(v);
-      d_hi[(size_t)b * ldc + c] = hi;
-      d_lo[(size_t)b * ldc + c] = __fsub_rn(v, hi);
-    }
+    if (b < Bp && c < ldc) split_store(v, d_hi, d_lo, (size_t)b * ldc + c);
   }
   __syncthreads();
   const int b2 = blockIdx.y * 32 + threadIdx.x;
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int c2 = blockIdx.x * 32 + r;
-    if (c2 < Cp && b2 < ldt) {
-      const float v = tile[threadIdx.x][r];
-      const float hi = tf32_round(v);
-      t_hi[(size_t)c2 * ldt + b2] = hi;
-      t_lo[(size_t)c2 * ldt + b2] = __fsub_rn(v, hi);
-    }
+    if (c2 < Cp && b2 < ldt) split_store(tile[threadIdx.x][r], t_hi, t_lo, (size_t)c2 * ldt + b2);
   }
 }
 
-// src [R][Cc] (hi + lo planes) -> transposed TF32 hi/lo planes [Cc][ldt] (zero padded to ldt)
-__global__ void __launch_bounds__(256) transpose_planes_kernel(const float* __restrict__ s_hi,
-                                                               const float* __restrict__ s_lo, int R, int Cc,
-                                                               float* __restrict__ t_hi, float* __restrict__ t_lo,
+// src [R][Cc] (two planes) -> transposed planes [Cc][ldt] (zero padded to ldt)
+template <class T>
+__global__ void __launch_bounds__(256) transpose_planes_kernel(const T* __restrict__ s_hi,
+                                                               const T* __restrict__ s_lo, int R, int Cc,
+                                                               T* __restrict__ t_hi, T* __restrict__ t_lo,
                                                                int ldt) {
-  __shared__ float th[32][33], tl[32][33];
+  __shared__ T th[32][33 + (sizeof(T) == 2 ? 1 : 0)], tl[32][33 + (sizeof(T) == 2 ? 1 : 0)];
+  const T zero = T(0.f);
   const int c = blockIdx.x * 32 + threadIdx.x;
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int row = blockIdx.y * 32 + r;
     const bool ok = row < R && c < Cc;
-    th[r][threadIdx.x] = ok ? s_hi[(size_t)row * Cc + c] : 0.f;
-    tl[r][threadIdx.x] = ok ? s_lo[(size_t)row * Cc + c] : 0.f;
+    th[r][threadIdx.x] = ok ? s_hi[(size_t)row * Cc + c] : zero;
+    tl[r][threadIdx.x] = ok ? s_lo[(size_t)row * Cc + c] : zero;
   }
   __syncthreads();
   const int row2 = blockIdx.y * 32 + threadIdx.x;
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(256) transpose_planes_kernel(const float* __re
 }
 
 // out_r = inv_r * (g_r - h_r (h_r . g_r)) with g = sum over `planes` partial planes (fixed order), h = hi + lo
-// normalised row; rows whose squared norm was clamped (inv == 1e6) are a plain scaling.  TPR threads own one row
+// normalised row (h_lo NULL: h_hi is the fp32 normalised row itself); rows whose squared norm was clamped (inv == 1e6) are a plain scaling.  TPR threads own one row
 // (TPR = 32: a warp per row, 8 rows per block, D <= 512; TPR = 256: a block per row, D <= 4096), one float4 group
 // per thread and pass: every load is independent and coalesced and the planes are read exactly once.
 template <int TPR>
@@ -216,7 +222,7 @@ __global__ void __launch_bounds__(256) arc_norm_bwd_kernel(const float* __restri
         a[t].x += v.x; a[t].y += v.y; a[t].z += v.z; a[t].w += v.w;
       }
       const float4 hh = *reinterpret_cast<const float4*>(h_hi + base + d);
-      const float4 hl = *reinterpret_cast<const float4*>(h_lo + base + d);
+      const float4 hl = h_lo ? *reinterpret_cast<const float4*>(h_lo + base + d) : make_float4(0.f, 0.f, 0.f, 0.f);
       h[t] = make_float4(hh.x + hl.x, hh.y + hl.y, hh.z + hl.z, hh.w + hl.w);
       dot += a[t].x * h[t].x + a[t].y * h[t].y + a[t].z * h[t].z + a[t].w * h[t].w;
     }
@@ -268,31 +274,27 @@ struct ArcWorkspace {
 };
 static thread_local ArcWorkspace g_arc;
 
-static int tmaps(CUtensorMap* maps, const float* a_hi, const float* a_lo, int M, const float* b_hi, const float* b_lo,
-                 int N, int K, int ldk) {
-  if (int rc = make_tmap_2d(&maps[0], a_hi, M, K, (uint64_t)ldk * 4, GEMM_BM, 32, 0)) return rc;
-  if (int rc = make_tmap_2d(&maps[1], a_lo, M, K, (uint64_t)ldk * 4, GEMM_BM, 32, 0)) return rc;
-  if (int rc = make_tmap_2d(&maps[2], b_hi, N, K, (uint64_t)ldk * 4, kArcBN / kArcCtas, 32, 0)) return rc;
-  if (int rc = make_tmap_2d(&maps[3], b_lo, N, K, (uint64_t)ldk * 4, kArcBN / kArcCtas, 32, 0)) return rc;
+template <class T>
+static int tmaps(CUtensorMap* maps, const T* a_hi, const T* a_lo, int M, const T* b_hi, const T* b_lo, int N, int K,
+                 int ldk) {
+  constexpr int esz = (int)sizeof(T), bf = esz == 2 ? 1 : 0;
+  constexpr uint32_t cols = 128 / esz;
+  if (int rc = make_tmap_2d(&maps[0], a_hi, M, K, (uint64_t)ldk * esz, GEMM_BM, cols, bf)) return rc;
+  if (int rc = make_tmap_2d(&maps[1], a_lo, M, K, (uint64_t)ldk * esz, GEMM_BM, cols, bf)) return rc;
+  if (int rc = make_tmap_2d(&maps[2], b_hi, N, K, (uint64_t)ldk * esz, kArcBN / kArcCtas, cols, bf)) return rc;
+  if (int rc = make_tmap_2d(&maps[3], b_lo, N, K, (uint64_t)ldk * esz, kArcBN / kArcCtas, cols, bf)) return rc;
   return DIF_OK;
 }
 
-}  // namespace dif
-
-using namespace dif;
-
-extern "C" int dif_arcface(const float* X, const float* W, const int32_t* y, int B, int C, int D, float s, float m,
-                           float* loss, const float* dloss, float* dX, float* dW, int precision, void* stream) {
-  DIF_REQUIRE(X && W && y && loss, DIF_ERR_INVALID, "dif_arcface: null argument");
-  DIF_REQUIRE(B >= 1 && C >= 2 && D >= 32 && D % 4 == 0 && D <= 4096, DIF_ERR_INVALID,
-              "dif_arcface: B %d, C %d, D %d (D a multiple of 4 in 32..4096)", B, C, D);
-  DIF_REQUIRE(precision == DIF_PREC_TF32X3, DIF_ERR_INVALID, "dif_arcface: only the fp32-exact path (precision 0) is implemented");
-  DIF_REQUIRE((dX == nullptr) == (dW == nullptr), DIF_ERR_INVALID, "dif_arcface: pass both dX and dW, or neither");
-  DIF_REQUIRE(device_sm_count() > 0, DIF_ERR_STATE, "dif_init has not succeeded on this process");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+// PREC 0: TF32 hi/lo planes (3xTF32);  PREC 3: bf16 b0/b1 planes (3xBF16, half the plane bytes and MMA time)
+template <int PREC>
+static int run_arcface(const float* X, const float* W, const int32_t* y, int B, int C, int D, float s, float m,
+                       float* loss, const float* dloss, float* dX, float* dW, cudaStream_t st) {
+  using T = typename std::conditional<PREC == 3, __nv_bfloat16, float>::type;
+  constexpr int esz = (int)sizeof(T), kChunk = 128 / esz;
   const bool bwd = dX != nullptr;
   const int sms = device_sm_count();
-  const int Bp = (B + 3) & ~3, Cp = (C + 3) & ~3;
+  const int Bp = (B + 7) & ~7, Cp = (C + 7) & ~7;   // plane pitches stay 16-byte multiples for TMA in both modes
   ArcMargin mg{s, cosf(m), sinf(m), cosf(3.14159265358979323846f - m), sinf(3.14159265358979323846f - m) * m};
 
   // ---- GEMM shapes
@@ -300,14 +302,14 @@ extern "C" int dif_arcface(const float* X, const float* W, const int32_t* y, int
   const int bm = GEMM_BM * kArcCtas, units = std::max(1, sms / kArcCtas);
   fwd.m_blocks = (B + bm - 1) / bm;
   fwd.n_tiles = (C + kArcBN - 1) / kArcBN;
-  fwd.k_chunks = (D + 31) / 32;
+  fwd.k_chunks = (D + kChunk - 1) / kChunk;
   fwd.n_splits = std::max(1, std::min(fwd.n_tiles, 2 * units / std::max(1, fwd.m_blocks)));
   fwd.tiles_per_split = (fwd.n_tiles + fwd.n_splits - 1) / fwd.n_splits;
   fwd.n_splits = (fwd.n_tiles + fwd.tiles_per_split - 1) / fwd.tiles_per_split;
   GemmShape gx{};   // dxh [B, D] = dcos [B, Cp] x whT [D, Cp]^T, split over K = classes
   gx.m_blocks = fwd.m_blocks;
   gx.n_tiles = (D + kArcBN - 1) / kArcBN;
-  gx.k_chunks = (Cp + 31) / 32;
+  gx.k_chunks = (Cp + kChunk - 1) / kChunk;
   gx.n_splits = gx.n_tiles;
   gx.tiles_per_split = 1;
   gx.k_splits = std::max(1, std::min(gx.k_chunks, units / std::max(1, gx.m_blocks * gx.n_tiles)));
@@ -316,7 +318,7 @@ extern "C" int dif_arcface(const float* X, const float* W, const int32_t* y, int
   GemmShape gw{};   // dwh [C, D] = dcosT [Cp, Bp] x xhT [D, Bp]^T
   gw.m_blocks = (C + bm - 1) / bm;
   gw.n_tiles = gx.n_tiles;
-  gw.k_chunks = (Bp + 31) / 32;
+  gw.k_chunks = (Bp + kChunk - 1) / kChunk;
   gw.n_splits = gw.n_tiles;
   gw.tiles_per_split = 1;
 
@@ -327,38 +329,50 @@ extern "C" int dif_arcface(const float* X, const float* W, const int32_t* y, int
     off += (bytes + 255) & ~(size_t)255;
     return at;
   };
-  const size_t o_xh = take((size_t)B * D * 4), o_xl = take((size_t)B * D * 4), o_xi = take((size_t)B * 4);
-  const size_t o_wh = take((size_t)C * D * 4), o_wl = take((size_t)C * D * 4), o_wi = take((size_t)C * 4);
+  // mode 0: xh / xl = hi / lo planes.  mode 3: xn = fp32 normalised rows (for the normalisation backward),
+  // xh / xl = bf16 planes
+  const size_t o_xn = PREC == 3 ? take((size_t)B * D * 4) : 0, o_wn = PREC == 3 ? take((size_t)C * D * 4) : 0;
+  const size_t o_xh = take((size_t)B * D * esz), o_xl = take((size_t)B * D * esz), o_xi = take((size_t)B * 4);
+  const size_t o_wh = take((size_t)C * D * esz), o_wl = take((size_t)C * D * esz), o_wi = take((size_t)C * 4);
   const size_t o_cos = take((size_t)B * Cp * 4);
   const size_t o_part = take((size_t)B * fwd.n_splits * 8);
   const size_t o_logz = take((size_t)B * 4), o_dphi = take((size_t)B * 4);
   size_t o_dh = 0, o_dl = 0, o_th = 0, o_tl = 0, o_wth = 0, o_wtl = 0, o_xth = 0, o_xtl = 0, o_gx = 0, o_gw = 0;
   if (bwd) {
-    o_dh = take((size_t)Bp * Cp * 4); o_dl = take((size_t)Bp * Cp * 4);
-    o_th = take((size_t)Cp * Bp * 4); o_tl = take((size_t)Cp * Bp * 4);
-    o_wth = take((size_t)D * Cp * 4); o_wtl = take((size_t)D * Cp * 4);
-    o_xth = take((size_t)D * Bp * 4); o_xtl = take((size_t)D * Bp * 4);
+    o_dh = take((size_t)Bp * Cp * esz); o_dl = take((size_t)Bp * Cp * esz);
+    o_th = take((size_t)Cp * Bp * esz); o_tl = take((size_t)Cp * Bp * esz);
+    o_wth = take((size_t)D * Cp * esz); o_wtl = take((size_t)D * Cp * esz);
+    o_xth = take((size_t)D * Bp * esz); o_xtl = take((size_t)D * Bp * esz);
     o_gx = take((size_t)gx.k_splits * B * D * 4);
     o_gw = take((size_t)C * D * 4);
   }
   if (int rc = g_arc.ensure(off)) return rc;
   char* ws = g_arc.base;
   auto F = [&](size_t o) { return reinterpret_cast<float*>(ws + o); };
+  auto P = [&](size_t o) { return reinterpret_cast<T*>(ws + o); };
 
   // ---- 0. normalise + TF32 planes
   PrepParams px{};
-  px.src = X; px.n = B; px.D = D; px.normalize = 1; px.split = 1;
-  px.p0 = F(o_xh); px.p1 = F(o_xl); px.inv = F(o_xi);
-  if (int rc = prep_launch(px, false, st)) return rc;
+  px.src = X; px.n = B; px.D = D; px.normalize = 1; px.inv = F(o_xi);
   PrepParams pw = px;
-  pw.src = W; pw.n = C; pw.p0 = F(o_wh); pw.p1 = F(o_wl); pw.inv = F(o_wi);
+  pw.src = W; pw.n = C; pw.inv = F(o_wi);
+  if (PREC == 3) {
+    px.split = 0; px.p0 = F(o_xn);
+    px.pb = reinterpret_cast<__nv_bfloat16*>(ws + o_xh); px.pb1 = reinterpret_cast<__nv_bfloat16*>(ws + o_xl);
+    pw.split = 0; pw.p0 = F(o_wn);
+    pw.pb = reinterpret_cast<__nv_bfloat16*>(ws + o_wh); pw.pb1 = reinterpret_cast<__nv_bfloat16*>(ws + o_wl);
+  } else {
+    px.split = 1; px.p0 = F(o_xh); px.p1 = F(o_xl);
+    pw.split = 1; pw.p0 = F(o_wh); pw.p1 = F(o_wl);
+  }
+  if (int rc = prep_launch(px, false, st)) return rc;
   if (int rc = prep_launch(pw, false, st)) return rc;
 
   // ---- 1. forward GEMM + online softmax
   CUtensorMap maps[4];
-  if (int rc = tmaps(maps, F(o_xh), F(o_xl), B, F(o_wh), F(o_wl), C, D, D)) return rc;
+  if (int rc = tmaps<T>(maps, P(o_xh), P(o_xl), B, P(o_wh), P(o_wl), C, D, D)) return rc;
   ArcFwdEpi::Params fp{F(o_cos), y, reinterpret_cast<float2*>(ws + o_part), B, C, Cp, fwd.n_splits, mg};
-  if (int rc = launch_nt_gemm<0, kArcBN, kArcCtas, 0, ArcFwdEpi>(maps, fwd, fp, units, st)) return rc;
+  if (int rc = launch_nt_gemm<PREC, kArcBN, kArcCtas, 0, ArcFwdEpi>(maps, fwd, fp, units, st)) return rc;
   // ---- 2. loss
   arc_loss_kernel<<<(B + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float2*>(ws + o_part), fwd.n_splits, F(o_cos), Cp,
                                                   y, B, mg, loss, F(o_logz), F(o_dphi));
@@ -366,28 +380,49 @@ extern "C" int dif_arcface(const float* X, const float* W, const int32_t* y, int
   if (!bwd) return DIF_OK;
 
   // ---- 3. d cos planes (both orientations) and transposed operand planes
-  arc_dcos_kernel<<<dim3((Cp + 31) / 32, (Bp + 31) / 32), dim3(32, 8), 0, st>>>(
-      F(o_cos), Cp, y, F(o_logz), F(o_dphi), dloss, B, C, mg, F(o_dh), F(o_dl), F(o_th), F(o_tl), Bp, Cp);
+  arc_dcos_kernel<T><<<dim3((Cp + 31) / 32, (Bp + 31) / 32), dim3(32, 8), 0, st>>>(
+      F(o_cos), Cp, y, F(o_logz), F(o_dphi), dloss, B, C, mg, P(o_dh), P(o_dl), P(o_th), P(o_tl), Bp, Cp, Bp);
   DIF_LAUNCH_OK();
-  transpose_planes_kernel<<<dim3((D + 31) / 32, (C + 31) / 32), dim3(32, 8), 0, st>>>(F(o_wh), F(o_wl), C, D, F(o_wth),
-                                                                                    F(o_wtl), Cp);
+  transpose_planes_kernel<T><<<dim3((D + 31) / 32, (C + 31) / 32), dim3(32, 8), 0, st>>>(P(o_wh), P(o_wl), C, D, P(o_wth),
+                                                                                       P(o_wtl), Cp);
   DIF_LAUNCH_OK();
-  transpose_planes_kernel<<<dim3((D + 31) / 32, (B + 31) / 32), dim3(32, 8), 0, st>>>(F(o_xh), F(o_xl), B, D, F(o_xth),
-                                                                                    F(o_xtl), Bp);
+  transpose_planes_kernel<T><<<dim3((D + 31) / 32, (B + 31) / 32), dim3(32, 8), 0, st>>>(P(o_xh), P(o_xl), B, D, P(o_xth),
+                                                                                       P(o_xtl), Bp);
   DIF_LAUNCH_OK();
   // ---- 4. dxh (split-K planes) and dwh
-  if (int rc = tmaps(maps, F(o_dh), F(o_dl), B, F(o_wth), F(o_wtl), D, Cp, Cp)) return rc;
+  if (int rc = tmaps<T>(maps, P(o_dh), P(o_dl), B, P(o_wth), P(o_wtl), D, Cp, Cp)) return rc;
   StoreEpi::Params sx{F(o_gx), B, D, D, gx.n_splits, (size_t)B * D};
-  if (int rc = launch_nt_gemm<0, kArcBN, kArcCtas, 0, StoreEpi>(maps, gx, sx, units, st)) return rc;
-  if (int rc = tmaps(maps, F(o_th), F(o_tl), C, F(o_xth), F(o_xtl), D, Bp, Bp)) return rc;
+  if (int rc = launch_nt_gemm<PREC, kArcBN, kArcCtas, 0, StoreEpi>(maps, gx, sx, units, st)) return rc;
+  if (int rc = tmaps<T>(maps, P(o_th), P(o_tl), C, P(o_xth), P(o_xtl), D, Bp, Bp)) return rc;
   StoreEpi::Params sw{F(o_gw), C, D, D, gw.n_splits, 0};
-  if (int rc = launch_nt_gemm<0, kArcBN, kArcCtas, 0, StoreEpi>(maps, gw, sw, units, st)) return rc;
+  if (int rc = launch_nt_gemm<PREC, kArcBN, kArcCtas, 0, StoreEpi>(maps, gw, sw, units, st)) return rc;
   // ---- 5. l2_normalize backward
-  launch_norm_bwd(F(o_gx), gx.k_splits, (size_t)B * D, F(o_xh), F(o_xl), F(o_xi), B, D, dX, st);
+  if (PREC == 3) launch_norm_bwd(F(o_gx), gx.k_splits, (size_t)B * D, F(o_xn), nullptr, F(o_xi), B, D, dX, st);
+  else launch_norm_bwd(F(o_gx), gx.k_splits, (size_t)B * D, F(o_xh), F(o_xl), F(o_xi), B, D, dX, st);
   DIF_LAUNCH_OK();
-  launch_norm_bwd(F(o_gw), 1, 0, F(o_wh), F(o_wl), F(o_wi), C, D, dW, st);
+  if (PREC == 3) launch_norm_bwd(F(o_gw), 1, 0, F(o_wn), nullptr, F(o_wi), C, D, dW, st);
+  else launch_norm_bwd(F(o_gw), 1, 0, F(o_wh), F(o_wl), F(o_wi), C, D, dW, st);
   DIF_LAUNCH_OK();
   return DIF_OK;
+}
+
+}  // namespace dif
+
+using namespace dif;
+
+extern "C" int dif_arcface(const float* X, const float* W, const int32_t* y, int B, int C, int D, float s, float m,
+                           float* loss, const float* dloss, float* dX, float* dW, int precision, void* stream) {
+  DIF_REQUIRE(X && W && y && loss, DIF_ERR_INVALID, "dif_arcface: null argument");
+  DIF_REQUIRE(precision == DIF_PREC_TF32X3 || precision == DIF_PREC_BF16X3, DIF_ERR_INVALID,
+              "dif_arcface: precision %d (0 = 3xTF32, 3 = 3xBF16; both fp32-class)", precision);
+  const int dmul = precision == DIF_PREC_BF16X3 ? 8 : 4, dmin = precision == DIF_PREC_BF16X3 ? 64 : 32;
+  DIF_REQUIRE(B >= 1 && C >= 2 && D >= dmin && D % dmul == 0 && D <= 4096, DIF_ERR_INVALID,
+              "dif_arcface: B %d, C %d, D %d (D a multiple of %d in %d..4096)", B, C, D, dmul, dmin);
+  DIF_REQUIRE((dX == nullptr) == (dW == nullptr), DIF_ERR_INVALID, "dif_arcface: pass both dX and dW, or neither");
+  DIF_REQUIRE(device_sm_count() > 0, DIF_ERR_STATE, "dif_init has not succeeded on this process");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return precision == DIF_PREC_BF16X3 ? run_arcface<3>(X, W, y, B, C, D, s, m, loss, dloss, dX, dW, st)
+                                      : run_arcface<0>(X, W, y, B, C, D, s, m, loss, dloss, dX, dW, st);
 }
 
 extern "C" int dif_arcface_host(const float* X_host, const float* W_host, const int32_t* y_host, int B, int C, int D,

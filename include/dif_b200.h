@@ -187,8 +187,9 @@ int dif_contrastive_loss(const float* y_true, const float* dist, int B, float ma
  * Absent from the reference; spec in DESIGN.md / oracle/losses_oracle.py:arcface (arXiv 1801.07698):
  * logits = s*cos(theta + m*onehot) over L2-normalised X [B,D] and W [C,D] (easy-margin fallback past
  * pi - m); loss [B] = per-sample cross-entropy; dX [B*D], dW [C*D] = gradients of sum_b dloss[b]*loss[b]
- * (dloss NULL -> 1/B each); pass dX = dW = NULL to skip the backward pass.  precision must be
- * DIF_PREC_TF32X3 (fp32-exact tensor-core path). */
+ * (dloss NULL -> 1/B each); pass dX = dW = NULL to skip the backward pass.  precision: DIF_PREC_TF32X3
+ * (TF32 hi/lo operand planes, D % 4 == 0, D >= 32) or DIF_PREC_BF16X3 (two bf16 planes per operand, D % 8 == 0,
+ * D >= 64; half the plane bytes and tensor time); both are within 1e-4 of the fp64 oracle. */
 int dif_arcface(const float* X, const float* W, const int32_t* y, int B, int C, int D, float s, float m,
                 float* loss, const float* dloss, float* dX, float* dW, int precision, void* stream);
 int dif_arcface_host(const float* X_host, const float* W_host, const int32_t* y_host, int B, int C, int D, float s,

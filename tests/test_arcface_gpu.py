@@ -19,18 +19,21 @@ def data(B, C, D, seed=2, wscale=0.01):
     return X, W, y
 
 
+@pytest.mark.parametrize("precision", ["tf32x3", "bf16x3"])
 @pytest.mark.parametrize("B,C,D", [(64, 300, 64), (130, 1000, 128), (512, 10000, 512), (72, 18, 128), (33, 1027, 96)])
-def test_arcface_forward_backward(gpu, B, C, D):
+def test_arcface_forward_backward(gpu, B, C, D, precision):
+    """Both fp32-class operand splits (TF32 hi/lo planes, bf16 b0/b1 planes) against the fp64 oracle at 1e-4."""
     from deep_insight_face_b200.arcface import arcface_loss
     from oracle import losses_oracle as lo
 
     X, W, y = data(B, C, D)
-    loss, dX, dW = arcface_loss(X, W, y, 64.0, 0.5)
+    loss, dX, dW = arcface_loss(X, W, y, 64.0, 0.5, precision=precision)
+
     want = lo.arcface(X, W, y, 64.0, 0.5)
     assert np.abs(loss - want["loss"]).max() <= RTOL * np.abs(want["loss"]).max()
     assert np.abs(dX - want["dX"]).max() <= RTOL * np.abs(want["dX"]).max()
     assert np.abs(dW - want["dW"]).max() <= RTOL * np.abs(want["dW"]).max()
-    fwd_only = arcface_loss(X, W, y, 64.0, 0.5, want_grad=False)
+    fwd_only = arcface_loss(X, W, y, 64.0, 0.5, want_grad=False, precision=precision)
     assert np.array_equal(fwd_only, loss)
 
 

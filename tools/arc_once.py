@@ -8,9 +8,10 @@ import torch
 from deep_insight_face_b200.arcface import ArcFaceStep
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+prec = sys.argv[4] if len(sys.argv) > 4 else "tf32x3"
 C = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
 D = int(sys.argv[3]) if len(sys.argv) > 3 else 512
-st = ArcFaceStep(B, C, D, graph=True)
+st = ArcFaceStep(B, C, D, graph=True, precision=prec)
 st.y.copy_(torch.randint(0, C, (B,), device="cuda").int())
 for _ in range(5):
     st()
@@ -21,4 +22,4 @@ for _ in range(100):
     st()
 e1.record()
 torch.cuda.synchronize()
-print("arcface B=%d C=%d D=%d us/step %.1f" % (B, C, D, e0.elapsed_time(e1) * 10))
+print("arcface %s B=%d C=%d D=%d us/step %.1f" % (prec, B, C, D, e0.elapsed_time(e1) * 10))
