@@ -264,7 +264,7 @@ struct ArcWorkspace {
   size_t bytes = 0;
   int ensure(size_t need) {
     if (need <= bytes) return DIF_OK;
-    cudaFree(base);
+    retire_device_block(base);
     base = nullptr;
     bytes = 0;
     DIF_CUDA_OK(cudaMalloc((void**)&base, need));

@@ -699,18 +699,18 @@ struct BhWorkspace {
   size_t row_cap = 0;
   int ensure(size_t n_rec, size_t n_rows) {
     if (n_rec > rec_cap) {
-      cudaFree(recs);
+      retire_device_block(recs);
       recs = nullptr;
       rec_cap = 0;
       DIF_CUDA_OK(cudaMalloc((void**)&recs, n_rec * sizeof(BhRec)));
       rec_cap = n_rec;
     }
     if (n_rows > row_cap) {
-      cudaFree(rows);
-      cudaFree(aux);
-      cudaFree(compact);
-      cudaFree(partials);
-      cudaFree(inv);
+      retire_device_block(rows);
+      retire_device_block(aux);
+      retire_device_block(compact);
+      retire_device_block(partials);
+      retire_device_block(inv);
       inv = nullptr;
       rows = nullptr;
       aux = nullptr;
@@ -1032,14 +1032,14 @@ struct BaWorkspace {
   size_t v_cap = 0;
   int ensure(size_t n_rows, size_t n_v) {
     if (n_rows > row_cap) {
-      cudaFree(rows); cudaFree(pos_loss);
+      retire_device_block(rows); retire_device_block(pos_loss);
       rows = nullptr; pos_loss = nullptr; row_cap = 0;
       DIF_CUDA_OK(cudaMalloc((void**)&rows, n_rows * sizeof(BaRow)));
       DIF_CUDA_OK(cudaMalloc((void**)&pos_loss, n_rows * sizeof(float)));
       row_cap = n_rows;
     }
     if (n_v > v_cap) {
-      cudaFree(vrec);
+      retire_device_block(vrec);
       vrec = nullptr; v_cap = 0;
       DIF_CUDA_OK(cudaMalloc((void**)&vrec, n_v * sizeof(float2)));
       v_cap = n_v;

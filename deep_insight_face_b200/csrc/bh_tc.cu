@@ -339,7 +339,7 @@ struct TcWorkspace {
   size_t cand_cap = 0;
   int ensure(size_t plane_elems, size_t n_cand) {
     if (plane_elems > plane_cap) {
-      cudaFree(hi); cudaFree(lo);
+      retire_device_block(hi); retire_device_block(lo);
       hi = lo = nullptr; plane_cap = 0;
       DIF_CUDA_OK(cudaMalloc((void**)&hi, plane_elems * 4));
       DIF_CUDA_OK(cudaMalloc((void**)&lo, plane_elems * 4));
@@ -347,7 +347,7 @@ struct TcWorkspace {
     }
     if (!gmax) DIF_CUDA_OK(cudaMalloc((void**)&gmax, 4));
     if (n_cand > cand_cap) {
-      cudaFree(cand);
+      retire_device_block(cand);
       cand = nullptr; cand_cap = 0;
       DIF_CUDA_OK(cudaMalloc((void**)&cand, n_cand * sizeof(BhCand)));
       cand_cap = n_cand;

@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "dif_common.cuh"
 
@@ -27,6 +28,14 @@ int count_launch(int n) {
 }
 
 int device_sm_count() { return g_sm_count; }
+
+void retire_device_block(void* p) {
+  static std::mutex mu;
+  static std::vector<void*>* retired = new std::vector<void*>();   // lives until the process exits
+  if (!p) return;
+  std::lock_guard<std::mutex> lock(mu);
+  retired->push_back(p);
+}
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;

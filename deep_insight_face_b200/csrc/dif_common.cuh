@@ -52,5 +52,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 int device_sm_count();
+// Loss workspaces only grow.  A block that is outgrown is retired, not freed: CUDA graphs captured earlier
+// (BatchHardStep / ArcFaceStep of another shape) hold its address in their kernel nodes and must stay valid.
+void retire_device_block(void* p);
 
 }  // namespace dif

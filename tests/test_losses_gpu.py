@@ -256,3 +256,30 @@ def test_soft_margin_extension(gpu, P, K, D):
         close(got, want["loss"])
         close(grad, want["grad"])
         assert (got > 0).all() and cls.from_config(loss.get_config()).soft
+
+
+def test_graphed_steps_survive_workspace_growth():
+    """A CUDA-graphed step keeps the library workspace addresses in its kernel nodes: a later, larger step makes the
+    workspace grow, and the outgrown block must stay valid (retired, not freed) for the earlier graph."""
+    import torch
+
+    from deep_insight_face_b200 import _ffi
+    from deep_insight_face_b200.common.losses import BatchHardStep
+
+    rng = np.random.default_rng(3)
+    small = BatchHardStep(640, 128, _ffi.LOSS_BH_COSINE, 0.35, "cuda:0", graph=True)
+    emb = rng.standard_normal((640, 128)).astype(np.float32)
+    small.emb.copy_(torch.from_numpy(emb))
+    small.labels.copy_(torch.from_numpy(np.repeat(np.arange(160), 4).astype(np.int32)))
+    small()
+    torch.cuda.synchronize()
+    before = [t.clone() for t in (small.loss, small.grad)]
+    big = BatchHardStep(3072, 128, _ffi.LOSS_BH_COSINE, 0.35, "cuda:0", graph=True)   # grows every workspace
+    big()
+    junk = torch.full((64 << 20,), 7.0, device="cuda")     # would land in the freed blocks if they had been freed
+    small.loss.zero_()
+    small.grad.zero_()
+    small()
+    torch.cuda.synchronize()
+    assert torch.equal(small.loss, before[0]) and torch.equal(small.grad, before[1])
+    del junk
