@@ -146,8 +146,12 @@ def check(rc: int) -> None:
         raise DifError(rc, last_error())
 
 
-def init(device: int = 0) -> None:
-    """Select `device`, verify it is sm_100 and create its context (idempotent per device)."""
+def init(device=None) -> None:
+    """Select `device`, verify it is sm_100 and create its context (idempotent).  The library serves ONE device
+    per process (dif_init refuses a second one): `device=None` means the device this process is already bound
+    to, or device 0 for a fresh process - what the host-array entry points use."""
+    if device is None:
+        device = next(iter(_inited_devices)) if _inited_devices else 0
     device = int(device)
     if device in _inited_devices:   # dif_init queries device properties (milliseconds): once per device is enough
         return

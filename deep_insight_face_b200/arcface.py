@@ -36,7 +36,7 @@ def arcface_loss(X, W, y, s: float = 64.0, m: float = 0.5, dloss=None, want_grad
                                    _ffi.ptr(dl), _ffi.ptr(dX), _ffi.ptr(dW), _ffi.precision_code(precision),
                                    _ffi.current_stream_ptr(x.device)))
         return (loss, dX, dW) if want_grad else loss
-    _ffi.init(0)
+    _ffi.init()
     x = _ffi.host_array(X, np.float32)
     w = _ffi.host_array(W, np.float32)
     yy = np.ascontiguousarray(_ffi.host_array(y, None), dtype=np.int32)

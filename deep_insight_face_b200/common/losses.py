@@ -74,7 +74,7 @@ def batch_hard(labels, embeddings, variant: int, alpha: float, dloss=None, want_
                                       _ffi.ptr(pos), _ffi.ptr(neg), _ffi.ptr(stats), _ffi.ptr(dl), _ffi.ptr(grad),
                                       _ffi.PREC_TF32X3, st))
         return loss, grad, {"pos_idx": pos, "neg_idx": neg, "stats": stats}
-    _ffi.init(0)
+    _ffi.init()
     emb = _ffi.host_array(embeddings, np.float32)
     if emb.ndim != 2:
         raise ValueError("embeddings must be [B, D]")

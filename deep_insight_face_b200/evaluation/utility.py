@@ -43,7 +43,7 @@ def distance(embeddings1, embeddings2, distance_metric=0, _mean=None):
     if distance_metric not in (0, 1):
         raise RuntimeError('Undefined distance metric %d' % distance_metric)
     lib = _ffi.load_library()
-    _ffi.init(0)
+    _ffi.init()
     if _ffi.is_device_tensor(embeddings1):
         torch = _torch()
         e1, e2 = _dev(embeddings1, torch.float32), _dev(embeddings2, torch.float32)
@@ -71,7 +71,7 @@ def get_emd_distance(embeddings1, embeddings2, distance_metric=0):
 def threshold_counts(dist, actual_issame, thresholds, fold=None, n_folds=1) -> np.ndarray:
     """counts[f, t] = (tp, fp, tn, fn) over the pairs of fold f with predict = dist < thresholds[t] (np.less)."""
     lib = _ffi.load_library()
-    _ffi.init(0)
+    _ffi.init()
     thr = np.ascontiguousarray(np.atleast_1d(np.asarray(thresholds, dtype=np.float64)))
     same = np.ascontiguousarray(np.asarray(actual_issame).astype(bool).astype(np.uint8))
     d = _ffi.host_array(dist, np.float32)
@@ -136,7 +136,7 @@ def _fold_distances(embeddings1, embeddings2, fold, nrof_folds, distance_metric,
         return [d] * nrof_folds
     torch = _torch()
     lib = _ffi.load_library()
-    _ffi.init(0)
+    _ffi.init()
     n, D = e1.shape
     d1, d2 = _dev(e1, torch.float32), _dev(e2, torch.float32)
     begin = np.concatenate([[0], np.cumsum(np.bincount(fold, minlength=nrof_folds))]).astype(np.int64)
