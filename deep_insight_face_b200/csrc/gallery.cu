@@ -835,7 +835,13 @@ int dif_gallery_search_host(dif_gallery_t* g, const float* queries_host, int n_q
   char* hp = (char*)g->h_pin;
   char* dp = (char*)g->d_stage;
   cudaStream_t st = g->own_stream;
-  {
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, queries_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  if (!pinned) cudaGetLastError();   // (older drivers report pageable memory as an error)
+  if (pinned) {
+    // page-locked caller buffer (cudaHostAlloc / cudaHostRegister / torch pin_memory): DMA straight from it
+    DIF_CUDA_OK(cudaMemcpyAsync(dp, queries_host, qb, cudaMemcpyHostToDevice, st));
+  } else {
     // staged in 1 MB pieces so the DMA of piece i overlaps the host memcpy of piece i + 1
     const size_t piece = (size_t)1 << 20;
     for (size_t off = 0; off < qb; off += piece) {

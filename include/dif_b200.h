@@ -92,7 +92,8 @@ int dif_gallery_reset(dif_gallery_t* g);
  * Slots beyond the gallery size hold id -1 / row -1. */
 int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, int k, float* scores,
                        int64_t* ids, int32_t* rows, void* stream);
-/* same call with HOST buffers: pinned staging, H2D of queries, D2H of results, synchronises */
+/* same call with HOST buffers: H2D of queries (straight from the caller's buffer when it is page-locked, through
+ * the handle's pinned staging otherwise), D2H of results, synchronises */
 int dif_gallery_search_host(dif_gallery_t* g, const float* queries_host, int n_queries, int k,
                             float* scores_host, int64_t* ids_host, int32_t* rows_host);
 /* counters of the last search: [0] queries that took the exact fallback, [1] kernels launched,

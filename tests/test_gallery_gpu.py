@@ -249,3 +249,20 @@ def test_incremental_remove_keeps_order_and_ids(gpu, orc, precision, explicit_id
         assert (got_ids[20:, 0] == np.arange(5) + 9_000_000).all()
         with pytest.raises(RuntimeError):
             g.remove(rows=[len(g)])
+
+
+def test_host_entry_accepts_pinned_and_pageable_buffers(gpu, orc):
+    """dif_gallery_search_host DMAs straight from a page-locked caller buffer and stages a pageable one: same result."""
+    import torch
+
+    from deep_insight_face_b200.gallery import Gallery
+
+    rows, q, _ = make(orc, 30000, 700, 128)
+    with Gallery(30000, 128, "cosine", "bf16x3") as g:
+        g.add(rows)
+        s0, i0 = g.search(q, 10)
+        pinned = torch.from_numpy(q).pin_memory()
+        s1, i1 = g.search(pinned.numpy(), 10)
+        assert np.array_equal(i0, i1) and np.array_equal(s0.view(np.uint32), s1.view(np.uint32))
+        ws, wr = orc.gallery_search(rows, q, 10, 1)
+        assert np.array_equal(i1, wr) and np.array_equal(s1.view(np.uint32), ws.view(np.uint32))
