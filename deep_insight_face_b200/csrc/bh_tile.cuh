@@ -72,15 +72,40 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
 // Load `n` rows [row0, row0+n) of x into smem (zero beyond B); cosine: normalise in place; writes the
 // canonical sum of squares (euclid) or inverse norm (cosine) of each row to aux[n] in smem.
 template <bool COSINE>
-__device__ __forceinline__ void stage_rows(const float* __restrict__ x, int B, int D, int row0, int n, float* dst,
-                                           float* aux) {
+__device__ __forceinline__ void stage_rows(const float* __restrict__ x, int B, int D, int row0, int n,
+                                           float* __restrict__ dst, float* __restrict__ aux) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kd = (D + 31) / 32;
+  // Phase A: copy this warp's rows (warp, warp + 4, ...) with 16 independent loads in flight per step.  A small
+  // batch is latency bound: one row at a time cost a full global-load round trip per row (8 per warp and tile).
+  for (int rb = warp; rb < n; rb += 4 * BH_WARPS) {
+    for (int c0 = 0; c0 < kd; c0 += 4) {
+      float t[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * BH_WARPS, gr = row0 + r;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int d = (c0 + cc) * 32 + lane;
+          t[u][cc] = (r < n && gr < B && d < D) ? x[(size_t)gr * D + d] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * BH_WARPS;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int d = (c0 + cc) * 32 + lane;
+          if (r < n && d < D) dst[r * D + d] = t[u][cc];
+        }
+      }
+    }
+  }
+  // Phase B: each lane re-reads only what it wrote itself (d = lane, lane + 32, ...): no barrier needed.
   for (int r = warp; r < n; r += BH_WARPS) {
-    const int gr = row0 + r;
     float acc = 0.f;
     for (int d = lane; d < D; d += 32) {
-      const float t = gr < B ? x[(size_t)gr * D + d] : 0.f;
-      dst[r * D + d] = t;
+      const float t = dst[r * D + d];
       acc = __fmaf_rn(t, t, acc);
     }
     const float ss = canon_tree(acc);
