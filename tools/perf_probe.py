@@ -44,7 +44,7 @@ def main():
         for ctas in (2, 1):
             g = Gallery(N, D, "cosine", mode)
             g.set_option("gemm_ctas", ctas)
-            g.set_option("l2_prefetch", int(os.environ.get("DIF_L2_PREFETCH", "1")))
+            g.set_option("l2_prefetch", int(os.environ.get("DIF_L2_PREFETCH", "0")))
             g.fill_synthetic(3, 0, N)
             for _ in range(2):
                 s, ids = g.search(q, k)
