@@ -230,7 +230,11 @@ def secondary_metrics(torch, device):
         "max_rel_diff_vs_tf32x3": float(((bstep.dW - astep.dW).abs().max() / astep.dW.abs().max()).item()),
         "note": "same step with the operands split into two bf16 planes (3xBF16) instead of TF32 hi/lo: fp32-class "
                 "(1e-4 of the fp64 oracle in tests), half the plane bytes and tensor time"}
+    t0 = time.perf_counter()
+    lo.arcface(X.cpu().numpy(), W.cpu().numpy(), y.cpu().numpy(), 64.0, 0.5)   # fp64 numpy oracle, one step
+    arc_cpu_s = time.perf_counter() - t0
     out["c2_arcface_512x512x10000"] = {"steps_per_s": 1e3 / ms, "ms_per_step": ms, "ungraphed_call_steps_per_s": 1e3 / ms_call,
+                                       "cpu_oracle_steps_per_s": 1.0 / arc_cpu_s,
                                        "alg_gflop": 6.0 * B * C * D / 1e9,
                                        "alg_tflops": 6.0 * B * C * D / ms / 1e9, "note": "fwd + bwd, 3xTF32 tcgen05 GEMMs; steps_per_s = CUDA-graphed ArcFaceStep"}
     return out
