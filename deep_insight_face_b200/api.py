@@ -23,10 +23,8 @@ def face_distance(face_encodings, face_to_compare):
 
 
 def compare_faces(known_face_encodings, face_encoding_to_check, tolerance=0.6):
-    """api.py:242-256."""
-    distance = face_distance(known_face_encodings[0], face_encoding_to_check[0])
-    if distance <= tolerance:
-        probability = gaussian_kernel_dist_to_prob(distance)
-    else:
-        probability = distance_to_proba(distance)
-    return distance, probability
+    """api.py:242-256: distance of the first known encoding to the first candidate and a match score - the
+    gaussian-kernel probability inside the tolerance, 1 / (1 + d) outside it."""
+    d = face_distance(known_face_encodings[0], face_encoding_to_check[0])
+    to_score = gaussian_kernel_dist_to_prob if d <= tolerance else distance_to_proba
+    return d, to_score(d)
