@@ -65,3 +65,19 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|from\s+\.\.?oracle|dif_oracle\.so|libdif_oracle", txt, re.M):
                     offenders.append(os.path.join(dp, f))
     assert not offenders, f"product code references the oracle: {offenders}"
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/dif_b200.h must compile as C99 (no C++ types, no torch types)."""
+    import os
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+
+        pytest.skip("gcc not available")
+    hdr = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "dif_b200.h")
+    res = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", hdr], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
