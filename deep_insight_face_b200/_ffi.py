@@ -24,6 +24,9 @@ MAX_TOPK = 24
 LOSS_BH_COSINE = 0
 LOSS_BH_EUCLIDEAN = 1
 LOSS_SOFT_MARGIN = 4
+TRANSPORT_NCCL = 0
+TRANSPORT_PEER = 1
+NCCL_ID_BYTES = 128
 
 _PRECISIONS = {"tf32x3": PREC_TF32X3, "fp32": PREC_TF32X3, "bf16": PREC_BF16, "tf32": PREC_TF32X1,
                "tf32x1": PREC_TF32X1, "bf16x3": PREC_BF16X3}
@@ -83,6 +86,15 @@ SIGNATURES = {
     "dif_gallery_last_kernel_ms": (_i32, [_vp, C.POINTER(_f32)]),
     "dif_gallery_get_rows": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "dif_topk_merge": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "dif_nccl_unique_id": (_i32, [_vp]),
+    "dif_nccl_comm_create": (_i32, [_i32, _i32, _vp, C.POINTER(_vp)]),
+    "dif_nccl_comm_destroy": (_i32, [_vp]),
+    "dif_shard_chunk_bytes": (_i64, [_i32, _i32, _i32]),
+    "dif_gallery_search_packed": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "dif_shard_merge": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "dif_gallery_shard_attach": (_i32, [_vp, _vp, _i32, _i32, _i64, _i32, _i32, _i32]),
+    "dif_gallery_search_sharded": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "dif_gallery_search_sharded_host": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "dif_synth_fill": (_i32, [_vp, _u64, _i64, _vp, _i64, _i32, _vp]),
     "dif_debug_nt_gemm": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
     "dif_debug_gemm_time": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_f32)]),

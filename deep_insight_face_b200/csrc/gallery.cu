@@ -26,7 +26,7 @@ namespace dif {
 constexpr int kRerankThreads = 128;
 constexpr int kRerankCap = 256;     // candidates inside the 2*eps window before a query is flagged
 constexpr int kExactChunks = 256;   // row chunks per flagged query in the exact scan
-constexpr int kExactMaxFlagged = 2048;  // flagged queries one exact-scan round has workspace for (rounds cover the rest)
+constexpr int kExactMaxFlagged = 4096;  // flagged queries one exact-scan round has workspace for (rounds cover the rest)
 constexpr int kExactThreads = 256;
 
 // ------------------------------------------------------------------------------------------
@@ -91,14 +91,14 @@ __device__ __forceinline__ void emit_result(const RerankParams& p, int q, int sl
   const size_t at = (size_t)q * p.k + slot;
   if (key == 0ull) {
     p.out_scores[at] = 0.f;
-    p.out_ids[at] = -1;
+    if (p.out_ids) p.out_ids[at] = -1;
     if (p.out_rows) p.out_rows[at] = -1;
     return;
   }
   const uint32_t row = key_index(key);
   const float better = key_score(key);
   p.out_scores[at] = p.metric == 1 ? better : -better;
-  p.out_ids[at] = p.ids ? p.ids[row] : p.id_base + (int64_t)row;
+  if (p.out_ids) p.out_ids[at] = p.ids ? p.ids[row] : p.id_base + (int64_t)row;
   if (p.out_rows) p.out_rows[at] = (int32_t)row;
 }
 
@@ -341,51 +341,7 @@ __global__ void __launch_bounds__(256) compact_rows_kernel(const uint32_t* __res
 }
 }  // namespace dif
 
-struct dif_gallery {
-  int device = 0;
-  int64_t capacity = 0;
-  int64_t size = 0;
-  int D = 0;
-  int metric = 1;
-  int precision = 0;
-  int64_t id_base = 0;
-  bool has_ids = false;
-  float* g0 = nullptr;
-  float* g1 = nullptr;
-  __nv_bfloat16* gb = nullptr;
-  __nv_bfloat16* gb1 = nullptr;   // second bf16 plane (3xBF16)
-  float* gsq = nullptr;  // [capacity + kGalBN]
-  unsigned int* gmax = nullptr;
-  int64_t* ids = nullptr;
-  // query-side workspace (grown on demand)
-  int q_cap = 0;
-  float* q0 = nullptr;
-  float* q1 = nullptr;
-  __nv_bfloat16* qb = nullptr;
-  __nv_bfloat16* qb1 = nullptr;
-  float* qsq = nullptr;
-  uint64_t* cand = nullptr;
-  size_t cand_elems = 0;
-  int* flagged = nullptr;  // [0] = count, [1..] = list
-  unsigned int* bound = nullptr;  // [q_cap] shared per-query lower bound on the k-th best score
-  unsigned int* maxima = nullptr; // [splits][q_cap] best score of each split's list
-  size_t maxima_elems = 0;
-  uint64_t* ex_keys = nullptr;
-  size_t ex_elems = 0;
-  // host staging for the *_host entry points
-  void* h_pin = nullptr;
-  size_t h_pin_bytes = 0;
-  void* d_stage = nullptr;
-  size_t d_stage_bytes = 0;
-  cudaStream_t own_stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  int64_t stats[6] = {0, 0, 0, 0, 0, 0};
-  int opt_ctas = 2;
-  int opt_force_fallback = 0;
-  int opt_resident = -1;   // -1 auto, 0 never, 1 whenever it fits
-  int opt_splits = 0;      // 0 auto
-  int opt_l2_prefetch = 0;   // measured: no gain at C3 (tiles are L2 hits already), so off by default
-};
+#include "gallery_state.cuh"
 
 namespace {
 
@@ -487,6 +443,7 @@ void dif_gallery_destroy(dif_gallery_t* g) {
   cudaFree(g->g0); cudaFree(g->g1); cudaFree(g->gb); cudaFree(g->gb1); cudaFree(g->gsq); cudaFree(g->gmax); cudaFree(g->ids);
   cudaFree(g->q0); cudaFree(g->q1); cudaFree(g->qb); cudaFree(g->qb1); cudaFree(g->qsq); cudaFree(g->cand); cudaFree(g->flagged);
   cudaFree(g->bound); cudaFree(g->maxima); cudaFree(g->ex_keys); cudaFree(g->d_stage);
+  dif::shard_state_destroy(g->shard);
   if (g->h_pin) cudaFreeHost(g->h_pin);
   if (g->own_stream) cudaStreamDestroy(g->own_stream);
   if (g->ev0) cudaEventDestroy(g->ev0);
@@ -535,16 +492,27 @@ static int gallery_append(dif_gallery_t* g, const float* rows, bool synth, uint6
   pp.sq = g->gsq + g->size;
   pp.gmax = g->gmax;
   if (int rc = prep_launch(pp, synth, st)) return rc;
-  if (ids) {
-    if (!g->ids) {
-      DIF_CUDA_OK(cudaMalloc((void**)&g->ids, (size_t)g->capacity * 8));
-      DIF_CUDA_OK(cudaMemsetAsync(g->ids, 0xFF, (size_t)g->capacity * 8, st));
+  if (ids || g->has_ids) {
+    if (!g->ids) DIF_CUDA_OK(cudaMalloc((void**)&g->ids, (size_t)g->capacity * 8));
+    if (!g->has_ids && g->size > 0) {
+      // earlier rows were enrolled without ids: their default ids (id_base + row) become explicit now
+      iota_ids_kernel<<<(unsigned)std::min<int64_t>((g->size + 255) / 256, 148 * 8), 256, 0, st>>>(g->ids, g->size, g->id_base);
+      DIF_LAUNCH_OK();
     }
-    DIF_CUDA_OK(cudaMemcpyAsync(g->ids + g->size, ids, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    if (ids) {
+      DIF_CUDA_OK(cudaMemcpyAsync(g->ids + g->size, ids, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+      g->user_ids = true;
+    } else {
+      DIF_REQUIRE(!g->user_ids, DIF_ERR_STATE, "this gallery was built with explicit ids; ids must be given on every add");
+      // default ids were frozen by a remove: rows enrolled without ids continue the id_base + n sequence, n = rows
+      // ever enrolled, so a new row never reuses the id of a surviving one
+      iota_ids_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(g->ids + g->size, n,
+                                                                                           g->id_base + g->enrolled);
+      DIF_LAUNCH_OK();
+    }
     g->has_ids = true;
-  } else {
-    DIF_REQUIRE(!g->has_ids, DIF_ERR_STATE, "this gallery was built with explicit ids; ids must be given on every add");
   }
+  g->enrolled += n;
   g->size += n;
   return DIF_OK;
 }
@@ -557,7 +525,9 @@ int dif_gallery_fill_synth(dif_gallery_t* g, uint64_t seed, int64_t row0, int64_
   return gallery_append(g, nullptr, true, seed, row0, nullptr, n, static_cast<cudaStream_t>(stream));
 }
 
-static int ensure_stage(dif_gallery_t* g, size_t bytes) {
+}  // extern "C"
+namespace dif {
+int gallery_ensure_stage(dif_gallery* g, size_t bytes) {
   if (bytes > g->h_pin_bytes) {
     if (g->h_pin) cudaFreeHost(g->h_pin);
     g->h_pin = nullptr;
@@ -574,6 +544,9 @@ static int ensure_stage(dif_gallery_t* g, size_t bytes) {
   }
   return DIF_OK;
 }
+}  // namespace dif
+static int ensure_stage(dif_gallery_t* g, size_t bytes) { return dif::gallery_ensure_stage(g, bytes); }
+extern "C" {
 
 int dif_gallery_add_host(dif_gallery_t* g, const float* rows_host, const int64_t* ids_host, int64_t n) {
   DIF_REQUIRE(g && (rows_host || n == 0), DIF_ERR_INVALID, "dif_gallery_add_host: null argument");
@@ -667,7 +640,9 @@ int64_t dif_gallery_size(const dif_gallery_t* g) { return g ? g->size : -1; }
 int dif_gallery_reset(dif_gallery_t* g) {
   DIF_REQUIRE(g, DIF_ERR_INVALID, "null gallery");
   g->size = 0;
+  g->enrolled = 0;
   g->has_ids = false;
+  g->user_ids = false;
   DIF_CUDA_OK(cudaMemset(g->gsq, 0, ((size_t)g->capacity + kGalBN) * 4));
   DIF_CUDA_OK(cudaMemset(g->gmax, 0, 4));
   return DIF_OK;
@@ -676,10 +651,17 @@ int dif_gallery_reset(dif_gallery_t* g) {
 int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, int k, float* scores, int64_t* ids,
                        int32_t* rows, void* stream) {
   DIF_REQUIRE(g && queries && scores && ids, DIF_ERR_INVALID, "dif_gallery_search: null argument");
+  return dif::gallery_search_impl(g, queries, n_queries, k, scores, ids, rows, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
+
+int dif::gallery_search_impl(dif_gallery* g, const float* queries, int n_queries, int k, float* scores, int64_t* ids,
+                             int32_t* rows, cudaStream_t st) {
+  DIF_REQUIRE(g && queries && scores, DIF_ERR_INVALID, "gallery search: null argument");
   DIF_REQUIRE(n_queries > 0 && k >= 1 && k <= DIF_MAX_TOPK, DIF_ERR_INVALID,
               "dif_gallery_search: n_queries %d, k %d (1..%d)", n_queries, k, DIF_MAX_TOPK);
   DIF_REQUIRE(device_sm_count() > 0, DIF_ERR_STATE, "dif_init has not succeeded on this process");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int D = g->D, kp = k;
   const int ctas = g->opt_ctas;
   const int64_t launches0 = dif_launch_count();
@@ -759,7 +741,7 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
     if (rc) return rc;
     DIF_CUDA_OK(cudaEventRecord(g->ev1, st));
   } else {
-    DIF_CUDA_OK(cudaMemsetAsync(g->cand, 0, (size_t)g->q_cap * splits * kp * 8, st));
+    DIF_CUDA_OK(cudaMemsetAsync(g->cand, 0, (size_t)round_up(n_queries, GEMM_BM * 2) * splits * kp * 8, st));
   }
 
   // 3. window + canonical re-rank
@@ -822,6 +804,8 @@ int dif_gallery_search(dif_gallery_t* g, const float* queries, int n_queries, in
   g->stats[3] = kp;
   return DIF_OK;
 }
+
+extern "C" {
 
 int dif_gallery_search_host(dif_gallery_t* g, const float* queries_host, int n_queries, int k, float* scores_host,
                             int64_t* ids_host, int32_t* rows_host) {

@@ -10,6 +10,7 @@ csrc/dif_canon.cuh, so ids AND scores are bit-reproducible whatever tensor-core 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -179,72 +180,153 @@ def shard_range(n_rows: int, rank: int, world: int) -> tuple[int, int]:
 
 
 class ShardedGallery:
-    """Gallery rows partitioned contiguously over the ranks of a torch.distributed process group.
+    """Gallery rows partitioned contiguously over the ranks of a torch.distributed process group (one process per GPU).
 
-    Each rank searches its shard (local top-k with global row ids), one all-gather exchanges the
-    k candidates per query per rank (Q*k*(4+8+8) bytes per rank) and every rank merges them with
-    the same ordering key (score best-first, global row ascending), so the result equals the
-    single-GPU search of the concatenated gallery bit for bit.
+    Each rank searches its shard, the k candidates per query per rank are exchanged as packed chunks (8 B per
+    candidate) and every rank merges them with the same ordering key (score best-first, global row ascending), so
+    the result equals the single-GPU search of the concatenated gallery bit for bit.  The whole step runs inside
+    libdif_b200.so (`dif_gallery_search_sharded`, csrc/shard.cu) on the process group's NCCL communicator:
+
+        transport="peer"  one kernel stores the chunk into every peer's buffer over NVLink (CUDA IPC), signals,
+                          waits and merges - the exchange fused with its consumer (default; falls back to "nccl"
+                          when the peers' buffers cannot be mapped, e.g. one visible device per process)
+        transport="nccl"  one in-place ncclAllGather, then the merge kernel
     """
 
     def __init__(self, n_rows_global: int, dim: int, metric="cosine", precision="tf32x3", device: int = 0,
-                 group=None):
+                 group=None, transport: str = "peer", single_rank_exchange: bool = False):
         import torch.distributed as dist
 
         self.group = group
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._dist = dist.is_initialized()
+        self.rank = dist.get_rank(group) if self._dist else 0
+        self.world = dist.get_world_size(group) if self._dist else 1
         self.n_rows_global = int(n_rows_global)
         self.row_lo, self.row_hi = shard_range(n_rows_global, self.rank, self.world)
         self.metric = _ffi.metric_code(metric)
         self.local = Gallery(max(1, self.row_hi - self.row_lo), dim, metric, precision, device)
         self.local.set_id_base(self.row_lo)
         self.device = device
-        self._explicit_ids = False
+        self.dim = int(dim)
+        if transport not in ("peer", "nccl"):
+            raise ValueError("transport must be 'peer' or 'nccl'")
+        self.transport = transport
+        self._lib = self.local._lib
+        self._comm = None          # ncclComm_t as an int
+        self._own_comm = False
+        self._attached = None      # (max_queries, max_k) the exchange buffers were sized for
+        # one rank has nobody to exchange with: search() is the plain local search unless a test asks for the full path
+        self._direct = self.world == 1 and not single_rank_exchange
 
+    # ------------------------------------------------------------------ building
     def fill_synthetic(self, seed: int) -> None:
         self.local.fill_synthetic(seed, self.row_lo, self.row_hi - self.row_lo)
 
     def add_local(self, rows, ids=None) -> None:
-        self._explicit_ids = self._explicit_ids or ids is not None
+        if ids is not None:
+            self._attached = None      # explicit ids change the packed chunk layout: exchange buffers are re-made
         self.local.add(rows, ids)
 
+    # ------------------------------------------------------------------ communicator
+    def _communicator(self) -> int:
+        """ncclComm_t of the group: torch's own communicator when it can be borrowed (ProcessGroupNCCL._comm_ptr),
+        else one created by the library from an id rank 0 broadcasts through the process group."""
+        if self._comm is not None:
+            return self._comm
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        dev = torch.device("cuda", self.device)
+        if self._dist and not os.environ.get("DIF_OWN_NCCL_COMM"):
+            try:
+                pg = self.group if self.group is not None else dist.distributed_c10d._get_default_group()
+                dist.all_reduce(torch.zeros(1, device=dev), group=self.group)   # the communicator exists after a collective
+                torch.cuda.synchronize(dev)
+                self._comm = int(pg._get_backend(dev)._comm_ptr())
+                return self._comm
+            except Exception:
+                self._comm = None
+        uid = (C.c_char * _ffi.NCCL_ID_BYTES)()
+        if self.rank == 0:
+            _ffi.check(self._lib.dif_nccl_unique_id(uid))
+        if self._dist:
+            box = [bytes(uid.raw)]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                                       group=self.group)
+            uid = (C.c_char * _ffi.NCCL_ID_BYTES).from_buffer_copy(box[0])
+        comm = C.c_void_p()
+        _ffi.check(self._lib.dif_nccl_comm_create(self.world, self.rank, uid, C.byref(comm)))
+        self._comm, self._own_comm = int(comm.value), True
+        return self._comm
+
+    def _attach(self, n_queries: int, k: int) -> None:
+        if self._attached and n_queries <= self._attached[0] and k <= self._attached[1]:
+            return
+        mq = max(n_queries, self._attached[0] if self._attached else 0)
+        mk = max(k, self._attached[1] if self._attached else 0)
+        comm = self._communicator()
+        code = _ffi.TRANSPORT_PEER if self.transport == "peer" else _ffi.TRANSPORT_NCCL
+        rc = self._lib.dif_gallery_shard_attach(self.local._h, comm, self.rank, self.world, self.row_lo, mq, mk, code)
+        if rc != 0 and code == _ffi.TRANSPORT_PEER and "DIF_TRANSPORT_PEER" in _ffi.last_error():
+            # the peers' regions cannot be mapped (every rank gets this status together): exchange through NCCL
+            self.transport = "nccl"
+            rc = self._lib.dif_gallery_shard_attach(self.local._h, comm, self.rank, self.world, self.row_lo, mq, mk,
+                                                    _ffi.TRANSPORT_NCCL)
+        _ffi.check(rc)
+        self._attached = (mq, mk)
+
+    # ------------------------------------------------------------------ search
     def search(self, queries, k: int = 10):
-        """queries: torch-CUDA [Q, dim], identical on every rank.  Returns (scores, ids, global_rows) tensors."""
+        """queries: torch-CUDA [Q, dim], identical on every rank.  Returns (scores, ids, global_rows) tensors;
+        stream-ordered on torch's current stream, no host synchronisation."""
         import torch
 
-        scores, ids, rows = self.local.search(queries, k, return_rows=True)
-        if not self._explicit_ids:
-            # ids = id_base + row with id_base = row_lo: the id IS the global row (-1 in empty slots), so two
-            # all-gathers (scores, ids) carry everything the merge needs
-            if self.world == 1:
-                return scores, ids, ids
-            g_scores, g_ids = exchange_candidates(scores, ids, group=self.group)
-            return merge_candidates(g_scores, g_ids, g_ids, self.metric)
-        grows = torch.where(rows >= 0, rows.to(torch.int64) + self.row_lo, torch.full_like(ids, -1))
-        if self.world == 1:
-            return scores, ids, grows
-        g_scores, g_ids, g_rows = exchange_candidates(scores, ids, grows, group=self.group)
-        return merge_candidates(g_scores, g_rows, g_ids, self.metric)
+        q = queries.contiguous().float()
+        if q.dim() != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [Q, {self.dim}]")
+        Q = q.shape[0]
+        if self._direct:
+            scores, ids, rows = self.local.search(q, k, return_rows=True)
+            return scores, ids, torch.where(rows >= 0, rows.to(torch.int64) + self.row_lo, torch.full_like(ids, -1))
+        self._attach(Q, k)
+        scores = torch.empty((Q, k), dtype=torch.float32, device=q.device)
+        ids = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+        grows = torch.empty((Q, k), dtype=torch.int64, device=q.device)
+        _ffi.check(self._lib.dif_gallery_search_sharded(self.local._h, self._comm, self.rank, self.world, _ffi.ptr(q), Q,
+                                                        int(k), _ffi.ptr(scores), _ffi.ptr(ids), _ffi.ptr(grows),
+                                                        _ffi.current_stream_ptr(q.device)))
+        return scores, ids, grows
 
+    def search_host(self, queries, k: int = 10, bcast_root: int = -1, want_result: bool = True):
+        """Host-facing call: numpy queries in, numpy (scores, ids) out, through dif_gallery_search_sharded_host.
 
-    def search_host(self, queries, k: int = 10):
-        """Host-facing call: numpy queries in, numpy (scores, ids) out.  One rank: the C-ABI host entry point
-        (pinned staging, H2D, search, D2H).  Several ranks: pinned H2D here, then search/exchange/merge, D2H."""
-        if self.world == 1:
-            return self.local.search(queries, k)
-        import torch
-
+        bcast_root < 0: every rank passes the (same) queries and uploads its own copy - straight from the caller's
+        buffer when it is page-locked.  bcast_root = r: only rank r's `queries` is read (the other ranks pass any
+        array of the same shape): uploaded once, NCCL-broadcast over NVLink.
+        want_result=False skips this rank's D2H (returns None)."""
+        i_upload = bcast_root < 0 or bcast_root == self.rank
         q = _ffi.host_array(queries, np.float32)
-        if getattr(self, "_pin", None) is None or self._pin.shape != q.shape:
-            self._pin = torch.empty(q.shape, dtype=torch.float32).pin_memory()
-        self._pin.numpy()[...] = q
-        qd = self._pin.to(f"cuda:{self.device}", non_blocking=True)
-        scores, ids, _ = self.search(qd, k)
-        return scores.cpu().numpy(), ids.cpu().numpy()
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [Q, {self.dim}]")
+        Q = q.shape[0]
+        if self._direct:
+            res = self.local.search(q, k)
+            return res if want_result else None
+        self._attach(Q, k)
+        scores = np.empty((Q, k), dtype=np.float32) if want_result else None
+        ids = np.empty((Q, k), dtype=np.int64) if want_result else None
+        _ffi.check(self._lib.dif_gallery_search_sharded_host(self.local._h, self._comm, self.rank, self.world,
+                                                             _ffi.ptr(q) if i_upload else None, int(bcast_root), Q, int(k),
+                                                             _ffi.ptr(scores), _ffi.ptr(ids), None))
+        return (scores, ids) if want_result else None
 
     def close(self) -> None:
-        self.local.close()
+        self.local.close()        # frees the shard state (exchange buffers, IPC mappings) with the handle
+        if self._own_comm and self._comm:
+            self._lib.dif_nccl_comm_destroy(self._comm)
+        self._comm = None
 
 
 def exchange_candidates(*tensors, group=None):

@@ -68,8 +68,9 @@ typedef struct dif_gallery dif_gallery_t;
 
 dif_gallery_t* dif_gallery_create(int device, int64_t capacity_rows, int dim, int metric, int precision);
 void dif_gallery_destroy(dif_gallery_t* g);
-int dif_gallery_add(dif_gallery_t* g, const float* rows, const int64_t* ids /* NULL: id = row index + id_base */,
-                    int64_t n, void* stream);
+/* ids NULL: id = id_base + row index.  The first add WITH ids makes the default ids of the rows enrolled so far
+ * explicit; from then on every add must carry ids (DIF_ERR_STATE otherwise). */
+int dif_gallery_add(dif_gallery_t* g, const float* rows, const int64_t* ids, int64_t n, void* stream);
 int dif_gallery_add_host(dif_gallery_t* g, const float* rows_host, const int64_t* ids_host, int64_t n);
 /* rows [row0, row0+n) of the synthetic gallery of oracle/dif_oracle.c:dif_synth_value (seed, dim) */
 int dif_gallery_fill_synth(dif_gallery_t* g, uint64_t seed, int64_t row0, int64_t n, void* stream);
@@ -77,7 +78,8 @@ int dif_gallery_set_id_base(dif_gallery_t* g, int64_t id_base); /* default ids =
 /* Incremental delete (the persistent identity index replacing the python dict of
  * deep_insight_face/predictions.py:112).  rows_host: n strictly ascending row numbers; the remaining rows keep
  * their order (so "ties -> lower row" still means "earlier enrolled") and their ids - default ids (id_base + row)
- * are frozen into explicit ids first, after which dif_gallery_add needs ids too.  Synchronises the stream. */
+ * are frozen first; rows added later without ids continue the default sequence at id_base + (rows ever enrolled), so
+ * an id is never reused.  Synchronises the stream. */
 int dif_gallery_remove(dif_gallery_t* g, const int64_t* rows_host, int64_t n, void* stream);
 /* ids of rows [row0, row0+n) into a DEVICE buffer */
 int dif_gallery_get_ids(dif_gallery_t* g, int64_t row0, int64_t n, int64_t* out, void* stream);
@@ -110,6 +112,55 @@ int dif_gallery_get_rows(dif_gallery_t* g, int64_t row0, int64_t n, float* out, 
  * (score best-first, global row ascending).  grows = global row index of each candidate. */
 int dif_topk_merge(const float* scores, const int64_t* grows, const int64_t* ids, int world, int n_queries,
                    int k, int metric, float* out_scores, int64_t* out_grows, int64_t* out_ids, void* stream);
+
+/* ---- row-sharded search over several GPUs (one process per GPU) ----------------------
+ * Rank r's gallery holds the contiguous global rows [shard_row0, shard_row0 + size).  One search =
+ *   local search (the four passes above) -> every rank's k candidates per query are exchanged -> every rank
+ *   merges world*k candidates per query with the key (score best-first, GLOBAL row ascending),
+ * so the result equals the single-gallery search of the concatenated rows bit for bit.  All ranks must call
+ * with the same n_queries / k / queries and galleries of the same metric that either all carry explicit ids
+ * or none does (default id = id_base + local row).
+ *
+ * The exchanged unit is a packed chunk per rank: scores f32 [Q*k] | local rows i32 [Q*k] | ids i64 [Q*k] (explicit
+ * ids only), 8 B per candidate without ids (5.24 MB per rank at 65 536 queries x top-10).
+ *
+ * transport (chosen at attach time): DIF_TRANSPORT_NCCL = one ncclAllGather of the chunks, then the merge
+ * kernel; DIF_TRANSPORT_PEER = ONE kernel that stores this rank's chunk straight into every peer's exchange buffer
+ * over NVLink (buffers mapped with CUDA IPC at attach time), publishes a per-peer epoch flag, waits for the
+ * peers' flags and merges - the candidate exchange fused with its consumer, no collective launch. */
+#define DIF_TRANSPORT_NCCL 0
+#define DIF_TRANSPORT_PEER 1
+#define DIF_NCCL_ID_BYTES 128
+/* NCCL is bound at run time (dlopen of the libnccl.so.2 already loaded in the process, else the system one), so
+ * the library still loads on a box without NCCL; these fail with DIF_ERR_STATE there. */
+int dif_nccl_unique_id(void* id_out_host /* DIF_NCCL_ID_BYTES */);
+/* ncclCommInitRank on the device of dif_init; *comm_out is an ncclComm_t owned by the caller (dif_nccl_comm_destroy) */
+int dif_nccl_comm_create(int world, int rank, const void* id_host, void** comm_out);
+int dif_nccl_comm_destroy(void* nccl_comm);
+/* bytes of one packed chunk */
+int64_t dif_shard_chunk_bytes(int n_queries, int k, int with_ids);
+/* local search writing the packed chunk (DEVICE pointer, dif_shard_chunk_bytes(...) bytes, 16-byte aligned) */
+int dif_gallery_search_packed(dif_gallery_t* g, const float* queries, int n_queries, int k, int with_ids, void* chunk,
+                              void* stream);
+/* merge of `world` packed chunks laid out back to back; shard_info DEVICE [world][2] int64 = {shard_row0, id_base}.
+ * scores [Q*k] f32, ids [Q*k] i64, grows [Q*k] i64 global rows (may be NULL); empty slots id -1 / row -1. */
+int dif_shard_merge(const void* chunks, const int64_t* shard_info, int world, int n_queries, int k, int metric,
+                    int with_ids, float* scores, int64_t* ids, int64_t* grows, void* stream);
+/* Binds the gallery to its place in the job: exchanges {shard_row0, id_base, ids?} of every rank once (and, for
+ * DIF_TRANSPORT_PEER, the CUDA IPC handles of the exchange buffers sized for max_queries x max_k), synchronises.
+ * nccl_comm: an ncclComm_t of `world` ranks (torch's ProcessGroupNCCL._comm_ptr(), or dif_nccl_comm_create). */
+int dif_gallery_shard_attach(dif_gallery_t* g, void* nccl_comm, int rank, int world, int64_t shard_row0,
+                             int max_queries, int max_k, int transport);
+/* The sharded search itself, stream-ordered, no host synchronisation.  queries: DEVICE [Q*D], identical on all ranks. */
+int dif_gallery_search_sharded(dif_gallery_t* g, void* nccl_comm, int rank, int world, const float* queries,
+                               int n_queries, int k, float* scores, int64_t* ids, int64_t* grows, void* stream);
+/* HOST buffers.  bcast_root < 0: every rank uploads its own copy of the queries (straight from the caller's buffer
+ * when it is page-locked); bcast_root = r: only rank r's queries_host is read, uploaded once and ncclBroadcast
+ * over NVLink (other ranks may pass NULL).  scores_host / ids_host / grows_host may be NULL on ranks that do not
+ * need the result (they skip the D2H).  Synchronises. */
+int dif_gallery_search_sharded_host(dif_gallery_t* g, void* nccl_comm, int rank, int world, const float* queries_host,
+                                    int bcast_root, int n_queries, int k, float* scores_host, int64_t* ids_host,
+                                    int64_t* grows_host);
 
 /* raw synthetic rows shared with the oracle (oracle/dif_oracle.c:dif_or_synth_value):
  * out[r*D + d] = synth(seed, row, d, D) with row = rows_idx ? rows_idx[r] : row0 + r (device pointers) */
