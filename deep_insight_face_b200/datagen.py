@@ -4,7 +4,6 @@ scripts/generate_pairs.py:60-76 and the pickled verification `.bin` of scripts/r
 Pure index / text logic - nothing here touches the GPU."""
 from __future__ import annotations
 
-import io
 import pickle
 from typing import List, Sequence, Tuple
 
@@ -16,27 +15,33 @@ def _paths_of(cls) -> Sequence:
 
 
 def sample_people(dataset, people_per_batch: int, images_per_person: int, rng=None):
-    """generator.py:15-41: shuffle the classes, take up to `images_per_person` shuffled images from each until
-    `people_per_batch * images_per_person` images are collected.  Returns (image_paths, num_per_class) as the
-    reference does; `rng` (np.random.Generator) replaces the reference's global np.random for reproducibility."""
-    rng = np.random.default_rng() if rng is None else rng
-    nrof_images = people_per_batch * images_per_person
-    class_indices = np.arange(len(dataset))
-    rng.shuffle(class_indices)
-    i = 0
-    image_paths: List = []
-    num_per_class: List[int] = []
-    while len(image_paths) < nrof_images:
-        if i >= len(class_indices):
-            raise ValueError("dataset has too few images for the requested batch")
-        paths = _paths_of(dataset[class_indices[i]])
-        image_indices = np.arange(len(paths))
-        rng.shuffle(image_indices)
-        n = min(len(paths), images_per_person, nrof_images - len(image_paths))
-        image_paths += [paths[j] for j in image_indices[:n]]
-        num_per_class.append(n)
-        i += 1
-    return image_paths, num_per_class
+    """PK sampler with the contract of generator.py:15-41: classes are visited in one random order; every visited
+    class contributes min(its size, images_per_person, images still missing) randomly chosen images, until
+    `people_per_batch * images_per_person` images are drawn.  Returns (image_paths, num_per_class).
+
+    The draws are one shuffle of the class order, then one shuffle of the member order per visited class.  With
+    `rng=None` they come from numpy's global generator, as in the reference - `np.random.seed(s)` therefore
+    reproduces the reference's batches exactly (tests/golden/host_reference.json holds batches produced by the
+    reference's own function); pass an `np.random.Generator` for a private stream."""
+    shuffle = np.random.shuffle if rng is None else rng.shuffle
+    missing = people_per_batch * images_per_person
+    order = np.arange(len(dataset))
+    shuffle(order)
+    picked: List = []
+    per_class: List[int] = []
+    for cls in order:
+        if missing == 0:
+            break
+        members = _paths_of(dataset[cls])
+        perm = np.arange(len(members))
+        shuffle(perm)
+        take = min(len(members), images_per_person, missing)
+        picked.extend(members[j] for j in perm[:take])
+        per_class.append(take)
+        missing -= take
+    if missing:
+        raise ValueError("dataset has too few images for the requested batch")
+    return picked, per_class
 
 
 def pk_labels(num_per_class: Sequence[int], one_hot: bool = True) -> np.ndarray:
@@ -51,16 +56,16 @@ Mismatch = Tuple[str, int, str, int]
 
 def write_pairs_to_file(fname: str, match_folds: List[List[Match]], mismatch_folds: List[List[Mismatch]],
                         num_folds: int, num_matches_mismatches: int) -> None:
-    """scripts/generate_pairs.py:60-76: header `folds\\tN`, then per fold `name\\ti\\tj` matches followed by
-    `name1\\ti\\tname2\\tj` mismatches."""
-    with io.open(fname, "w", io.DEFAULT_BUFFER_SIZE, encoding="utf-8") as f:
-        f.write("{}\t{}\n".format(num_folds, num_matches_mismatches))
-        for match_fold, mismatch_fold in zip(match_folds, mismatch_folds):
-            for m in match_fold:
-                f.write("{}\t{}\t{}\n".format(m[0], m[1], m[2]))
-            for mm in mismatch_fold:
-                f.write("{}\t{}\t{}\t{}\n".format(mm[0], mm[1], mm[2], mm[3]))
-        f.flush()
+    """The pairs.txt layout of scripts/generate_pairs.py:60-76 (byte-identical, see tests/golden): a header
+    `folds<TAB>N`, then per fold its matches `name<TAB>i<TAB>j` followed by its mismatches
+    `name1<TAB>i<TAB>name2<TAB>j`, one record per line."""
+    records = [(num_folds, num_matches_mismatches)]
+    for same, different in zip(match_folds, mismatch_folds):
+        records.extend(tuple(m[:3]) for m in same)
+        records.extend(tuple(mm[:4]) for mm in different)
+    text = "".join("\t".join(str(field) for field in rec) + "\n" for rec in records)
+    with open(fname, "w", encoding="utf-8") as f:
+        f.write(text)
 
 
 def pairs_issame(pairs) -> np.ndarray:

@@ -155,18 +155,31 @@ def calculate_roc(thresholds, embeddings1, embeddings2, actual_issame, nrof_fold
     assert embeddings1.shape[1] == embeddings2.shape[1]
     actual_issame = np.asarray(actual_issame)
     nrof_pairs = min(len(actual_issame), embeddings1.shape[0])
+    fold = kfold_ids(nrof_pairs, nrof_folds)
+    dists = _fold_distances(embeddings1[:nrof_pairs], embeddings2[:nrof_pairs], fold, nrof_folds, distance_metric,
+                            subtract_mean)
+    return roc_from_distances(thresholds, dists, actual_issame[:nrof_pairs], nrof_folds, per_fold=subtract_mean)
+
+
+def roc_from_distances(thresholds, dists, actual_issame, nrof_folds=10, per_fold=False):
+    """The k-fold threshold selection of utility.py:150-171 on PRECOMPUTED distances: `dists` is one [N] vector, or
+    (per_fold=True, the subtract_mean case) a list with one vector per fold.  Counts come from one histogram pass
+    per vector; the ratios are the reference's float64 formulas on integer counts, so the result is bit-identical
+    to the reference's whenever the distances are (tests feed it the reference's own distances)."""
+    actual_issame = np.asarray(actual_issame)
+    nrof_pairs = len(actual_issame)
     nrof_thresholds = len(thresholds)
     fold = kfold_ids(nrof_pairs, nrof_folds)
+    if not per_fold and not isinstance(dists, (list, tuple)):
+        dists = [dists] * nrof_folds
     tprs = np.zeros((nrof_folds, nrof_thresholds))
     fprs = np.zeros((nrof_folds, nrof_thresholds))
     accuracy = np.zeros((nrof_folds))
     f1scores = np.zeros((nrof_folds))
-    dists = _fold_distances(embeddings1[:nrof_pairs], embeddings2[:nrof_pairs], fold, nrof_folds, distance_metric,
-                            subtract_mean)
     shared = None
     for fold_idx in range(nrof_folds):
-        if subtract_mean or shared is None:
-            shared = threshold_counts(dists[fold_idx], actual_issame[:nrof_pairs], thresholds, fold, nrof_folds)
+        if per_fold or shared is None:
+            shared = threshold_counts(dists[fold_idx], actual_issame, thresholds, fold, nrof_folds)
         counts = shared
         test = counts[fold_idx]                       # [T, 4]
         train = counts.sum(axis=0) - test             # exact integer arithmetic

@@ -49,8 +49,9 @@ def contrastive_loss(y_true, y_pred, return_grad=False):
     return val
 
 
-def _accuracy(y_true, y_pred, threshold=0.5):
-    """siamese.py:42-45: mean(y_true == (y_pred < threshold)); a [B] comparison, host-side."""
+def _accuracy(y_true, y_pred, threshold=0.4):
+    """siamese.py:42-45: mean(y_true == (y_pred < threshold)), default threshold 0.4 as in the reference (it is
+    compiled as `metrics=[_accuracy]`, siamese.py:158, so the default is what training reports); host-side."""
     y = np.reshape(_ffi.host_array(y_true, None), -1)
     d = np.reshape(_ffi.host_array(y_pred, None), -1)
     return float(np.mean(y == (d < threshold).astype(y.dtype)))

@@ -8,7 +8,7 @@ bit for bit with the GPU.  TensorFlow semantics that the reference relies on but
   tf.where gradient flows only into the selected branch;  tf.maximum(x, 0) passes the gradient to x when x >= 0;
   Keras AUTO reduction = mean over the batch (default dloss = 1/B).
 PARITY UNPINNED by the reference: TensorFlow cannot be installed here and the reference ships no golden
-vectors; tests/test_losses_oracle.py cross-checks these rules against torch autograd.
+vectors; tests/test_oracle_cpu.py cross-checks these rules against torch autograd.
 """
 from __future__ import annotations
 
@@ -189,8 +189,8 @@ def contrastive_loss(y_true, dist, margin=1.0):
     return float(np.mean(y * d * d + (1.0 - y) * m * m)), (2 * y * d - 2 * (1 - y) * m) / y.size
 
 
-def siamese_accuracy(y_true, dist, threshold=0.5):
-    """networks/siamese.py:42-45: mean(y == (d < threshold))."""
+def siamese_accuracy(y_true, dist, threshold=0.4):
+    """networks/siamese.py:42-45: mean(y == (d < threshold)), reference default threshold 0.4."""
     y = np.asarray(y_true).reshape(-1)
     d = np.asarray(dist).reshape(-1)
     return float(np.mean(y == (d < threshold).astype(y.dtype)))
