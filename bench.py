@@ -539,6 +539,7 @@ def main():
                 torch.cuda.synchronize()
                 kms.append(g.local.last_kernel_ms())
         out["kernel_ms"] = float(np.mean(kms))
+        out["phases_ms"] = g.local.last_phase_ms()    # of the last search: prep / filter / re-rank / exact / exchange + merge
         if full:
             # end to end through the host-facing call: numpy in -> numpy out (rank 0 reads the result)
             q_host = q_dev.cpu().pin_memory().numpy()   # the step's inputs start in pinned host memory (bench contract)
@@ -589,6 +590,7 @@ def main():
             "peak_source": f"{peaks['source']} bf16 {'sustained' if sustained else 'burst'}" + ("" if on_bf16_pipe else " / 2 (TF32 not measured)"),
             "tensor_passes_per_flop": passes, "hardware_frac": achieved * passes / tensor_peak,
             "share_of_step": res["kernel_ms"] / res["ms_per_step"],
+            "phases_ms_of_one_search": res.get("phases_ms"),
         }
 
     host_cache = {}

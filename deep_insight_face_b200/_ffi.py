@@ -84,6 +84,7 @@ SIGNATURES = {
     "dif_gallery_search_host": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "dif_gallery_last_stats": (_i32, [_vp, C.POINTER(_i64)]),
     "dif_gallery_last_kernel_ms": (_i32, [_vp, C.POINTER(_f32)]),
+    "dif_gallery_last_phase_ms": (_i32, [_vp, C.POINTER(_f32)]),
     "dif_gallery_get_rows": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "dif_topk_merge": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "dif_nccl_unique_id": (_i32, [_vp]),

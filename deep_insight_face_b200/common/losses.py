@@ -152,16 +152,20 @@ def _torch_function():
     import torch
 
     class _BatchHardFn(torch.autograd.Function):
+        """loss [B] (differentiable) plus the by-products of the mining pass: statistics and mined columns."""
+
         @staticmethod
         def forward(ctx, emb, labels, variant, alpha):
             loss, _, info = batch_hard(labels, emb, variant, alpha, want_grad=False)
             ctx.save_for_backward(emb)
             ctx.labels, ctx.variant, ctx.alpha = labels, variant, alpha
-            ctx.info = info
-            return loss
+            ctx.mark_non_differentiable(info["stats"], info["pos_idx"], info["neg_idx"])
+            return loss, info["stats"], info["pos_idx"], info["neg_idx"]
 
         @staticmethod
-        def backward(ctx, dloss):
+        def backward(ctx, dloss, *_unused):
+            # the gradient kernels need the cotangent, which only exists now: one fused call mines again (the B x B
+            # matrix is never stored) and scatters dloss into the mined rows
             (emb,) = ctx.saved_tensors
             _, grad, _ = batch_hard(ctx.labels, emb, ctx.variant, ctx.alpha, dloss=dloss, want_grad=True)
             return grad, None, None, None
@@ -200,30 +204,44 @@ class TripletLossWapper(_LossBase):
         return cls(**config)
 
     # ---- shared implementation of the subclasses
-    def _dispatch(self, labels, embeddings, alpha):
-        if _tf is not None and isinstance(embeddings, (_tf.Tensor, _tf.Variable)):  # pragma: no cover
+    def _dispatch(self, labels, embeddings, alpha=None):
+        """Per-sample loss with margin `alpha` (None: `_current_alpha()`, which AutoAlpha maps to its state variable).
+        torch-CUDA embeddings stay on the device and are differentiable; TensorFlow tensors go through
+        tf.custom_gradient; anything else is treated as a host array."""
+        if _tf is not None and isinstance(embeddings, (_tf.Tensor, _tf.Variable)):
             return self._tf_call(labels, embeddings, alpha)
+        alpha = self._current_alpha() if alpha is None else alpha
         if _ffi.is_device_tensor(embeddings):
-            out = _torch_function().apply(embeddings, labels, self._code(), float(alpha))
-            return out
-        loss, _, info = batch_hard(labels, embeddings, self._code(), alpha, want_grad=False)
+            loss, stats, pos, neg = _torch_function().apply(embeddings, labels, self._code(), float(alpha))
+            info = {"stats": stats, "pos_idx": pos, "neg_idx": neg}
+        else:
+            loss, _, info = batch_hard(labels, embeddings, self._code(), alpha, want_grad=False)
+        self._after_step(info)
         self.last_info = info
         return loss
 
-    def _tf_call(self, labels, embeddings, alpha):  # pragma: no cover - needs TensorFlow
+    def _tf_call(self, labels, embeddings, alpha=None):
+        """TensorFlow bridge (Keras `fit` in graph mode: networks/triplet.py:182,209,211, training/triplet.py:51-57):
+        the kernels run inside tf.numpy_function, the gradient is attached with tf.custom_gradient.  The margin is
+        read when the step RUNS (AutoAlpha's state changes between steps), and the backward pass reuses the margin
+        its forward pass saw."""
         variant = self._code()
+        used = {}
 
         @_tf.custom_gradient
         def op(emb):
             def fwd(e, l):
-                loss, _, _ = batch_hard(l, e, variant, alpha, want_grad=False)
+                used["alpha"] = float(self._current_alpha() if alpha is None else alpha)
+                loss, _, info = batch_hard(l, e, variant, used["alpha"], want_grad=False)
+                self._after_step(info)
+                self.last_info = info
                 return loss
 
             loss = _tf.numpy_function(fwd, [emb, labels], _tf.float32)
 
             def grad_fn(dloss):
                 def bwd(e, l, dl):
-                    _, g, _ = batch_hard(l, e, variant, alpha, dloss=dl, want_grad=True)
+                    _, g, _ = batch_hard(l, e, variant, used["alpha"], dloss=dl, want_grad=True)
                     return g
 
                 return _tf.numpy_function(bwd, [emb, labels, dloss], _tf.float32)
@@ -276,19 +294,30 @@ class BatchHardTripletLossEuclideanAutoAlpha(TripletLossWapper):
 
     def __init__(self, alpha=0.1, init_auto_alpha=1, **kwargs):
         super().__init__(alpha=alpha, **kwargs)
+        self._mean_dists = None
         self.auto_alpha = float(init_auto_alpha)
+
+    @property
+    def auto_alpha(self) -> float:
+        """The state variable of losses.py:93.  After a device-side step it is held as mean(dists) on the device and
+        only read back (one 4-byte copy) when the next step needs the number - by then the kernel has long finished."""
+        if self._mean_dists is not None:
+            self._auto_alpha = float(self._mean_dists) * self.alpha     # :113
+            self._mean_dists = None
+        return self._auto_alpha
+
+    @auto_alpha.setter
+    def auto_alpha(self, value):
+        self._auto_alpha, self._mean_dists = float(value), None
 
     def _current_alpha(self):
         return self.auto_alpha
 
     def _after_step(self, info):
-        self.auto_alpha = float(info["stats"][0]) * self.alpha
+        self._mean_dists = info["stats"][0]     # numpy scalar or 0-d device tensor: no synchronisation here
 
     def __calculate_triplet_loss__(self, labels, embeddings, alpha):
-        loss, _, info = batch_hard(labels, embeddings, self._code(), self.auto_alpha, want_grad=False)
-        self._after_step(info)
-        self.last_info = info
-        return loss
+        return self._dispatch(labels, embeddings)     # `alpha` (the 0.1 factor) only scales the next margin
 
 
 def batch_all(labels, embeddings, alpha: float, dloss=None, want_grad: bool = True):

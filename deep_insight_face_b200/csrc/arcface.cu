@@ -4,14 +4,18 @@
 //   target logit s * phi(cos_y), phi = cos(theta + m) if cos_y > cos(pi - m) else cos_y - m sin(pi - m); others s * cos
 //   loss_b = logsumexp(logits_b) - logits_b[y_b];   dX, dW = gradients of sum_b dloss_b * loss_b (default 1/B)
 //
-// All three contractions run on the tcgen05/TMA NT-GEMM skeleton in 3xTF32 (fp32-exact to ~1e-6):
-//   1. arc_fwd     cos = xh wh^T with a fused epilogue: clip, margin on the target column, scale, online
-//                  softmax (running max / sum per class split) in registers; cos is also written out once
-//   2. arc_loss    merges the per-split (max, sum) pairs -> logZ, loss, d phi / d cos
-//   3. arc_dcos    p - onehot -> d cos, written as TF32 hi/lo planes in both orientations ([B,C] and [C,B])
-//   4. dxh = dcos wh        (NT GEMM over K = C, split-K planes summed in a fixed order)
-//      dwh = dcos^T xh      (NT GEMM over K = B)
-//   5. arc_norm_bwd  l2_normalize backward for X rows and W rows
+// All three contractions run on the tcgen05/TMA GEMM skeleton (nt_gemm.cuh) in 3xTF32 / 3xBF16 (fp32-exact to ~1e-6);
+// a step is 6 launches and NO operand is transposed in HBM - the backward GEMMs read the planes the forward pass
+// made through MN-major shared-memory descriptors:
+//   1. prep        x and w rows -> normalised operand planes (one launch for both)
+//   2. arc_fwd     cos = xh wh^T with a fused epilogue: clip, margin on the target column, scale, online softmax
+//                  (running max / sum per class split) in registers; cos is also written out once.  The tile
+//                  width is chosen per shape so the class tiles fill the SMs in whole waves (plan_tiles)
+//   3. arc_dcos    merges the per-split (max, sum) pairs -> logZ, loss, d phi / d cos, then p - onehot -> d cos as
+//                  operand planes [B][C], written once
+//   4. dxh = dcos wh        A = dcos K-major, B = wh planes [C][D] read MN-major; split over K = classes
+//      dwh = dcos^T xh      A = dcos read MN-major, B = xh planes [B][D] read MN-major
+//   5. arc_norm_bwd  l2_normalize backward for the X rows and the W rows (one launch)
 #include <algorithm>
 
 #include "prep_rows.cuh"
@@ -100,27 +104,6 @@ struct ArcFwdEpi {
   }
 };
 
-// one thread per sample: merge the split partials, loss, logZ (natural log units), target phi and d phi
-__global__ void arc_loss_kernel(const float2* __restrict__ part, int n_slots, const float* __restrict__ cosbuf, int ldc,
-                                const int32_t* __restrict__ y, int B, ArcMargin mg, float* __restrict__ loss,
-                                float* __restrict__ logz, float* __restrict__ dphi) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  float m2 = -INFINITY, l2 = 0.f;
-  for (int s = 0; s < n_slots; ++s) {
-    const float2 q = part[(size_t)b * n_slots + s];
-    if (q.x == -INFINITY) continue;
-    const float mn = fmaxf(m2, q.x);
-    l2 = l2 * exp2f(m2 - mn) + q.y * exp2f(q.x - mn);
-    m2 = mn;
-  }
-  const float lz = (m2 + log2f(l2)) / kLog2e;
-  const float ct = fminf(fmaxf(cosbuf[(size_t)b * ldc + y[b]], -1.f), 1.f);
-  loss[b] = lz - mg.s * arc_phi(ct, mg);
-  logz[b] = lz;
-  dphi[b] = arc_dphi(ct, mg);
-}
-
 // Operand planes: T = float -> TF32 hi + exact residual lo (mode 0); T = bf16 -> b0 = bf16(v), b1 = bf16(v - b0) (mode 3)
 __device__ __forceinline__ void split_store(float v, float* hi, float* lo, size_t i) {
   const float h = tf32_round(v);
@@ -133,63 +116,70 @@ __device__ __forceinline__ void split_store(float v, __nv_bfloat16* p0, __nv_bfl
   p1[i] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(b0)));
 }
 
-// d cos in both orientations as operand planes.  Tile 32 samples x 32 classes per block (32 x 8 threads).
+// Loss + d cos.  Block = kDcosRows samples x a chunk of classes.  One warp per sample first merges the forward
+// pass's per-split (max, sum) pairs -> logZ, target phi / d phi (and the loss, written by the blocks of class chunk 0);
+// then the block streams its class chunk: cos -> p - onehot -> d cos, split into the two operand planes.
+constexpr int kDcosRows = 8;
 template <class T>
-__global__ void __launch_bounds__(256) arc_dcos_kernel(const float* __restrict__ cosbuf, int ldc,
-                                                       const int32_t* __restrict__ y, const float* __restrict__ logz,
-                                                       const float* __restrict__ dphi, const float* __restrict__ dloss,
-                                                       int B, int C, ArcMargin mg, T* __restrict__ d_hi,
-                                                       T* __restrict__ d_lo,    // [Bp][ldc]
-                                                       T* __restrict__ t_hi, T* __restrict__ t_lo, int ldt,
-                                                       int Cp, int Bp) {            // [Cp][ldt]
-  __shared__ float tile[32][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int b = blockIdx.y * 32 + r;
-    float v = 0.f;
-    if (b < B && c < C) {
-      const float raw = cosbuf[(size_t)b * ldc + c];
-      const float ct = fminf(fmaxf(raw, -1.f), 1.f);
-      const float g = dloss ? dloss[b] : 1.f / (float)B;
-      const bool tgt = (c == y[b]);
-      const float logit = mg.s * (tgt ? arc_phi(ct, mg) : ct);
-      const float pr = expf(logit - logz[b]);
-      v = mg.s * g * (pr - (tgt ? 1.f : 0.f)) * (tgt ? dphi[b] : 1.f);
-      if (raw < -1.f || raw > 1.f) v = 0.f;   // clip_by_value passes no gradient outside the bounds
+__global__ void __launch_bounds__(256) arc_dcos_kernel(const float2* __restrict__ part, int n_slots,
+                                                       const float* __restrict__ cosbuf, int ldc,
+                                                       const int32_t* __restrict__ y, const float* __restrict__ dloss,
+                                                       int B, int C, int chunk, ArcMargin mg, float* __restrict__ loss,
+                                                       T* __restrict__ d_hi, T* __restrict__ d_lo) {
+  __shared__ float s_logz[kDcosRows], s_dphi[kDcosRows], s_g[kDcosRows];
+  __shared__ int s_y[kDcosRows];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = blockIdx.y * kDcosRows;
+  if (warp < kDcosRows) {
+    const int b = b0 + warp;
+    if (b < B) {
+      float m2 = -INFINITY, l2 = 0.f;
+      for (int s = lane; s < n_slots; s += 32) {
+        const float2 q = part[(size_t)b * n_slots + s];
+        if (q.x == -INFINITY) continue;
+        const float mn = fmaxf(m2, q.x);
+        l2 = l2 * exp2f(m2 - mn) + q.y * exp2f(q.x - mn);
+        m2 = mn;
+      }
+      for (int o = 16; o >= 1; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m2, o), ol = __shfl_xor_sync(0xffffffffu, l2, o);
+        const float mn = fmaxf(m2, om);
+        l2 = (m2 == -INFINITY ? 0.f : l2 * exp2f(m2 - mn)) + (om == -INFINITY ? 0.f : ol * exp2f(om - mn));
+        m2 = mn;
+      }
+      if (lane == 0) {
+        const float lz = (m2 + log2f(l2)) / kLog2e;
+        const int yb = y[b];
+        const float ct = fminf(fmaxf(cosbuf[(size_t)b * ldc + yb], -1.f), 1.f);
+        if (blockIdx.x == 0) loss[b] = lz - mg.s * arc_phi(ct, mg);
+        s_logz[warp] = lz;
+        s_dphi[warp] = arc_dphi(ct, mg);
+        s_g[warp] = dloss ? dloss[b] : 1.f / (float)B;
+        s_y[warp] = yb;
+      }
+    } else if (lane == 0) {
+      s_y[warp] = -1;
     }
-    tile[r][threadIdx.x] = v;
-    if (b < Bp && c < ldc) split_store(v, d_hi, d_lo, (size_t)b * ldc + c);
   }
   __syncthreads();
-  const int b2 = blockIdx.y * 32 + threadIdx.x;
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int c2 = blockIdx.x * 32 + r;
-    if (c2 < Cp && b2 < ldt) split_store(tile[threadIdx.x][r], t_hi, t_lo, (size_t)c2 * ldt + b2);
-  }
-}
-
-// src [R][Cc] (two planes) -> transposed planes [Cc][ldt] (zero padded to ldt)
-template <class T>
-__global__ void __launch_bounds__(256) transpose_planes_kernel(const T* __restrict__ s_hi,
-                                                               const T* __restrict__ s_lo, int R, int Cc,
-                                                               T* __restrict__ t_hi, T* __restrict__ t_lo,
-                                                               int ldt) {
-  __shared__ T th[32][33 + (sizeof(T) == 2 ? 1 : 0)], tl[32][33 + (sizeof(T) == 2 ? 1 : 0)];
-  const T zero = T(0.f);
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int row = blockIdx.y * 32 + r;
-    const bool ok = row < R && c < Cc;
-    th[r][threadIdx.x] = ok ? s_hi[(size_t)row * Cc + c] : zero;
-    tl[r][threadIdx.x] = ok ? s_lo[(size_t)row * Cc + c] : zero;
-  }
-  __syncthreads();
-  const int row2 = blockIdx.y * 32 + threadIdx.x;
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int c2 = blockIdx.x * 32 + r;
-    if (c2 < Cc && row2 < ldt) {
-      t_hi[(size_t)c2 * ldt + row2] = th[threadIdx.x][r];
-      t_lo[(size_t)c2 * ldt + row2] = tl[threadIdx.x][r];
+  if (!d_hi) return;
+  const int c_begin = blockIdx.x * chunk, c_end = min(ldc, c_begin + chunk);
+  for (int c = c_begin + (int)threadIdx.x; c < c_end; c += 256) {
+#pragma unroll
+    for (int r = 0; r < kDcosRows; ++r) {
+      const int b = b0 + r;
+      if (b >= B) break;
+      float v = 0.f;
+      if (c < C) {
+        const float raw = cosbuf[(size_t)b * ldc + c];
+        const float ct = fminf(fmaxf(raw, -1.f), 1.f);
+        const bool tgt = (c == s_y[r]);
+        const float logit = mg.s * (tgt ? arc_phi(ct, mg) : ct);
+        const float pr = expf(logit - s_logz[r]);
+        v = mg.s * s_g[r] * (pr - (tgt ? 1.f : 0.f)) * (tgt ? s_dphi[r] : 1.f);
+        if (raw < -1.f || raw > 1.f) v = 0.f;   // clip_by_value passes no gradient outside the bounds
+      }
+      split_store(v, d_hi, d_lo, (size_t)b * ldc + c);
     }
   }
 }
@@ -198,16 +188,26 @@ __global__ void __launch_bounds__(256) transpose_planes_kernel(const T* __restri
 // normalised row (h_lo NULL: h_hi is the fp32 normalised row itself); rows whose squared norm was clamped (inv == 1e6) are a plain scaling.  TPR threads own one row
 // (TPR = 32: a warp per row, 8 rows per block, D <= 512; TPR = 256: a block per row, D <= 4096), one float4 group
 // per thread and pass: every load is independent and coalesced and the planes are read exactly once.
+struct NormBwdJob {
+  const float* g;        // [planes][R][D] partial gradients wrt the normalised rows
+  int planes;
+  size_t plane_stride;
+  const float* h_hi;     // normalised rows (hi plane, or the fp32 rows themselves when h_lo is NULL)
+  const float* h_lo;
+  const float* inv;      // [R] inverse norms
+  int R;
+  float* out;            // [R][D]
+};
+
 template <int TPR>
-__global__ void __launch_bounds__(256) arc_norm_bwd_kernel(const float* __restrict__ g, int planes, size_t plane_stride,
-                                                           const float* __restrict__ h_hi, const float* __restrict__ h_lo,
-                                                           const float* __restrict__ inv, int R, int D,
-                                                           float* __restrict__ out) {
+__global__ void __launch_bounds__(256) arc_norm_bwd_kernel(NormBwdJob j0, NormBwdJob j1, int blocks0, int D) {
   __shared__ float red[8];
   constexpr int kRows = 256 / TPR;
-  const int r = blockIdx.x * kRows + (int)threadIdx.x / TPR;
+  const bool first = (int)blockIdx.x < blocks0;
+  const NormBwdJob& j = first ? j0 : j1;
+  const int r = ((int)blockIdx.x - (first ? 0 : blocks0)) * kRows + (int)threadIdx.x / TPR;
   const int lane = (int)threadIdx.x % TPR;
-  const bool live = r < R;
+  const bool live = r < j.R;
   const size_t base = (size_t)r * D;
   float dot = 0.f;
   float4 a[4], h[4];
@@ -217,12 +217,12 @@ __global__ void __launch_bounds__(256) arc_norm_bwd_kernel(const float* __restri
     a[t] = make_float4(0.f, 0.f, 0.f, 0.f);
     h[t] = a[t];
     if (live && d < D) {
-      for (int s = 0; s < planes; ++s) {
-        const float4 v = *reinterpret_cast<const float4*>(g + (size_t)s * plane_stride + base + d);
+      for (int s = 0; s < j.planes; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(j.g + (size_t)s * j.plane_stride + base + d);
         a[t].x += v.x; a[t].y += v.y; a[t].z += v.z; a[t].w += v.w;
       }
-      const float4 hh = *reinterpret_cast<const float4*>(h_hi + base + d);
-      const float4 hl = h_lo ? *reinterpret_cast<const float4*>(h_lo + base + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 hh = *reinterpret_cast<const float4*>(j.h_hi + base + d);
+      const float4 hl = j.h_lo ? *reinterpret_cast<const float4*>(j.h_lo + base + d) : make_float4(0.f, 0.f, 0.f, 0.f);
       h[t] = make_float4(hh.x + hl.x, hh.y + hl.y, hh.z + hl.z, hh.w + hl.w);
       dot += a[t].x * h[t].x + a[t].y * h[t].y + a[t].z * h[t].z + a[t].w * h[t].w;
     }
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) arc_norm_bwd_kernel(const float* __restri
     for (int w = 0; w < 8; ++w) dot += red[w];
   }
   if (!live) return;
-  const float iv = inv[r];
+  const float iv = j.inv[r];
   const bool clamped = iv >= 0.99e6f;   // 1 / sqrt(1e-12)
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
@@ -246,17 +246,46 @@ __global__ void __launch_bounds__(256) arc_norm_bwd_kernel(const float* __restri
       o4.y = clamped ? iv * a[t].y : iv * (a[t].y - h[t].y * dot);
       o4.z = clamped ? iv * a[t].z : iv * (a[t].z - h[t].z * dot);
       o4.w = clamped ? iv * a[t].w : iv * (a[t].w - h[t].w * dot);
-      *reinterpret_cast<float4*>(out + base + d) = o4;
+      *reinterpret_cast<float4*>(j.out + base + d) = o4;
     }
   }
 }
 
-static void launch_norm_bwd(const float* g, int planes, size_t plane_stride, const float* h_hi, const float* h_lo,
-                            const float* inv, int R, int D, float* out, cudaStream_t st) {
-  if (D <= 512)
-    arc_norm_bwd_kernel<32><<<(R + 7) / 8, 256, 0, st>>>(g, planes, plane_stride, h_hi, h_lo, inv, R, D, out);
-  else
-    arc_norm_bwd_kernel<256><<<R, 256, 0, st>>>(g, planes, plane_stride, h_hi, h_lo, inv, R, D, out);
+static void launch_norm_bwd(const NormBwdJob& j0, const NormBwdJob& j1, int D, cudaStream_t st) {
+  if (D <= 512) {
+    const int b0 = (j0.R + 7) / 8, b1 = (j1.R + 7) / 8;
+    arc_norm_bwd_kernel<32><<<b0 + b1, 256, 0, st>>>(j0, j1, b0, D);
+  } else {
+    arc_norm_bwd_kernel<256><<<j0.R + j1.R, 256, 0, st>>>(j0, j1, j0.R, D);
+  }
+}
+
+// Tile width and split for one GEMM: columns `N` in tiles of `bn`, m_blocks row blocks, `units` persistent CTA pairs.
+// An item = (row block, tiles_per_split consecutive tiles).  Cost model per K step of one SM of a pair (clocks):
+// max(tensor time 1.59 bn, shared-memory port time 160 + 0.625 bn) - below ~166 columns a tile is bound by the
+// 128 B/clk port (the A block is re-read for every tile), so narrower is not automatically better.  The plan with the
+// lowest waves x tiles_per_split x cost(bn) wins.
+struct TilePlan {
+  int bn, n_tiles, n_splits, tiles_per_split;
+};
+static TilePlan plan_tiles(int N, int m_blocks, int units, int bn_step, bool single_tile_items) {
+  TilePlan best{256, (N + 255) / 256, 1, (N + 255) / 256};
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 64; bn -= bn_step) {
+    const int n_tiles = (N + bn - 1) / bn;
+    for (int tps = 1; tps <= n_tiles; ++tps) {
+      if (single_tile_items && tps > 1) break;
+      const int n_splits = (n_tiles + tps - 1) / tps;
+      const int waves = (m_blocks * n_splits + units - 1) / units;
+      const double cyc = std::max(1.59 * bn, 160.0 + 0.625 * bn);
+      const double cost = (double)waves * tps * cyc * (1.0 + 0.02 * n_splits / 40.0);   // mild preference for fewer slots
+      if (cost < best_cost) {
+        best_cost = cost;
+        best = TilePlan{bn, n_tiles, n_splits, tps};
+      }
+    }
+  }
+  return best;
 }
 
 struct ArcWorkspace {
@@ -274,16 +303,19 @@ struct ArcWorkspace {
 };
 static thread_local ArcWorkspace g_arc;
 
+// One operand's tensor maps (hi, lo).  K-major: global [rows][K], box [box_rows][one 128-byte K chunk].
+// MN-major: global [K][rows] (row index contiguous), box [K chunk rows][one 128-byte slab of rows].
 template <class T>
-static int tmaps(CUtensorMap* maps, const T* a_hi, const T* a_lo, int M, const T* b_hi, const T* b_lo, int N, int K,
-                 int ldk) {
+static int operand_maps(CUtensorMap* hi, CUtensorMap* lo, const T* p_hi, const T* p_lo, int rows, int K, int pitch,
+                        int box_rows, bool mn_major) {
   constexpr int esz = (int)sizeof(T), bf = esz == 2 ? 1 : 0;
   constexpr uint32_t cols = 128 / esz;
-  if (int rc = make_tmap_2d(&maps[0], a_hi, M, K, (uint64_t)ldk * esz, GEMM_BM, cols, bf)) return rc;
-  if (int rc = make_tmap_2d(&maps[1], a_lo, M, K, (uint64_t)ldk * esz, GEMM_BM, cols, bf)) return rc;
-  if (int rc = make_tmap_2d(&maps[2], b_hi, N, K, (uint64_t)ldk * esz, kArcBN / kArcCtas, cols, bf)) return rc;
-  if (int rc = make_tmap_2d(&maps[3], b_lo, N, K, (uint64_t)ldk * esz, kArcBN / kArcCtas, cols, bf)) return rc;
-  return DIF_OK;
+  if (mn_major) {
+    if (int rc = make_tmap_2d(hi, p_hi, K, rows, (uint64_t)pitch * esz, cols, cols, bf)) return rc;
+    return make_tmap_2d(lo, p_lo, K, rows, (uint64_t)pitch * esz, cols, cols, bf);
+  }
+  if (int rc = make_tmap_2d(hi, p_hi, rows, K, (uint64_t)pitch * esz, box_rows, cols, bf)) return rc;
+  return make_tmap_2d(lo, p_lo, rows, K, (uint64_t)pitch * esz, box_rows, cols, bf);
 }
 
 // PREC 0: TF32 hi/lo planes (3xTF32);  PREC 3: bf16 b0/b1 planes (3xBF16, half the plane bytes and MMA time)
@@ -294,33 +326,38 @@ static int run_arcface(const float* X, const float* W, const int32_t* y, int B, 
   constexpr int esz = (int)sizeof(T), kChunk = 128 / esz;
   const bool bwd = dX != nullptr;
   const int sms = device_sm_count();
-  const int Bp = (B + 7) & ~7, Cp = (C + 7) & ~7;   // plane pitches stay 16-byte multiples for TMA in both modes
+  const int Cp = (C + 7) & ~7;   // d cos / cos pitch: a 16-byte multiple for TMA in both modes
   ArcMargin mg{s, cosf(m), sinf(m), cosf(3.14159265358979323846f - m), sinf(3.14159265358979323846f - m) * m};
 
   // ---- GEMM shapes
-  GemmShape fwd{};
   const int bm = GEMM_BM * kArcCtas, units = std::max(1, sms / kArcCtas);
+  GemmShape fwd{};
   fwd.m_blocks = (B + bm - 1) / bm;
-  fwd.n_tiles = (C + kArcBN - 1) / kArcBN;
+  const TilePlan pf = plan_tiles(C, fwd.m_blocks, units, 32, false);
+  fwd.bn = pf.bn;
+  fwd.n_tiles = pf.n_tiles;
+  fwd.n_splits = pf.n_splits;
+  fwd.tiles_per_split = pf.tiles_per_split;
   fwd.k_chunks = (D + kChunk - 1) / kChunk;
-  fwd.n_splits = std::max(1, std::min(fwd.n_tiles, 2 * units / std::max(1, fwd.m_blocks)));
-  fwd.tiles_per_split = (fwd.n_tiles + fwd.n_splits - 1) / fwd.n_splits;
-  fwd.n_splits = (fwd.n_tiles + fwd.tiles_per_split - 1) / fwd.tiles_per_split;
-  GemmShape gx{};   // dxh [B, D] = dcos [B, Cp] x whT [D, Cp]^T, split over K = classes
+  constexpr int kMnStep = 2 * kChunk;   // MN-major B in a CTA pair: each CTA's half tile is a whole number of slabs
+  GemmShape gx{};   // dxh [B, D] = dcos [B, C] x wh [C, D], split over K = classes
   gx.m_blocks = fwd.m_blocks;
-  gx.n_tiles = (D + kArcBN - 1) / kArcBN;
-  gx.k_chunks = (Cp + kChunk - 1) / kChunk;
+  gx.bn = D <= 128 ? 128 : 256;
+  gx.n_tiles = (D + gx.bn - 1) / gx.bn;
+  gx.k_chunks = (C + kChunk - 1) / kChunk;
   gx.n_splits = gx.n_tiles;
   gx.tiles_per_split = 1;
   gx.k_splits = std::max(1, std::min(gx.k_chunks, units / std::max(1, gx.m_blocks * gx.n_tiles)));
   gx.chunks_per_ksplit = (gx.k_chunks + gx.k_splits - 1) / gx.k_splits;
   gx.k_splits = (gx.k_chunks + gx.chunks_per_ksplit - 1) / gx.chunks_per_ksplit;
-  GemmShape gw{};   // dwh [C, D] = dcosT [Cp, Bp] x xhT [D, Bp]^T
+  GemmShape gw{};   // dwh [C, D] = dcos^T [C, B] x xh [B, D]
   gw.m_blocks = (C + bm - 1) / bm;
-  gw.n_tiles = gx.n_tiles;
-  gw.k_chunks = (Bp + kChunk - 1) / kChunk;
-  gw.n_splits = gw.n_tiles;
-  gw.tiles_per_split = 1;
+  const TilePlan pw = plan_tiles(D, gw.m_blocks, units, kMnStep, false);
+  gw.bn = pw.bn;
+  gw.n_tiles = pw.n_tiles;
+  gw.n_splits = pw.n_splits;
+  gw.tiles_per_split = pw.tiles_per_split;
+  gw.k_chunks = (B + kChunk - 1) / kChunk;
 
   // ---- workspace carve-up (256-byte aligned pieces)
   size_t off = 0;
@@ -336,13 +373,9 @@ static int run_arcface(const float* X, const float* W, const int32_t* y, int B, 
   const size_t o_wh = take((size_t)C * D * esz), o_wl = take((size_t)C * D * esz), o_wi = take((size_t)C * 4);
   const size_t o_cos = take((size_t)B * Cp * 4);
   const size_t o_part = take((size_t)B * fwd.n_splits * 8);
-  const size_t o_logz = take((size_t)B * 4), o_dphi = take((size_t)B * 4);
-  size_t o_dh = 0, o_dl = 0, o_th = 0, o_tl = 0, o_wth = 0, o_wtl = 0, o_xth = 0, o_xtl = 0, o_gx = 0, o_gw = 0;
+  size_t o_dh = 0, o_dl = 0, o_gx = 0, o_gw = 0;
   if (bwd) {
-    o_dh = take((size_t)Bp * Cp * esz); o_dl = take((size_t)Bp * Cp * esz);
-    o_th = take((size_t)Cp * Bp * esz); o_tl = take((size_t)Cp * Bp * esz);
-    o_wth = take((size_t)D * Cp * esz); o_wtl = take((size_t)D * Cp * esz);
-    o_xth = take((size_t)D * Bp * esz); o_xtl = take((size_t)D * Bp * esz);
+    o_dh = take((size_t)B * Cp * esz); o_dl = take((size_t)B * Cp * esz);
     o_gx = take((size_t)gx.k_splits * B * D * 4);
     o_gw = take((size_t)C * D * 4);
   }
@@ -351,57 +384,57 @@ static int run_arcface(const float* X, const float* W, const int32_t* y, int B, 
   auto F = [&](size_t o) { return reinterpret_cast<float*>(ws + o); };
   auto P = [&](size_t o) { return reinterpret_cast<T*>(ws + o); };
 
-  // ---- 0. normalise + TF32 planes
+  // ---- 1. normalise + operand planes, X and W in one launch
   PrepParams px{};
   px.src = X; px.n = B; px.D = D; px.normalize = 1; px.inv = F(o_xi);
-  PrepParams pw = px;
-  pw.src = W; pw.n = C; pw.inv = F(o_wi);
+  PrepParams pw2 = px;
+  pw2.src = W; pw2.n = C; pw2.inv = F(o_wi);
   if (PREC == 3) {
     px.split = 0; px.p0 = F(o_xn);
     px.pb = reinterpret_cast<__nv_bfloat16*>(ws + o_xh); px.pb1 = reinterpret_cast<__nv_bfloat16*>(ws + o_xl);
-    pw.split = 0; pw.p0 = F(o_wn);
-    pw.pb = reinterpret_cast<__nv_bfloat16*>(ws + o_wh); pw.pb1 = reinterpret_cast<__nv_bfloat16*>(ws + o_wl);
+    pw2.split = 0; pw2.p0 = F(o_wn);
+    pw2.pb = reinterpret_cast<__nv_bfloat16*>(ws + o_wh); pw2.pb1 = reinterpret_cast<__nv_bfloat16*>(ws + o_wl);
   } else {
     px.split = 1; px.p0 = F(o_xh); px.p1 = F(o_xl);
-    pw.split = 1; pw.p0 = F(o_wh); pw.p1 = F(o_wl);
+    pw2.split = 1; pw2.p0 = F(o_wh); pw2.p1 = F(o_wl);
   }
-  if (int rc = prep_launch(px, false, st)) return rc;
-  if (int rc = prep_launch(pw, false, st)) return rc;
+  if (int rc = prep_launch_pair(px, pw2, st)) return rc;
 
-  // ---- 1. forward GEMM + online softmax
+  // ---- 2. forward GEMM + online softmax
   CUtensorMap maps[4];
-  if (int rc = tmaps<T>(maps, P(o_xh), P(o_xl), B, P(o_wh), P(o_wl), C, D, D)) return rc;
+  if (int rc = operand_maps<T>(&maps[0], &maps[1], P(o_xh), P(o_xl), B, D, D, GEMM_BM, false)) return rc;
+  if (int rc = operand_maps<T>(&maps[2], &maps[3], P(o_wh), P(o_wl), C, D, D, fwd.bn / kArcCtas, false)) return rc;
   ArcFwdEpi::Params fp{F(o_cos), y, reinterpret_cast<float2*>(ws + o_part), B, C, Cp, fwd.n_splits, mg};
   if (int rc = launch_nt_gemm<PREC, kArcBN, kArcCtas, 0, ArcFwdEpi>(maps, fwd, fp, units, st)) return rc;
-  // ---- 2. loss
-  arc_loss_kernel<<<(B + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float2*>(ws + o_part), fwd.n_splits, F(o_cos), Cp,
-                                                  y, B, mg, loss, F(o_logz), F(o_dphi));
-  DIF_LAUNCH_OK();
+
+  // ---- 3. loss (+ d cos planes)
+  {
+    const int row_groups = (B + kDcosRows - 1) / kDcosRows;
+    int chunks = bwd ? std::max(1, std::min((Cp + 255) / 256, (4 * sms + row_groups - 1) / row_groups)) : 1;
+    const int chunk = ((Cp + chunks - 1) / chunks + 255) & ~255;
+    chunks = (Cp + chunk - 1) / chunk;
+    arc_dcos_kernel<T><<<dim3(chunks, row_groups), 256, 0, st>>>(reinterpret_cast<const float2*>(ws + o_part), fwd.n_splits,
+                                                                 F(o_cos), Cp, y, dloss, B, C, chunk, mg, loss,
+                                                                 bwd ? P(o_dh) : nullptr, bwd ? P(o_dl) : nullptr);
+    DIF_LAUNCH_OK();
+  }
   if (!bwd) return DIF_OK;
 
-  // ---- 3. d cos planes (both orientations) and transposed operand planes
-  arc_dcos_kernel<T><<<dim3((Cp + 31) / 32, (Bp + 31) / 32), dim3(32, 8), 0, st>>>(
-      F(o_cos), Cp, y, F(o_logz), F(o_dphi), dloss, B, C, mg, P(o_dh), P(o_dl), P(o_th), P(o_tl), Bp, Cp, Bp);
-  DIF_LAUNCH_OK();
-  transpose_planes_kernel<T><<<dim3((D + 31) / 32, (C + 31) / 32), dim3(32, 8), 0, st>>>(P(o_wh), P(o_wl), C, D, P(o_wth),
-                                                                                       P(o_wtl), Cp);
-  DIF_LAUNCH_OK();
-  transpose_planes_kernel<T><<<dim3((D + 31) / 32, (B + 31) / 32), dim3(32, 8), 0, st>>>(P(o_xh), P(o_xl), B, D, P(o_xth),
-                                                                                       P(o_xtl), Bp);
-  DIF_LAUNCH_OK();
-  // ---- 4. dxh (split-K planes) and dwh
-  if (int rc = tmaps<T>(maps, P(o_dh), P(o_dl), B, P(o_wth), P(o_wtl), D, Cp, Cp)) return rc;
+  // ---- 4. dxh (split-K planes): A = d cos K-major, B = the W planes read MN-major
+  if (int rc = operand_maps<T>(&maps[0], &maps[1], P(o_dh), P(o_dl), B, Cp, Cp, GEMM_BM, false)) return rc;
+  if (int rc = operand_maps<T>(&maps[2], &maps[3], P(o_wh), P(o_wl), D, C, D, 0, true)) return rc;
   StoreEpi::Params sx{F(o_gx), B, D, D, gx.n_splits, (size_t)B * D};
-  if (int rc = launch_nt_gemm<PREC, kArcBN, kArcCtas, 0, StoreEpi>(maps, gx, sx, units, st)) return rc;
-  if (int rc = tmaps<T>(maps, P(o_th), P(o_tl), C, P(o_xth), P(o_xtl), D, Bp, Bp)) return rc;
+  if (int rc = launch_nt_gemm<PREC, kArcBN, kArcCtas, 0, StoreEpi, 0, 1>(maps, gx, sx, units, st)) return rc;
+  //      dwh: A = d cos read MN-major (classes are the rows of the product), B = the X planes read MN-major
+  if (int rc = operand_maps<T>(&maps[0], &maps[1], P(o_dh), P(o_dl), C, B, Cp, 0, true)) return rc;
+  if (int rc = operand_maps<T>(&maps[2], &maps[3], P(o_xh), P(o_xl), D, B, D, 0, true)) return rc;
   StoreEpi::Params sw{F(o_gw), C, D, D, gw.n_splits, 0};
-  if (int rc = launch_nt_gemm<PREC, kArcBN, kArcCtas, 0, StoreEpi>(maps, gw, sw, units, st)) return rc;
-  // ---- 5. l2_normalize backward
-  if (PREC == 3) launch_norm_bwd(F(o_gx), gx.k_splits, (size_t)B * D, F(o_xn), nullptr, F(o_xi), B, D, dX, st);
-  else launch_norm_bwd(F(o_gx), gx.k_splits, (size_t)B * D, F(o_xh), F(o_xl), F(o_xi), B, D, dX, st);
-  DIF_LAUNCH_OK();
-  if (PREC == 3) launch_norm_bwd(F(o_gw), 1, 0, F(o_wn), nullptr, F(o_wi), C, D, dW, st);
-  else launch_norm_bwd(F(o_gw), 1, 0, F(o_wh), F(o_wl), F(o_wi), C, D, dW, st);
+  if (int rc = launch_nt_gemm<PREC, kArcBN, kArcCtas, 0, StoreEpi, 1, 1>(maps, gw, sw, units, st)) return rc;
+
+  // ---- 5. l2_normalize backward, X rows and W rows in one launch
+  NormBwdJob jx{F(o_gx), gx.k_splits, (size_t)B * D, PREC == 3 ? F(o_xn) : F(o_xh), PREC == 3 ? nullptr : F(o_xl), F(o_xi), B, dX};
+  NormBwdJob jw{F(o_gw), 1, 0, PREC == 3 ? F(o_wn) : F(o_wh), PREC == 3 ? nullptr : F(o_wl), F(o_wi), C, dW};
+  launch_norm_bwd(jx, jw, D, st);
   DIF_LAUNCH_OK();
   return DIF_OK;
 }

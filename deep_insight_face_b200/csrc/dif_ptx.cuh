@@ -193,7 +193,20 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor, dense, fp32 accumulate, both operands K-major.
+// Shared-memory matrix descriptor, MN-major operand staged as 128-byte-wide slabs [K rows][128 B] (SWIZZLE_128B):
+// canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units - the MN index runs along the 128-byte row and
+// repeats every LBO = slab_bytes; 8 consecutive K rows form one 1024-byte swizzle atom, atoms SBO = 1024 B apart.
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t slab_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((slab_bytes >> 4) & 0x3FFFu) << 16;   // LBO
+  d |= (uint64_t)(1024u >> 4) << 32;                    // SBO
+  d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor, dense, fp32 accumulate; K-major operands (OR in bit 15 / 16 for an MN-major A / B).
 // fmt: 0 = f16, 1 = bf16, 2 = tf32 (same code for A and B).
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t m, uint32_t n) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);

@@ -430,6 +430,7 @@ dif_gallery_t* dif_gallery_create(int device, int64_t capacity_rows, int dim, in
   ok = ok && cudaMemset(g->gmax, 0, 4) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&g->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaEventCreate(&g->ev0) == cudaSuccess && cudaEventCreate(&g->ev1) == cudaSuccess;
+  for (cudaEvent_t& e : g->ev_phase) ok = ok && cudaEventCreate(&e) == cudaSuccess;
   if (!ok) {
     set_error("dif_gallery_create: device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     dif_gallery_destroy(g);
@@ -448,6 +449,8 @@ void dif_gallery_destroy(dif_gallery_t* g) {
   if (g->own_stream) cudaStreamDestroy(g->own_stream);
   if (g->ev0) cudaEventDestroy(g->ev0);
   if (g->ev1) cudaEventDestroy(g->ev1);
+  for (cudaEvent_t e : g->ev_phase)
+    if (e) cudaEventDestroy(e);
   delete g;
 }
 
@@ -693,6 +696,8 @@ int dif::gallery_search_impl(dif_gallery* g, const float* queries, int n_queries
 
   if (int rc = ensure_query_ws(g, n_queries, splits, kp)) return rc;
 
+  DIF_CUDA_OK(cudaEventRecord(g->ev_phase[0], st));
+  g->phase_sharded = false;
   // 1. queries -> canonical planes
   PrepParams pp{};
   pp.src = queries;
@@ -775,6 +780,7 @@ int dif::gallery_search_impl(dif_gallery* g, const float* queries, int n_queries
     DIF_CUDA_OK(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));
   rerank_kernel<<<n_queries, kRerankThreads, rr_smem, st>>>(rp);
   DIF_LAUNCH_OK();
+  DIF_CUDA_OK(cudaEventRecord(g->ev_phase[1], st));
 
   // 4. exact path for flagged queries (grids sized for the hardware, work read from the device counter)
   if (g->size > 0) {
@@ -799,6 +805,7 @@ int dif::gallery_search_impl(dif_gallery* g, const float* queries, int n_queries
       DIF_LAUNCH_OK();
     }
   }
+  DIF_CUDA_OK(cudaEventRecord(g->ev_phase[2], st));
   g->stats[1] = dif_launch_count() - launches0;
   g->stats[2] = splits;
   g->stats[3] = kp;
@@ -863,6 +870,19 @@ int dif_gallery_last_stats(const dif_gallery_t* g, int64_t out[6]) {
 int dif_gallery_last_kernel_ms(dif_gallery_t* g, float* ms) {
   DIF_REQUIRE(g && ms, DIF_ERR_INVALID, "null argument");
   DIF_CUDA_OK(cudaEventElapsedTime(ms, g->ev0, g->ev1));
+  return DIF_OK;
+}
+
+int dif_gallery_last_phase_ms(dif_gallery_t* g, float out[5]) {
+  DIF_REQUIRE(g && out, DIF_ERR_INVALID, "null argument");
+  for (int i = 0; i < 5; ++i) out[i] = 0.f;
+  if (g->size > 0) {
+    DIF_CUDA_OK(cudaEventElapsedTime(&out[0], g->ev_phase[0], g->ev0));     // query prep + workspace memsets
+    DIF_CUDA_OK(cudaEventElapsedTime(&out[1], g->ev0, g->ev1));             // tensor-core filter
+    DIF_CUDA_OK(cudaEventElapsedTime(&out[2], g->ev1, g->ev_phase[1]));     // window + canonical re-rank
+  }
+  DIF_CUDA_OK(cudaEventElapsedTime(&out[3], g->ev_phase[1], g->ev_phase[2]));   // exact path for flagged queries
+  if (g->phase_sharded) DIF_CUDA_OK(cudaEventElapsedTime(&out[4], g->ev_phase[2], g->ev_phase[3]));   // exchange + merge
   return DIF_OK;
 }
 

@@ -48,7 +48,9 @@ struct dif_gallery {
   void* d_stage = nullptr;
   size_t d_stage_bytes = 0;
   cudaStream_t own_stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // around the tensor-core pass
+  cudaEvent_t ev_phase[4] = {nullptr, nullptr, nullptr, nullptr};   // search start, after re-rank, after exact path, after exchange + merge
+  bool phase_sharded = false;   // the last search recorded ev_phase[3]
   int64_t stats[6] = {0, 0, 0, 0, 0, 0};
   int opt_ctas = 2;
   int opt_force_fallback = 0;

@@ -19,6 +19,17 @@
 //             B streams through the ring: halves the L2->smem traffic per MMA, which is what bounds a
 //             128x256 tile at tensor-core speed ("operand feed").
 // NBUF accumulator buffers in TMEM let the epilogue of tile t overlap the MMAs of tile t+1.
+//
+// Operand majors (AMN / BMN): 0 = the operand's global matrix is [rows][K] with K contiguous (K-major, "NT");
+// 1 = it is [K][rows] with the ROW index contiguous (MN-major): the same matrix can then serve a second GEMM
+// that contracts over its other dimension without a transposed copy in HBM (ArcFace backward: dcos and the
+// normalised weights are each read in both roles).  An MN-major K-chunk is staged as 128-byte-wide slabs
+// ([K rows][32 fp32 | 64 bf16], one TMA box each, SWIZZLE_128B) and described to the tensor core with the
+// MN-major canonical layout (LBO = slab stride, SBO = 1024 B between 8-row groups, idesc major bits 15 / 16).
+//
+// Tile width: `shape.bn` (a multiple of 32, <= BN, runtime) columns of B per tile - the MMA's N and the TMA box
+// height come from it - so the host can pick the width that fills the SMs with whole waves (10 000 classes over
+// 74 CTA pairs is two waves of 256-wide tiles but one wave of three 96-wide ones).
 #pragma once
 #include <cuda.h>
 
@@ -56,6 +67,7 @@ struct GemmShape {
   int k_splits;         // the K range is cut into k_splits pieces -> items *= k_splits (0/1: no split)
   int chunks_per_ksplit;
   int l2_prefetch;      // 1: the producer prefetches B tiles into L2 two tiles ahead
+  int bn;               // columns of B per tile (multiple of 32, <= BN); 0 = BN.  n_tiles counts tiles of this width
 };
 
 template <int PREC, int BN, int CTAS>
@@ -125,7 +137,20 @@ __device__ __forceinline__ Epi make_epi(const typename Epi::Params& p, uint8_t* 
   else return Epi(p, smem, row);
 }
 
-template <int PREC, int BN, int CTAS, int ARES, class Epi>
+// MN-major operand: K-chunk kc of rows [row0, row0 + n_rows) -> n_rows / slab 128-byte-wide slabs at dst
+template <int PREC, int CTAS>
+__device__ __forceinline__ void tma_load_mn_slabs(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int row0, int n_rows,
+                                                  int k0) {
+  using PT = PrecTraits<PREC>;
+  constexpr int kSlabElems = GEMM_SWZ / PT::kElemBytes;          // rows (MN index) per slab
+  constexpr int kSlabBytes = PT::kChunkElems * GEMM_SWZ;         // [K chunk rows][128 B]
+  for (int j = 0; j * kSlabElems < n_rows; ++j) {
+    if (CTAS == 1) tma_load_2d(dst + j * kSlabBytes, tm, bar, row0 + j * kSlabElems, k0);
+    else tma_load_2d_pair(dst + j * kSlabBytes, tm, bar, row0 + j * kSlabElems, k0);
+  }
+}
+
+template <int PREC, int BN, int CTAS, int ARES, class Epi, int AMN = 0, int BMN = 0>
 __global__ void __launch_bounds__((2 + EpiWarps<Epi>::value) * 32, 1)
 nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                        const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -135,8 +160,11 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
   constexpr int NBUF = T::kAccBufs;
   constexpr int EW = EpiWarps<Epi>::value;
   static_assert(EW == 4 || EW == 8, "4 or 8 epilogue warps");
-  constexpr int CPW = (BN / 32) / (EW / 4);   // 32-column chunks of a tile per epilogue warp
-  static_assert(CPW >= 2 && CPW % 2 == 0, "the chunk loop is unrolled by two");
+  static_assert(!(ARES && AMN), "the resident-A schedule stages A K-major");
+  const int bn = shape.bn;                    // tile width (host: 0 < bn <= BN, multiple of 32, even chunk count if EW == 8)
+  const int CPW = (bn / 32) / (EW / 4);       // 32-column chunks of a tile per epilogue warp
+  const int b_rows = bn / CTAS;               // rows of B this CTA stages per tile
+  const uint32_t stage_tx = (uint32_t)(PT::kPlanes * ((ARES ? 0 : T::kATile) + b_rows * GEMM_SWZ));
   constexpr int kStage = PT::kPlanes * ((ARES ? 0 : T::kATile) + T::kBTile);
   constexpr int kBOff = ARES ? 0 : PT::kPlanes * T::kATile;  // offset of the B planes inside a stage
 
@@ -228,11 +256,11 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
           }
         }
         for (int t = t0; t < t1; ++t) {
-          const int b_row = t * BN + (int)cta_rank * (BN / CTAS);
+          const int b_row = t * bn + (int)cta_rank * b_rows;
           // warm L2 with this CTA's rows of the B tile two tiles ahead: the ring only buffers ~1.3 us of MMA work,
           // less than a DRAM round trip under load, so first-touch tiles would otherwise stall the tensor pipe
           if (shape.l2_prefetch && t + 2 < t1) {
-            const int p_row = (t + 2) * BN + (int)cta_rank * (BN / CTAS);
+            const int p_row = (t + 2) * bn + (int)cta_rank * b_rows;
             for (int kc = kc0; kc < kc1; ++kc) {
               tma_prefetch_l2_2d(&tm_b_hi, kc * PT::kChunkElems, p_row);
               if (PT::kPlanes == 2) tma_prefetch_l2_2d(&tm_b_lo, kc * PT::kChunkElems, p_row);
@@ -244,23 +272,22 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             mbar_wait(&empty_bar[s], ph ^ 1u);
             uint8_t* st = stage_base + s * kStage;
             const int kx = kc * PT::kChunkElems;
-            if (CTAS == 1) {
-              mbar_arrive_expect_tx(&full_bar[s], kStage);
-              if (!ARES) tma_load_2d(st, &tm_a_hi, &full_bar[s], kx, a_row);
-              tma_load_2d(st + kBOff, &tm_b_hi, &full_bar[s], kx, b_row);
-              if (PT::kPlanes == 2) {
-                if (!ARES) tma_load_2d(st + T::kATile, &tm_a_lo, &full_bar[s], kx, a_row);
-                tma_load_2d(st + kBOff + T::kBTile, &tm_b_lo, &full_bar[s], kx, b_row);
+            // Pairs: both CTAs' bytes are credited to the leader's barrier (see a_full above).
+            if (CTAS == 1) mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+            else if (leader) mbar_arrive_expect_tx(&full_bar[s], stage_tx * 2);
+            for (int pl = 0; pl < PT::kPlanes; ++pl) {
+              const CUtensorMap* ta = pl ? &tm_a_lo : &tm_a_hi;
+              const CUtensorMap* tb = pl ? &tm_b_lo : &tm_b_hi;
+              if (!ARES) {
+                uint8_t* da = st + pl * T::kATile;
+                if (AMN) tma_load_mn_slabs<PREC, CTAS>(da, ta, &full_bar[s], a_row, GEMM_BM, kx);
+                else if (CTAS == 1) tma_load_2d(da, ta, &full_bar[s], kx, a_row);
+                else tma_load_2d_pair(da, ta, &full_bar[s], kx, a_row);
               }
-            } else {
-              // Both CTAs' bytes are credited to the leader's barrier (see a_full above).
-              if (leader) mbar_arrive_expect_tx(&full_bar[s], kStage * 2);
-              if (!ARES) tma_load_2d_pair(st, &tm_a_hi, &full_bar[s], kx, a_row);
-              tma_load_2d_pair(st + kBOff, &tm_b_hi, &full_bar[s], kx, b_row);
-              if (PT::kPlanes == 2) {
-                if (!ARES) tma_load_2d_pair(st + T::kATile, &tm_a_lo, &full_bar[s], kx, a_row);
-                tma_load_2d_pair(st + kBOff + T::kBTile, &tm_b_lo, &full_bar[s], kx, b_row);
-              }
+              uint8_t* db = st + kBOff + pl * T::kBTile;
+              if (BMN) tma_load_mn_slabs<PREC, CTAS>(db, tb, &full_bar[s], b_row, b_rows, kx);
+              else if (CTAS == 1) tma_load_2d(db, tb, &full_bar[s], kx, b_row);
+              else tma_load_2d_pair(db, tb, &full_bar[s], kx, b_row);
             }
           }
         }
@@ -269,7 +296,12 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
   } else if (warp == 5) {
     // ===================== MMA issuer (one lane of the leader CTA) =====================
     if (leader && lane_id() == 0) {
-      constexpr uint32_t idesc = make_idesc(PT::kFmt, GEMM_BM * CTAS, BN);
+      const uint32_t idesc = make_idesc(PT::kFmt, GEMM_BM * CTAS, (uint32_t)bn) | ((uint32_t)AMN << 15) | ((uint32_t)BMN << 16);
+      constexpr uint32_t kSlabBytes = PT::kChunkElems * GEMM_SWZ;
+      // descriptor start-address step per MMA, in 16-byte units: 32 B of K inside the swizzle row (K-major) or one
+      // MMA's worth of K rows of 128 B each (MN-major: 8 rows for TF32, 16 for bf16)
+      constexpr uint64_t kAdvA = AMN ? (uint64_t)((32 / PT::kElemBytes) * GEMM_SWZ / 16) : 2ull;
+      constexpr uint64_t kAdvB = BMN ? (uint64_t)((32 / PT::kElemBytes) * GEMM_SWZ / 16) : 2ull;
       uint32_t it = 0, tc = 0, n_item = 0;
       for (int item = unit; item < n_items; item += n_units, ++n_item) {
         const int ks = item / items_per_ks;
@@ -295,20 +327,21 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             const uint32_t st = smem_u32(stage_base + s * kStage);
             const uint32_t a_addr = ARES ? smem_u32(a_res + kc * T::kATile) : st;
             const uint32_t a_lo_addr = ARES ? a_addr + (uint32_t)(shape.k_chunks * T::kATile) : st + T::kATile;
-            const uint64_t a_hi = make_kmajor_desc<GEMM_SWZ>(a_addr);
-            const uint64_t b_hi = make_kmajor_desc<GEMM_SWZ>(st + kBOff);
+            const uint64_t a_hi = AMN ? make_mnmajor_desc(a_addr, kSlabBytes) : make_kmajor_desc<GEMM_SWZ>(a_addr);
+            const uint64_t b_hi = BMN ? make_mnmajor_desc(st + kBOff, kSlabBytes) : make_kmajor_desc<GEMM_SWZ>(st + kBOff);
 #pragma unroll
             for (int kstep = 0; kstep < PT::kKSteps; ++kstep) {
-              const uint64_t adv = (uint64_t)(kstep * 2);  // 32 bytes of K, in 16-byte units
+              const uint64_t adva = (uint64_t)kstep * kAdvA, advb = (uint64_t)kstep * kAdvB;
               if (PT::kPlanes == 2) {
-                const uint64_t a_lo = make_kmajor_desc<GEMM_SWZ>(a_lo_addr);
-                const uint64_t b_lo = make_kmajor_desc<GEMM_SWZ>(st + kBOff + T::kBTile);
+                const uint64_t a_lo = AMN ? make_mnmajor_desc(a_lo_addr, kSlabBytes) : make_kmajor_desc<GEMM_SWZ>(a_lo_addr);
+                const uint64_t b_lo = BMN ? make_mnmajor_desc(st + kBOff + T::kBTile, kSlabBytes)
+                                          : make_kmajor_desc<GEMM_SWZ>(st + kBOff + T::kBTile);
                 // small cross terms first, dominant term last
-                tc_mma<CTAS, PT::kTf32>(d_tmem, a_lo + adv, b_hi + adv, idesc, ((kc - kc0) | kstep) != 0);
-                tc_mma<CTAS, PT::kTf32>(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                tc_mma<CTAS, PT::kTf32>(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
+                tc_mma<CTAS, PT::kTf32>(d_tmem, a_lo + adva, b_hi + advb, idesc, ((kc - kc0) | kstep) != 0);
+                tc_mma<CTAS, PT::kTf32>(d_tmem, a_hi + adva, b_lo + advb, idesc, 1u);
+                tc_mma<CTAS, PT::kTf32>(d_tmem, a_hi + adva, b_hi + advb, idesc, 1u);
               } else {
-                tc_mma<CTAS, PT::kTf32>(d_tmem, a_hi + adv, b_hi + adv, idesc, ((kc - kc0) | kstep) != 0);
+                tc_mma<CTAS, PT::kTf32>(d_tmem, a_hi + adva, b_hi + advb, idesc, ((kc - kc0) | kstep) != 0);
               }
             }
             tc_commit<CTAS>(&empty_bar[s]);   // smem slot reusable once these MMAs retire
@@ -336,24 +369,29 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
       const int m_row = (mb * CTAS + (int)cta_rank) * GEMM_BM + row;
       const int t0 = (rem / shape.m_blocks) * shape.tiles_per_split;
       const int t1 = min(t0 + shape.tiles_per_split, shape.n_tiles);
-      epi.begin_item(m_row, split, t0 * BN);
+      epi.begin_item(m_row, split, t0 * bn);
       for (int t = t0; t < t1; ++t, ++tc) {
         const int buf = tc % NBUF;
         const uint32_t aph = (tc / NBUF) & 1u;
-        epi.begin_tile(t * BN);
+        epi.begin_tile(t * bn);
         mbar_wait(&acc_full[buf], aph);
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * BN);
         uint32_t va[32], vb[32];
         tmem_ld32(taddr + (uint32_t)(cb * 32), va);
+        int c = cb;
 #pragma unroll 1
-        for (int c = cb; c < cb + CPW; c += 2) {
+        for (; c + 1 < cb + CPW; c += 2) {
           tmem_ld_wait(va);
           tmem_ld32(taddr + (uint32_t)((c + 1) * 32), vb);
-          epi.consume(t * BN + c * 32, va, taddr + (uint32_t)(c * 32), vb);
+          epi.consume(t * bn + c * 32, va, taddr + (uint32_t)(c * 32), vb);
           tmem_ld_wait(vb);
           if (c + 2 < cb + CPW) tmem_ld32(taddr + (uint32_t)((c + 2) * 32), va);
-          epi.consume(t * BN + (c + 1) * 32, vb, taddr + (uint32_t)((c + 1) * 32), va);
+          epi.consume(t * bn + (c + 1) * 32, vb, taddr + (uint32_t)((c + 1) * 32), va);
+        }
+        if (c < cb + CPW) {   // odd chunk count (narrow tiles): the last chunk is already in flight in `va`
+          tmem_ld_wait(va);
+          epi.consume(t * bn + c * 32, va, taddr + (uint32_t)(c * 32), vb);
         }
         // all of this warp's TMEM reads of `buf` have completed (wait::ld above)
         tc_fence_before_sync();
@@ -379,9 +417,18 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
 // Host-side launch of one instantiation.  maps = {A hi, A lo, B hi, B lo}; single-plane modes pass
 // the hi map twice.  n_units = persistent CTAs (CTAS == 1) or CTA pairs (CTAS == 2).
 // shape.stages is filled in here from the shared-memory plan.
-template <int PREC, int BN, int CTAS, int ARES, class Epi>
+template <int PREC, int BN, int CTAS, int ARES, class Epi, int AMN = 0, int BMN = 0>
 int launch_nt_gemm(const CUtensorMap* maps, GemmShape shape, const typename Epi::Params& ep, int n_units,
                    cudaStream_t stream) {
+  if (shape.bn <= 0) shape.bn = BN;
+  {
+    constexpr int kSlab = GEMM_SWZ / PrecTraits<PREC>::kElemBytes;
+    const int chunks = shape.bn / 32;
+    DIF_REQUIRE(shape.bn <= BN && shape.bn % 32 == 0 && (EpiWarps<Epi>::value == 4 || chunks % 2 == 0) &&
+                    (!BMN || (shape.bn / CTAS) % kSlab == 0) && (CTAS == 1 || shape.bn % 16 == 0),
+                DIF_ERR_INVALID, "nt_gemm: tile width %d is not valid for this instantiation (BN %d, %d CTAs, MN-major B %d)",
+                shape.bn, BN, CTAS, BMN);
+  }
   GemmSmemPlan plan;
   const bool fits = plan_gemm_smem<PREC, BN, CTAS, ARES>(shape.k_chunks, Epi::smem_bytes(ep), &plan);
   DIF_REQUIRE(fits, DIF_ERR_CAPACITY, "nt_gemm: K = %d chunks does not fit the shared-memory plan (ARES=%d)",
@@ -392,7 +439,7 @@ int launch_nt_gemm(const CUtensorMap* maps, GemmShape shape, const typename Epi:
     shape.chunks_per_ksplit = shape.k_chunks;
   }
   DIF_REQUIRE(!(ARES && shape.k_splits > 1), DIF_ERR_INVALID, "nt_gemm: the resident-A schedule does not split K");
-  auto kern = nt_gemm_rowscan_kernel<PREC, BN, CTAS, ARES, Epi>;
+  auto kern = nt_gemm_rowscan_kernel<PREC, BN, CTAS, ARES, Epi, AMN, BMN>;
   static bool configured = false;   // per instantiation
   if (!configured) {
     DIF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_MAX));

@@ -497,6 +497,8 @@ int dif_gallery_search_sharded(dif_gallery_t* g, void* nccl_comm, int rank, int 
     shard_peer_exchange_merge_kernel<<<grid, kMergeThreads, merge_smem(world, k), st>>>(mp, pp);
     DIF_LAUNCH_OK();
   }
+  DIF_CUDA_OK(cudaEventRecord(g->ev_phase[3], st));
+  g->phase_sharded = true;
   g->stats[1] = dif_launch_count() - launches0;
   return DIF_OK;
 }

@@ -172,6 +172,13 @@ class Gallery:
         return float(ms.value)
 
 
+    def last_phase_ms(self) -> dict:
+        """Phase durations of the last search (synchronise the stream first)."""
+        out = (C.c_float * 5)()
+        _ffi.check(self._lib.dif_gallery_last_phase_ms(self._h, out))
+        return {"prep": out[0], "filter": out[1], "rerank": out[2], "exact": out[3], "exchange_merge": out[4]}
+
+
 def shard_range(n_rows: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous row range [lo, hi) of `rank`: the first n_rows % world ranks hold one extra row."""
     base, rem = divmod(int(n_rows), int(world))

@@ -105,6 +105,10 @@ int dif_gallery_last_stats(const dif_gallery_t* g, int64_t out[6]);
 /* duration in ms of the last search's tensor-core kernel (CUDA events on the launch stream);
  * only valid after the stream has been synchronised */
 int dif_gallery_last_kernel_ms(dif_gallery_t* g, float* ms);
+/* durations in ms of the last search's phases (CUDA events on the launch stream, valid after the stream has been
+ * synchronised): [0] query prep, [1] tensor-core filter, [2] window + canonical re-rank, [3] exact path for flagged
+ * queries, [4] candidate exchange + merge (sharded searches, else 0) */
+int dif_gallery_last_phase_ms(dif_gallery_t* g, float out[5]);
 /* copy canonical stored rows (normalised for cosine) back out: out [n*dim] fp32 */
 int dif_gallery_get_rows(dif_gallery_t* g, int64_t row0, int64_t n, float* out, void* stream);
 

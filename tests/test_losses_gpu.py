@@ -283,3 +283,94 @@ def test_graphed_steps_survive_workspace_growth():
     torch.cuda.synchronize()
     assert torch.equal(small.loss, before[0]) and torch.equal(small.grad, before[1])
     del junk
+
+
+def test_auto_alpha_is_differentiable_on_device_tensors(gpu):
+    """BatchHardTripletLossEuclideanAutoAlpha.call on torch-CUDA embeddings must carry a grad_fn like the
+    other three classes, use the PREVIOUS auto_alpha (losses.py:112) and update the state afterwards (:113)."""
+    import torch
+
+    from deep_insight_face_b200.common.losses import BatchHardTripletLossEuclideanAutoAlpha
+    from oracle import losses_oracle as lo
+
+    emb, lab = pk_batch(18, 4, 128, 1.5)
+    auto = BatchHardTripletLossEuclideanAutoAlpha(alpha=0.1, init_auto_alpha=1)
+    x = torch.from_numpy(emb).cuda().requires_grad_(True)
+    y = torch.from_numpy(lab).cuda()
+    per_sample = auto.call(y, x)
+    assert per_sample.requires_grad and per_sample.grad_fn is not None
+    per_sample.mean().backward()
+    want = lo.batch_hard_euclidean(lab, emb, 1.0)
+    close(per_sample.detach().cpu().numpy(), want["loss"], scale=np.abs(want["hardest_pos"]).max())
+    close(x.grad.cpu().numpy(), want["grad"])
+    assert abs(auto.auto_alpha - want["stats"][0] * 0.1) <= 1e-4 * want["stats"][0]
+    x.grad = None
+    second = auto.call(y, x)        # now with margin mean(dists) * 0.1
+    second.mean().backward()
+    want2 = lo.batch_hard_euclidean(lab, emb, float(want["stats"][0]) * 0.1)
+    close(second.detach().cpu().numpy(), want2["loss"], scale=np.abs(want2["hardest_pos"]).max())
+    close(x.grad.cpu().numpy(), want2["grad"])
+
+
+class _FakeTensor:
+    """The slice of tf.Tensor the bridge touches."""
+
+    def __init__(self, a):
+        self.a = np.asarray(a)
+
+    def numpy(self):
+        return self.a
+
+
+class _FakeTF:
+    """A stand-in `tensorflow` module with the four entry points _tf_call uses, executed eagerly: Tensor / Variable
+    types, float32, custom_gradient (keeps the grad_fn so the test can drive the backward pass) and numpy_function."""
+
+    Tensor = _FakeTensor
+    Variable = _FakeTensor
+    float32 = np.float32
+
+    def __init__(self):
+        self.grad_fns = []
+        self.numpy_calls = 0
+
+    def custom_gradient(self, f):
+        def wrapped(*args):
+            out, grad_fn = f(*args)
+            self.grad_fns.append(grad_fn)
+            return out
+
+        return wrapped
+
+    def numpy_function(self, fn, inputs, dtype):
+        self.numpy_calls += 1
+        args = [i.numpy() if isinstance(i, _FakeTensor) else np.asarray(i) for i in inputs]
+        return _FakeTensor(np.asarray(fn(*args), dtype=dtype))
+
+
+def test_tf_bridge_executes_under_a_fake_tensorflow(gpu, monkeypatch):
+    """TensorFlow is not installable here, so the tf.custom_gradient + tf.numpy_function bridge (the path Keras `fit`
+    takes: reference networks/triplet.py:182,209,211) is driven through a minimal fake module: forward and backward
+    must reach the kernels and reproduce the oracle, and AutoAlpha must read its margin when the step runs."""
+    from deep_insight_face_b200.common import losses as L
+    from oracle import losses_oracle as lo
+
+    fake = _FakeTF()
+    monkeypatch.setattr(L, "_tf", fake)
+    emb, lab = pk_batch(18, 4, 128, 1.5)
+    onehot = np.eye(18, dtype=np.float32)[lab]
+    loss = L.BatchHardTripletLoss(alpha=0.2)
+    out = loss.call(_FakeTensor(onehot), _FakeTensor(emb))
+    assert isinstance(out, _FakeTensor) and fake.numpy_calls == 1
+    want = lo.batch_hard_cosine(lab, emb, 0.2)
+    close(out.numpy(), want["loss"])
+    dl = np.full(72, 1.0 / 72, dtype=np.float32)
+    g = fake.grad_fns[-1](_FakeTensor(dl))
+    close(g.numpy(), want["grad"])
+    auto = L.BatchHardTripletLossEuclideanAutoAlpha(alpha=0.1, init_auto_alpha=1)
+    first = auto.call(_FakeTensor(onehot), _FakeTensor(emb))
+    want1 = lo.batch_hard_euclidean(lab, emb, 1.0)
+    close(first.numpy(), want1["loss"], scale=np.abs(want1["hardest_pos"]).max())
+    g1 = fake.grad_fns[-1](_FakeTensor(dl))            # backward of step 1 still uses margin 1.0
+    close(g1.numpy(), want1["grad"])
+    assert abs(auto.auto_alpha - want1["stats"][0] * 0.1) <= 1e-4 * want1["stats"][0]

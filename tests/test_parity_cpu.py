@@ -1,0 +1,137 @@
+"""Pins that need no GPU: host-side code against fixtures produced by the REFERENCE's own functions
+(tests/golden/host_reference.json, made by tests/golden/make_golden_host.py in the build container), the mirrored
+default arguments, and the ArcFace oracle against an independently written torch fp64 autograd formulation."""
+import inspect
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def host_ref():
+    with open(os.path.join(HERE, "golden", "host_reference.json")) as f:
+        return json.load(f)
+
+
+def test_sample_people_reproduces_the_reference_batches(host_ref):
+    """generator.py:15-41 executed from the reference's source under np.random.seed(s) vs datagen.sample_people."""
+    from make_golden_host import dataset
+
+    from deep_insight_face_b200 import datagen
+
+    for case in host_ref["sample_people"]:
+        ds = dataset(case["dataset_seed"], case["n_people"])
+        np.random.seed(case["seed"])
+        paths, counts = datagen.sample_people(ds, case["P"], case["K"])
+        assert paths == case["image_paths"]
+        assert [int(c) for c in counts] == case["num_per_class"]
+    # a private generator leaves numpy's global stream alone
+    np.random.seed(7)
+    before = np.random.get_state()[1].copy()
+    datagen.sample_people(dataset(100, 40), 18, 4, rng=np.random.default_rng(0))
+    assert np.array_equal(before, np.random.get_state()[1])
+
+
+def test_pairs_txt_is_byte_identical_to_the_reference_writer(host_ref, tmp_path):
+    from deep_insight_face_b200 import datagen
+    from deep_insight_face_b200.evaluation import utility as U
+
+    ref = host_ref["pairs_txt"]
+    fn = tmp_path / "pairs.txt"
+    datagen.write_pairs_to_file(str(fn), [[tuple(m) for m in f] for f in ref["matches"]],
+                                [[tuple(m) for m in f] for f in ref["mismatches"]], ref["num_folds"], ref["n"])
+    assert fn.read_bytes() == ref["text"].encode("utf-8")
+    pairs = U.read_pairs(str(fn))                      # evaluation/utility.py:256-262 (header skipped)
+    assert len(pairs) == 12 and list(pairs[0]) == ["p0_0", "1", "2"] and list(pairs[3]) == ["p0_0", "1", "q0_0", "7"]
+
+
+def test_mirrored_defaults_equal_the_reference(host_ref):
+    from deep_insight_face_b200 import api, predictions
+    from deep_insight_face_b200.common import losses
+    from deep_insight_face_b200.evaluation import utility
+    from deep_insight_face_b200.networks import siamese, triplet
+
+    d = host_ref["defaults"]
+
+    def dflt(fn, name):
+        return inspect.signature(fn).parameters[name].default
+
+    assert dflt(losses.TripletLossWapper.__init__, "alpha") == d["TripletLossWapper.__init__"]["alpha"] == 0.35
+    auto = d["BatchHardTripletLossEuclideanAutoAlpha.__init__"]
+    assert dflt(losses.BatchHardTripletLossEuclideanAutoAlpha.__init__, "alpha") == auto["alpha"]
+    assert dflt(losses.BatchHardTripletLossEuclideanAutoAlpha.__init__, "init_auto_alpha") == auto["init_auto_alpha"]
+    assert dflt(triplet.triplet_loss, "alpha") == d["triplet_loss"]["alpha"]
+    assert dflt(siamese._accuracy, "threshold") == d["_accuracy"]["threshold"] == 0.4     # was 0.5
+    assert dflt(predictions.TripletPrediction.verify, "threshold") == d["TripletPrediction.verify"]["threshold"]
+    assert dflt(predictions.SiamesePrediction.verify, "threshold") == d["SiamesePrediction.verify"]["threshold"]
+    assert dflt(api.compare_faces, "tolerance") == d["compare_faces"]["tolerance"]
+    assert dflt(utility.evaluate, "nrof_folds") == d["evaluate"]["nrof_folds"]
+    assert dflt(utility.evaluate, "distance_metric") == d["evaluate"]["distance_metric"]
+    assert dflt(utility.evaluate, "subtract_mean") == d["evaluate"]["subtract_mean"]
+    assert dflt(utility.distance, "distance_metric") == d["distance"]["distance_metric"]
+
+
+def test_siamese_accuracy_default_threshold():
+    from deep_insight_face_b200.networks.siamese import _accuracy
+    from oracle import losses_oracle as lo
+
+    d = np.array([0.1, 0.39, 0.41, 0.45, 0.7], dtype=np.float32)
+    y = np.array([1, 1, 1, 0, 0], dtype=np.float32)
+    assert _accuracy(y, d) == lo.siamese_accuracy(y, d) == 0.8          # threshold 0.4: 0.41 is a miss, 0.45 is right
+    assert _accuracy(y, d, 0.5) == 0.8 and _accuracy(y, d, 0.42) == 1.0
+
+
+def _arcface_torch(X, W, y, s, m):
+    """Independent formulation: cos(theta + m) through acos, autograd for every derivative, fp64."""
+    import torch
+
+    x = torch.tensor(X, dtype=torch.float64, requires_grad=True)
+    w = torch.tensor(W, dtype=torch.float64, requires_grad=True)
+    lab = torch.tensor(y, dtype=torch.int64)
+    xn = x / torch.sqrt(torch.clamp((x * x).sum(1, keepdim=True), min=1e-12))
+    wn = w / torch.sqrt(torch.clamp((w * w).sum(1, keepdim=True), min=1e-12))
+    cos = torch.clamp(xn @ wn.T, -1.0, 1.0)
+    cy = cos[torch.arange(len(y)), lab]
+    theta = torch.acos(torch.clamp(cy, -1 + 1e-15, 1 - 1e-15))
+    margin = torch.where(theta + m < math.pi, torch.cos(theta + m), cy - m * math.sin(math.pi - m))
+    onehot = torch.nn.functional.one_hot(lab, W.shape[0]).bool()
+    logits = s * torch.where(onehot, margin[:, None], cos)
+    loss = -(torch.log_softmax(logits, dim=1)[torch.arange(len(y)), lab])
+    loss.mean().backward()
+    return loss.detach().numpy(), x.grad.numpy(), w.grad.numpy()
+
+
+@pytest.mark.parametrize("s,m", [(64.0, 0.5), (30.0, 0.35), (16.0, 1.2)])
+def test_arcface_oracle_against_torch_autograd(s, m):
+    """the ArcFace oracle had no independent cross-check.  Includes rows past the easy-margin
+    switch (theta + m > pi: the sample points away from its class centre) and a non-target cosine that rounds above 1
+    (clip edge: tf.clip_by_value / torch.clamp pass no gradient outside the bounds)."""
+    from oracle import losses_oracle as lo
+
+    rng = np.random.default_rng(11)
+    B, C, D = 48, 37, 24
+    X = rng.standard_normal((B, D))
+    W = rng.standard_normal((C, D))
+    y = rng.integers(0, C, size=B)
+    for i in range(0, 12):           # easy-margin branch: x close to -w_y
+        X[i] = -W[y[i]] * (0.5 + i) + 0.05 * rng.standard_normal(D)
+    for i in range(12, 18):          # near the switch from both sides
+        ang = math.pi - m + (i - 14.5) * 0.02
+        u = W[y[i]] / np.linalg.norm(W[y[i]])
+        v = rng.standard_normal(D)
+        v -= u * (u @ v)
+        v /= np.linalg.norm(v)
+        X[i] = 3.0 * (math.cos(ang) * u + math.sin(ang) * v)
+    X[20] = 2.5 * W[(y[20] + 1) % C]  # exactly parallel to a NON-target centre: raw cosine may round to > 1
+    want = lo.arcface(X, W, y, s, m)
+    loss, dX, dW = _arcface_torch(X, W, y, s, m)
+    easy = want["cos_target"] <= math.cos(math.pi - m)
+    assert easy[:12].all() and easy[12:18].any() and not easy[12:18].all()
+    np.testing.assert_allclose(want["loss"], loss, rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(want["dX"], dX, rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(want["dW"], dW, rtol=1e-7, atol=1e-10)
