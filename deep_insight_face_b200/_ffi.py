@@ -98,6 +98,7 @@ SIGNATURES = {
     "dif_gallery_search_sharded_host": (_i32, [_vp, _vp, _i32, _i32, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "dif_synth_fill": (_i32, [_vp, _u64, _i64, _vp, _i64, _i32, _vp]),
     "dif_debug_nt_gemm": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _vp]),
+    "dif_debug_gemm_layout": (_i32, [_vp, _vp, _i32, _i32, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "dif_debug_gemm_time": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_f32)]),
     "dif_batch_hard": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "dif_batch_hard_host": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),

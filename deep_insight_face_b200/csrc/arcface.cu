@@ -116,6 +116,24 @@ __device__ __forceinline__ void split_store(float v, __nv_bfloat16* p0, __nv_bfl
   p1[i] = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(b0)));
 }
 
+__device__ __forceinline__ void split_store4(const float (&v)[4], float* hi, float* lo, size_t i) {
+  float4 h, l;
+  h.x = tf32_round(v[0]); h.y = tf32_round(v[1]); h.z = tf32_round(v[2]); h.w = tf32_round(v[3]);
+  l.x = __fsub_rn(v[0], h.x); l.y = __fsub_rn(v[1], h.y); l.z = __fsub_rn(v[2], h.z); l.w = __fsub_rn(v[3], h.w);
+  *reinterpret_cast<float4*>(hi + i) = h;
+  *reinterpret_cast<float4*>(lo + i) = l;
+}
+__device__ __forceinline__ void split_store4(const float (&v)[4], __nv_bfloat16* p0, __nv_bfloat16* p1, size_t i) {
+  __nv_bfloat16 a[4], b[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    a[k] = __float2bfloat16_rn(v[k]);
+    b[k] = __float2bfloat16_rn(__fsub_rn(v[k], __bfloat162float(a[k])));
+  }
+  *reinterpret_cast<uint2*>(p0 + i) = *reinterpret_cast<const uint2*>(a);
+  *reinterpret_cast<uint2*>(p1 + i) = *reinterpret_cast<const uint2*>(b);
+}
+
 // Loss + d cos.  Block = kDcosRows samples x a chunk of classes.  One warp per sample first merges the forward
 // pass's per-split (max, sum) pairs -> logZ, target phi / d phi (and the loss, written by the blocks of class chunk 0);
 // then the block streams its class chunk: cos -> p - onehot -> d cos, split into the two operand planes.
@@ -163,37 +181,44 @@ __global__ void __launch_bounds__(256) arc_dcos_kernel(const float2* __restrict_
   }
   __syncthreads();
   if (!d_hi) return;
-  const int c_begin = blockIdx.x * chunk, c_end = min(ldc, c_begin + chunk);
-  for (int c = c_begin + (int)threadIdx.x; c < c_end; c += 256) {
+  // Four classes per thread and step, the kDcosRows row loads issued together: 8 x 16 B in flight per thread (with one
+  // 4-byte load at a time the 20 MB of cosines arrive at ~1 TB/s - the kernel was a chain of DRAM round trips).
+  const int c_begin = blockIdx.x * chunk, c_end = min(ldc, c_begin + chunk);   // ldc and chunk are multiples of 4
+  const int n_rows = min(kDcosRows, B - b0);
+  for (int c = c_begin + 4 * (int)threadIdx.x; c < c_end; c += 4 * 256) {
+    float4 raw[kDcosRows];
+#pragma unroll
+    for (int r = 0; r < kDcosRows; ++r)
+      raw[r] = r < n_rows ? *reinterpret_cast<const float4*>(cosbuf + (size_t)(b0 + r) * ldc + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < kDcosRows; ++r) {
-      const int b = b0 + r;
-      if (b >= B) break;
-      float v = 0.f;
-      if (c < C) {
-        const float raw = cosbuf[(size_t)b * ldc + c];
-        const float ct = fminf(fmaxf(raw, -1.f), 1.f);
-        const bool tgt = (c == s_y[r]);
-        const float logit = mg.s * (tgt ? arc_phi(ct, mg) : ct);
-        const float pr = expf(logit - s_logz[r]);
-        v = mg.s * s_g[r] * (pr - (tgt ? 1.f : 0.f)) * (tgt ? s_dphi[r] : 1.f);
-        if (raw < -1.f || raw > 1.f) v = 0.f;   // clip_by_value passes no gradient outside the bounds
+      if (r >= n_rows) break;
+      const float in[4] = {raw[r].x, raw[r].y, raw[r].z, raw[r].w};
+      float v[4];
+      const float sg = mg.s * s_g[r], lz = s_logz[r];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float ct = fminf(fmaxf(in[i], -1.f), 1.f);
+        v[i] = sg * expf(mg.s * ct - lz);                         // every class but the target: s g p
+        if (c + i >= C || in[i] < -1.f || in[i] > 1.f) v[i] = 0.f;   // padding; clip_by_value passes no gradient outside
       }
-      split_store(v, d_hi, d_lo, (size_t)b * ldc + c);
+      const int yt = s_y[r] - c;
+      if (yt >= 0 && yt < 4) {                                     // the target column: margin logit, d phi / d cos
+        const float ct = fminf(fmaxf(in[yt], -1.f), 1.f);
+        const float pr = expf(mg.s * arc_phi(ct, mg) - lz);
+        v[yt] = (in[yt] < -1.f || in[yt] > 1.f) ? 0.f : sg * (pr - 1.f) * s_dphi[r];
+      }
+      split_store4(v, d_hi, d_lo, (size_t)(b0 + r) * ldc + c);
     }
   }
 }
 
-// out_r = inv_r * (g_r - h_r (h_r . g_r)) with g = sum over `planes` partial planes (fixed order), h = hi + lo
-// normalised row (h_lo NULL: h_hi is the fp32 normalised row itself); rows whose squared norm was clamped (inv == 1e6) are a plain scaling.  TPR threads own one row
-// (TPR = 32: a warp per row, 8 rows per block, D <= 512; TPR = 256: a block per row, D <= 4096), one float4 group
-// per thread and pass: every load is independent and coalesced and the planes are read exactly once.
 struct NormBwdJob {
   const float* g;        // [planes][R][D] partial gradients wrt the normalised rows
   int planes;
   size_t plane_stride;
-  const float* h_hi;     // normalised rows (hi plane, or the fp32 rows themselves when h_lo is NULL)
-  const float* h_lo;
+  const float* src;      // [R][D] the ORIGINAL rows: the normalised row is src * inv, exactly what prep stored (x * inv
+                         // rounded once; its hi + lo planes add back to the same float), at half the bytes of two planes
   const float* inv;      // [R] inverse norms
   int R;
   float* out;            // [R][D]
@@ -211,6 +236,7 @@ __global__ void __launch_bounds__(256) arc_norm_bwd_kernel(NormBwdJob j0, NormBw
   const size_t base = (size_t)r * D;
   float dot = 0.f;
   float4 a[4], h[4];
+  const float iv = live ? j.inv[r] : 0.f;
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     const int d = (lane + t * TPR) * 4;
@@ -221,9 +247,8 @@ __global__ void __launch_bounds__(256) arc_norm_bwd_kernel(NormBwdJob j0, NormBw
         const float4 v = *reinterpret_cast<const float4*>(j.g + (size_t)s * j.plane_stride + base + d);
         a[t].x += v.x; a[t].y += v.y; a[t].z += v.z; a[t].w += v.w;
       }
-      const float4 hh = *reinterpret_cast<const float4*>(j.h_hi + base + d);
-      const float4 hl = j.h_lo ? *reinterpret_cast<const float4*>(j.h_lo + base + d) : make_float4(0.f, 0.f, 0.f, 0.f);
-      h[t] = make_float4(hh.x + hl.x, hh.y + hl.y, hh.z + hl.z, hh.w + hl.w);
+      const float4 x = *reinterpret_cast<const float4*>(j.src + base + d);
+      h[t] = make_float4(__fmul_rn(x.x, iv), __fmul_rn(x.y, iv), __fmul_rn(x.z, iv), __fmul_rn(x.w, iv));
       dot += a[t].x * h[t].x + a[t].y * h[t].y + a[t].z * h[t].z + a[t].w * h[t].w;
     }
   }
@@ -235,7 +260,6 @@ __global__ void __launch_bounds__(256) arc_norm_bwd_kernel(NormBwdJob j0, NormBw
     for (int w = 0; w < 8; ++w) dot += red[w];
   }
   if (!live) return;
-  const float iv = j.inv[r];
   const bool clamped = iv >= 0.99e6f;   // 1 / sqrt(1e-12)
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
@@ -310,9 +334,9 @@ static int operand_maps(CUtensorMap* hi, CUtensorMap* lo, const T* p_hi, const T
                         int box_rows, bool mn_major) {
   constexpr int esz = (int)sizeof(T), bf = esz == 2 ? 1 : 0;
   constexpr uint32_t cols = 128 / esz;
-  if (mn_major) {
-    if (int rc = make_tmap_2d(hi, p_hi, K, rows, (uint64_t)pitch * esz, cols, cols, bf)) return rc;
-    return make_tmap_2d(lo, p_lo, K, rows, (uint64_t)pitch * esz, cols, cols, bf);
+  if (mn_major) {   // fp32 planes: the 32-byte-atom swizzle (see make_mnmajor_desc)
+    if (int rc = make_tmap_2d(hi, p_hi, K, rows, (uint64_t)pitch * esz, cols, cols, bf, !bf)) return rc;
+    return make_tmap_2d(lo, p_lo, K, rows, (uint64_t)pitch * esz, cols, cols, bf, !bf);
   }
   if (int rc = make_tmap_2d(hi, p_hi, rows, K, (uint64_t)pitch * esz, box_rows, cols, bf)) return rc;
   return make_tmap_2d(lo, p_lo, rows, K, (uint64_t)pitch * esz, box_rows, cols, bf);
@@ -366,9 +390,7 @@ static int run_arcface(const float* X, const float* W, const int32_t* y, int B, 
     off += (bytes + 255) & ~(size_t)255;
     return at;
   };
-  // mode 0: xh / xl = hi / lo planes.  mode 3: xn = fp32 normalised rows (for the normalisation backward),
-  // xh / xl = bf16 planes
-  const size_t o_xn = PREC == 3 ? take((size_t)B * D * 4) : 0, o_wn = PREC == 3 ? take((size_t)C * D * 4) : 0;
+  // mode 0: xh / xl = TF32 hi / lo planes.  mode 3: xh / xl = bf16 b0 / b1 planes
   const size_t o_xh = take((size_t)B * D * esz), o_xl = take((size_t)B * D * esz), o_xi = take((size_t)B * 4);
   const size_t o_wh = take((size_t)C * D * esz), o_wl = take((size_t)C * D * esz), o_wi = take((size_t)C * 4);
   const size_t o_cos = take((size_t)B * Cp * 4);
@@ -390,9 +412,9 @@ static int run_arcface(const float* X, const float* W, const int32_t* y, int B, 
   PrepParams pw2 = px;
   pw2.src = W; pw2.n = C; pw2.inv = F(o_wi);
   if (PREC == 3) {
-    px.split = 0; px.p0 = F(o_xn);
+    px.split = 0; px.p0 = nullptr;
     px.pb = reinterpret_cast<__nv_bfloat16*>(ws + o_xh); px.pb1 = reinterpret_cast<__nv_bfloat16*>(ws + o_xl);
-    pw2.split = 0; pw2.p0 = F(o_wn);
+    pw2.split = 0; pw2.p0 = nullptr;
     pw2.pb = reinterpret_cast<__nv_bfloat16*>(ws + o_wh); pw2.pb1 = reinterpret_cast<__nv_bfloat16*>(ws + o_wl);
   } else {
     px.split = 1; px.p0 = F(o_xh); px.p1 = F(o_xl);
@@ -432,8 +454,8 @@ static int run_arcface(const float* X, const float* W, const int32_t* y, int B, 
   if (int rc = launch_nt_gemm<PREC, kArcBN, kArcCtas, 0, StoreEpi, 1, 1>(maps, gw, sw, units, st)) return rc;
 
   // ---- 5. l2_normalize backward, X rows and W rows in one launch
-  NormBwdJob jx{F(o_gx), gx.k_splits, (size_t)B * D, PREC == 3 ? F(o_xn) : F(o_xh), PREC == 3 ? nullptr : F(o_xl), F(o_xi), B, dX};
-  NormBwdJob jw{F(o_gw), 1, 0, PREC == 3 ? F(o_wn) : F(o_wh), PREC == 3 ? nullptr : F(o_wl), F(o_wi), C, dW};
+  NormBwdJob jx{F(o_gx), gx.k_splits, (size_t)B * D, X, F(o_xi), B, dX};
+  NormBwdJob jw{F(o_gw), 1, 0, W, F(o_wi), C, dW};
   launch_norm_bwd(jx, jw, D, st);
   DIF_LAUNCH_OK();
   return DIF_OK;

@@ -51,7 +51,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
-                 uint32_t box_rows, uint32_t box_cols, int dtype) {
+                 uint32_t box_rows, uint32_t box_cols, int dtype, int atom32) {
   auto fn = get_encode_fn();
   DIF_REQUIRE(fn != nullptr, DIF_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const int esz = dtype == 0 ? 4 : 2;
@@ -65,7 +65,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(out, dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DIF_REQUIRE(r == CUDA_SUCCESS, DIF_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return DIF_OK;

@@ -46,8 +46,10 @@ int count_launch(int n = 1);   // bumps the library-wide launch counter (dif_lau
 
 // 2-D row-major [rows][cols] tensor of `elem_bytes` elements, box = [box_rows][box_cols],
 // 128-byte swizzle (box_cols * elem_bytes must be 128).  dtype: 0 = fp32 (consumed as tf32), 1 = bf16.
+// atom32 = 1: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (32-byte chunks swizzled over 4 rows) - the only shared-memory
+// layout the tensor core accepts for an MN-major TF32 operand (UMMA layout type SWIZZLE_128B_BASE32B).
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
-                 uint32_t box_rows, uint32_t box_cols, int dtype);
+                 uint32_t box_rows, uint32_t box_cols, int dtype, int atom32 = 0);
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 

@@ -193,16 +193,20 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 
-// Shared-memory matrix descriptor, MN-major operand staged as 128-byte-wide slabs [K rows][128 B] (SWIZZLE_128B):
-// canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units - the MN index runs along the 128-byte row and
-// repeats every LBO = slab_bytes; 8 consecutive K rows form one 1024-byte swizzle atom, atoms SBO = 1024 B apart.
+// Shared-memory matrix descriptor, MN-major operand staged as 128-byte-wide slabs [K rows][128 B]: the MN index runs
+// along the 128-byte row and repeats every LBO = slab_bytes; consecutive K rows are 128 B apart.
+//   16-bit operands: SWIZZLE_128B, canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units - 8 K rows form a 1024-byte
+//                    swizzle atom, atoms SBO = 1024 B apart;
+//   TF32 operands:   SWIZZLE_128B_BASE32B (layout type 1; TMA: SWIZZLE_128B_ATOM_32B) is the only MN-major layout the
+//                    tensor core takes for 32-bit elements - 32-byte chunks swizzled over 4 K rows, atoms SBO = 512 B apart.
+template <bool TF32>
 __device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t slab_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((slab_bytes >> 4) & 0x3FFFu) << 16;   // LBO
-  d |= (uint64_t)(1024u >> 4) << 32;                    // SBO
-  d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                               // SWIZZLE_128B
+  d |= (uint64_t)((slab_bytes >> 4) & 0x3FFFu) << 16;          // LBO
+  d |= (uint64_t)((TF32 ? 512u : 1024u) >> 4) << 32;           // SBO
+  d |= (uint64_t)1 << 46;                                      // descriptor version (Blackwell)
+  d |= (uint64_t)(TF32 ? 1 : 2) << 61;                         // SWIZZLE_128B_BASE32B | SWIZZLE_128B
   return d;
 }
 

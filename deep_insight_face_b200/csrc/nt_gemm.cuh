@@ -24,8 +24,9 @@
 // 1 = it is [K][rows] with the ROW index contiguous (MN-major): the same matrix can then serve a second GEMM
 // that contracts over its other dimension without a transposed copy in HBM (ArcFace backward: dcos and the
 // normalised weights are each read in both roles).  An MN-major K-chunk is staged as 128-byte-wide slabs
-// ([K rows][32 fp32 | 64 bf16], one TMA box each, SWIZZLE_128B) and described to the tensor core with the
-// MN-major canonical layout (LBO = slab stride, SBO = 1024 B between 8-row groups, idesc major bits 15 / 16).
+// ([K rows][32 fp32 | 64 bf16], one TMA box each) and described to the tensor core with the MN-major canonical
+// layout (LBO = slab stride, idesc major bits 15 / 16): SWIZZLE_128B for bf16, SWIZZLE_128B_BASE32B for TF32 - the
+// only MN-major layout 32-bit operands have - with the matching TMA mode (make_tmap_2d, atom32).
 //
 // Tile width: `shape.bn` (a multiple of 32, <= BN, runtime) columns of B per tile - the MMA's N and the TMA box
 // height come from it - so the host can pick the width that fills the SMs with whole waves (10 000 classes over
@@ -88,12 +89,13 @@ struct GemmSmemPlan {
   int total = 0;
 };
 template <int PREC, int BN, int CTAS, int ARES>
-inline bool plan_gemm_smem(int k_chunks, int epi_smem, GemmSmemPlan* out) {
+inline bool plan_gemm_smem(int k_chunks, int epi_smem, GemmSmemPlan* out, int bn = BN) {
   using T = GemmTiles<PREC, BN, CTAS>;
   using PT = PrecTraits<PREC>;
   GemmSmemPlan p;
   p.a_res_bytes = ARES ? PT::kPlanes * k_chunks * T::kATile : 0;
-  p.stage_bytes = PT::kPlanes * ((ARES ? 0 : T::kATile) + T::kBTile);
+  // a stage holds the tile width actually used: narrower tiles buy a deeper ring (more TMA bytes in flight)
+  p.stage_bytes = PT::kPlanes * ((ARES ? 0 : T::kATile) + (bn / CTAS) * GEMM_SWZ);
   const int avail = GEMM_SMEM_MAX - 1024 /*align slack*/ - GEMM_BAR_BYTES - epi_smem - p.a_res_bytes;
   if (avail < 2 * p.stage_bytes) return false;
   p.stages = avail / p.stage_bytes;
@@ -164,9 +166,9 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
   const int bn = shape.bn;                    // tile width (host: 0 < bn <= BN, multiple of 32, even chunk count if EW == 8)
   const int CPW = (bn / 32) / (EW / 4);       // 32-column chunks of a tile per epilogue warp
   const int b_rows = bn / CTAS;               // rows of B this CTA stages per tile
-  const uint32_t stage_tx = (uint32_t)(PT::kPlanes * ((ARES ? 0 : T::kATile) + b_rows * GEMM_SWZ));
-  constexpr int kStage = PT::kPlanes * ((ARES ? 0 : T::kATile) + T::kBTile);
-  constexpr int kBOff = ARES ? 0 : PT::kPlanes * T::kATile;  // offset of the B planes inside a stage
+  const int kBTileRt = b_rows * GEMM_SWZ;     // bytes of one B plane of a stage (a multiple of 1024: b_rows % 16 == 0)
+  const int kStage = PT::kPlanes * ((ARES ? 0 : T::kATile) + kBTileRt);
+  const uint32_t stage_tx = (uint32_t)kStage;
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment.
@@ -184,6 +186,8 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
   uint64_t* a_empty = a_full + 1;                              // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
   uint8_t* epi_smem = reinterpret_cast<uint8_t*>(bars) + GEMM_BAR_BYTES;
+
+  constexpr int kBOff = ARES ? 0 : PT::kPlanes * T::kATile;  // offset of the B planes inside a stage
 
   const int warp = threadIdx.x >> 5;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
@@ -284,7 +288,7 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
                 else if (CTAS == 1) tma_load_2d(da, ta, &full_bar[s], kx, a_row);
                 else tma_load_2d_pair(da, ta, &full_bar[s], kx, a_row);
               }
-              uint8_t* db = st + kBOff + pl * T::kBTile;
+              uint8_t* db = st + kBOff + pl * kBTileRt;
               if (BMN) tma_load_mn_slabs<PREC, CTAS>(db, tb, &full_bar[s], b_row, b_rows, kx);
               else if (CTAS == 1) tma_load_2d(db, tb, &full_bar[s], kx, b_row);
               else tma_load_2d_pair(db, tb, &full_bar[s], kx, b_row);
@@ -327,15 +331,15 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             const uint32_t st = smem_u32(stage_base + s * kStage);
             const uint32_t a_addr = ARES ? smem_u32(a_res + kc * T::kATile) : st;
             const uint32_t a_lo_addr = ARES ? a_addr + (uint32_t)(shape.k_chunks * T::kATile) : st + T::kATile;
-            const uint64_t a_hi = AMN ? make_mnmajor_desc(a_addr, kSlabBytes) : make_kmajor_desc<GEMM_SWZ>(a_addr);
-            const uint64_t b_hi = BMN ? make_mnmajor_desc(st + kBOff, kSlabBytes) : make_kmajor_desc<GEMM_SWZ>(st + kBOff);
+            const uint64_t a_hi = AMN ? make_mnmajor_desc<PT::kTf32>(a_addr, kSlabBytes) : make_kmajor_desc<GEMM_SWZ>(a_addr);
+            const uint64_t b_hi = BMN ? make_mnmajor_desc<PT::kTf32>(st + kBOff, kSlabBytes) : make_kmajor_desc<GEMM_SWZ>(st + kBOff);
 #pragma unroll
             for (int kstep = 0; kstep < PT::kKSteps; ++kstep) {
               const uint64_t adva = (uint64_t)kstep * kAdvA, advb = (uint64_t)kstep * kAdvB;
               if (PT::kPlanes == 2) {
-                const uint64_t a_lo = AMN ? make_mnmajor_desc(a_lo_addr, kSlabBytes) : make_kmajor_desc<GEMM_SWZ>(a_lo_addr);
-                const uint64_t b_lo = BMN ? make_mnmajor_desc(st + kBOff + T::kBTile, kSlabBytes)
-                                          : make_kmajor_desc<GEMM_SWZ>(st + kBOff + T::kBTile);
+                const uint64_t a_lo = AMN ? make_mnmajor_desc<PT::kTf32>(a_lo_addr, kSlabBytes) : make_kmajor_desc<GEMM_SWZ>(a_lo_addr);
+                const uint64_t b_lo = BMN ? make_mnmajor_desc<PT::kTf32>(st + kBOff + kBTileRt, kSlabBytes)
+                                          : make_kmajor_desc<GEMM_SWZ>(st + kBOff + kBTileRt);
                 // small cross terms first, dominant term last
                 tc_mma<CTAS, PT::kTf32>(d_tmem, a_lo + adva, b_hi + advb, idesc, ((kc - kc0) | kstep) != 0);
                 tc_mma<CTAS, PT::kTf32>(d_tmem, a_hi + adva, b_lo + advb, idesc, 1u);
@@ -430,7 +434,7 @@ int launch_nt_gemm(const CUtensorMap* maps, GemmShape shape, const typename Epi:
                 shape.bn, BN, CTAS, BMN);
   }
   GemmSmemPlan plan;
-  const bool fits = plan_gemm_smem<PREC, BN, CTAS, ARES>(shape.k_chunks, Epi::smem_bytes(ep), &plan);
+  const bool fits = plan_gemm_smem<PREC, BN, CTAS, ARES>(shape.k_chunks, Epi::smem_bytes(ep), &plan, shape.bn);
   DIF_REQUIRE(fits, DIF_ERR_CAPACITY, "nt_gemm: K = %d chunks does not fit the shared-memory plan (ARES=%d)",
               shape.k_chunks, ARES);
   shape.stages = plan.stages;

@@ -11,7 +11,7 @@ namespace dif {
 // ------------------------------------------------------------------------------------------
 // K5: rows -> canonical planes.  One warp per row.
 //   SRC 0: rows read from `src`; SRC 1: synthetic rows (seed, row0 + r).
-//   p0/p1: fp32 planes (TF32x3: p0 = tf32(x), p1 = x - p0 exactly; otherwise p0 = x, p1 unused)
+//   p0/p1: fp32 planes (TF32x3: p0 = tf32(x), p1 = x - p0 exactly; otherwise p0 = x (may be NULL), p1 unused)
 //   pb   : bf16 plane (bf16 modes);  pb1: second bf16 plane, bf16(x - pb) (3xBF16 mode)
 //   sq[r] = canonical sum of squares of the STORED row
 //   gmax : running max of sq (orderable uint), may be NULL
@@ -52,7 +52,7 @@ __device__ __forceinline__ void prep_one_row(const PrepParams& p, int64_t r, int
       const float hi = tf32_round(x);
       p.p0[r * p.D + d] = hi;
       p.p1[r * p.D + d] = __fsub_rn(x, hi);
-    } else {
+    } else if (p.p0) {
       p.p0[r * p.D + d] = x;
     }
     if (p.pb) {

@@ -176,6 +176,13 @@ int dif_synth_fill(float* out, uint64_t seed, int64_t row0, const int64_t* rows_
 int dif_debug_nt_gemm(const float* A, const float* B, int M, int N, int K, float* C, int precision, int ctas,
                       int n_splits, void* stream);
 
+/* diagnostic for the skeleton's operand-major and tile-width options: C [M][N] = A B^T with A given as [M][K]
+ * (a_mn = 0) or [K][M] (a_mn = 1: read through an MN-major shared-memory descriptor, no transposed copy) and B as
+ * [N][K] or [K][N]; precision DIF_PREC_TF32X3 | DIF_PREC_BF16X3; CTA pairs; tile width bn <= 256, a multiple of 32
+ * (of 64 for TF32 / 128 for bf16 planes when b_mn = 1).  Used by tests/test_gemm_gpu.py. */
+int dif_debug_gemm_layout(const float* A, const float* B, int M, int N, int K, float* C, int precision, int a_mn, int b_mn,
+                          int bn, int n_splits, void* stream);
+
 /* diagnostic: average ms of the NT-GEMM main loop alone (checksum epilogue) on synthetic operands */
 int dif_debug_gemm_time(int M, int N, int K, int precision, int ctas, int n_splits, int iters, float* ms_out);
 
