@@ -237,18 +237,23 @@ __global__ void __launch_bounds__(256) arc_norm_bwd_kernel(NormBwdJob j0, NormBw
   float dot = 0.f;
   float4 a[4], h[4];
   const float iv = live ? j.inv[r] : 0.f;
+  // all eight 16-byte loads of a thread are issued before the first use (the class-weight rows are 60 MB of traffic)
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     const int d = (lane + t * TPR) * 4;
-    a[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    h[t] = a[t];
+    const bool on = live && d < D;
+    a[t] = on ? *reinterpret_cast<const float4*>(j.g + base + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+    h[t] = on ? *reinterpret_cast<const float4*>(j.src + base + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int d = (lane + t * TPR) * 4;
     if (live && d < D) {
-      for (int s = 0; s < j.planes; ++s) {
+      for (int s = 1; s < j.planes; ++s) {   // split-K partial planes, summed in a fixed order
         const float4 v = *reinterpret_cast<const float4*>(j.g + (size_t)s * j.plane_stride + base + d);
         a[t].x += v.x; a[t].y += v.y; a[t].z += v.z; a[t].w += v.w;
       }
-      const float4 x = *reinterpret_cast<const float4*>(j.src + base + d);
-      h[t] = make_float4(__fmul_rn(x.x, iv), __fmul_rn(x.y, iv), __fmul_rn(x.z, iv), __fmul_rn(x.w, iv));
+      h[t] = make_float4(__fmul_rn(h[t].x, iv), __fmul_rn(h[t].y, iv), __fmul_rn(h[t].z, iv), __fmul_rn(h[t].w, iv));
       dot += a[t].x * h[t].x + a[t].y * h[t].y + a[t].z * h[t].z + a[t].w * h[t].w;
     }
   }
@@ -420,7 +425,29 @@ static int run_arcface(const float* X, const float* W, const int32_t* y, int B, 
     px.split = 1; px.p0 = F(o_xh); px.p1 = F(o_xl);
     pw2.split = 1; pw2.p0 = F(o_wh); pw2.p1 = F(o_wl);
   }
+  // DIF_ARC_PROFILE=1 (development aid): CUDA events between the launches, printed after a synchronise
+  static const bool profile = getenv("DIF_ARC_PROFILE") != nullptr;
+  static cudaEvent_t pev[8];
+  static bool pev_made = false;
+  if (profile && !pev_made) {
+    for (cudaEvent_t& e : pev) cudaEventCreate(&e);
+    pev_made = true;
+  }
+  int pn = 0;
+  auto mark = [&] {
+    if (profile) cudaEventRecord(pev[pn++], st);
+  };
+  static unsigned long long* trace_d = nullptr;
+  if (profile && !trace_d) cudaMalloc((void**)&trace_d, 3 * 148 * 8 * 8);
+  if (profile) {
+    cudaMemsetAsync(trace_d, 0, 3 * 148 * 8 * 8, st);
+    fwd.trace = trace_d;
+    gx.trace = trace_d + 148 * 8;
+    gw.trace = trace_d + 2 * 148 * 8;
+  }
+  mark();
   if (int rc = prep_launch_pair(px, pw2, st)) return rc;
+  mark();
 
   // ---- 2. forward GEMM + online softmax
   CUtensorMap maps[4];
@@ -428,6 +455,7 @@ static int run_arcface(const float* X, const float* W, const int32_t* y, int B, 
   if (int rc = operand_maps<T>(&maps[2], &maps[3], P(o_wh), P(o_wl), C, D, D, fwd.bn / kArcCtas, false)) return rc;
   ArcFwdEpi::Params fp{F(o_cos), y, reinterpret_cast<float2*>(ws + o_part), B, C, Cp, fwd.n_splits, mg};
   if (int rc = launch_nt_gemm<PREC, kArcBN, kArcCtas, 0, ArcFwdEpi>(maps, fwd, fp, units, st)) return rc;
+  mark();
 
   // ---- 3. loss (+ d cos planes)
   {
@@ -440,6 +468,7 @@ static int run_arcface(const float* X, const float* W, const int32_t* y, int B, 
                                                                  bwd ? P(o_dh) : nullptr, bwd ? P(o_dl) : nullptr);
     DIF_LAUNCH_OK();
   }
+  mark();
   if (!bwd) return DIF_OK;
 
   // ---- 4. dxh (split-K planes): A = d cos K-major, B = the W planes read MN-major
@@ -447,17 +476,56 @@ static int run_arcface(const float* X, const float* W, const int32_t* y, int B, 
   if (int rc = operand_maps<T>(&maps[2], &maps[3], P(o_wh), P(o_wl), D, C, D, 0, true)) return rc;
   StoreEpi::Params sx{F(o_gx), B, D, D, gx.n_splits, (size_t)B * D};
   if (int rc = launch_nt_gemm<PREC, kArcBN, kArcCtas, 0, StoreEpi, 0, 1>(maps, gx, sx, units, st)) return rc;
+  mark();
   //      dwh: A = d cos read MN-major (classes are the rows of the product), B = the X planes read MN-major
   if (int rc = operand_maps<T>(&maps[0], &maps[1], P(o_dh), P(o_dl), C, B, Cp, 0, true)) return rc;
   if (int rc = operand_maps<T>(&maps[2], &maps[3], P(o_xh), P(o_xl), D, B, D, 0, true)) return rc;
   StoreEpi::Params sw{F(o_gw), C, D, D, gw.n_splits, 0};
   if (int rc = launch_nt_gemm<PREC, kArcBN, kArcCtas, 0, StoreEpi, 1, 1>(maps, gw, sw, units, st)) return rc;
+  mark();
 
   // ---- 5. l2_normalize backward, X rows and W rows in one launch
   NormBwdJob jx{F(o_gx), gx.k_splits, (size_t)B * D, X, F(o_xi), B, dX};
   NormBwdJob jw{F(o_gw), 1, 0, W, F(o_wi), C, dW};
   launch_norm_bwd(jx, jw, D, st);
   DIF_LAUNCH_OK();
+  mark();
+  if (profile) {
+    cudaStreamSynchronize(st);
+    static const char* names[] = {"prep", "fwd", "dcos", "dx", "dw", "norm_bwd"};
+    fprintf(stderr, "arcface phases (us): fwd bn %d tps %d splits %d | dw bn %d tps %d splits %d | dx ksplits %d |", fwd.bn,
+            fwd.tiles_per_split, fwd.n_splits, gw.bn, gw.tiles_per_split, gw.n_splits, gx.k_splits);
+    for (int i = 0; i + 1 < pn; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, pev[i], pev[i + 1]);
+      fprintf(stderr, " %s %.1f", names[i], ms * 1e3f);
+    }
+    fprintf(stderr, "\n");
+    static unsigned long long th[3 * 148 * 8];
+    cudaMemcpy(th, trace_d, sizeof(th), cudaMemcpyDeviceToHost);
+    const char* gn[3] = {"fwd", "dx", "dw"};
+    for (int g = 0; g < 3; ++g) {
+      const unsigned long long* t = th + g * 148 * 8;
+      unsigned long long t00 = ~0ull;
+      for (int c = 0; c < 148; ++c)
+        if (t[c * 8]) t00 = std::min(t00, t[c * 8]);
+      fprintf(stderr, "  %s trace (us after the first CTA started; avg / max over CTAs that did work):", gn[g]);
+      static const char* sn[8] = {"entry", "setup", "1st_full", "mma_done", "1st_acc", "epi_done", "pre_sync", "exit"};
+      for (int k = 0; k < 8; ++k) {
+        double sum = 0, mx = 0;
+        int n = 0;
+        for (int c = 0; c < 148; ++c) {
+          if (!t[c * 8 + k] || !t[c * 8 + 5] || !t[c * 8 + 4]) continue;
+          const double v = (double)(t[c * 8 + k] - t00) * 1e-3;
+          sum += v;
+          mx = std::max(mx, v);
+          ++n;
+        }
+        if (n) fprintf(stderr, " %s %.1f/%.1f", sn[k], sum / n, mx);
+      }
+      fprintf(stderr, "\n");
+    }
+  }
   return DIF_OK;
 }
 

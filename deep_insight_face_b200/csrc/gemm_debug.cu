@@ -69,7 +69,7 @@ static int run_debug(const void* a0, const void* a1, const void* b0, const void*
 
 template <int PREC, int CTAS>
 static int run_time(const void* a0, const void* a1, const void* b0, const void* b1, int M, int N, int K, float* rs,
-                    int n_splits, int ares, cudaStream_t st) {
+                    int n_splits, int ares, cudaStream_t st, int bn = 256) {
   constexpr int BN = 256;
   const bool bf = PREC == 1;
   const int esz = bf ? 2 : 4;
@@ -77,11 +77,12 @@ static int run_time(const void* a0, const void* a1, const void* b0, const void* 
   CUtensorMap maps[4];
   if (int rc = make_tmap_2d(&maps[0], a0, M, K, (uint64_t)K * esz, GEMM_BM, bcols, bf)) return rc;
   if (int rc = make_tmap_2d(&maps[1], a1, M, K, (uint64_t)K * esz, GEMM_BM, bcols, bf)) return rc;
-  if (int rc = make_tmap_2d(&maps[2], b0, N, K, (uint64_t)K * esz, BN / CTAS, bcols, bf)) return rc;
-  if (int rc = make_tmap_2d(&maps[3], b1, N, K, (uint64_t)K * esz, BN / CTAS, bcols, bf)) return rc;
+  if (int rc = make_tmap_2d(&maps[2], b0, N, K, (uint64_t)K * esz, bn / CTAS, bcols, bf)) return rc;
+  if (int rc = make_tmap_2d(&maps[3], b1, N, K, (uint64_t)K * esz, bn / CTAS, bcols, bf)) return rc;
   GemmShape shape{};
+  shape.bn = bn;
   shape.m_blocks = (M + GEMM_BM * CTAS - 1) / (GEMM_BM * CTAS);
-  shape.n_tiles = (N + BN - 1) / BN;
+  shape.n_tiles = (N + bn - 1) / bn;
   shape.k_chunks = (K + (int)bcols - 1) / (int)bcols;
   shape.n_splits = std::max(1, std::min(n_splits, shape.n_tiles));
   shape.tiles_per_split = (shape.n_tiles + shape.n_splits - 1) / shape.n_splits;
@@ -202,6 +203,7 @@ extern "C" int dif_debug_gemm_layout(const float* A, const float* B, int M, int 
 extern "C" int dif_debug_gemm_time(int M, int N, int K, int precision, int ctas, int n_splits, int iters,
                                    float* ms_out) {
   const int ares = (ctas & 16) ? 1 : 0;
+  const int bn = (ctas >> 8) ? (ctas >> 8) : 256;   // tile width rides in the upper bits of `ctas` (0 = 256)
   ctas &= 15;
   DIF_REQUIRE(M > 0 && N > 0 && K >= 64 && K % 8 == 0 && ms_out && iters > 0, DIF_ERR_INVALID, "dif_debug_gemm_time: bad shape");
   DIF_REQUIRE(precision >= 0 && precision <= 2 && (ctas == 1 || ctas == 2), DIF_ERR_INVALID, "bad precision/ctas");
@@ -231,14 +233,14 @@ extern "C" int dif_debug_gemm_time(int M, int N, int K, int precision, int ctas,
   for (int i = 0; i < iters + 2 && rc == DIF_OK; ++i) {
     if (i == 2) cudaEventRecord(e0, nullptr);
     if (precision == DIF_PREC_BF16)
-      rc = ctas == 2 ? run_time<1, 2>(ab, ab, bb, bb, M, N, K, rs, n_splits, ares, nullptr)
-                     : run_time<1, 1>(ab, ab, bb, bb, M, N, K, rs, n_splits, ares, nullptr);
+      rc = ctas == 2 ? run_time<1, 2>(ab, ab, bb, bb, M, N, K, rs, n_splits, ares, nullptr, bn)
+                     : run_time<1, 1>(ab, ab, bb, bb, M, N, K, rs, n_splits, ares, nullptr, bn);
     else if (precision == DIF_PREC_TF32X1)
-      rc = ctas == 2 ? run_time<2, 2>(a, a, b, b, M, N, K, rs, n_splits, ares, nullptr)
-                     : run_time<2, 1>(a, a, b, b, M, N, K, rs, n_splits, ares, nullptr);
+      rc = ctas == 2 ? run_time<2, 2>(a, a, b, b, M, N, K, rs, n_splits, ares, nullptr, bn)
+                     : run_time<2, 1>(a, a, b, b, M, N, K, rs, n_splits, ares, nullptr, bn);
     else  // 3xTF32 timing uses the same plane for hi and lo: identical instruction stream and traffic
-      rc = ctas == 2 ? run_time<0, 2>(a, a, b, b, M, N, K, rs, n_splits, ares, nullptr)
-                     : run_time<0, 1>(a, a, b, b, M, N, K, rs, n_splits, ares, nullptr);
+      rc = ctas == 2 ? run_time<0, 2>(a, a, b, b, M, N, K, rs, n_splits, ares, nullptr, bn)
+                     : run_time<0, 1>(a, a, b, b, M, N, K, rs, n_splits, ares, nullptr, bn);
   }
   cudaEventRecord(e1, nullptr);
   cudaError_t e = cudaDeviceSynchronize();

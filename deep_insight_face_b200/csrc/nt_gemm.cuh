@@ -69,6 +69,7 @@ struct GemmShape {
   int chunks_per_ksplit;
   int l2_prefetch;      // 1: the producer prefetches B tiles into L2 two tiles ahead
   int bn;               // columns of B per tile (multiple of 32, <= BN); 0 = BN.  n_tiles counts tiles of this width
+  unsigned long long* trace;   // development aid: [CTA][8] globaltimer stamps of the kernel's phases (NULL: off)
 };
 
 template <int PREC, int BN, int CTAS>
@@ -189,6 +190,14 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
 
   constexpr int kBOff = ARES ? 0 : PT::kPlanes * T::kATile;  // offset of the B planes inside a stage
 
+  auto stamp = [&](int slot) {
+    if (shape.trace) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      shape.trace[(size_t)blockIdx.x * 8 + slot] = t;
+    }
+  };
+  if (threadIdx.x == 0) stamp(0);
   const int warp = threadIdx.x >> 5;
   const uint32_t cta_rank = (CTAS == 2) ? cluster_ctarank() : 0u;
   const bool leader = (cta_rank == 0);
@@ -226,6 +235,7 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stamp(1);
 
   if (warp == 4) {
     // ===================== TMA producer (one lane) =====================
@@ -328,6 +338,7 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(&full_bar[s], ph);
             tc_fence_after_sync();
+            if (it == 0) stamp(2);
             const uint32_t st = smem_u32(stage_base + s * kStage);
             const uint32_t a_addr = ARES ? smem_u32(a_res + kc * T::kATile) : st;
             const uint32_t a_lo_addr = ARES ? a_addr + (uint32_t)(shape.k_chunks * T::kATile) : st + T::kATile;
@@ -354,6 +365,7 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
         }
         if (ARES) tc_commit<CTAS>(a_empty);   // resident A block reusable once the item's MMAs retire
       }
+      stamp(3);
     }
   } else {
     // ===================== epilogue warps 0..3 (and 6..9 when EW == 8) =====================
@@ -380,6 +392,7 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
         epi.begin_tile(t * bn);
         mbar_wait(&acc_full[buf], aph);
         tc_fence_after_sync();
+        if (tc == 0 && threadIdx.x == 0) stamp(4);
         const uint32_t taddr = tmem_base + lane_base + (uint32_t)(buf * BN);
         uint32_t va[32], vb[32];
         tmem_ld32(taddr + (uint32_t)(cb * 32), va);
@@ -407,15 +420,18 @@ nt_gemm_rowscan_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid
       }
       epi.end_item(m_row, split);
     }
+    if (threadIdx.x == 0) stamp(5);
   }
 
   __syncwarp();  // single-lane roles rejoin their warp before the aligned barriers below
   tc_fence_before_sync();
+  if (threadIdx.x == 0) stamp(6);
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 5) {
     tc_fence_after_sync();
     tmem_dealloc<CTAS>(tmem_base, 512);
   }
+  if (threadIdx.x == 0) stamp(7);
 }
 
 // Host-side launch of one instantiation.  maps = {A hi, A lo, B hi, B lo}; single-plane modes pass

@@ -37,6 +37,7 @@ template <int SRC>
 __device__ __forceinline__ void prep_one_row(const PrepParams& p, int64_t r, int lane) {
   const float* s = SRC == 0 ? p.src + r * p.D : nullptr;
   float acc = 0.f;
+#pragma unroll 8   // the loads of a row are independent of the fma chain: keep several in flight
   for (int d = lane; d < p.D; d += 32) {
     const float x = SRC == 0 ? s[d] : synth_value(p.seed, (uint64_t)(p.row0 + r), (uint64_t)d, (uint64_t)p.D);
     acc = __fmaf_rn(x, x, acc);
@@ -44,6 +45,7 @@ __device__ __forceinline__ void prep_one_row(const PrepParams& p, int64_t r, int
   const float ss = canon_tree(acc);
   const float inv = p.normalize ? canon_inv_norm(ss) : 1.0f;
   float acc2 = 0.f;
+#pragma unroll 4
   for (int d = lane; d < p.D; d += 32) {
     float x = SRC == 0 ? s[d] : synth_value(p.seed, (uint64_t)(p.row0 + r), (uint64_t)d, (uint64_t)p.D);
     if (p.normalize) x = __fmul_rn(x, inv);

@@ -183,7 +183,8 @@ int dif_debug_nt_gemm(const float* A, const float* B, int M, int N, int K, float
 int dif_debug_gemm_layout(const float* A, const float* B, int M, int N, int K, float* C, int precision, int a_mn, int b_mn,
                           int bn, int n_splits, void* stream);
 
-/* diagnostic: average ms of the NT-GEMM main loop alone (checksum epilogue) on synthetic operands */
+/* diagnostic: average ms of the NT-GEMM main loop alone (checksum epilogue) on synthetic operands;
+ * ctas = 1 | 2 (+16: resident-A schedule; + (bn << 8): tile width bn instead of 256) */
 int dif_debug_gemm_time(int M, int N, int K, int precision, int ctas, int n_splits, int iters, float* ms_out);
 
 /* ---- batch-hard triplet losses ------------------------------------------------------------
