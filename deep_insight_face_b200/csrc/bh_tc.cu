@@ -56,32 +56,34 @@ struct MineEpi {
   // two warps per TMEM lane quarter: the epilogue (about 37 instructions per column) is latency bound with one
   static constexpr int kEpiWarps = 8;
   static constexpr int kEpiThreads = kEpiWarps * 32;
-  // labels + sq of the current tile, then a [16][256] scratch the insert path indexes dynamically (half a chunk
-  // at a time: a [32][256] scratch would leave no room for two 96 KB operand stages)
-  static int smem_bytes(const Params&) { return kMineBN * 8 + 16 * kEpiThreads * 4; }
+  // labels + sq of the current tile, then the label range [min, max] of each 32-column chunk
+  static int smem_bytes(const Params&) { return kMineBN * 8 + 2 * (kMineBN / 32) * 4; }
 
   const Params& p;
   int* s_lab;
   float* s_sq;
-  float* s_dv;   // this thread's column of the scratch: element i at s_dv[i * kEpiThreads]
+  int* s_lmin;   // [kMineBN / 32] smallest / largest label of each chunk of the current tile: a warp none of whose
+  int* s_lmax;   // anchors' labels falls inside a chunk's range has no positives there and skips the label compares
   int e_tid;     // index among the 256 epilogue threads: half * 128 + row
   float pv[kMineM], nv[kMineM], av[kMineM];
   int pi[kMineM], ni[kMineM], ai[kMineM];
+  float bp, bn, ba;   // best signed value seen so far per class (positives, negatives, overall): the window's anchor
   float row_sum, my_sq, win;
   int n_pos, my_lab, my_row, tile0;
 
   __device__ MineEpi(const Params& pp, uint8_t* smem, int row, int half)
       : p(pp), s_lab(reinterpret_cast<int*>(smem)), s_sq(reinterpret_cast<float*>(smem) + kMineBN),
-        s_dv(reinterpret_cast<float*>(smem) + 2 * kMineBN + half * GEMM_BM + row), e_tid(half * GEMM_BM + row),
-        row_sum(0.f), my_sq(0.f), win(0.f), n_pos(0), my_lab(-1), my_row(0), tile0(0) {}
+        s_lmin(reinterpret_cast<int*>(smem) + 2 * kMineBN), s_lmax(reinterpret_cast<int*>(smem) + 2 * kMineBN + kMineBN / 32),
+        e_tid(half * GEMM_BM + row), bp(-INFINITY), bn(-INFINITY), ba(-INFINITY), row_sum(0.f), my_sq(0.f), win(0.f),
+        n_pos(0), my_lab(-1), my_row(0), tile0(0) {}
 
   __device__ void begin_item(int m_row, int, int) {
     my_row = m_row;
     my_lab = m_row < p.B ? p.labels[m_row] : -1;
     my_sq = (!COSINE && m_row < p.B) ? p.sq[m_row] : 0.f;
     // A candidate only matters if it lies inside the re-rank window (2 eps of bh_rerank_kernel) of the row's best:
-    // accepting "better than the 4th kept OR within `win` of the best kept" keeps every such candidate (or fills
-    // the list inside the window, which the re-rank detects) and cuts the insert traffic roughly threefold.
+    // a column is inserted iff it is within `win` of the best value of its class seen so far in this work item (a
+    // list that fills up inside the window is detected by the re-rank, which then re-scans the row canonically).
     if (COSINE) {
       win = 4.1e-5f;
     } else {
@@ -94,6 +96,7 @@ struct MineEpi {
       pi[s] = ni[s] = ai[s] = -1;
     }
     if (COSINE) av[0] = -INFINITY;
+    bp = bn = ba = -INFINITY;
     row_sum = 0.f;
     n_pos = 0;
   }
@@ -108,6 +111,19 @@ struct MineEpi {
     }
     tile0 = col_begin;
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (e_tid < kMineBN / 32) {   // PK batches arrive grouped by identity: most chunks hold no positive of a given warp
+      int lo = 0x7fffffff, hi = -0x7fffffff;
+      for (int i = 0; i < 32; ++i) {
+        const int l = s_lab[e_tid * 32 + i];
+        if (col_begin + e_tid * 32 + i < p.B) {   // columns past the batch do not count
+          lo = min(lo, l);
+          hi = max(hi, l);
+        }
+      }
+      s_lmin[e_tid] = lo;
+      s_lmax[e_tid] = hi;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
   }
 
   __device__ __forceinline__ float dist_of(uint32_t acc_bits, int jl) const {
@@ -115,64 +131,92 @@ struct MineEpi {
     return COSINE ? a : __fsub_rn(__fadd_rn(my_sq, s_sq[jl]), __fmul_rn(2.f, a));
   }
 
-  // One chunk of 32 columns.  Branch-free pass: every column is tested against the worst kept candidate of its
-  // class (a signed compare: x = -d where smaller is better) and sets a bit of the lane's hit mask; only lanes
-  // with hits park the chunk in smem (registers cannot be indexed dynamically) and insert.  With 32 anchors in
-  // lockstep and lists that restart every work item some lane hits in most chunks, so the hit path has to be
-  // cheap: no second pass over the chunk.  CHECK = the chunk straddles the end of the batch (TMA zero fill).
-  template <bool CHECK>
-  __device__ __forceinline__ void consume_impl(int col0, const uint32_t (&acc)[32], uint32_t (&pending)[32]) {
+  // v[i] for a run-time i (registers cannot be indexed dynamically): five levels of selects
+  __device__ __forceinline__ static float pick32(const float (&v)[32], int i) {
+    float a[16], b[8], c[4];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = (i & 16) ? v[16 + k] : v[k];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b[k] = (i & 8) ? a[8 + k] : a[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[k] = (i & 4) ? b[4 + k] : b[k];
+    const float d0 = (i & 2) ? c[2] : c[0], d1 = (i & 2) ? c[3] : c[1];
+    return (i & 1) ? d1 : d0;
+  }
+
+  // One chunk of 32 columns, in the shape of the gallery's TopkEpi.  "Signed" space: q = -d where smaller is better, so
+  // larger q always wins.  Fast path, values only: per column a label compare, two selects and running maxima of the
+  // positives' and the negatives' q (plus the row sum / row maximum for the statistics of losses.py:72-80) - no
+  // indices, no lists.  Only a column within `win` (the re-rank window) of the best value seen so far can matter, so
+  // the chunk is left alone unless its maximum reaches best - win.  Slow path (warp-uniform): the thresholds are first
+  // raised by the chunk's own maxima - a column further than `win` below ANY value of its class is dead - then each
+  // lane builds the mask of its surviving columns and inserts them (see pick32).  With 32 anchors in lockstep most
+  // chunks of a fresh work item still take the slow path, but it now costs one mask pass plus about one insert.
+  // CHECK = the chunk straddles the end of the batch (TMA zero fill).
+  // NOPOS = no anchor of this warp has a positive in the chunk (label ranges): every column is a negative
+  template <bool CHECK, bool NOPOS>
+  __device__ __forceinline__ void consume_impl(int col0, const uint32_t (&acc)[32], uint32_t taddr, uint32_t (&pending)[32]) {
     const int base = col0 - tile0;
     constexpr float kSgnN = COSINE ? 1.f : -1.f;           // negatives: cosine keeps the largest, euclid the smallest
-    // an open list accepts anything
-    // (signed space: larger is better) the worst kept candidate, raised to best - win once a best exists
-    const float tp = fmaxf(pi[kMineM - 1] < 0 ? -INFINITY : -kSgnN * pv[kMineM - 1],
-                           pi[0] < 0 ? -INFINITY : -kSgnN * pv[0] - win);
-    const float tn = fmaxf(ni[kMineM - 1] < 0 ? -INFINITY : kSgnN * nv[kMineM - 1],
-                           ni[0] < 0 ? -INFINITY : kSgnN * nv[0] - win);
-    const float ta = fmaxf(ai[kMineM - 1] < 0 ? -INFINITY : av[kMineM - 1], ai[0] < 0 ? -INFINITY : av[0] - win);
     float dv[32];
-    float m_all = -INFINITY, rs = 0.f;
-    uint32_t mask = 0;
+    float cp = -INFINITY, cn = -INFINITY, ca = -INFINITY, rs = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       dv[i] = dist_of(acc[i], base + i);
       const bool valid = !CHECK || (col0 + i < p.B);
-      const bool same = s_lab[base + i] == my_lab;
+      const bool same = !NOPOS && s_lab[base + i] == my_lab;   // columns past the batch carry label -2: never "same"
       const float sx = kSgnN * dv[i];
-      bool hit = (same ? -sx : sx) > (same ? tp : tn);
-      if (!COSINE) hit = hit || dv[i] > ta;
-      mask |= (valid && hit) ? (1u << i) : 0u;
-      if (COSINE) m_all = fmaxf(m_all, valid ? dv[i] : -INFINITY);
+      if (!NOPOS) cp = fmaxf(cp, same ? -sx : -INFINITY);
+      cn = fmaxf(cn, (same || !valid) ? -INFINITY : sx);
+      if (!(NOPOS && COSINE)) ca = fmaxf(ca, valid ? dv[i] : -INFINITY);
       rs += valid ? dv[i] : 0.f;
     }
+    if (NOPOS && COSINE) ca = cn;   // all columns are negatives: the chunk's maximum is the negatives' maximum
     row_sum += rs;
-    if (COSINE) av[0] = fmaxf(av[0], m_all);   // running row maximum for the max(dists) statistic
-    if (__any_sync(0xffffffffu, mask != 0u)) {
-      tmem_ld_wait(pending);   // warp-uniform: no tcgen05.ld in flight while registers are shuffled below
+    if (COSINE) av[0] = fmaxf(av[0], ca);   // running row maximum for the max(dists) statistic
+    // (a class absent from the chunk has maximum -inf, which must not pass against a still-empty best of -inf)
+    const bool hit = (cp > -INFINITY && cp >= bp - win) || (cn > -INFINITY && cn >= bn - win) ||
+                     (!COSINE && ca > -INFINITY && ca >= ba - win);
+    if (!__any_sync(0xffffffffu, hit)) return;
+    tmem_ld_wait(pending);   // warp-uniform: no tcgen05.ld in flight while registers are shuffled below
+    bp = fmaxf(bp, cp);
+    bn = fmaxf(bn, cn);
+    if (!COSINE) ba = fmaxf(ba, ca);
+    const float tp = bp - win, tn = bn - win, ta = ba - win;
+    uint32_t mask = 0, mask_a = 0;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t m16 = (mask >> (16 * h)) & 0xFFFFu;
-        if (!m16) continue;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) s_dv[i * kEpiThreads] = dv[16 * h + i];
-        while (m16) {          // per-lane loop, no collectives inside
-          const int i = __ffs((int)m16) - 1;
-          m16 &= m16 - 1;
-          const float d = s_dv[i * kEpiThreads];
-          const int j = col0 + 16 * h + i;
-          if (s_lab[base + 16 * h + i] == my_lab) cand_insert<COSINE>(pv, pi, d, j);
-          else cand_insert<!COSINE>(nv, ni, d, j);
-          if (!COSINE) cand_insert<false>(av, ai, d, j);
-        }
+    for (int i = 0; i < 32; ++i) {
+      const bool valid = !CHECK || (col0 + i < p.B);
+      const bool same = !NOPOS && s_lab[base + i] == my_lab;
+      const float sx = kSgnN * dv[i];
+      const bool h = valid && ((same ? -sx : sx) >= (same ? tp : tn));
+      mask |= h ? (1u << i) : 0u;
+      if (!COSINE) mask_a |= (valid && dv[i] >= ta) ? (1u << i) : 0u;
+    }
+    // per-lane loop over the lane's own hits (usually one: the chunk's new best).  The value comes out of the
+    // register block through a 31-select tree: a TMEM re-read costs a few hundred cycles of latency PER column and the
+    // union of 32 lanes' hits is several columns in most chunks of a fresh work item.
+    uint32_t todo = mask | mask_a;
+    while (todo) {
+      const int i = __ffs((int)todo) - 1;
+      todo &= todo - 1;
+      const float d = pick32(dv, i);
+      const int j = col0 + i;
+      if ((mask >> i) & 1u) {
+        if (!NOPOS && s_lab[base + i] == my_lab) cand_insert<COSINE>(pv, pi, d, j);
+        else cand_insert<!COSINE>(nv, ni, d, j);
       }
+      if (!COSINE && ((mask_a >> i) & 1u)) cand_insert<false>(av, ai, d, j);
     }
   }
 
-  __device__ __forceinline__ void consume(int col0, const uint32_t (&acc)[32], uint32_t, uint32_t (&pending)[32]) {
+  __device__ __forceinline__ void consume(int col0, const uint32_t (&acc)[32], uint32_t taddr, uint32_t (&pending)[32]) {
     if (col0 >= p.B) return;                       // warp-uniform: the whole chunk is zero fill
-    if (col0 + 32 <= p.B) consume_impl<false>(col0, acc, pending);
-    else consume_impl<true>(col0, acc, pending);
+    const int ch = (col0 - tile0) >> 5;
+    const bool may_have_pos = my_lab >= s_lmin[ch] && my_lab <= s_lmax[ch];
+    if (col0 + 32 > p.B) consume_impl<true, false>(col0, acc, taddr, pending);
+    else if (__any_sync(0xffffffffu, may_have_pos)) consume_impl<false, false>(col0, acc, taddr, pending);
+    else consume_impl<false, true>(col0, acc, taddr, pending);
   }
 
   __device__ void end_item(int m_row, int slot) {
@@ -367,9 +411,20 @@ int bh_mine_tensor(const float* emb, const int32_t* labels, int B, int D, BhRec*
   shape.m_blocks = (B + GEMM_BM - 1) / GEMM_BM;
   shape.n_tiles = (B + kMineBN - 1) / kMineBN;
   shape.k_chunks = (D + 31) / 32;
-  shape.n_splits = std::max(1, std::min(shape.n_tiles, (2 * sms + shape.m_blocks - 1) / shape.m_blocks));
-  shape.tiles_per_split = (shape.n_tiles + shape.n_splits - 1) / shape.n_splits;
-  shape.n_splits = (shape.n_tiles + shape.tiles_per_split - 1) / shape.tiles_per_split;
+  // work item = (128 anchors, tiles_per_split column tiles): the split with the fewest waves x tiles wins, ties go to
+  // the longer item (the candidate lists restart with every item and the re-rank reads one record per split)
+  {
+    long best_cost = -1;
+    for (int tps = 1; tps <= shape.n_tiles; ++tps) {
+      const int ns = (shape.n_tiles + tps - 1) / tps;
+      const long cost = (long)((shape.m_blocks * ns + sms - 1) / sms) * tps;
+      if (best_cost < 0 || cost <= best_cost) {
+        best_cost = cost;
+        shape.tiles_per_split = tps;
+        shape.n_splits = ns;
+      }
+    }
+  }
   const int n_slots = 2 * shape.n_splits;   // one candidate record per (column range, epilogue half)
   if (int rc = g_tc.ensure((size_t)B * D, (size_t)n_slots * B)) return rc;
   DIF_CUDA_OK(cudaMemsetAsync(g_tc.gmax, 0, 4, st));

@@ -72,8 +72,11 @@ struct RerankParams {
 __device__ __forceinline__ float exact_score_warp(const float* __restrict__ q0, const float* __restrict__ q1,
                                                   const float* __restrict__ g0, const float* __restrict__ g1, int D,
                                                   int metric) {
-  // every operand is rebuilt as p0 + p1 (exact) when a lo plane exists
+  // every operand is rebuilt as p0 + p1 (exact) when a lo plane exists.  Unrolled: the loads of a row do not depend
+  // on the fma chain, and a candidate row is a cold 2-4 KB read - one load at a time is one DRAM round trip per
+  // 128 bytes (this loop was the serial tail of the sharded search, where every rank re-ranks the full query batch).
   float acc = 0.f;
+#pragma unroll 8
   for (int d = (int)(threadIdx.x & 31u); d < D; d += 32) {
     const float a = q1 ? __fadd_rn(q0[d], q1[d]) : q0[d];
     const float b = g1 ? __fadd_rn(g0[d], g1[d]) : g0[d];
@@ -104,7 +107,7 @@ __device__ __forceinline__ void emit_result(const RerankParams& p, int q, int sl
 
 // K7: one block per query.
 __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) {
-  extern __shared__ uint64_t sm_keys[];  // [S * kp]
+  extern __shared__ uint64_t sm_keys[];  // [S * kp] keys, then the query [D] floats
   __shared__ uint64_t red[32];
   __shared__ uint64_t ekeys[kRerankCap];
   __shared__ uint32_t rrows[kRerankCap];
@@ -120,6 +123,10 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
   }
   const uint64_t* src = p.cand + (size_t)q * n;
   for (int i = tid; i < n; i += blockDim.x) sm_keys[i] = src[i];
+  // the exact query (hi + lo) is staged once: every candidate of the window is scored against it
+  float* sm_q = reinterpret_cast<float*>(sm_keys + n);
+  for (int d = tid; d < p.D; d += blockDim.x)
+    sm_q[d] = p.q1 ? __fadd_rn(p.q0[(size_t)q * p.D + d], p.q1[(size_t)q * p.D + d]) : p.q0[(size_t)q * p.D + d];
   __syncthreads();
 
   // k-th largest approximate key (keys are unique: the row index is part of the key)
@@ -161,9 +168,8 @@ __global__ void __launch_bounds__(kRerankThreads) rerank_kernel(RerankParams p) 
   const int warp = tid >> 5, nw = blockDim.x >> 5;
   for (int i = warp; i < nr; i += nw) {
     const uint32_t row = rrows[i];
-    const float s = exact_score_warp(p.q0 + (size_t)q * p.D, p.q1 ? p.q1 + (size_t)q * p.D : nullptr,
-                                     p.g0 + (size_t)row * p.D, p.g1 ? p.g1 + (size_t)row * p.D : nullptr, p.D,
-                                     p.metric);
+    const float s = exact_score_warp(sm_q, nullptr, p.g0 + (size_t)row * p.D, p.g1 ? p.g1 + (size_t)row * p.D : nullptr,
+                                     p.D, p.metric);
     if ((tid & 31) == 0) ekeys[i] = make_key(p.metric == 1 ? s : -s, row);
   }
   __syncthreads();
@@ -774,7 +780,7 @@ int dif::gallery_search_impl(dif_gallery* g, const float* queries, int n_queries
   rp.flagged_count = g->flagged;
   rp.flagged_list = g->flagged + 1;
   rp.force_flag = g->opt_force_fallback;
-  const size_t rr_smem = (size_t)splits * kp * 8;
+  const size_t rr_smem = (size_t)splits * kp * 8 + (size_t)D * 4;
   DIF_REQUIRE(rr_smem <= 160 * 1024, DIF_ERR_CAPACITY, "candidate lists too large for the re-rank kernel");
   if (rr_smem > 40 * 1024)
     DIF_CUDA_OK(cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rr_smem));

@@ -509,13 +509,16 @@ int dif_gallery_search_sharded_host(dif_gallery_t* g, void* nccl_comm, int rank,
   DIF_REQUIRE(g, DIF_ERR_INVALID, "dif_gallery_search_sharded_host: null gallery");
   dif_shard_state* s = g->shard;
   DIF_REQUIRE(s, DIF_ERR_STATE, "dif_gallery_shard_attach has not been called on this gallery");
-  DIF_REQUIRE(bcast_root < world, DIF_ERR_INVALID, "bcast_root %d out of range", bcast_root);
+  DIF_REQUIRE(bcast_root < world && bcast_root >= DIF_UPLOAD_SLICED, DIF_ERR_INVALID, "bcast_root %d out of range", bcast_root);
+  const bool sliced = bcast_root == DIF_UPLOAD_SLICED && world > 1;
   const bool i_upload = bcast_root < 0 || bcast_root == rank;
   DIF_REQUIRE(!i_upload || queries_host, DIF_ERR_INVALID, "dif_gallery_search_sharded_host: this rank must supply the queries");
   DIF_REQUIRE(n_queries > 0 && n_queries <= s->max_q && k >= 1 && k <= s->max_k, DIF_ERR_CAPACITY,
               "attached for at most %d queries x top-%d; got %d x %d", s->max_q, s->max_k, n_queries, k);
   DIF_REQUIRE((scores_host != nullptr) == (ids_host != nullptr), DIF_ERR_INVALID, "pass both scores_host and ids_host, or neither");
-  const size_t qb = (size_t)n_queries * g->D * 4;
+  const size_t row_bytes = (size_t)g->D * 4;
+  const int slice_rows = (n_queries + world - 1) / world;          // sliced upload: rows each rank sends over PCIe
+  const size_t qb = sliced ? (size_t)slice_rows * world * row_bytes : (size_t)n_queries * row_bytes;
   const size_t nk = (size_t)n_queries * k;
   const size_t grows_off = (nk * 12 + 7) & ~(size_t)7;
   const size_t ob = grows_off + nk * 8;
@@ -525,19 +528,32 @@ int dif_gallery_search_sharded_host(dif_gallery_t* g, void* nccl_comm, int rank,
   float* dq = static_cast<float*>(g->d_stage);
   cudaStream_t st = g->own_stream;
   if (i_upload) {
+    // sliced: this rank moves only rows [rank * slice_rows, ...) over its PCIe link; NVLink assembles the batch below
+    const int row0 = sliced ? std::min(n_queries, rank * slice_rows) : 0;
+    const int rows = sliced ? std::min(slice_rows, n_queries - row0) : n_queries;
+    const size_t off0 = (size_t)row0 * row_bytes, ub = (size_t)rows * row_bytes;
+    const char* src = reinterpret_cast<const char*>(queries_host) + off0;
+    char* dst = reinterpret_cast<char*>(dq) + off0;
     cudaPointerAttributes attr{};
     const bool pinned = cudaPointerGetAttributes(&attr, queries_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     if (!pinned) cudaGetLastError();
     if (pinned) {
-      DIF_CUDA_OK(cudaMemcpyAsync(dq, queries_host, qb, cudaMemcpyHostToDevice, st));
+      if (ub) DIF_CUDA_OK(cudaMemcpyAsync(dst, src, ub, cudaMemcpyHostToDevice, st));
     } else {
       const size_t piece = (size_t)1 << 20;
-      for (size_t off = 0; off < qb; off += piece) {
-        const size_t n = std::min(piece, qb - off);
-        memcpy(hp + off, reinterpret_cast<const char*>(queries_host) + off, n);
-        DIF_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(dq) + off, hp + off, n, cudaMemcpyHostToDevice, st));
+      for (size_t off = 0; off < ub; off += piece) {
+        const size_t n = std::min(piece, ub - off);
+        memcpy(hp + off, src + off, n);
+        DIF_CUDA_OK(cudaMemcpyAsync(dst + off, hp + off, n, cudaMemcpyHostToDevice, st));
       }
     }
+  }
+  if (sliced) {
+    const NcclApi* api = nccl_api();
+    DIF_REQUIRE(api, DIF_ERR_STATE, "NCCL is not available in this process");
+    const size_t sb = (size_t)slice_rows * row_bytes;
+    DIF_NCCL_OK(api, api->AllGather(reinterpret_cast<char*>(dq) + (size_t)rank * sb, dq, sb, kNcclUint8,
+                                    static_cast<ncclComm_t>(nccl_comm), st));
   }
   if (bcast_root >= 0 && world > 1) {
     const NcclApi* api = nccl_api();

@@ -309,9 +309,10 @@ class ShardedGallery:
     def search_host(self, queries, k: int = 10, bcast_root: int = -1, want_result: bool = True):
         """Host-facing call: numpy queries in, numpy (scores, ids) out, through dif_gallery_search_sharded_host.
 
-        bcast_root < 0: every rank passes the (same) queries and uploads its own copy - straight from the caller's
-        buffer when it is page-locked.  bcast_root = r: only rank r's `queries` is read (the other ranks pass any
-        array of the same shape): uploaded once, NCCL-broadcast over NVLink.
+        bcast_root = -1: every rank passes the (same) queries and uploads its own copy - straight from the caller's
+        buffer when it is page-locked.  bcast_root = -2: every rank uploads 1/world of the rows, one NCCL all-gather
+        over NVLink assembles the batch (the PCIe bytes per rank shrink by the world size).  bcast_root = r >= 0: only
+        rank r's `queries` is read (the other ranks pass any array of the same shape): uploaded once, NCCL-broadcast.
         want_result=False skips this rank's D2H (returns None)."""
         i_upload = bcast_root < 0 or bcast_root == self.rank
         q = _ffi.host_array(queries, np.float32)

@@ -158,10 +158,16 @@ int dif_gallery_shard_attach(dif_gallery_t* g, void* nccl_comm, int rank, int wo
 /* The sharded search itself, stream-ordered, no host synchronisation.  queries: DEVICE [Q*D], identical on all ranks. */
 int dif_gallery_search_sharded(dif_gallery_t* g, void* nccl_comm, int rank, int world, const float* queries,
                                int n_queries, int k, float* scores, int64_t* ids, int64_t* grows, void* stream);
-/* HOST buffers.  bcast_root < 0: every rank uploads its own copy of the queries (straight from the caller's buffer
- * when it is page-locked); bcast_root = r: only rank r's queries_host is read, uploaded once and ncclBroadcast
- * over NVLink (other ranks may pass NULL).  scores_host / ids_host / grows_host may be NULL on ranks that do not
- * need the result (they skip the D2H).  Synchronises. */
+/* HOST buffers.  How the (identical) query batch reaches every GPU:
+ *   bcast_root = DIF_UPLOAD_EACH   (-1)  every rank uploads its own full copy over its PCIe link;
+ *   bcast_root = DIF_UPLOAD_SLICED (-2)  every rank uploads 1/world of the rows of its copy and one ncclAllGather
+ *                                        over NVLink assembles the batch on every GPU (PCIe bytes per rank / world);
+ *   bcast_root = r >= 0                  only rank r's queries_host is read, uploaded once and ncclBroadcast (other
+ *                                        ranks may pass NULL).
+ * Uploads go straight from the caller's buffer when it is page-locked.  scores_host / ids_host / grows_host may be NULL
+ * on ranks that do not need the result (they skip the D2H).  Synchronises. */
+#define DIF_UPLOAD_EACH (-1)
+#define DIF_UPLOAD_SLICED (-2)
 int dif_gallery_search_sharded_host(dif_gallery_t* g, void* nccl_comm, int rank, int world, const float* queries_host,
                                     int bcast_root, int n_queries, int k, float* scores_host, int64_t* ids_host,
                                     int64_t* grows_host);

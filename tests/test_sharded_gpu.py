@@ -94,6 +94,8 @@ def test_sharded_search_on_a_one_rank_communicator(gpu, orc, transport):
         hs, hi = g.search_host(pinned, k, bcast_root=0)
         assert np.array_equal(hi, wr) and np.array_equal(hs.view(np.uint32), ws.view(np.uint32))
         assert g.search_host(q, k, want_result=False) is None
+        hs, hi = g.search_host(q, k, bcast_root=-2)      # sliced upload degenerates to a full upload on one rank
+        assert np.array_equal(hi, wr) and np.array_equal(hs.view(np.uint32), ws.view(np.uint32))
         # more queries and a larger k than the buffers were attached for
         q2 = np.concatenate([q, q[:50] * 2.0])
         ws2, wr2 = orc.gallery_search(rows, q2, 24, 1)
@@ -164,7 +166,7 @@ def _two_rank_worker(rank, world, port, out_dir):
                         good = (np.array_equal(gr.cpu().numpy(), wr) and np.array_equal(ids.cpu().numpy(), want_ids)
                                 and np.array_equal(s.cpu().numpy().view(np.uint32), ws.view(np.uint32)))
                         ok = ok and good
-                    for root in (-1, 0, 1):
+                    for root in (-2, -1, 0, 1):
                         res = g.search_host(q if (root < 0 or root == rank) else np.zeros_like(q), k, bcast_root=root,
                                             want_result=(rank == 0))
                         if rank == 0:
