@@ -131,19 +131,6 @@ struct MineEpi {
     return COSINE ? a : __fsub_rn(__fadd_rn(my_sq, s_sq[jl]), __fmul_rn(2.f, a));
   }
 
-  // v[i] for a run-time i (registers cannot be indexed dynamically): five levels of selects
-  __device__ __forceinline__ static float pick32(const float (&v)[32], int i) {
-    float a[16], b[8], c[4];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) a[k] = (i & 16) ? v[16 + k] : v[k];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) b[k] = (i & 8) ? a[8 + k] : a[k];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) c[k] = (i & 4) ? b[4 + k] : b[k];
-    const float d0 = (i & 2) ? c[2] : c[0], d1 = (i & 2) ? c[3] : c[1];
-    return (i & 1) ? d1 : d0;
-  }
-
   // One chunk of 32 columns, in the shape of the gallery's TopkEpi.  "Signed" space: q = -d where smaller is better, so
   // larger q always wins.  Fast path, values only: per column a label compare, two selects and running maxima of the
   // positives' and the negatives' q (plus the row sum / row maximum for the statistics of losses.py:72-80) - no

@@ -37,9 +37,10 @@ __device__ __forceinline__ float key_score(uint64_t key) { return orderable_to_f
 //
 // Fast path per 32 columns: a max-reduction of the 32 scores and one compare against the thread's
 // drop threshold; the warp leaves it only if some lane has a score above its threshold.  The slow
-// path builds each lane's bitmask of such columns, ORs the masks across the warp and re-reads just
-// those accumulator columns from TMEM in a warp-uniform loop, so there is a single call site of
-// insert() and no per-column code replication.
+// path builds each lane's bitmask of such columns and every lane walks its own mask, fetching the
+// score with a register select tree (pick32): a single call site of insert(), no per-column code
+// replication, and no TMEM re-read (round 1 re-read the union of the warp's hit columns one at a
+// time, a few hundred cycles of tcgen05.ld latency each).
 //
 // Drop threshold of a thread = max(minimum of its own list once full,
 //                                  shared lower bound on the query's k-th best score - margin).
@@ -216,16 +217,12 @@ struct TopkEpi {
       tmem_ld_wait(pending);  // no tcgen05.ld in flight while this path shuffles registers
       uint32_t mask = 0;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mask |= (v[i] > thr) ? (1u << i) : 0u;
-      uint32_t todo = __reduce_or_sync(0xffffffffu, mask);
-      while (todo) {  // warp-uniform
-        const int i = __ffs((int)todo) - 1;
-        todo &= todo - 1;
-        const uint32_t bits = tmem_ld1(taddr + (uint32_t)i);
-        if (i < valid) {
-          const float s = score_of(bits, col0 + i);
-          if (s > thr) insert(s, col0 + i);
-        }
+      for (int i = 0; i < 32; ++i) mask |= (v[i] > thr) ? (1u << i) : 0u;   // (columns past the gallery hold -inf)
+      while (mask) {  // per lane: its own hits, in column order; the score comes out of the chunk in registers
+        const int i = __ffs((int)mask) - 1;
+        mask &= mask - 1;
+        const float s = pick32(v, i);
+        if (s > thr) insert(s, col0 + i);   // thr rises with every insert into a full list
       }
     }
   }

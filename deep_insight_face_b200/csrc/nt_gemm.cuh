@@ -122,6 +122,21 @@ inline bool plan_gemm_smem(int k_chunks, int epi_smem, GemmSmemPlan* out, int bn
 //     __device__ void end_item(int m_row, int split);
 //   };
 
+// v[i] for a run-time i: registers cannot be indexed dynamically, five levels of selects can.  Slow paths of the row
+// epilogues use it to fetch "the column that hit" from the chunk they already hold - re-reading one accumulator
+// column from TMEM instead costs a few hundred cycles of latency per column.
+__device__ __forceinline__ float pick32(const float (&v)[32], int i) {
+  float a[16], b[8], c[4];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = (i & 16) ? v[16 + k] : v[k];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) b[k] = (i & 8) ? a[8 + k] : a[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c[k] = (i & 4) ? b[4 + k] : b[k];
+  const float d0 = (i & 2) ? c[2] : c[0], d1 = (i & 2) ? c[3] : c[1];
+  return (i & 1) ? d1 : d0;
+}
+
 // An epilogue that declares `static constexpr int kEpiWarps = 8` gets TWO warps per TMEM lane quarter (warps 0-3
 // and 6-9): both own the same 32 rows and each consumes half of a tile's column chunks, so a latency-bound
 // epilogue has two warps per scheduler to hide behind.  Such an Epi is constructed with (params, smem, row, half)
