@@ -147,12 +147,14 @@ struct MineEpi {
     constexpr float kSgnN = COSINE ? 1.f : -1.f;           // negatives: cosine keeps the largest, euclid the smallest
     float dv[32];
     float cp = -INFINITY, cn = -INFINITY, ca = -INFINITY, rs = 0.f;
+    int np = 0;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
       dv[i] = dist_of(acc[i], base + i);
       const bool valid = !CHECK || (col0 + i < p.B);
       const bool same = !NOPOS && s_lab[base + i] == my_lab;   // columns past the batch carry label -2: never "same"
       const float sx = kSgnN * dv[i];
+      if (!NOPOS) np += same ? 1 : 0;
       if (!NOPOS) cp = fmaxf(cp, same ? -sx : -INFINITY);
       cn = fmaxf(cn, (same || !valid) ? -INFINITY : sx);
       if (!(NOPOS && COSINE)) ca = fmaxf(ca, valid ? dv[i] : -INFINITY);
@@ -160,6 +162,7 @@ struct MineEpi {
     }
     if (NOPOS && COSINE) ca = cn;   // all columns are negatives: the chunk's maximum is the negatives' maximum
     row_sum += rs;
+    n_pos += np;   // positives of this anchor (itself included) among the columns of this work item
     if (COSINE) av[0] = fmaxf(av[0], ca);   // running row maximum for the max(dists) statistic
     // (a class absent from the chunk has maximum -inf, which must not pass against a still-empty best of -inf)
     const bool hit = (cp > -INFINITY && cp >= bp - win) || (cn > -INFINITY && cn >= bn - win) ||
@@ -216,7 +219,7 @@ struct MineEpi {
       c.av[s] = av[s]; c.ai[s] = ai[s];
     }
     c.row_sum = row_sum;
-    c.n_pos = 0;   // counted by the re-rank kernel
+    c.n_pos = n_pos;
     p.cand[(size_t)slot * p.B + m_row] = c;
   }
 };
@@ -337,20 +340,25 @@ __global__ void __launch_bounds__(128) bh_rerank_kernel(const BhCand* __restrict
       else fold<!COSINE>(d, j, rec.neg_val, rec.neg_idx, rec.neg_cnt);
     }
   }
+  // row sum and number of positives (the anchor itself included): one record per lane, folded by a fixed butterfly
   float rs = 0.f;
-  for (int s = 0; s < n_slots; ++s) rs += cand[(size_t)s * B + r].row_sum;
-  int np_ = 0;   // positives of this anchor (itself included): label matches over the batch
-  {
-    const int my_l = labels[r];
-    for (int j = lane; j < B; j += 32) np_ += labels[j] == my_l ? 1 : 0;
-    for (int o = 16; o >= 1; o >>= 1) np_ += __shfl_xor_sync(0xffffffffu, np_, o);
+  int np_ = 0;
+  for (int s = lane; s < n_slots; s += 32) {
+    const BhCand& c = cand[(size_t)s * B + r];
+    rs += c.row_sum;
+    np_ += c.n_pos;
+  }
+  for (int o = 16; o >= 1; o >>= 1) {
+    rs += __shfl_xor_sync(0xffffffffu, rs, o);
+    np_ += __shfl_xor_sync(0xffffffffu, np_, o);
   }
   rec.row_sum = rs;
   rec.n_pos = np_;
   rec.pos_sum = 0.f;
   if (COSINE) {   // max(dists) is only a printed statistic for the cosine loss: the filter's value is exact enough
     float am = -INFINITY;
-    for (int s = 0; s < n_slots; ++s) am = fmaxf(am, cand[(size_t)s * B + r].av[0]);
+    for (int s = lane; s < n_slots; s += 32) am = fmaxf(am, cand[(size_t)s * B + r].av[0]);
+    for (int o = 16; o >= 1; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
     rec.all_max = am;
     rec.all_idx = 0;
     rec.all_cnt = 1;
