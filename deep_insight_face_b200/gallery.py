@@ -222,6 +222,7 @@ class ShardedGallery:
         self._comm = None          # ncclComm_t as an int
         self._own_comm = False
         self._attached = None      # (max_queries, max_k) the exchange buffers were sized for
+        self._explicit_ids = False
         # one rank has nobody to exchange with: search() is the plain local search unless a test asks for the full path
         self._direct = self.world == 1 and not single_rank_exchange
 
@@ -232,6 +233,7 @@ class ShardedGallery:
     def add_local(self, rows, ids=None) -> None:
         if ids is not None:
             self._attached = None      # explicit ids change the packed chunk layout: exchange buffers are re-made
+            self._explicit_ids = True
         self.local.add(rows, ids)
 
     # ------------------------------------------------------------------ communicator
@@ -296,6 +298,8 @@ class ShardedGallery:
         Q = q.shape[0]
         if self._direct:
             scores, ids, rows = self.local.search(q, k, return_rows=True)
+            if not self._explicit_ids:      # default ids are row_lo + row: the id IS the global row
+                return scores, ids, ids
             return scores, ids, torch.where(rows >= 0, rows.to(torch.int64) + self.row_lo, torch.full_like(ids, -1))
         self._attach(Q, k)
         scores = torch.empty((Q, k), dtype=torch.float32, device=q.device)
