@@ -494,7 +494,7 @@ def main():
         return float(t.item())
 
     def measure(precision: str, steps: int, warmup: int, full: bool, rows: int, queries: int, min_seconds: float = 0.0,
-                e2e_steps: int = 0, clocks: bool = False, keep: int = 16):
+                e2e_steps: int = 0, clocks: bool = False, keep: int = 64):
         """One precision mode on one workload (SPMD: every rank runs this).  Returns a dict of timings."""
         g = ShardedGallery(rows, D, "cosine", precision, device=local_rank, transport=args.transport)
         g.fill_synthetic(SEED_GALLERY)

@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include "bh_tile.cuh"
+#include "dif_ptx.cuh"
 
 namespace dif {
 
@@ -485,7 +486,7 @@ __device__ __forceinline__ void bh_grad_body(const float* __restrict__ x, const 
   __shared__ int4 s_c[CSR ? 1 : BH_GRAD_CHUNK];
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * BH_GRAD_WARPS + (threadIdx.x >> 5);
-  const bool active = r < B;
+  const bool active = r < B && (threadIdx.x >> 5) < BH_GRAD_WARPS;   // (the cluster step's block has spare warps)
   float acc[BH_MAX_KD];
 #pragma unroll
   for (int c = 0; c < BH_MAX_KD; ++c) acc[c] = 0.f;
@@ -661,6 +662,177 @@ __global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_merge_grad_kernel(
   bh_grad_body<COSINE, false>(x, labels, B, D, aux, s_rows, s_compact, nullptr, demb);
 }
 
+// Small batches in ONE launch (B <= 128: the reference's own configuration is P x K = 18 x 4 = 72 rows of 128
+// floats, common/losses.py:33-85 at training/triplet.py's batch shape).  At this size a step is a chain of
+// global-memory round trips, so the whole step runs inside one thread-block CLUSTER of ceil(B / 8) CTAs and nothing
+// but the inputs and the results touches global memory:
+//   1. every CTA stages the whole batch in its shared memory (36 KB at C1) and normalises it (cosine);
+//   2. CTA g mines anchors 8g..8g+7: its eight warps take interleaved 4-column steps of the canonical tile code
+//      (bh_tile.cuh), the per-warp partial records are merged in shared memory;
+//   3. the eight merged records (48 B each) are stored into EVERY CTA's shared memory (distributed shared memory,
+//      st.shared::cluster) and one cluster barrier publishes them;
+//   4. every CTA finalises all anchors from its copy (bh_merge_body with one "split": fillers, loss, coefficients,
+//      statistics; CTA 0 writes the outputs) and runs the gradient gather for its own 8 rows.
+// Same arithmetic, same records, same gradient code as the two-launch path (bit-identical indices and gradients; the
+// statistics' float sums are folded in a different - fixed - order).
+constexpr int BH_CL_WARPS = 8;    // (sixteen warps were tried: staging 0.7 us faster, mining and exchange 1.7 us slower)
+constexpr int BH_CL_MAX_B = 128;
+template <bool COSINE>
+__global__ void __launch_bounds__(BH_CL_WARPS * 32) bh_cluster_step_kernel(
+    const float* __restrict__ x, const int32_t* __restrict__ labels, int B, int D, float alpha, int soft,
+    const float* __restrict__ dloss, float* __restrict__ loss, int32_t* __restrict__ pos_idx_out,
+    int32_t* __restrict__ neg_idx_out, float* __restrict__ stats, float* __restrict__ demb,
+    unsigned long long* __restrict__ trace /* development aid: [CTA][6] globaltimer stamps, NULL = off */) {
+  extern __shared__ float sm[];
+  auto stamp = [&](int k) {
+    if (trace && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      trace[blockIdx.x * 6 + k] = t;
+    }
+  };
+  stamp(0);
+  const int G = (int)gridDim.x, Bp = G * BH_TI;
+  float* s_x = sm;                                         // [Bp][D] staged rows (cosine: normalised)
+  float* s_raw = COSINE ? s_x + (size_t)Bp * D : s_x;      // [Bp][D] the rows as given (cosine keeps both: the gradient
+                                                           // code recomputes x * inv and must find x where it looks)
+  float* s_aux = s_raw + (size_t)Bp * D;                   // [Bp] inverse norm | sum of squares
+  int* s_lab = reinterpret_cast<int*>(s_aux + Bp);         // [Bp]
+  BhRec* s_recs = reinterpret_cast<BhRec*>(s_lab + Bp);    // [Bp] merged record of every anchor (filled by all CTAs)
+  BhRec* s_part = s_recs + Bp;                             // [BH_CL_WARPS][BH_TI] this CTA's per-warp partials
+  __shared__ BhRow s_rows[BH_CL_MAX_B];
+  __shared__ int4 s_compact[BH_CL_MAX_B];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = (int)blockIdx.x;
+  const int kd = (D + 31) / 32;
+
+  // 1. stage: ONE bulk copy (TMA engine, no registers, a single round trip) brings the whole batch into shared
+  //    memory; then warp w normalises rows w, w + 8, ... out of it.  (Loading rows in register batches cost one
+  //    global round trip per batch: 6.4 us of the step at C1.)
+  __shared__ __align__(8) uint64_t s_bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+    const uint32_t bytes = (uint32_t)((size_t)B * D * 4);      // host: a multiple of 16, x 16-byte aligned
+    mbar_arrive_expect_tx(&s_bar, bytes);
+    bulk_load_1d(s_raw, x, bytes, &s_bar);
+  }
+  for (int r = B + warp; r < Bp; r += BH_CL_WARPS)             // rows past the batch are zero
+    for (int d = lane; d < D; d += 32) s_raw[(size_t)r * D + d] = 0.f;
+  for (int r = threadIdx.x; r < Bp; r += blockDim.x) s_lab[r] = r < B ? labels[r] : -2;
+  __syncthreads();                                             // the barrier is initialised for everyone
+  mbar_wait(&s_bar, 0);
+  for (int r = warp; r < Bp; r += BH_CL_WARPS) {
+    float v[BH_MAX_KD];
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < BH_MAX_KD; ++c) {
+      const int d = c * 32 + lane;
+      v[c] = (c < kd && d < D) ? s_raw[(size_t)r * D + d] : 0.f;
+      if (c < kd) acc = __fmaf_rn(v[c], v[c], acc);            // chain `lane`: d = lane, lane + 32, ... as in dif_canon.cuh
+    }
+    const float ss = canon_tree(acc);
+    const float inv = canon_inv_norm(ss);
+    if (COSINE) {
+#pragma unroll
+      for (int c = 0; c < BH_MAX_KD; ++c) {
+        const int d = c * 32 + lane;
+        if (c < kd && d < D) s_x[(size_t)r * D + d] = __fmul_rn(v[c], inv);
+      }
+    }
+    if (lane == 0) s_aux[r] = COSINE ? inv : ss;
+  }
+  __syncthreads();
+  stamp(1);
+
+  // 2. mine anchors 8g .. 8g + 7: warp w takes the column steps 4w, 4w + 32, ...
+  {
+    const int my_i = lane >> 2, gi = g * BH_TI + my_i;
+    const int my_lab = gi < B ? s_lab[gi] : -1;
+    const float my_aux = s_aux[gi];
+    float pos_val = COSINE ? INFINITY : -INFINITY, neg_val = COSINE ? -INFINITY : INFINITY, all_max = -INFINITY;
+    int pos_idx = -1, neg_idx = -1, all_idx = -1, pos_cnt = 0, neg_cnt = 0, all_cnt = 0, n_pos = 0;
+    float row_sum = 0.f, pos_sum = 0.f;
+    for (int j0 = warp * BH_TJ; j0 < B; j0 += BH_CL_WARPS * BH_TJ) {
+      const float dot = tile_step_dot(s_x + (size_t)g * BH_TI * D, s_x, D, kd, 0, lane, j0);
+      const int gj = j0 + (lane & 3);
+      if (gj < B && gi < B) {
+        const float dist = COSINE ? dot : __fsub_rn(__fadd_rn(my_aux, s_aux[gj]), __fmul_rn(2.f, dot));
+        row_sum += dist;
+        fold<false>(dist, gj, all_max, all_idx, all_cnt);
+        if (s_lab[gj] == my_lab) {
+          ++n_pos;
+          pos_sum += dist;
+          fold<COSINE>(dist, gj, pos_val, pos_idx, pos_cnt);
+        } else {
+          fold<!COSINE>(dist, gj, neg_val, neg_idx, neg_cnt);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {   // the 4 lanes of an anchor
+      const float pv = __shfl_xor_sync(0xffffffffu, pos_val, o);
+      const int pi = __shfl_xor_sync(0xffffffffu, pos_idx, o), pc = __shfl_xor_sync(0xffffffffu, pos_cnt, o);
+      const float nv = __shfl_xor_sync(0xffffffffu, neg_val, o);
+      const int ni = __shfl_xor_sync(0xffffffffu, neg_idx, o), nc = __shfl_xor_sync(0xffffffffu, neg_cnt, o);
+      const float av = __shfl_xor_sync(0xffffffffu, all_max, o);
+      const int ai = __shfl_xor_sync(0xffffffffu, all_idx, o), ac = __shfl_xor_sync(0xffffffffu, all_cnt, o);
+      merge<COSINE>(pv, pi, pc, pos_val, pos_idx, pos_cnt);
+      merge<!COSINE>(nv, ni, nc, neg_val, neg_idx, neg_cnt);
+      merge<false>(av, ai, ac, all_max, all_idx, all_cnt);
+      row_sum = __fadd_rn(row_sum, __shfl_xor_sync(0xffffffffu, row_sum, o));
+      pos_sum = __fadd_rn(pos_sum, __shfl_xor_sync(0xffffffffu, pos_sum, o));
+      n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
+    }
+    if ((lane & 3) == 0) {
+      BhRec r;
+      r.pos_val = pos_val; r.pos_idx = pos_idx; r.pos_cnt = pos_cnt;
+      r.neg_val = neg_val; r.neg_idx = neg_idx; r.neg_cnt = neg_cnt;
+      r.all_max = all_max; r.all_idx = all_idx; r.all_cnt = all_cnt;
+      r.row_sum = row_sum; r.n_pos = n_pos; r.pos_sum = pos_sum;
+      s_part[warp * BH_TI + my_i] = r;
+    }
+  }
+  __syncthreads();
+  stamp(2);
+  // merge the eight warps' partials of each anchor (fixed warp order), then hand the record to every CTA
+  if (threadIdx.x < BH_TI) {
+    const int a = threadIdx.x;
+    BhRec m = s_part[a];
+    for (int w = 1; w < BH_CL_WARPS; ++w) {
+      const BhRec& q = s_part[w * BH_TI + a];
+      merge<COSINE>(q.pos_val, q.pos_idx, q.pos_cnt, m.pos_val, m.pos_idx, m.pos_cnt);
+      merge<!COSINE>(q.neg_val, q.neg_idx, q.neg_cnt, m.neg_val, m.neg_idx, m.neg_cnt);
+      merge<false>(q.all_max, q.all_idx, q.all_cnt, m.all_max, m.all_idx, m.all_cnt);
+      m.row_sum = __fadd_rn(m.row_sum, q.row_sum);
+      m.pos_sum = __fadd_rn(m.pos_sum, q.pos_sum);
+      m.n_pos += q.n_pos;
+    }
+    s_part[a] = m;
+  }
+  __syncthreads();
+  {
+    constexpr int kWords = (int)(sizeof(BhRec) / 4) * BH_TI;   // the CTA's eight merged records
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(s_part);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_recs + (size_t)g * BH_TI);
+    for (int t = threadIdx.x; t < kWords * G; t += blockDim.x) {
+      const int cta = t / kWords, w = t - cta * kWords;
+      st_cluster_u32(dst + w, (uint32_t)cta, src[w]);
+    }
+  }
+  cluster_sync_all();   // release / acquire: every CTA now holds all Bp merged records
+  stamp(3);
+
+  // 4. finalize every anchor locally (one "split"), CTA 0 writes loss / indices / statistics; then the gradient
+  bh_merge_body<COSINE>(s_recs, 1, B, alpha, soft, dloss, loss, pos_idx_out, neg_idx_out, stats, s_rows, s_compact, g == 0);
+  __syncthreads();
+  stamp(4);
+  // the gradient gather reads rows, labels and norms out of shared memory: at this size its cost is the latency of
+  // its dependent loads (mined index -> row -> ...), a few cycles here against an L2 round trip each
+  if (demb) bh_grad_body<COSINE, false>(s_raw, s_lab, B, D, s_aux, s_rows, s_compact, nullptr, demb);
+  stamp(5);
+}
+
 // one-hot [B, C] -> int32 class ids (tf.argmax(labels, axis=1): first maximum), losses.py:35
 __global__ void argmax_rows_kernel(const float* __restrict__ onehot, int B, int C, int32_t* __restrict__ out) {
   const int lane = threadIdx.x & 31;
@@ -771,6 +943,62 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
   if (!configured) {
     DIF_CUDA_OK(cudaFuncSetAttribute(bh_mine_kernel<COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
+  }
+  // small batches: the whole step in one cluster launch
+  if (g_bh_force_path == 0 || g_bh_force_path == 3) {
+    const int G = (B + BH_TI - 1) / BH_TI;
+    const size_t cl_smem = ((size_t)G * BH_TI * D * (COSINE ? 2 : 1) + 2 * (size_t)G * BH_TI) * 4 +
+                           ((size_t)G * BH_TI + BH_CL_WARPS * BH_TI) * sizeof(BhRec);
+    if (B <= BH_CL_MAX_B && G <= 16 && D <= 32 * BH_MAX_KD && cl_smem <= 160 * 1024 && ((size_t)B * D * 4) % 16 == 0 &&
+        (reinterpret_cast<uintptr_t>(emb) & 15u) == 0) {
+      static int cluster_ok = -1;   // per instantiation: can a cluster of this kernel be scheduled at all?
+      auto kern = bh_cluster_step_kernel<COSINE>;
+      if (cluster_ok < 0) {
+        cluster_ok = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) == cudaSuccess &&
+                     cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+        if (!cluster_ok) cudaGetLastError();
+      }
+      if (cluster_ok) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)G);
+        cfg.blockDim = dim3(BH_CL_WARPS * 32);
+        cfg.dynamicSmemBytes = cl_smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)G;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        static const bool profile = getenv("DIF_BH_PROFILE") != nullptr;   // development aid
+        static unsigned long long* trace_d = nullptr;
+        if (profile && !trace_d) cudaMalloc((void**)&trace_d, 16 * 6 * 8);
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, emb, labels, B, D, alpha, soft, dloss, loss, pos_idx, neg_idx, stats, demb,
+                                                 profile ? trace_d : (unsigned long long*)nullptr);
+        if (e == cudaSuccess) {
+          count_launch();
+          if (profile) {
+            unsigned long long th[16 * 6];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(th, trace_d, sizeof(th), cudaMemcpyDeviceToHost);
+            unsigned long long t0 = ~0ull;
+            for (int c = 0; c < G; ++c) t0 = std::min(t0, th[c * 6]);
+            static const char* nm[6] = {"entry", "staged", "mined", "exchanged", "finalized", "gradient"};
+            fprintf(stderr, "bh cluster step (us after the first CTA started, CTA 0 / max over CTAs):");
+            for (int k = 0; k < 6; ++k) {
+              unsigned long long mx = 0;
+              for (int c = 0; c < G; ++c) mx = std::max(mx, th[c * 6 + k]);
+              fprintf(stderr, " %s %.1f/%.1f", nm[k], (double)(th[k] - t0) * 1e-3, (double)(mx - t0) * 1e-3);
+            }
+            fprintf(stderr, "\n");
+          }
+          return DIF_OK;
+        }
+        cudaGetLastError();   // (a cluster this large does not fit this device / partition: use the two-launch path)
+        cluster_ok = 0;
+      }
+    }
   }
   // large batches: tensor-core filter + canonical re-rank (bh_tc.cu), then a multi-block finalize
   const bool tensor_path = (g_bh_force_path == 2 || (g_bh_force_path == 0 && B >= 512)) && D >= 32 && D % 4 == 0;
@@ -1155,7 +1383,8 @@ int dif_batch_all(const float* emb, const int32_t* labels, int B, int D, float a
 }
 
 int dif_batch_hard_set_path(int path) {
-  DIF_REQUIRE(path >= 0 && path <= 2, DIF_ERR_INVALID, "dif_batch_hard_set_path: 0 auto, 1 CUDA-core miner, 2 tensor-core miner");
+  DIF_REQUIRE(path >= 0 && path <= 3, DIF_ERR_INVALID,
+              "dif_batch_hard_set_path: 0 auto, 1 CUDA-core miner (two launches), 2 tensor-core miner, 3 one-launch cluster step");
   g_bh_force_path = path;
   return DIF_OK;
 }

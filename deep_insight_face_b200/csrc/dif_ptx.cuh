@@ -96,6 +96,18 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// distributed shared memory: store one word at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void st_cluster_u32(void* local_smem_ptr, uint32_t cta, uint32_t v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_smem_ptr)), "r"(cta));
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
@@ -106,6 +118,14 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int32_t c0,
                "r"(c0), "r"(c1)
                : "memory");
 }
+// 1-D bulk copy global -> shared::cta (no tensor map): `bytes` a multiple of 16, both addresses 16-byte aligned;
+// completion is credited to the CTA-local mbarrier like a TMA tile.
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // 2-D tiled load global -> shared::cta, completion on a CTA-local mbarrier.
 __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, uint64_t* bar, int32_t c0, int32_t c1) {
   asm volatile(

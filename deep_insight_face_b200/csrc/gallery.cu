@@ -583,12 +583,11 @@ int dif_gallery_remove(dif_gallery_t* g, const int64_t* rows_host, int64_t n, vo
                 "dif_gallery_remove: rows must be strictly ascending and below the gallery size %lld (entry %lld = %lld)",
                 (long long)g->size, (long long)i, (long long)rows_host[i]);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int64_t* removed = nullptr;
-  DIF_CUDA_OK(cudaMalloc((void**)&removed, (size_t)n * 8));
-  struct Free {
-    void* p;
-    ~Free() { cudaFree(p); }
-  } guard{removed};
+  // the sorted row list lives behind the compaction chunk in the handle's device staging block: no allocation per call
+  const int64_t chunk = std::max<int64_t>(1, (int64_t)(32u << 20) / (g->D * 4));
+  const size_t list_off = ((size_t)chunk * g->D * 4 + 255) & ~(size_t)255;
+  if (int rc = ensure_stage(g, list_off + (size_t)n * 8)) return rc;
+  int64_t* removed = reinterpret_cast<int64_t*>(static_cast<char*>(g->d_stage) + list_off);
   DIF_CUDA_OK(cudaMemcpyAsync(removed, rows_host, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   if (!g->has_ids) {   // ids were the row numbers: make them explicit before rows move
     if (!g->ids) DIF_CUDA_OK(cudaMalloc((void**)&g->ids, (size_t)g->capacity * 8));
@@ -597,8 +596,6 @@ int dif_gallery_remove(dif_gallery_t* g, const int64_t* rows_host, int64_t n, vo
     g->has_ids = true;
   }
   const int64_t first = rows_host[0];
-  const int64_t chunk = std::max<int64_t>(1, (int64_t)(32u << 20) / (g->D * 4));
-  if (int rc = ensure_stage(g, (size_t)chunk * g->D * 4)) return rc;
   struct Arr {
     void* base;
     int words;   // 4-byte words per row
@@ -620,7 +617,7 @@ int dif_gallery_remove(dif_gallery_t* g, const int64_t* rows_host, int64_t n, vo
     }
   }
   DIF_CUDA_OK(cudaMemsetAsync(g->gsq + (g->size - n), 0, (size_t)n * 4, st));
-  DIF_CUDA_OK(cudaStreamSynchronize(st));   // `removed` is freed on return
+  DIF_CUDA_OK(cudaStreamSynchronize(st));   // rows_host (pageable) and the staging block may be reused on return
   g->size -= n;
   return DIF_OK;
 }

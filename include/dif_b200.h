@@ -214,8 +214,10 @@ int dif_batch_hard(const float* emb, const int32_t* labels, int B, int D, int va
 int dif_batch_hard_host(const float* emb_host, const int32_t* labels_host, int B, int D, int variant, float alpha,
                         float* loss_host, int32_t* pos_idx_host, int32_t* neg_idx_host, float* stats_host,
                         const float* dloss_host, float* demb_host, int precision);
-/* test knob: 0 = automatic (tensor-core filter + canonical re-rank for B >= 512, CUDA-core miner below),
- * 1 = always the CUDA-core miner, 2 = always the tensor-core miner.  Results are identical. */
+/* test knob: 0 = automatic (B <= 128: the whole step in one thread-block-cluster launch; B >= 512: tensor-core filter +
+ * canonical re-rank; CUDA-core miner + fused merge / gradient in between), 1 = always the CUDA-core miner (two
+ * launches), 2 = always the tensor-core miner, 3 = the cluster step where it fits.  Mined indices, losses and
+ * gradients are identical; the printed statistics' float sums are folded in a path-specific fixed order. */
 int dif_batch_hard_set_path(int path);
 /* deep_insight_face/common/losses.py:131-148 (BatchAllTripletLoss, cosine): loss [B] = pos_loss + neg_loss;
  * demb [B*D] gradient of sum_i dloss[i]*loss[i] (dloss NULL -> 1/B each; demb NULL skips the backward pass). */

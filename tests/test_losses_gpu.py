@@ -374,3 +374,53 @@ def test_tf_bridge_executes_under_a_fake_tensorflow(gpu, monkeypatch):
     g1 = fake.grad_fns[-1](_FakeTensor(dl))            # backward of step 1 still uses margin 1.0
     close(g1.numpy(), want1["grad"])
     assert abs(auto.auto_alpha - want1["stats"][0] * 0.1) <= 1e-4 * want1["stats"][0]
+
+
+@pytest.mark.parametrize("B,D", [(72, 128), (8, 64), (128, 256), (100, 96), (33, 512), (5, 32)])
+@pytest.mark.parametrize("variant", ["cosine", "euclid", "euclid_soft"])
+def test_one_launch_cluster_step_equals_the_two_launch_path(gpu, lib, B, D, variant):
+    """B <= 128 runs as ONE thread-block-cluster launch (csrc/batch_hard.cu:bh_cluster_step_kernel).  It must give the
+    same loss bits, mined indices and gradient bits as the CUDA-core miner + merge / gradient launches, and the
+    oracle's answer - on a batch with duplicates, a zero row and a singleton identity."""
+    import torch
+
+    from deep_insight_face_b200 import _ffi
+    from deep_insight_face_b200.common.losses import batch_hard
+    from oracle import losses_oracle as lo
+
+    rng = np.random.default_rng(B + D)
+    P = max(1, B // 4)
+    lab = (np.arange(B) % P).astype(np.int32)
+    lab[-1] = P + 7                                   # an identity with a single sample
+    emb = (rng.standard_normal((P + 8, D))[lab % (P + 8)] + 0.7 * rng.standard_normal((B, D))).astype(np.float32)
+    if B >= 8:
+        emb[3] = emb[1]                               # exact duplicates: tied extremes split the gradient
+        emb[6] = 0.0                                  # a zero row
+    code = {"cosine": _ffi.LOSS_BH_COSINE, "euclid": _ffi.LOSS_BH_EUCLIDEAN,
+            "euclid_soft": _ffi.LOSS_BH_EUCLIDEAN | _ffi.LOSS_SOFT_MARGIN}[variant]
+    alpha = 0.35 if variant == "cosine" else 0.3 * D
+    x = torch.from_numpy(emb).cuda()
+    y = torch.from_numpy(lab).cuda()
+    dl = torch.from_numpy(rng.random(B).astype(np.float32)).cuda()
+    out = {}
+    try:
+        for path in (1, 3):
+            _ffi.check(lib.dif_batch_hard_set_path(path))
+            n0 = _ffi.launch_count()
+            loss, grad, info = batch_hard(y, x, code, alpha, dloss=dl)
+            torch.cuda.synchronize()
+            out[path] = (loss.cpu().numpy(), grad.cpu().numpy(), info["pos_idx"].cpu().numpy(), info["neg_idx"].cpu().numpy(),
+                         info["stats"].cpu().numpy(), _ffi.launch_count() - n0)
+    finally:
+        _ffi.check(lib.dif_batch_hard_set_path(0))
+    fits = ((B + 7) // 8 * 8) * D * 4 * (2 if variant == "cosine" else 1) <= 150 * 1024   # the staged batch must fit one SM
+    assert out[1][5] >= 2 and out[3][5] == (1 if fits else out[1][5])   # one launch vs miner + merge / gradient
+    assert np.array_equal(out[1][0].view(np.uint32), out[3][0].view(np.uint32))
+    assert np.array_equal(out[1][2], out[3][2]) and np.array_equal(out[1][3], out[3][3])
+    assert np.array_equal(out[1][1].view(np.uint32), out[3][1].view(np.uint32))
+    np.testing.assert_allclose(out[3][4], out[1][4], rtol=1e-5)
+    fn = lo.batch_hard_cosine if variant == "cosine" else lo.batch_hard_euclidean
+    want = fn(lab, emb, alpha, dloss=dl.cpu().numpy(), soft=variant.endswith("soft"))
+    assert np.array_equal(out[3][2], want["pos_idx"]) and np.array_equal(out[3][3], want["neg_idx"])
+    close(out[3][0], want["loss"], scale=max(1.0, np.abs(want["loss"]).max()))
+    close(out[3][1], want["grad"])
