@@ -209,7 +209,8 @@ def secondary_metrics(torch, device, peaks, lib):
         out[name] = {"steps_per_s": 1e3 / ms, "ms_per_step": ms, "ungraphed_call_steps_per_s": 1e3 / ms_call,
                      "e2e_steps_per_s": 1e3 / host_ms, "e2e_ms": host_ms, "launches_per_step": n_launch,
                      "path": "tcgen05 3xTF32 filter + canonical re-rank + inverse-list gradient" if B >= 512 else
-                             "canonical fp32 CUDA-core miner, fused merge + gradient",
+                             "one thread-block-cluster launch: bulk-copy staging, canonical fp32 mining, DSMEM record exchange, "
+                             "finalize + gradient out of shared memory",
                      "alg_gflop_fwd": flops / 1e9, "roofline": roof,
                      "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "steps/s", "cores": cores, "kind": "port",
                                       "sample": f"{cpu_n} full steps (fwd + bwd), oracle/cpu_paths.py:batch_hard_step "

@@ -374,8 +374,8 @@ static int run_arcface(const float* X, const float* W, const int32_t* y, int B, 
   // dxh is 2 B C D over a long K (classes), dwh the same flops over many row blocks.
   static const bool serial = getenv("DIF_ARC_SERIAL") != nullptr;   // development aid: one after the other, all pairs each
   const bool side_by_side = bwd && !serial && units >= 8;
-  // (46 % of the pairs to dxh measured best at C2: 36 % 131.5 us, 41 % 125.6, 46 % 123.5, 52 % 150.5 - one pair short of
-  // a whole wave of dxh items doubles its time)
+  // (46 % of the pairs to dxh measured best at C2: 36 % 131.5 us, 41 % 125.6, 46 % 123.5, 52 % 150.5 - there dwh's 120
+  // items need a fourth wave on the remaining 36 pairs)
   const int units_x = side_by_side ? std::max(2, (units * 46) / 100) : units, units_w = side_by_side ? units - units_x : units;
   GemmShape gx{};   // dxh [B, D] = dcos [B, C] x wh [C, D], split over K = classes
   gx.m_blocks = fwd.m_blocks;
