@@ -114,6 +114,44 @@ __global__ void __launch_bounds__(256) sweep_hist_kernel(const float* __restrict
     atomicAdd(&hist[((size_t)f * 2 + (issame[i] ? 1 : 0)) * (T + 1) + lo], 1u);
   }
 }
+// Same histogram with block-private bins in shared memory (and the thresholds staged beside them): every distance
+// costs a binary search in shared memory and one shared-memory atomic; a block adds its non-empty bins to the global
+// histogram once at the end.  The global-atomic form above serialises when the distances crowd into a few bins -
+// 1M pairs that all exceed the last threshold are 1M atomics on two addresses (0.35 ms; 14 us here).
+__global__ void __launch_bounds__(512) sweep_hist_smem_kernel(const float* __restrict__ dist,
+                                                              const uint8_t* __restrict__ issame,
+                                                              const int32_t* __restrict__ fold, int64_t n, int F,
+                                                              const double* __restrict__ thr, int T,
+                                                              unsigned int* __restrict__ hist /* [F][2][T+1] */) {
+  extern __shared__ double s_thr_raw[];
+  double* s_thr = s_thr_raw;                                          // [T]
+  unsigned int* s_h = reinterpret_cast<unsigned int*>(s_thr + T);     // [F][2][T+1]
+  const int bins = F * 2 * (T + 1);
+  for (int t = threadIdx.x; t < T; t += blockDim.x) s_thr[t] = thr[t];
+  for (int b = threadIdx.x; b < bins; b += blockDim.x) s_h[b] = 0u;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double d = (double)dist[i];
+    int lo = 0, hi = T;  // first t in [0, T] with d < thr[t]; T = none
+    if (d != d) {
+      lo = T;
+    } else {
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (d < s_thr[mid]) hi = mid;
+        else lo = mid + 1;
+      }
+    }
+    const int f = fold ? fold[i] : 0;
+    if (f < 0 || f >= F) continue;
+    atomicAdd(&s_h[(f * 2 + (issame[i] ? 1 : 0)) * (T + 1) + lo], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < bins; b += blockDim.x) {
+    const unsigned int v = s_h[b];
+    if (v) atomicAdd(&hist[b], v);
+  }
+}
 // one block per (fold, class): inclusive scan of the histogram -> counts
 __global__ void __launch_bounds__(256) sweep_scan_kernel(const unsigned int* __restrict__ hist, int T,
                                                          int64_t* __restrict__ counts /* [F][T][4] */) {
@@ -404,8 +442,20 @@ int dif_threshold_sweep(const float* dist, const uint8_t* issame, const int32_t*
     const size_t hb = (size_t)n_folds * 2 * (T + 1) * sizeof(unsigned int);
     DIF_CUDA_OK(cudaMemsetAsync(workspace, 0, hb, st));
     if (N > 0) {
-      const int blocks = (int)std::min<int64_t>((N + 255) / 256, (int64_t)device_sm_count() * 8);
-      sweep_hist_kernel<<<blocks, 256, 0, st>>>(dist, issame, fold, N, n_folds, thresholds, T, workspace);
+      const size_t sm_bytes = (size_t)T * 8 + hb;
+      if (sm_bytes <= 200 * 1024 && N >= 4096) {   // block-private bins fit one SM's shared memory
+        static bool configured = false;
+        if (!configured) {
+          DIF_CUDA_OK(cudaFuncSetAttribute(sweep_hist_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          configured = true;
+        }
+        const int per_sm = sm_bytes <= 100 * 1024 ? 2 : 1;
+        const int blocks = (int)std::min<int64_t>((N + 511) / 512, (int64_t)device_sm_count() * per_sm);
+        sweep_hist_smem_kernel<<<blocks, 512, sm_bytes, st>>>(dist, issame, fold, N, n_folds, thresholds, T, workspace);
+      } else {
+        const int blocks = (int)std::min<int64_t>((N + 255) / 256, (int64_t)device_sm_count() * 8);
+        sweep_hist_kernel<<<blocks, 256, 0, st>>>(dist, issame, fold, N, n_folds, thresholds, T, workspace);
+      }
       DIF_LAUNCH_OK();
     }
     sweep_scan_kernel<<<n_folds * 2, 256, 0, st>>>(workspace, T, counts);
