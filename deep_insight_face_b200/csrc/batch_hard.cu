@@ -337,10 +337,12 @@ __device__ __forceinline__ void bh_stats_body(const double* __restrict__ partial
     for (int k = 0; k < 5; ++k) t[k] += __shfl_xor_sync(0xffffffffu, t[k], o);
   if (lane == 0) {
     const uint32_t gmax_o = (uint32_t)(*gmax_key >> 32);
-    stats[0] = (float)(t[0] / ((double)B * (double)B));
-    stats[1] = (float)(t[1] / (double)B);
-    stats[2] = (float)(t[2] / (double)B);
-    stats[3] = __uint_as_float((gmax_o & 0x80000000u) ? (gmax_o ^ 0x80000000u) : ~gmax_o);
+    if (stats) {
+      stats[0] = (float)(t[0] / ((double)B * (double)B));
+      stats[1] = (float)(t[1] / (double)B);
+      stats[2] = (float)(t[2] / (double)B);
+      stats[3] = __uint_as_float((gmax_o & 0x80000000u) ? (gmax_o ^ 0x80000000u) : ~gmax_o);
+    }
     *cg_out = t[4] > 0.0 ? (float)(t[3] / t[4]) : 0.f;
   }
 }
@@ -349,94 +351,6 @@ __global__ void bh_stats_kernel(const double* __restrict__ partials, int n_parts
                                 const unsigned long long* __restrict__ gmax_key, float* __restrict__ stats,
                                 float* __restrict__ cg_out) {
   bh_stats_body(partials, n_parts, B, gmax_key, stats, cg_out);
-}
-
-// Statistics (warp 0) + the inverse of the mining relation for the gradient gather, one block:
-//   off [B+1], csr [off[B]] : the anchors whose (untied) mined positive or negative is row r, CSR by r.  Counts,
-//                             the exclusive scan and the cursors live in shared memory, so nothing persists
-//                             between steps; entries of one row land in atomic (arbitrary) order and the gradient
-//                             warp walks them in ascending anchor order, which keeps the sums reproducible.
-//   tied [n_tied]           : anchors whose extreme is tied (compact x / y == -2), ascending (ordered compaction).
-constexpr int BH_INV_THREADS = 1024;
-constexpr int BH_INV_MAX_B = 8192;
-__global__ void __launch_bounds__(BH_INV_THREADS) bh_stats_inverse_kernel(
-    const double* __restrict__ partials, int n_parts, int B, const unsigned long long* __restrict__ gmax_key,
-    float* __restrict__ stats, float* __restrict__ cg_out, const int4* __restrict__ compact, int* __restrict__ off,
-    int* __restrict__ csr, int* __restrict__ tied, int* __restrict__ n_tied_out) {
-  extern __shared__ int s_inv[];
-  int* s_off = s_inv;            // [B + 1] counts, then exclusive offsets
-  int* s_cur = s_inv + B + 1;    // [B] fill cursors
-  __shared__ int s_warp[BH_INV_THREADS / 32];
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  if (warp == 0) bh_stats_body(partials, n_parts, B, gmax_key, stats, cg_out);
-  for (int i = t; i <= B; i += BH_INV_THREADS) {
-    s_off[i] = 0;
-    if (i < B) s_cur[i] = 0;
-  }
-  __syncthreads();
-  for (int a = t; a < B; a += BH_INV_THREADS) {
-    const int4 c = compact[a];
-    if (c.x >= 0) atomicAdd(&s_off[c.x], 1);
-    if (c.y >= 0) atomicAdd(&s_off[c.y], 1);
-  }
-  __syncthreads();
-  // exclusive scan: a contiguous run per thread, then a two-level scan of the run totals
-  const int per = (B + BH_INV_THREADS - 1) / BH_INV_THREADS;
-  const int r0 = min(B, t * per), r1 = min(B, r0 + per);
-  int run = 0;
-  for (int i = r0; i < r1; ++i) run += s_off[i];
-  int incl = run;
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    int w = s_warp[lane];
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += v;
-    }
-    s_warp[lane] = w;   // inclusive totals of the warps
-  }
-  __syncthreads();
-  int base = (warp > 0 ? s_warp[warp - 1] : 0) + incl - run;
-  for (int i = r0; i < r1; ++i) {
-    const int d = s_off[i];
-    s_off[i] = base;
-    base += d;
-  }
-  if (t == BH_INV_THREADS - 1) s_off[B] = s_warp[BH_INV_THREADS / 32 - 1];
-  __syncthreads();
-  for (int i = t; i <= B; i += BH_INV_THREADS) off[i] = s_off[i];
-  for (int a = t; a < B; a += BH_INV_THREADS) {
-    const int4 c = compact[a];
-    if (c.x >= 0) csr[s_off[c.x] + atomicAdd(&s_cur[c.x], 1)] = a;
-    if (c.y >= 0) csr[s_off[c.y] + atomicAdd(&s_cur[c.y], 1)] = a;
-  }
-  // tied anchors, ascending
-  int filled = 0;
-  for (int a0 = 0; a0 < B; a0 += BH_INV_THREADS) {
-    const int a = a0 + t;
-    bool is_tied = false;
-    if (a < B) {
-      const int4 c = compact[a];
-      is_tied = c.x == -2 || c.y == -2;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, is_tied);
-    __syncthreads();
-    if (lane == 0) s_warp[warp] = __popc(m);
-    __syncthreads();
-    int before = filled, total = 0;
-    for (int w = 0; w < BH_INV_THREADS / 32; ++w) {
-      if (w < warp) before += s_warp[w];
-      total += s_warp[w];
-    }
-    if (is_tied) tied[before + __popc(m & ((1u << lane) - 1u))] = a;
-    filled += total;
-  }
-  if (t == 0) *n_tied_out = filled;
 }
 
 // canonical dist(r, j) recomputed by one warp (tie resolution)
@@ -473,17 +387,15 @@ __device__ __forceinline__ void axpy_row(float (&acc)[BH_MAX_KD], float w, const
 constexpr int BH_GRAD_WARPS = 8;
 constexpr int BH_GRAD_CHUNK = 1024;   // compact records staged per pass (16 KB)
 
-// CSR = false: every block stages the compact records of all anchors and its warps scan them (O(B) per row);
-// CSR = true : the rows that mined r come from the inverse lists of bh_stats_inverse_kernel (O(in-degree) per row).
+// MODE 0: every block stages the compact records of all anchors and its warps scan them (O(B) per row);
+// MODE 2: the rows that mined r come from the bitmaps bh_grad_map_kernel built in shared memory (O(in-degree) per row).
 // Both visit the contributing anchors in ascending order, so the two variants give bit-identical gradients.
-template <bool COSINE, bool CSR>
+template <bool COSINE, int MODE>
 __device__ __forceinline__ void bh_grad_body(const float* __restrict__ x, const int32_t* __restrict__ labels, int B, int D,
                                              const float* __restrict__ aux,   // inv norm | sum sq
                                              const BhRow* rows, const int4* compact, const float* __restrict__ cg_dev,
-                                             float* __restrict__ demb, const int* __restrict__ off = nullptr,
-                                             const int* __restrict__ csr = nullptr, const int* __restrict__ tied = nullptr,
-                                             const int* __restrict__ n_tied_ptr = nullptr) {
-  __shared__ int4 s_c[CSR ? 1 : BH_GRAD_CHUNK];
+                                             float* __restrict__ demb, const unsigned* s_bits = nullptr) {
+  __shared__ int4 s_c[MODE != 0 ? 1 : BH_GRAD_CHUNK];
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * BH_GRAD_WARPS + (threadIdx.x >> 5);
   const bool active = r < B && (threadIdx.x >> 5) < BH_GRAD_WARPS;   // (the cluster step's block has spare warps)
@@ -513,36 +425,40 @@ __device__ __forceinline__ void bh_grad_body(const float* __restrict__ x, const 
         if (labels[j] != my_lab && warp_dist<COSINE>(x, aux, D, r, j) == me.neg_val)
           axpy_row<COSINE>(acc, me.coef_neg, x, aux, D, r, j);
   }
-  if (CSR) {
-    // --- rows that mined r, from the inverse lists, merged with the (usually empty) tied list in ascending order
+  if (MODE == 2) {
+    // --- rows that mined r, from this warp's bitmap over the anchors (bit a set = anchor a mined r, or a is tied):
+    // set bits come out in ascending anchor order, the order of the staged scan below
     if (active) {
-      const int beg = off[r], end = off[r + 1], n_tied = *n_tied_ptr;
-      const int mine = beg + lane < end ? csr[beg + lane] : 0x7fffffff;   // lists of <= 32 entries stay in registers
-      int last = -1, ti = 0;
-      while (true) {
-        int nc = mine > last ? mine : 0x7fffffff;
-        for (int t = beg + 32 + lane; t < end; t += 32) {
-          const int a = csr[t];
-          if (a > last && a < nc) nc = a;
+      const int W = (B + 31) >> 5;
+      const unsigned* bm = s_bits + (threadIdx.x >> 5) * W;
+      const unsigned* tm = s_bits + BH_GRAD_WARPS * W;
+      for (int w0 = 0; w0 < W; w0 += 32) {
+        const int wi = w0 + lane;
+        const unsigned mb = wi < W ? bm[wi] : 0u, tb = wi < W ? tm[wi] : 0u;
+        unsigned any = __ballot_sync(0xffffffffu, (mb | tb) != 0u);
+        while (any) {
+          const int src = __ffs((int)any) - 1;
+          any &= any - 1;
+          const unsigned tw = __shfl_sync(0xffffffffu, tb, src);
+          unsigned u = __shfl_sync(0xffffffffu, mb, src) | tw;
+          while (u) {
+            const int bit = __ffs((int)u) - 1;
+            u &= u - 1;
+            const int jj = (w0 + src) * 32 + bit;
+            const int4 c = compact[jj];
+            float w = 0.f;
+            if (c.x == r) w += __int_as_float(c.z);
+            if (c.y == r) w += __int_as_float(c.w);
+            if ((tw >> bit) & 1u) {
+              const BhRow o = rows[jj];
+              const float dv = warp_dist<COSINE>(x, aux, D, jj, r);
+              const bool same = labels[jj] == my_lab;
+              if (c.x == -2 && same && dv == o.pos_val) w += o.coef_pos;
+              if (c.y == -2 && !same && dv == o.neg_val) w += o.coef_neg;
+            }
+            if (w != 0.f) axpy_row<COSINE>(acc, w, x, aux, D, r, jj);
+          }
         }
-        for (int o = 16; o >= 1; o >>= 1) nc = min(nc, __shfl_xor_sync(0xffffffffu, nc, o));
-        const int nt = ti < n_tied ? tied[ti] : 0x7fffffff;
-        const int jj = min(nc, nt);
-        if (jj == 0x7fffffff) break;
-        const int4 c = compact[jj];
-        float w = 0.f;
-        if (c.x == r) w += __int_as_float(c.z);
-        if (c.y == r) w += __int_as_float(c.w);
-        if (jj == nt) {
-          ++ti;
-          const BhRow o = rows[jj];
-          const float dv = warp_dist<COSINE>(x, aux, D, jj, r);
-          const bool same = labels[jj] == my_lab;
-          if (c.x == -2 && same && dv == o.pos_val) w += o.coef_pos;
-          if (c.y == -2 && !same && dv == o.neg_val) w += o.coef_neg;
-        }
-        if (w != 0.f) axpy_row<COSINE>(acc, w, x, aux, D, r, jj);
-        last = jj;
       }
     }
   } else
@@ -632,16 +548,39 @@ __global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_grad_kernel(const float
                                                                      const int4* __restrict__ compact,
                                                                      const float* __restrict__ cg_dev,
                                                                      float* __restrict__ demb) {
-  bh_grad_body<COSINE, false>(x, labels, B, D, aux, rows, compact, cg_dev, demb);
+  bh_grad_body<COSINE, 0>(x, labels, B, D, aux, rows, compact, cg_dev, demb);
 }
 
+// Tensor-core path: statistics + "who mined me" + gradient gather in ONE launch (round 2 had a one-block kernel build
+// inverse CSR lists first: 15 us of a 68 us step at B = 4096).  Every block folds the finalize kernel's partial sums
+// itself (a fixed order, so every block gets the same filler share; block 0 also writes the statistics), scans the
+// compact records of all anchors once (16 B each, L2 resident) and sets bit a of row r's bitmap in shared memory when
+// anchor a mined one of the block's 8 rows, plus a bitmap of the tied anchors; each warp then walks the set bits of
+// its row in ascending anchor order - the summation order of the staged scan, so the gradients stay bit-identical.
+constexpr int BH_MAP_MAX_B = 32768;   // (8 + 1) bitmaps of B bits: 36 KB of shared memory
 template <bool COSINE>
-__global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_grad_csr_kernel(
+__global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_grad_map_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ labels, int B, int D, const float* __restrict__ aux,
-    const BhRow* __restrict__ rows, const int4* __restrict__ compact, const float* __restrict__ cg_dev,
-    float* __restrict__ demb, const int* __restrict__ off, const int* __restrict__ csr, const int* __restrict__ tied,
-    const int* __restrict__ n_tied) {
-  bh_grad_body<COSINE, true>(x, labels, B, D, aux, rows, compact, cg_dev, demb, off, csr, tied, n_tied);
+    const BhRow* __restrict__ rows, const int4* __restrict__ compact, const double* __restrict__ partials, int n_parts,
+    const unsigned long long* __restrict__ gmax_key, float* __restrict__ stats, float* __restrict__ demb) {
+  extern __shared__ unsigned s_map[];   // [BH_GRAD_WARPS + 1][W]
+  __shared__ float s_cg;
+  const int W = (B + 31) >> 5;
+  const int r0 = blockIdx.x * BH_GRAD_WARPS;
+  for (int i = threadIdx.x; i < (BH_GRAD_WARPS + 1) * W; i += blockDim.x) s_map[i] = 0u;
+  if ((threadIdx.x >> 5) == 0 && (!COSINE || blockIdx.x == 0))
+    bh_stats_body(partials, n_parts, B, gmax_key, blockIdx.x == 0 ? stats : nullptr, &s_cg);
+  __syncthreads();
+#pragma unroll 4
+  for (int a = threadIdx.x; a < B; a += BH_GRAD_WARPS * 32) {
+    const int4 c = compact[a];
+    const unsigned ux = (unsigned)(c.x - r0), uy = (unsigned)(c.y - r0), bit = 1u << (a & 31);
+    if (ux < (unsigned)BH_GRAD_WARPS) atomicOr(&s_map[ux * W + (a >> 5)], bit);
+    if (uy < (unsigned)BH_GRAD_WARPS) atomicOr(&s_map[uy * W + (a >> 5)], bit);
+    if (c.x == -2 || c.y == -2) atomicOr(&s_map[BH_GRAD_WARPS * W + (a >> 5)], bit);
+  }
+  __syncthreads();
+  bh_grad_body<COSINE, 2>(x, labels, B, D, aux, rows, compact, COSINE ? nullptr : &s_cg, demb, s_map);
 }
 
 // Small batches (B <= 256): merge + gradient in one launch.  Every block redoes the (tiny) merge of all anchors
@@ -659,7 +598,7 @@ __global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_merge_grad_kernel(
   bh_merge_body<COSINE>(recs, n_splits, B, alpha, soft, dloss, loss, pos_idx_out, neg_idx_out, stats, s_rows, s_compact,
                         blockIdx.x == 0);
   __syncthreads();
-  bh_grad_body<COSINE, false>(x, labels, B, D, aux, s_rows, s_compact, nullptr, demb);
+  bh_grad_body<COSINE, 0>(x, labels, B, D, aux, s_rows, s_compact, nullptr, demb);
 }
 
 // Small batches in ONE launch (B <= 128: the reference's own configuration is P x K = 18 x 4 = 72 rows of 128
@@ -681,7 +620,7 @@ template <bool COSINE>
 __global__ void __launch_bounds__(BH_CL_WARPS * 32) bh_cluster_step_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ labels, int B, int D, float alpha, int soft,
     const float* __restrict__ dloss, float* __restrict__ loss, int32_t* __restrict__ pos_idx_out,
-    int32_t* __restrict__ neg_idx_out, float* __restrict__ stats, float* __restrict__ demb,
+    int32_t* __restrict__ neg_idx_out, float* __restrict__ stats, float* __restrict__ demb, int sliced,
     unsigned long long* __restrict__ trace /* development aid: [CTA][6] globaltimer stamps, NULL = off */) {
   extern __shared__ float sm[];
   auto stamp = [&](int k) {
@@ -715,7 +654,17 @@ __global__ void __launch_bounds__(BH_CL_WARPS * 32) bh_cluster_step_kernel(
     fence_mbar_init();
     const uint32_t bytes = (uint32_t)((size_t)B * D * 4);      // host: a multiple of 16, x 16-byte aligned
     mbar_arrive_expect_tx(&s_bar, bytes);
-    bulk_load_1d(s_raw, x, bytes, &s_bar);
+    if (!sliced) bulk_load_1d(s_raw, x, bytes, &s_bar);
+  }
+  if (sliced) {
+    // the batch lives in page-locked HOST memory (dif_batch_hard_host): G whole-batch reads would cross PCIe G times,
+    // so CTA g fetches only its own 8 rows and the copy engine multicasts them into every CTA of the cluster
+    cluster_sync_all();   // every CTA's barrier is armed before the first slice can land
+    if (threadIdx.x == 0) {
+      const size_t off = (size_t)g * BH_TI * D;
+      const uint32_t slice = (uint32_t)((size_t)min(BH_TI, B - g * BH_TI) * D * 4);   // host: D % 4 == 0
+      bulk_load_1d_multicast(s_raw + off, x + off, slice, &s_bar, (uint16_t)((1u << G) - 1u));
+    }
   }
   for (int r = B + warp; r < Bp; r += BH_CL_WARPS)             // rows past the batch are zero
     for (int d = lane; d < D; d += 32) s_raw[(size_t)r * D + d] = 0.f;
@@ -829,7 +778,7 @@ __global__ void __launch_bounds__(BH_CL_WARPS * 32) bh_cluster_step_kernel(
   stamp(4);
   // the gradient gather reads rows, labels and norms out of shared memory: at this size its cost is the latency of
   // its dependent loads (mined index -> row -> ...), a few cycles here against an L2 round trip each
-  if (demb) bh_grad_body<COSINE, false>(s_raw, s_lab, B, D, s_aux, s_rows, s_compact, nullptr, demb);
+  if (demb) bh_grad_body<COSINE, 0>(s_raw, s_lab, B, D, s_aux, s_rows, s_compact, nullptr, demb);
   stamp(5);
 }
 
@@ -866,7 +815,6 @@ struct BhWorkspace {
   float* aux = nullptr;
   int4* compact = nullptr;
   double* partials = nullptr;              // [ceil(rows / 256)][5]
-  int* inv = nullptr;                      // off [rows + 1] | csr [2 rows] | tied [rows] | n_tied [1]
   unsigned long long* gmax_key = nullptr;  // [1] + float cg right behind it
   size_t row_cap = 0;
   int ensure(size_t n_rec, size_t n_rows) {
@@ -882,8 +830,6 @@ struct BhWorkspace {
       retire_device_block(aux);
       retire_device_block(compact);
       retire_device_block(partials);
-      retire_device_block(inv);
-      inv = nullptr;
       rows = nullptr;
       aux = nullptr;
       compact = nullptr;
@@ -893,7 +839,6 @@ struct BhWorkspace {
       DIF_CUDA_OK(cudaMalloc((void**)&aux, n_rows * sizeof(float)));
       DIF_CUDA_OK(cudaMalloc((void**)&compact, n_rows * sizeof(int4)));
       DIF_CUDA_OK(cudaMalloc((void**)&partials, ((n_rows + 255) / 256) * 5 * sizeof(double)));
-      DIF_CUDA_OK(cudaMalloc((void**)&inv, (4 * n_rows + 2) * sizeof(int)));
       if (!gmax_key) DIF_CUDA_OK(cudaMalloc((void**)&gmax_key, 16));
       row_cap = n_rows;
     }
@@ -922,6 +867,7 @@ struct BhHostStage {
 };
 static thread_local BhHostStage g_bh_stage;
 
+static thread_local bool g_bh_host_input = false;   // set by dif_batch_hard_host around its zero-copy call
 static int g_bh_force_path = 0;   // 0 auto, 1 CUDA-core miner, 2 tensor-core miner (tests)
 
 template <bool COSINE>
@@ -974,8 +920,10 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
         static const bool profile = getenv("DIF_BH_PROFILE") != nullptr;   // development aid
         static unsigned long long* trace_d = nullptr;
         if (profile && !trace_d) cudaMalloc((void**)&trace_d, 16 * 6 * 8);
+        static const bool force_sliced = getenv("DIF_BH_SLICED") != nullptr;   // A/B switch
+        const int sliced = ((g_bh_host_input || force_sliced) && D % 4 == 0) ? 1 : 0;
         const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, emb, labels, B, D, alpha, soft, dloss, loss, pos_idx, neg_idx, stats, demb,
-                                                 profile ? trace_d : (unsigned long long*)nullptr);
+                                                 sliced, profile ? trace_d : (unsigned long long*)nullptr);
         if (e == cudaSuccess) {
           count_launch();
           if (profile) {
@@ -1012,23 +960,10 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
     DIF_LAUNCH_OK();
     float* cg = reinterpret_cast<float*>(g_ws.gmax_key + 1);
     cg_dev = cg;
-    if (demb && B <= BH_INV_MAX_B) {
-      // statistics + inverse mining lists in one block, then the O(in-degree) gradient gather
-      static bool inv_configured = false;
-      if (!inv_configured) {
-        DIF_CUDA_OK(cudaFuncSetAttribute(bh_stats_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (2 * BH_INV_MAX_B + 1) * (int)sizeof(int)));
-        inv_configured = true;
-      }
-      int* off = g_ws.inv;
-      int* csr = off + B + 1;
-      int* tied = csr + 2 * (size_t)B;
-      int* n_tied = tied + B;
-      bh_stats_inverse_kernel<<<1, BH_INV_THREADS, (2 * (size_t)B + 1) * sizeof(int), st>>>(
-          g_ws.partials, fb, B, g_ws.gmax_key, stats, cg, g_ws.compact, off, csr, tied, n_tied);
-      DIF_LAUNCH_OK();
-      bh_grad_csr_kernel<COSINE><<<(B + BH_GRAD_WARPS - 1) / BH_GRAD_WARPS, BH_GRAD_WARPS * 32, 0, st>>>(
-          emb, labels, B, D, g_ws.aux, g_ws.rows, g_ws.compact, cg_dev, demb, off, csr, tied, n_tied);
+    if (demb && B <= BH_MAP_MAX_B) {
+      const size_t map_smem = (size_t)(BH_GRAD_WARPS + 1) * ((B + 31) / 32) * sizeof(unsigned);
+      bh_grad_map_kernel<COSINE><<<(B + BH_GRAD_WARPS - 1) / BH_GRAD_WARPS, BH_GRAD_WARPS * 32, map_smem, st>>>(
+          emb, labels, B, D, g_ws.aux, g_ws.rows, g_ws.compact, g_ws.partials, fb, g_ws.gmax_key, stats, demb);
       DIF_LAUNCH_OK();
       return DIF_OK;
     }
@@ -1318,15 +1253,25 @@ int dif_batch_hard_host(const float* emb_host, const int32_t* labels_host, int B
   memcpy(h + eb, labels_host, (size_t)B * 4);
   if (dloss_host) memcpy(h + eb + lb, dloss_host, (size_t)B * 4);
   cudaStream_t st = g_bh_stage.st;
-  DIF_CUDA_OK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st));
+  // The reference's own batch (18 x 4 rows of 128 floats) is one cluster launch of ~16 us: two DMA copies around it
+  // would cost more than the step.  The page-locked staging block is device-visible (unified addressing), so the
+  // kernel reads its 36 KB of input and writes its 37 KB of results across PCIe itself: one launch, one wait.
+  static const bool staged_only = getenv("DIF_BH_HOST_STAGED") != nullptr;   // A/B switch
+  const bool zero_copy = !staged_only && B <= BH_CL_MAX_B && (g_bh_force_path == 0 || g_bh_force_path == 3);
+  if (zero_copy) d = h;
+  else DIF_CUDA_OK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, st));
   char* o = d + in_bytes;
+  struct HostInputScope {
+    explicit HostInputScope(bool on) { g_bh_host_input = on && getenv("DIF_BH_HOST_UNSLICED") == nullptr; }
+    ~HostInputScope() { g_bh_host_input = false; }
+  } scope(zero_copy);
   if (int rc = dif_batch_hard((const float*)d, (const int32_t*)(d + eb), B, D, variant, alpha, (float*)o,
                               (int32_t*)(o + lb), (int32_t*)(o + 2 * lb), (float*)(o + 3 * lb),
                               dloss_host ? (const float*)(d + eb + lb) : nullptr,
                               demb_host ? (float*)(o + 3 * lb + 256) : nullptr, precision, st))
     return rc;
   const size_t back = demb_host ? out_bytes : 3 * lb + 256;
-  DIF_CUDA_OK(cudaMemcpyAsync(h + in_bytes, o, back, cudaMemcpyDeviceToHost, st));
+  if (!zero_copy) DIF_CUDA_OK(cudaMemcpyAsync(h + in_bytes, o, back, cudaMemcpyDeviceToHost, st));
   DIF_CUDA_OK(cudaStreamSynchronize(st));
   char* ho = h + in_bytes;
   memcpy(loss_host, ho, (size_t)B * 4);
