@@ -61,6 +61,141 @@ __global__ void __launch_bounds__(BH_WARPS * 32) tfa_pdist_kernel(const float* _
   }
 }
 
+// ---------------------------------------------------------------- K1 (D <= 128): the same matrix, one thread per entry
+// The canonical dot product (dif_canon.cuh) is 32 strided fma chains plus a fixed pairing tree.  Nothing in that
+// definition needs 32 lanes: here ONE thread runs all 32 chains of its 4 x 4 entries one after the other - visiting
+// them in bit-reversed order (0, 16, 8, 24, ...) turns the butterfly t[i] += t[i ^ o], o = 16 .. 1, into a binary
+// counter over at most six pending partial sums - so an entry costs 128 fma + 31 add, no shuffles, and the operands
+// come out of shared memory as one 16-byte load per (chain, row): rows are staged chain-major, [chain][row][k], with
+// the row index XOR-swizzled by the chain so that the staging stores spread over all banks.  Bit-identical to
+// tfa_pdist_kernel (same products, same order; padding terms are fma(0, 0, acc) = acc).
+constexpr int PF_T = 64;          // block tile: 64 x 64 entries, 16 x 16 threads
+constexpr int PF_THREADS = 256;
+
+__global__ void __launch_bounds__(256) tfa_sqnorm_kernel(const float* __restrict__ x, int B, int D, float* __restrict__ sq) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= B) return;
+  float acc = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float t = x[(size_t)r * D + d];
+    acc = __fmaf_rn(t, t, acc);
+  }
+  acc = canon_tree(acc);
+  if (lane == 0) sq[r] = acc;
+}
+
+__device__ __forceinline__ int pf_slot(int l, int row) { return (l * PF_T + (row ^ ((l >> 2) & 7))) * 4; }
+
+// rows [row0, row0 + 64) -> dst [32 chains][64 rows][4]: element d = l + 32 k of a row lands at (l, row, k)
+__device__ __forceinline__ void pf_stage(const float* __restrict__ x, int B, int D, int row0, float* __restrict__ dst,
+                                         bool vec) {
+  if (vec) {   // D % 4 == 0, 16-byte aligned rows: one float4 per lane, four conflict-free scalar stores
+    for (int idx = threadIdx.x; idx < PF_T * 32; idx += PF_THREADS) {
+      const int row = idx >> 5, q = idx & 31, d0 = q * 4, gr = row0 + row;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gr < B && d0 < D) v = *reinterpret_cast<const float4*>(x + (size_t)gr * D + d0);
+      const int k = d0 >> 5, l0 = d0 & 31;
+      dst[pf_slot(l0, row) + k] = v.x;
+      dst[pf_slot(l0 + 1, row) + k] = v.y;
+      dst[pf_slot(l0 + 2, row) + k] = v.z;
+      dst[pf_slot(l0 + 3, row) + k] = v.w;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < PF_T * 128; idx += PF_THREADS) {
+      const int row = idx >> 7, d = idx & 127, gr = row0 + row;
+      dst[pf_slot(d & 31, row) + (d >> 5)] = (gr < B && d < D) ? x[(size_t)gr * D + d] : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(PF_THREADS, 2) tfa_pdist_fast_kernel(const float* __restrict__ x, const float* __restrict__ sq,
+                                                                       int B, int D, int tiles_per_block, int squared, int vec,
+                                                                       float* __restrict__ P, int ldp) {
+  extern __shared__ __align__(16) float pf_sm[];
+  float* sA = pf_sm;                    // [32][64][4]
+  float* sB = pf_sm + 32 * PF_T * 4;    // the same for the column tile; afterwards the 64 x 65 transpose buffer
+  // warp w owns rows 8w .. 8w + 7 (its A loads are whole-warp broadcasts), lane t columns t and t + 32 (its B loads
+  // are 512 distinct contiguous bytes): 10 shared-memory loads per 64 fma, none of them redundant
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int bi = blockIdx.y, row0 = bi * PF_T;
+  const int n_tiles = (B + PF_T - 1) / PF_T;
+  // P is symmetric bit for bit (products and the two norms commute): only tiles on or above the diagonal are
+  // computed, each off-diagonal tile is also written transposed
+  if ((int)(blockIdx.x + 1) * tiles_per_block <= bi) return;
+  pf_stage(x, B, D, row0, sA, vec != 0);
+  float sq_a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sq_a[i] = row0 + ty * 8 + i < B ? sq[row0 + ty * 8 + i] : 0.f;
+  for (int t = 0; t < tiles_per_block; ++t) {
+    const int bj = blockIdx.x * tiles_per_block + t;
+    if (bj >= n_tiles) break;   // block-uniform
+    if (bj < bi) continue;
+    const int c0 = bj * PF_T;
+    __syncthreads();            // the previous tile's readers are done
+    pf_stage(x, B, D, c0, sB, vec != 0);
+    __syncthreads();
+    float st[6][8][2];
+#pragma unroll
+    for (int n = 0; n < 32; ++n) {
+      const int l = ((n & 1) << 4) | ((n & 2) << 2) | (n & 4) | ((n & 8) >> 2) | ((n & 16) >> 4);   // bit reversal
+      float4 b[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) b[j] = *reinterpret_cast<const float4*>(sB + pf_slot(l, tx + 32 * j));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(sA + pf_slot(l, ty * 8 + i));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float s = __fmaf_rn(a.x, b[j].x, 0.f);
+          s = __fmaf_rn(a.y, b[j].y, s);
+          s = __fmaf_rn(a.z, b[j].z, s);
+          s = __fmaf_rn(a.w, b[j].w, s);
+          int lvl = 0;
+#pragma unroll
+          for (int m = n; m & 1; m >>= 1) {
+            s = __fadd_rn(st[lvl][i][j], s);
+            ++lvl;
+          }
+          st[lvl][i][j] = s;
+        }
+      }
+    }
+    float sq_b[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) sq_b[j] = c0 + tx + 32 * j < B ? sq[c0 + tx + 32 * j] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int gi = row0 + ty * 8 + i, gj = c0 + tx + 32 * j;
+        float v = __fsub_rn(__fadd_rn(sq_a[i], sq_b[j]), __fmul_rn(2.f, st[5][i][j]));
+        v = fmaxf(v, 0.f);
+        const bool err = v <= 0.f;
+        float d = squared ? v : __fsqrt_rn(__fadd_rn(v, err ? 1e-16f : 0.f));
+        if (err || gj == gi) d = 0.f;
+        st[5][i][j] = d;
+        if (gi < B && gj < B) P[(size_t)gi * ldp + gj] = d;
+      }
+    if (bj > bi) {
+      __syncthreads();          // sB is free
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) sB[(tx + 32 * j) * (PF_T + 1) + ty * 8 + i] = st[5][i][j];
+      __syncthreads();
+      for (int r = ty; r < PF_T; r += PF_THREADS / 32) {
+        const int gj = c0 + r;
+        if (gj >= B) break;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int gi = row0 + tx + 32 * h;
+          if (gi < B) P[(size_t)gj * ldp + gi] = sB[r * (PF_T + 1) + tx + 32 * h];
+        }
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- block-wide (value, first index, tie count)
 template <bool MIN>
 __device__ __forceinline__ void block_extreme(float& v, int& i, int& c, float* s_v, int* s_i, int* s_c) {
@@ -106,12 +241,68 @@ struct TfaRow {
 // ---------------------------------------------------------------- K2: one block per anchor
 // srow = P_b, sflag: 0 diagonal, 1 positive, 2 negative; Cf_b (unscaled: the common factor dloss / B or
 // dloss / #pairs is applied by the gradient kernel) is built in smem and written once.
+// Coefficient rows are sparse (hard: the tied extremes; semi-hard: the positives and their selected negatives), so a
+// row leaves the kernel as a short list of (column, w = dL/dP * dP/d(squared distance) factor) sorted by column;
+// only a row with more than TFA_LIST_CAP non-zeros is written densely into Cf (count = -1).
+constexpr int TFA_LIST_CAP = 32;
+struct TfaLists {
+  int* count;     // [B]  entries of the row's list, -1 = the row is dense in Cf
+  int* cols;      // [B][TFA_LIST_CAP] ascending
+  float* wts;     // [B][TFA_LIST_CAP]
+};
+
+// dL/dP -> the weight of (x_i - x_j): 1 / P for the L2 metric, 2 for squared-L2, nothing through P == 0
+__device__ __forceinline__ float tfa_weight(float cf, float p, int squared) {
+  return (p > 0.f && cf != 0.f) ? (squared ? 2.f * cf : cf / p) : 0.f;
+}
+
+// Block-wide: the non-zero weights of one row, produced by `weight_of(j)`, become the row's sorted list - or, past
+// the cap, a dense row of Cf.
+template <typename F>
+__device__ __forceinline__ void tfa_emit_row(int b, int B, int ldp, const TfaLists& L, float* __restrict__ Cf, F weight_of) {
+  __shared__ int s_n;
+  __shared__ int s_col[TFA_LIST_CAP];
+  __shared__ float s_w[TFA_LIST_CAP];
+  const int t = threadIdx.x;
+  __syncthreads();
+  if (t == 0) s_n = 0;
+  __syncthreads();
+  for (int j = t; j < B; j += TFA_THREADS) {
+    const float w = weight_of(j);
+    if (w != 0.f) {
+      const int slot = atomicAdd(&s_n, 1);
+      if (slot < TFA_LIST_CAP) {
+        s_col[slot] = j;
+        s_w[slot] = w;
+      }
+    }
+  }
+  __syncthreads();
+  const int n = s_n;
+  if (n <= TFA_LIST_CAP) {
+    if (t < 32) {   // rank sort by column: the lists are consumed in ascending order, whatever order the atomics gave
+      const int c = t < n ? s_col[t] : 0x7fffffff;
+      const float w = t < n ? s_w[t] : 0.f;
+      int rank = 0;
+      for (int e = 0; e < n; ++e) rank += s_col[e] < c ? 1 : 0;
+      if (t < n) {
+        L.cols[(size_t)b * TFA_LIST_CAP + rank] = c;
+        L.wts[(size_t)b * TFA_LIST_CAP + rank] = w;
+      }
+      if (t == 0) L.count[b] = n;
+    }
+  } else {
+    for (int j = t; j < B; j += TFA_THREADS) Cf[(size_t)b * ldp + j] = weight_of(j);
+    if (t == 0) L.count[b] = -1;
+  }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(TFA_THREADS) tfa_row_kernel(const float* __restrict__ P, int ldp,
                                                               const int32_t* __restrict__ labels, int B, float margin,
-                                                              int soft, TfaRow* __restrict__ rows,
+                                                              int soft, int squared, TfaRow* __restrict__ rows,
                                                               int32_t* __restrict__ pos_idx, int32_t* __restrict__ neg_idx,
-                                                              float* __restrict__ Cf) {
+                                                              float* __restrict__ Cf, TfaLists L) {
   extern __shared__ float sm[];
   float* srow = sm;                                          // [B]
   float* scf = srow + B;                                     // [B]
@@ -170,13 +361,13 @@ __global__ void __launch_bounds__(TFA_THREADS) tfa_row_kernel(const float* __res
       const float c_pos = hp_c > 0 ? g / (float)hp_c : 0.f;
       const float c_neg = m_tied > 0 ? g / (float)n_tied : 0.f;
       const float c_max = vmin == 0.f ? g * (1.f - (float)m_tied / (float)n_tied) / (float)rmax_c : 0.f;
-      for (int j = t; j < B; j += TFA_THREADS) {
+      tfa_emit_row(b, B, ldp, L, Cf, [&](int j) {
         float cf = 0.f;
         if (sflag[j] == 1 && srow[j] == hp_v) cf += c_pos;
         if (sflag[j] == 2 && __fsub_rn(srow[j], rmax) == vmin) cf -= c_neg;
         if (srow[j] == rmax) cf -= c_max;                   // gradient through the rowmax term of _masked_minimum
-        Cf[(size_t)b * ldp + j] = cf;
-      }
+        return tfa_weight(cf, srow[j], squared);
+      });
     }
     return;
   }
@@ -229,7 +420,18 @@ __global__ void __launch_bounds__(TFA_THREADS) tfa_row_kernel(const float* __res
     const float lm = __fadd_rn(margin, __fsub_rn(pa, sh));
     loss_sum += (double)fmaxf(lm, 0.f);
     if (Cf && lm >= 0.f) {
-      if (outside) {
+      // the usual case touches two entries: +1 on the positive, -1 on the one selected negative
+      if (outside && out_c == 1 && out_v != 0.f) {
+        if (t == 0) {
+          scf[a] += 1.f;
+          scf[out_i] -= 1.f;
+        }
+      } else if (!outside && in_c == 1) {
+        if (t == 0) {
+          scf[a] += 1.f;
+          scf[in_i] -= 1.f;
+        }
+      } else if (outside) {
         int n_tied = out_c;
         if (out_v == 0.f) n_tied += B - block_count(n_mask_t, s_c);   // every unmasked entry ties at 0
         const float c_neg = 1.f / (float)n_tied;
@@ -256,8 +458,154 @@ __global__ void __launch_bounds__(TFA_THREADS) tfa_row_kernel(const float* __res
     rows[b].loss_sum = loss_sum;
     rows[b].n_pos = n_pos;
   }
-  if (Cf)
-    for (int j = t; j < B; j += TFA_THREADS) Cf[(size_t)b * ldp + j] = scf[j];   // each thread re-reads its own entries
+  if (Cf) tfa_emit_row(b, B, ldp, L, Cf, [&](int j) { return tfa_weight(scf[j], srow[j], squared); });
+}
+
+// ---------------------------------------------------------------- K2 (hard): two light passes per anchor
+// The generic kernel above carries (value, first index, tie count) triples through every reduction.  The hard loss
+// only needs VALUES first - rowmax, the farthest positive, the closest negative (the shifted minimum of
+// _masked_minimum is monotone in P, so min((P - rowmax) * mask) = fl(min P - rowmax)) - and then one membership pass:
+// which columns tie with those values (first index, count), appended to the row's weight list as they are found.
+struct TfaHardRed {
+  float rmax, hp, nmin;
+  int n_pos;
+};
+__global__ void __launch_bounds__(TFA_THREADS) tfa_hard_row_kernel(const float* __restrict__ P, int ldp,
+                                                                   const int32_t* __restrict__ labels, int B, float margin,
+                                                                   int soft, int squared, TfaRow* __restrict__ rows,
+                                                                   int32_t* __restrict__ pos_idx, int32_t* __restrict__ neg_idx,
+                                                                   float* __restrict__ Cf, TfaLists L) {
+  extern __shared__ float sm[];
+  float* srow = sm;                                                    // [B]
+  unsigned char* sflag = reinterpret_cast<unsigned char*>(srow + B);   // [B] 0 diagonal, 1 positive, 2 negative
+  __shared__ TfaHardRed s_red[TFA_WARPS];
+  __shared__ int s_cnt[3], s_first[2], s_n;
+  __shared__ int s_col[TFA_LIST_CAP];
+  __shared__ unsigned char s_bits[TFA_LIST_CAP];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int my_lab = labels[b];
+  if (t < 3) s_cnt[t] = 0;
+  if (t < 2) s_first[t] = 0x7fffffff;
+  if (t == 0) s_n = 0;
+  // pass 1: values only
+  TfaHardRed me{-INFINITY, -INFINITY, INFINITY, 0};
+  for (int j = t; j < B; j += TFA_THREADS) {
+    const float v = P[(size_t)b * ldp + j];
+    const int f = j == b ? 0 : (labels[j] == my_lab ? 1 : 2);
+    srow[j] = v;
+    sflag[j] = (unsigned char)f;
+    me.rmax = fmaxf(me.rmax, v);
+    me.hp = fmaxf(me.hp, f == 1 ? v : -INFINITY);
+    me.nmin = fminf(me.nmin, f == 2 ? v : INFINITY);
+    me.n_pos += f == 1;
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    me.rmax = fmaxf(me.rmax, __shfl_xor_sync(0xffffffffu, me.rmax, o));
+    me.hp = fmaxf(me.hp, __shfl_xor_sync(0xffffffffu, me.hp, o));
+    me.nmin = fminf(me.nmin, __shfl_xor_sync(0xffffffffu, me.nmin, o));
+    me.n_pos += __shfl_xor_sync(0xffffffffu, me.n_pos, o);
+  }
+  if (lane == 0) s_red[warp] = me;
+  __syncthreads();
+  me = s_red[0];
+#pragma unroll
+  for (int w = 1; w < TFA_WARPS; ++w) {
+    me.rmax = fmaxf(me.rmax, s_red[w].rmax);
+    me.hp = fmaxf(me.hp, s_red[w].hp);
+    me.nmin = fminf(me.nmin, s_red[w].nmin);
+    me.n_pos += s_red[w].n_pos;
+  }
+  const float rmax = me.rmax, hp_v = me.hp;
+  const int n_pos = me.n_pos, n_neg = B - 1 - n_pos;
+  const bool has_pos = n_pos > 0, has_neg = n_neg > 0;
+  const float vmin = has_neg ? __fsub_rn(me.nmin, rmax) : 0.f;   // unmasked entries contribute (P - rowmax) * 0
+  const bool through_max = vmin == 0.f;                         // reduce_min then ties with every unmasked entry
+  // pass 2: membership.  bit 0: a positive at hp; bit 1: a negative whose shifted value is vmin; bit 2: a row maximum
+  // (only when the gradient reaches the rowmax term)
+  int c_p = 0, c_n = 0, c_m = 0, f_p = 0x7fffffff, f_n = 0x7fffffff;
+  for (int j = t; j < B; j += TFA_THREADS) {
+    const float v = srow[j];
+    const int f = sflag[j];
+    const bool pt = f == 1 && v == hp_v;
+    const bool nt = f == 2 && __fsub_rn(v, rmax) == vmin;
+    const bool mt = through_max && v == rmax;
+    if (pt | nt | mt) {
+      c_p += pt;
+      c_n += nt;
+      c_m += mt;
+      if (pt) f_p = min(f_p, j);
+      if (nt) f_n = min(f_n, j);
+      if (Cf) {
+        const int slot = atomicAdd(&s_n, 1);
+        if (slot < TFA_LIST_CAP) {
+          s_col[slot] = j;
+          s_bits[slot] = (unsigned char)((pt ? 1 : 0) | (nt ? 2 : 0) | (mt ? 4 : 0));
+        }
+      }
+    }
+  }
+  if (c_p) atomicAdd(&s_cnt[0], c_p);
+  if (c_n) atomicAdd(&s_cnt[1], c_n);
+  if (c_m) atomicAdd(&s_cnt[2], c_m);
+  if (f_p != 0x7fffffff) atomicMin(&s_first[0], f_p);
+  if (f_n != 0x7fffffff) atomicMin(&s_first[1], f_n);
+  __syncthreads();
+  const int hp_c = s_cnt[0], mn_c = s_cnt[1], rmax_c = s_cnt[2];
+  const float hp = has_pos ? hp_v : 0.f;                     // _masked_maximum: row minimum (the 0 diagonal) as filler
+  const float hn = __fadd_rn(vmin, rmax);
+  const float xd = __fsub_rn(hp, hn);
+  float loss, g;
+  if (soft) {
+    loss = log1pf(expf(xd));
+    g = 1.f / (1.f + expf(-xd));
+  } else {
+    const float basic = __fadd_rn(xd, margin);
+    loss = fmaxf(basic, 0.f);
+    g = basic >= 0.f ? 1.f : 0.f;
+  }
+  if (t == 0) {
+    rows[b].loss_sum = (double)loss;
+    rows[b].n_pos = n_pos;
+    if (pos_idx) pos_idx[b] = has_pos ? s_first[0] : -1;
+    if (neg_idx) neg_idx[b] = has_neg ? s_first[1] : -1;
+  }
+  if (!Cf) return;
+  // reduce_min tie set: masked entries at vmin, plus every unmasked entry when vmin == 0
+  const int m_tied = mn_c;
+  const int n_tied = through_max ? m_tied + (B - n_neg) : m_tied;
+  const float c_pos = hp_c > 0 ? g / (float)hp_c : 0.f;
+  const float c_neg = m_tied > 0 ? g / (float)n_tied : 0.f;
+  const float c_max = through_max ? g * (1.f - (float)m_tied / (float)n_tied) / (float)rmax_c : 0.f;
+  auto weight_of = [&](int j, int bits) {
+    float cf = 0.f;
+    if (bits & 1) cf += c_pos;
+    if (bits & 2) cf -= c_neg;
+    if (bits & 4) cf -= c_max;                               // gradient through the rowmax term of _masked_minimum
+    return tfa_weight(cf, srow[j], squared);
+  };
+  const int n = s_n;
+  if (n <= TFA_LIST_CAP) {
+    if (t < 32) {   // rank sort by column
+      const int c = t < n ? s_col[t] : 0x7fffffff;
+      int rank = 0;
+      for (int e = 0; e < n; ++e) rank += s_col[e] < c ? 1 : 0;
+      if (t < n) {
+        L.cols[(size_t)b * TFA_LIST_CAP + rank] = c;
+        L.wts[(size_t)b * TFA_LIST_CAP + rank] = weight_of(c, s_bits[t]);
+      }
+      if (t == 0) L.count[b] = n;
+    }
+  } else {
+    for (int j = t; j < B; j += TFA_THREADS) {
+      const float v = srow[j];
+      const int f = sflag[j];
+      const int bits = ((f == 1 && v == hp_v) ? 1 : 0) | ((f == 2 && __fsub_rn(v, rmax) == vmin) ? 2 : 0) |
+                       ((through_max && v == rmax) ? 4 : 0);
+      Cf[(size_t)b * ldp + j] = weight_of(j, bits);
+    }
+    if (t == 0) L.count[b] = -1;
+  }
 }
 
 // ---------------------------------------------------------------- K3: scalar loss and the backward scale
@@ -288,79 +636,186 @@ __global__ void __launch_bounds__(1024) tfa_finalize_kernel(const TfaRow* __rest
   }
 }
 
-// ---------------------------------------------------------------- K4: P_ij <- (Cf_ij + Cf_ji) * dP_ij/d(sq)-factor
-// L2: d P_ij / d x_i = (x_i - x_j) / P_ij;  squared-L2: 2 (x_i - x_j);  nothing where P_ij == 0 (error mask, diagonal)
-__global__ void __launch_bounds__(256) tfa_fold_kernel(float* __restrict__ P, const float* __restrict__ Cf, int ldp, int B,
-                                                       int squared) {
-  __shared__ float tile[32][33];
-  const int j = blockIdx.x * 32 + threadIdx.x;
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    // the mirrored tile of Cf: rows of the j range, columns of the i range, read coalesced
-    const int ti = blockIdx.x * 32 + r, tj = blockIdx.y * 32 + threadIdx.x;
-    tile[r][threadIdx.x] = (ti < B && tj < B) ? Cf[(size_t)ti * ldp + tj] : 0.f;
+// ---------------------------------------------------------------- K4: dX_r = scale * sum_j (W_rj + W_jr) (x_r - x_j)
+// W = the rows' weight lists.  The transposed half needs "which anchors list r": every block scans the columns of all
+// lists once (L2 resident) and sets bit a of row r's bitmap in shared memory when anchor a lists one of the block's
+// rows (dense anchors go to a bitmap of their own); each warp then gathers its row - own list in ascending column
+// order, then the listing anchors in ascending order - so the sums are reproducible without atomics on the result.
+constexpr int TFA_GRAD_WARPS = 16;
+constexpr int TFA_INV_CAP = 32;   // listing anchors kept per row in shared memory; a busier row walks its bitmap
+__global__ void __launch_bounds__(TFA_GRAD_WARPS * 32) tfa_grad_sparse_kernel(TfaLists L, const float* __restrict__ Cf, int ldp,
+                                                                              const float* __restrict__ x, int B, int D,
+                                                                              const float* __restrict__ scale,
+                                                                              float* __restrict__ dX) {
+  extern __shared__ unsigned s_map[];   // [TFA_GRAD_WARPS + 1][W]
+  __shared__ int s_cnt[TFA_GRAD_WARPS];
+  __shared__ int s_anchor[TFA_GRAD_WARPS][TFA_INV_CAP];
+  __shared__ float s_weight[TFA_GRAD_WARPS][TFA_INV_CAP];
+  const int W = (B + 31) >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * TFA_GRAD_WARPS;
+  for (int i = threadIdx.x; i < (TFA_GRAD_WARPS + 1) * W; i += blockDim.x) s_map[i] = 0u;
+  if (threadIdx.x < TFA_GRAD_WARPS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  // scan: counts of 4 anchors, then the first four columns of each, are in flight together (most lists are that short)
+  auto note = [&](int a, int e, int col) {
+    const unsigned u = (unsigned)(col - r0);
+    if (u < (unsigned)TFA_GRAD_WARPS) {
+      atomicOr(&s_map[u * W + (a >> 5)], 1u << (a & 31));
+      const int slot = atomicAdd(&s_cnt[u], 1);
+      if (slot < TFA_INV_CAP) {
+        s_anchor[u][slot] = a;
+        s_weight[u][slot] = L.wts[(size_t)a * TFA_LIST_CAP + e];
+      }
+    }
+  };
+  for (int a0 = threadIdx.x; a0 < B; a0 += 4 * TFA_GRAD_WARPS * 32) {
+    int n[4];
+    int4 c[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int a = a0 + q * TFA_GRAD_WARPS * 32;
+      n[q] = a < B ? L.count[a] : 0;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int a = a0 + q * TFA_GRAD_WARPS * 32;
+      c[q] = n[q] > 0 ? *reinterpret_cast<const int4*>(L.cols + (size_t)a * TFA_LIST_CAP) : make_int4(-1, -1, -1, -1);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int a = a0 + q * TFA_GRAD_WARPS * 32;
+      if (n[q] < 0) atomicOr(&s_map[TFA_GRAD_WARPS * W + (a >> 5)], 1u << (a & 31));
+      if (n[q] > 0) note(a, 0, c[q].x);
+      if (n[q] > 1) note(a, 1, c[q].y);
+      if (n[q] > 2) note(a, 2, c[q].z);
+      if (n[q] > 3) note(a, 3, c[q].w);
+      for (int e = 4; e < n[q]; ++e) note(a, e, L.cols[(size_t)a * TFA_LIST_CAP + e]);
+    }
   }
   __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int i = blockIdx.y * 32 + r;
-    if (i < B && j < B) {
-      const float p = P[(size_t)i * ldp + j];
-      const float c = Cf[(size_t)i * ldp + j] + tile[threadIdx.x][r];   // tile[x][r] = Cf[j][i]
-      P[(size_t)i * ldp + j] = (p > 0.f && c != 0.f) ? (squared ? 2.f * c : c / p) : 0.f;
+  const int r = r0 + warp;
+  if (r >= B) return;
+  float xr[BH_MAX_KD], acc[BH_MAX_KD];
+#pragma unroll
+  for (int c = 0; c < BH_MAX_KD; ++c) {
+    const int d = c * 32 + lane;
+    xr[c] = d < D ? x[(size_t)r * D + d] : 0.f;
+    acc[c] = 0.f;
+  }
+  auto axpy = [&](float w, int j) {
+    const float* xj = x + (size_t)j * D;
+#pragma unroll
+    for (int c = 0; c < BH_MAX_KD; ++c) {
+      const int d = c * 32 + lane;
+      if (d < D) acc[c] = __fmaf_rn(w, xr[c] - xj[d], acc[c]);
+    }
+  };
+  // a list held one entry per lane: rows are fetched four at a time, added in list order
+  auto gather = [&](int n, int my_j, float my_w) {
+    if (D <= 128) {
+      for (int e0 = 0; e0 < n; e0 += 4) {
+        float v[4][4], w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int src = min(e0 + u, n - 1);
+          const int j = __shfl_sync(0xffffffffu, my_j, src);
+          w[u] = e0 + u < n ? __shfl_sync(0xffffffffu, my_w, src) : 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[u][c] = c * 32 + lane < D ? x[(size_t)j * D + c * 32 + lane] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (e0 + u < n) acc[c] = __fmaf_rn(w[u], xr[c] - v[u][c], acc[c]);
+      }
+    } else {
+      for (int e = 0; e < n; ++e) axpy(__shfl_sync(0xffffffffu, my_w, e), __shfl_sync(0xffffffffu, my_j, e));
+    }
+  };
+  // own row
+  const int n_own = L.count[r];
+  if (n_own >= 0) {
+    gather(n_own, lane < n_own ? L.cols[(size_t)r * TFA_LIST_CAP + lane] : 0,
+           lane < n_own ? L.wts[(size_t)r * TFA_LIST_CAP + lane] : 0.f);
+  } else {
+    for (int j0 = 0; j0 < B; j0 += 32) {
+      const float w = j0 + lane < B ? Cf[(size_t)r * ldp + j0 + lane] : 0.f;
+      unsigned nz = __ballot_sync(0xffffffffu, w != 0.f);
+      while (nz) {
+        const int src = __ffs((int)nz) - 1;
+        nz &= nz - 1;
+        axpy(__shfl_sync(0xffffffffu, w, src), j0 + src);
+      }
     }
   }
-}
-
-// ---------------------------------------------------------------- K5: dX_i = scale * sum_j W_ij (x_i - x_j)
-template <int KQ>
-__global__ void __launch_bounds__(TFA_THREADS) tfa_grad_kernel(const float* __restrict__ Wt, int ldp,
-                                                               const float* __restrict__ x, int B, int D,
-                                                               const float* __restrict__ scale, float* __restrict__ dX) {
-  __shared__ int s_j[TFA_THREADS];
-  __shared__ float s_w[TFA_THREADS];
-  __shared__ int s_n[TFA_WARPS];
-  const int i = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  float xi[KQ], acc[KQ];
-#pragma unroll
-  for (int q = 0; q < KQ; ++q) {
-    const int d = t + q * TFA_THREADS;
-    xi[q] = d < D ? x[(size_t)i * D + d] : 0.f;
-    acc[q] = 0.f;
-  }
-  for (int c0 = 0; c0 < B; c0 += TFA_THREADS) {
-    const int j = c0 + t;
-    const float w = j < B ? Wt[(size_t)i * ldp + j] : 0.f;
-    const unsigned nz = __ballot_sync(0xffffffffu, w != 0.f);
-    __syncthreads();   // previous list consumed
-    if (lane == 0) s_n[warp] = __popc(nz);
-    __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int wv = 0; wv < TFA_WARPS; ++wv) {
-      if (wv < warp) base += s_n[wv];
-      total += s_n[wv];
+  // anchors that list r
+  const unsigned* dm = s_map + TFA_GRAD_WARPS * W;
+  bool any_dense = false;
+  for (int wi = lane; wi < W; wi += 32) any_dense |= dm[wi] != 0u;
+  const int n_inv = s_cnt[warp];
+  if (n_inv <= TFA_INV_CAP && !__any_sync(0xffffffffu, any_dense)) {
+    // the usual case: the scan already holds (anchor, weight) of every listing anchor; rank them by anchor
+    const int a = lane < n_inv ? s_anchor[warp][lane] : 0x7fffffff;
+    const float w = lane < n_inv ? s_weight[warp][lane] : 0.f;
+    int rank = 0;
+    for (int e = 0; e < n_inv; ++e) rank += s_anchor[warp][e] < a ? 1 : 0;
+    __syncwarp();
+    if (lane < n_inv) {
+      s_anchor[warp][rank] = a;
+      s_weight[warp][rank] = w;
     }
-    if (total == 0) continue;   // block-uniform
-    if (w != 0.f) {
-      const int at = base + __popc(nz & ((1u << lane) - 1u));
-      s_j[at] = j;
-      s_w[at] = w;
-    }
-    __syncthreads();
-    for (int e = 0; e < total; ++e) {   // ascending column order: fixed summation order
-      const float we = s_w[e];
-      const float* xj = x + (size_t)s_j[e] * D;
+    __syncwarp();
+    gather(n_inv, lane < n_inv ? s_anchor[warp][lane] : 0, lane < n_inv ? s_weight[warp][lane] : 0.f);
+  } else {
+    // a row many anchors list (hub rows: the hardest negative of dozens of anchors), or dense anchors around: walk the
+    // bitmap 32 words at a time, hand the set bits to the lanes in ascending order, 32 anchors per round; every lane
+    // looks its own anchor's weight up (the lookups run side by side), then the rows are gathered as above
+    const unsigned* bm = s_map + warp * W;
+    for (int w0 = 0; w0 < W; w0 += 32) {
+      const int wi = w0 + lane;
+      const unsigned db = wi < W ? dm[wi] : 0u;
+      const unsigned word = (wi < W ? bm[wi] : 0u) | db;
+      const int cnt = __popc(word);
+      int incl = cnt;
 #pragma unroll
-      for (int q = 0; q < KQ; ++q) {
-        const int d = t + q * TFA_THREADS;
-        if (d < D) acc[q] = __fmaf_rn(we, xi[q] - xj[d], acc[q]);
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31), first = incl - cnt;
+      for (int base = 0; base < total; base += 32) {
+        __syncwarp();
+        unsigned u = word;
+        for (int k = first; u; ++k) {
+          const int bit = __ffs((int)u) - 1;
+          u &= u - 1;
+          if (k >= base && k < base + 32) s_anchor[warp][k - base] = wi * 32 + bit;
+        }
+        __syncwarp();
+        const int n = min(32, total - base);
+        int a = 0;
+        float w = 0.f;
+        if (lane < n) {
+          a = s_anchor[warp][lane];
+          const int na = L.count[a];
+          if (na < 0) {
+            w = Cf[(size_t)a * ldp + r];
+          } else {
+            for (int e = 0; e < na; ++e)
+              if (L.cols[(size_t)a * TFA_LIST_CAP + e] == r) w = L.wts[(size_t)a * TFA_LIST_CAP + e];
+          }
+        }
+        gather(n, a, w);
       }
     }
   }
   const float sc = scale[0];
 #pragma unroll
-  for (int q = 0; q < KQ; ++q) {
-    const int d = t + q * TFA_THREADS;
-    if (d < D) dX[(size_t)i * D + d] = sc * acc[q];
+  for (int c = 0; c < BH_MAX_KD; ++c) {
+    const int d = c * 32 + lane;
+    if (d < D) dX[(size_t)r * D + d] = sc * acc[c];
   }
 }
 
@@ -369,6 +824,8 @@ struct TfaWorkspace {
   float* Cf = nullptr;
   TfaRow* rows = nullptr;
   float* scale = nullptr;
+  float* sq = nullptr;   // [rows] canonical sum of squares (fast pairwise kernel)
+  TfaLists lists{nullptr, nullptr, nullptr};
   size_t mat_cap = 0, row_cap = 0;
   int ensure(size_t mat, size_t n_rows, bool want_cf) {
     if (mat > mat_cap) {
@@ -382,9 +839,19 @@ struct TfaWorkspace {
     if (want_cf && !Cf) DIF_CUDA_OK(cudaMalloc((void**)&Cf, mat_cap * sizeof(float)));
     if (n_rows > row_cap) {
       cudaFree(rows);
+      cudaFree(sq);
+      cudaFree(lists.count);
+      cudaFree(lists.cols);
+      cudaFree(lists.wts);
       rows = nullptr;
+      sq = nullptr;
+      lists = TfaLists{nullptr, nullptr, nullptr};
       row_cap = 0;
       DIF_CUDA_OK(cudaMalloc((void**)&rows, n_rows * sizeof(TfaRow)));
+      DIF_CUDA_OK(cudaMalloc((void**)&sq, n_rows * sizeof(float)));
+      DIF_CUDA_OK(cudaMalloc((void**)&lists.count, n_rows * sizeof(int)));
+      DIF_CUDA_OK(cudaMalloc((void**)&lists.cols, n_rows * TFA_LIST_CAP * sizeof(int)));
+      DIF_CUDA_OK(cudaMalloc((void**)&lists.wts, n_rows * TFA_LIST_CAP * sizeof(float)));
       row_cap = n_rows;
     }
     if (!scale) DIF_CUDA_OK(cudaMalloc((void**)&scale, 16));
@@ -418,37 +885,56 @@ extern "C" int dif_tfa_triplet(const float* emb, const int32_t* labels, int B, i
     configured = true;
   }
   // K1
-  const int row_blocks = (B + BH_RB - 1) / BH_RB;
   const int sms = std::max(1, device_sm_count());
-  int splits = std::max(1, std::min((2 * sms + row_blocks - 1) / row_blocks, (B + BH_CB - 1) / BH_CB));
-  int cols = (B + splits - 1) / splits;
-  cols = (cols + BH_CB - 1) / BH_CB * BH_CB;
-  splits = (B + cols - 1) / cols;
-  const size_t smem1 = ((size_t)(BH_RB + BH_CB) * D + BH_RB + BH_CB) * sizeof(float);
-  tfa_pdist_kernel<<<dim3(row_blocks, splits), BH_WARPS * 32, smem1, st>>>(emb, B, D, cols, squared, g_tfa.P, ldp);
-  DIF_LAUNCH_OK();
+  static const bool slow_pdist = getenv("DIF_TFA_SLOW_PDIST") != nullptr;   // A/B switch
+  if (D <= 128 && B >= 256 && !slow_pdist) {
+    static bool fast_configured = false;
+    const size_t smem_f = 2 * 32 * PF_T * 4 * sizeof(float);   // 64 KB
+    if (!fast_configured) {
+      DIF_CUDA_OK(cudaFuncSetAttribute(tfa_pdist_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+      fast_configured = true;
+    }
+    tfa_sqnorm_kernel<<<(B + 7) / 8, 256, 0, st>>>(emb, B, D, g_tfa.sq);
+    DIF_LAUNCH_OK();
+    const int tiles = (B + PF_T - 1) / PF_T;
+    // the row tile stays staged while a block walks `tpb` column tiles (only those on or above the diagonal do work)
+    const int tpb = tiles * tiles / 2 >= 8 * sms ? 2 : 1;
+    const int vec = (D % 4 == 0 && (reinterpret_cast<uintptr_t>(emb) & 15u) == 0) ? 1 : 0;
+    tfa_pdist_fast_kernel<<<dim3((tiles + tpb - 1) / tpb, tiles), PF_THREADS, smem_f, st>>>(emb, g_tfa.sq, B, D, tpb, squared,
+                                                                                        vec, g_tfa.P, ldp);
+    DIF_LAUNCH_OK();
+  } else {
+    const int row_blocks = (B + BH_RB - 1) / BH_RB;
+    int splits = std::max(1, std::min((2 * sms + row_blocks - 1) / row_blocks, (B + BH_CB - 1) / BH_CB));
+    int cols = (B + splits - 1) / splits;
+    cols = (cols + BH_CB - 1) / BH_CB * BH_CB;
+    splits = (B + cols - 1) / cols;
+    const size_t smem1 = ((size_t)(BH_RB + BH_CB) * D + BH_RB + BH_CB) * sizeof(float);
+    tfa_pdist_kernel<<<dim3(row_blocks, splits), BH_WARPS * 32, smem1, st>>>(emb, B, D, cols, squared, g_tfa.P, ldp);
+    DIF_LAUNCH_OK();
+  }
   // K2
   const size_t smem2 = (size_t)B * 11 + 32;   // row, coefficient row (fp32), flags (u8), positives list (u16)
   float* cf = demb ? g_tfa.Cf : nullptr;
-  if (base == DIF_TFA_HARD)
-    tfa_row_kernel<DIF_TFA_HARD><<<B, TFA_THREADS, smem2, st>>>(g_tfa.P, ldp, labels, B, margin, soft, g_tfa.rows, pos_idx,
-                                                               neg_idx, cf);
+  static const bool generic_hard = getenv("DIF_TFA_GENERIC_HARD") != nullptr;   // A/B switch
+  if (base == DIF_TFA_HARD && !generic_hard)
+    tfa_hard_row_kernel<<<B, TFA_THREADS, (size_t)B * 5 + 16, st>>>(g_tfa.P, ldp, labels, B, margin, soft, squared, g_tfa.rows,
+                                                                   pos_idx, neg_idx, cf, g_tfa.lists);
+  else if (base == DIF_TFA_HARD)
+    tfa_row_kernel<DIF_TFA_HARD><<<B, TFA_THREADS, smem2, st>>>(g_tfa.P, ldp, labels, B, margin, soft, squared, g_tfa.rows,
+                                                               pos_idx, neg_idx, cf, g_tfa.lists);
   else
-    tfa_row_kernel<DIF_TFA_SEMIHARD><<<B, TFA_THREADS, smem2, st>>>(g_tfa.P, ldp, labels, B, margin, 0, g_tfa.rows, nullptr,
-                                                                   nullptr, cf);
+    tfa_row_kernel<DIF_TFA_SEMIHARD><<<B, TFA_THREADS, smem2, st>>>(g_tfa.P, ldp, labels, B, margin, 0, squared, g_tfa.rows,
+                                                                   nullptr, nullptr, cf, g_tfa.lists);
   DIF_LAUNCH_OK();
   // K3
   tfa_finalize_kernel<<<1, 1024, 0, st>>>(g_tfa.rows, B, base, dloss, loss, g_tfa.scale);
   DIF_LAUNCH_OK();
   if (!demb) return DIF_OK;
-  // K4, K5
-  const int tb = (B + 31) / 32;
-  tfa_fold_kernel<<<dim3(tb, tb), dim3(32, 8), 0, st>>>(g_tfa.P, g_tfa.Cf, ldp, B, squared);
-  DIF_LAUNCH_OK();
-  const int kq = (D + TFA_THREADS - 1) / TFA_THREADS;
-  if (kq <= 1) tfa_grad_kernel<1><<<B, TFA_THREADS, 0, st>>>(g_tfa.P, ldp, emb, B, D, g_tfa.scale, demb);
-  else if (kq <= 2) tfa_grad_kernel<2><<<B, TFA_THREADS, 0, st>>>(g_tfa.P, ldp, emb, B, D, g_tfa.scale, demb);
-  else tfa_grad_kernel<4><<<B, TFA_THREADS, 0, st>>>(g_tfa.P, ldp, emb, B, D, g_tfa.scale, demb);
+  // K4
+  const size_t map_smem = (size_t)(TFA_GRAD_WARPS + 1) * ((B + 31) / 32) * sizeof(unsigned);
+  tfa_grad_sparse_kernel<<<(B + TFA_GRAD_WARPS - 1) / TFA_GRAD_WARPS, TFA_GRAD_WARPS * 32, map_smem, st>>>(
+      g_tfa.lists, g_tfa.Cf, ldp, emb, B, D, g_tfa.scale, demb);
   DIF_LAUNCH_OK();
   return DIF_OK;
 }

@@ -124,6 +124,50 @@ def test_large_batch_forward_and_determinism():
     assert ls == ls2 and np.array_equal(gs, gs2) and np.isfinite(gs).all()
 
 
+def test_rows_past_the_list_cap_fall_back_to_dense_coefficients():
+    """The backward pass carries each anchor's coefficients as a sorted list of at most 32 (column, weight) pairs;
+    an anchor with more non-zeros (large identities in the semi-hard loss: one entry per positive plus its selected
+    negatives) is written densely instead.  Mixed batch: two identities of 40, ten of 4."""
+    from deep_insight_face_b200.common.tfa_losses import TripletHardLoss, TripletSemiHardLoss
+    from oracle import tfa_oracle as orc
+
+    rng = np.random.default_rng(21)
+    lab = np.concatenate([np.repeat([0, 1], 40), np.repeat(np.arange(2, 12), 4)]).astype(np.int32)
+    cent = rng.normal(size=(12, 64)) * 0.3
+    x = (cent[lab] + 0.5 * rng.normal(size=(lab.size, 64))).astype(np.float32)
+    perm = rng.permutation(lab.size)
+    lab, x = lab[perm], x[perm]
+    for metric in ("L2", "squared-L2"):
+        sq = metric == "squared-L2"
+        loss, grad, _ = TripletSemiHardLoss(distance_metric=metric).loss_and_grad(lab, x)
+        l64, g64 = orc.torch_shadow("semihard", lab, x, squared=sq)
+        assert abs(loss - l64) <= RTOL * max(abs(l64), 1e-6) and _close(grad, g64)
+        loss2, grad2, _ = TripletSemiHardLoss(distance_metric=metric).loss_and_grad(lab, x)
+        assert loss == loss2 and np.array_equal(grad, grad2)
+    loss, grad, _ = TripletHardLoss().loss_and_grad(lab, x)
+    l64, g64 = orc.torch_shadow("hard", lab, x)
+    assert abs(loss - l64) <= RTOL * max(abs(l64), 1e-6) and _close(grad, g64)
+
+
+def test_gradients_on_the_large_batch_path():
+    """B >= 256 takes the one-thread-per-entry pairwise kernel and the list gather: gradients against the fp32-faithful
+    autograd shadow (hard at B = 2048; semi-hard at B = 288, where the shadow's O(B^3) tensors still fit)."""
+    from deep_insight_face_b200.common.tfa_losses import TripletHardLoss, TripletSemiHardLoss
+    from oracle import tfa_oracle as orc
+
+    lab, x = _pk(512, 4, 128, seed=12, scale=0.05)
+    x[100] = x[7]   # an exact duplicate: zero distance, tied extremes
+    for soft in (False, True):
+        loss, grad, _ = TripletHardLoss(soft=soft).loss_and_grad(lab, x)
+        l64, g64 = orc.torch_shadow("hard", lab, x, soft=soft)
+        assert abs(loss - l64) <= RTOL * max(abs(l64), 1e-6) and _close(grad, g64)
+    lab, x = _pk(72, 4, 96, seed=13, scale=0.1)
+    for metric in ("L2", "squared-L2"):
+        loss, grad, _ = TripletSemiHardLoss(distance_metric=metric).loss_and_grad(lab, x)
+        l64, g64 = orc.torch_shadow("semihard", lab, x, squared=metric == "squared-L2")
+        assert abs(loss - l64) <= RTOL * max(abs(l64), 1e-6) and _close(grad, g64)
+
+
 def test_torch_autograd_and_config_roundtrip():
     import torch
 
