@@ -173,6 +173,16 @@ def secondary_metrics(torch, device, peaks, lib):
                 "note": ("algorithmic FLOP of the whole step over the whole step's time (all launches); 3xTF32 issues 3 "
                          "MMAs per product, ceiling 1/3" + (" - " + note if note else ""))}
 
+    def fp32_roofline(flops, ms, note=""):
+        # CUDA-core kernels (canonical fp32 order): 148 SMs x 128 lanes x 2 FLOP per fma at the maximum SM clock
+        props = torch.cuda.get_device_properties(device)
+        peak = props.multi_processor_count * 128 * 2 * 1.965e9 / 1e12
+        ach = flops / (ms * 1e-3) / 1e12
+        return {"bound": "fp32-fma", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "peak_source": "SM count x 128 fma lanes x 2 x 1965 MHz (nominal; CUDA cores are not in MEASURED_PEAKS.json)",
+                "traffic": None,
+                "note": "algorithmic FLOP of the whole step over the whole step's time (all launches)" + (" - " + note if note else "")}
+
     def hbm_roofline(nbytes, ms, note=""):
         ach = nbytes / (ms * 1e-3) / 1e9
         return {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
@@ -208,7 +218,7 @@ def secondary_metrics(torch, device, peaks, lib):
                                "fraction only means something at B = 4096")
         out[name] = {"steps_per_s": 1e3 / ms, "ms_per_step": ms, "ungraphed_call_steps_per_s": 1e3 / ms_call,
                      "e2e_steps_per_s": 1e3 / host_ms, "e2e_ms": host_ms, "launches_per_step": n_launch,
-                     "path": "tcgen05 3xTF32 filter + canonical re-rank + inverse-list gradient" if B >= 512 else
+                     "path": "tcgen05 3xTF32 filter + canonical re-rank + finalize + bitmap gather gradient (statistics in the same launch)" if B >= 512 else
                              "one thread-block-cluster launch: bulk-copy staging, canonical fp32 mining, DSMEM record exchange, "
                              "finalize + gradient out of shared memory",
                      "alg_gflop_fwd": flops / 1e9, "roofline": roof,
@@ -249,7 +259,13 @@ def secondary_metrics(torch, device, peaks, lib):
         ms_s = timed(lambda: tfa_triplet(ld, xd, TFA_SEMIHARD, 1.0), iters)
         cpu_s, cpu_n = cpu_timed(lambda: cp.tfa_hard_step(lab, emb, 1.0))
         out[name] = {"hard_steps_per_s": 1e3 / ms_h, "semihard_steps_per_s": 1e3 / ms_s, "hard_ms": ms_h, "semihard_ms": ms_s,
-                     "roofline": tensor_roofline(2.0 * B * B * D, ms_h, "hard loss; forward distance matrix only counted"),
+                     "roofline": fp32_roofline(2.0 * B * B * D, ms_h, "hard loss; the full B x B distance matrix counted (the "
+                                               "kernel computes the upper triangle once: P is symmetric bit for bit), plus 31 "
+                                               "adds per entry for the canonical 32-chain tree that are not counted"),
+                     "path": ("canonical fp32 pairwise matrix, one thread per entry (32 fma chains folded by a bit-reversed "
+                              "counter tree, upper triangle + transposed store), value-first hard-row kernel, sorted weight "
+                              "lists, bitmap gather gradient") if B >= 256 else
+                             "canonical fp32 warp tiles (bh_tile.cuh), row kernel, sorted weight lists, bitmap gather gradient",
                      "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "steps/s (hard)", "cores": cores, "kind": "port",
                                       "sample": f"{cpu_n} full steps, oracle/cpu_paths.py:tfa_hard_step"},
                      "note": "fwd + bwd, device tensors in/out"}

@@ -119,17 +119,6 @@ __global__ void __launch_bounds__(BH_WARPS * 32) bh_mine_kernel(const float* __r
   }
 }
 
-// compact per-anchor record for the "who mined me" scan: x = positive column (-1 none, -2 tied: see BhRow),
-// y = negative column, z / w = the two coefficients as float bits
-__device__ __forceinline__ int4 make_compact(const BhRow& r) {
-  int4 c;
-  c.x = r.coef_pos == 0.f ? -1 : (r.pos_cnt == 1 ? r.pos_idx : -2);
-  c.y = r.coef_neg == 0.f ? -1 : (r.neg_cnt == 1 ? r.neg_idx : -2);
-  c.z = __float_as_int(r.coef_pos);
-  c.w = __float_as_int(r.coef_neg);
-  return c;
-}
-
 __device__ __forceinline__ double block_sum(double v, double* red) {
   for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   __syncthreads();
@@ -141,20 +130,6 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 }
 
 // One block.  stats = {mean(dists), mean(hardest_pos), mean(hardest_neg), max(dists)}
-// Per-anchor loss and cotangent scale from the hardest positive / negative (x = hn - hp for cosine similarities,
-// hp - hn for distances).  Hard margin (the reference, losses.py:47-51,81-85): max(x + alpha, 0), gradient 1 when
-// x + alpha >= 0 (tf.maximum).  Soft margin (arXiv 1703.07737 eq. 4, not in the reference): log(1 + exp(x)),
-// gradient sigmoid(x).  `basic` is the reference's own expression so the hard loss keeps its fp32 rounding.
-__device__ __forceinline__ void bh_loss_rule(float basic, float x, int soft, float dl, float& loss, float& g) {
-  if (!soft) {
-    loss = fmaxf(basic, 0.f);
-    g = basic >= 0.f ? dl : 0.f;
-  } else {
-    loss = x > 0.f ? x + log1pf(expf(-x)) : log1pf(expf(x));
-    g = dl / (1.f + expf(-x));
-  }
-}
-
 // Body shared by bh_merge_kernel (one block) and the fused small-batch kernel (every block redoes it into its own
 // shared memory; `write_out` selects the block that also writes loss / indices / statistics).
 template <bool COSINE>
@@ -280,43 +255,9 @@ __global__ void __launch_bounds__(256) bh_finalize_kernel(const BhRec* __restric
   const uint32_t gmax_o = (uint32_t)(*gmax_key >> 32);
   const float gmax = __uint_as_float((gmax_o & 0x80000000u) ? (gmax_o ^ 0x80000000u) : ~gmax_o);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double s_d = 0.0, s_hp = 0.0, s_hn = 0.0, s_gm = 0.0, s_cnt = 0.0;
-  if (i < B) {
-    const BhRec q = recs[i];
-    BhRow r;
-    r.pos_val = q.pos_val; r.neg_val = q.neg_val; r.pos_idx = q.pos_idx; r.neg_idx = q.neg_idx;
-    r.pos_cnt = q.pos_cnt; r.neg_cnt = q.neg_cnt; r.all_max = q.all_max; r.all_idx = q.all_idx; r.all_cnt = q.all_cnt;
-    const int n_pos = q.n_pos, n_non = B - n_pos;
-    const float fill_p = COSINE ? 1.f : 0.f, fill_n = COSINE ? -1.f : gmax;
-    float hp = r.pos_val, hn = r.neg_val;
-    int tie_p = r.pos_cnt, tie_n = r.neg_cnt, pidx = r.pos_idx, nidx = r.neg_idx;
-    if (n_non > 0) {
-      if (r.pos_cnt == 0 || (COSINE ? fill_p < hp : fill_p > hp)) { hp = fill_p; tie_p = n_non; pidx = -1; r.pos_cnt = 0; }
-      else if (fill_p == hp) tie_p += n_non;
-    }
-    if (n_pos > 0) {
-      if (r.neg_cnt == 0 || (COSINE ? fill_n > hn : fill_n < hn)) { hn = fill_n; tie_n = n_pos; nidx = -1; r.neg_cnt = 0; }
-      else if (fill_n == hn) tie_n += n_pos;
-    }
-    const float basic = COSINE ? __fadd_rn(__fsub_rn(hn, hp), alpha) : __fsub_rn(__fadd_rn(hp, alpha), hn);
-    float li, g;
-    bh_loss_rule(basic, COSINE ? hn - hp : hp - hn, soft, dloss ? dloss[i] : 1.f / (float)B, li, g);
-    loss[i] = li;
-    if (pos_idx_out) pos_idx_out[i] = pidx;
-    if (neg_idx_out) neg_idx_out[i] = nidx;
-    r.coef_pos = r.pos_cnt > 0 ? (COSINE ? -g : g) / (float)tie_p : 0.f;
-    r.coef_neg = r.neg_cnt > 0 ? (COSINE ? g : -g) / (float)tie_n : 0.f;
-    r.pos_idx = pidx;
-    r.neg_idx = nidx;
-    r.coef_gmax = (!COSINE && r.all_max == gmax) ? 1.f : 0.f;   // flag: bh_grad_kernel substitutes the real share
-    rows[i] = r;
-    compact[i] = make_compact(r);
-    s_d = (double)q.row_sum;
-    s_hp = (double)hp;
-    s_hn = (double)hn;
-    if (!COSINE && n_pos > 0 && hn == gmax) s_gm = (double)(-g) * (double)n_pos / (double)tie_n;
-    if (r.all_max == gmax) s_cnt = (double)r.all_cnt;
-  }
+  double sums[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (i < B) bh_finalize_row<COSINE>(recs[i], i, B, alpha, soft, dloss, gmax, loss, pos_idx_out, neg_idx_out, rows, compact, sums);
+  const double s_d = sums[0], s_hp = sums[1], s_hn = sums[2], s_gm = sums[3], s_cnt = sums[4];
   const double t_d = block_sum(s_d, red), t_hp = block_sum(s_hp, red), t_hn = block_sum(s_hn, red);
   const double t_gm = block_sum(s_gm, red), t_cnt = block_sum(s_cnt, red);
   if (threadIdx.x == 0) {
@@ -838,7 +779,7 @@ struct BhWorkspace {
       DIF_CUDA_OK(cudaMalloc((void**)&rows, n_rows * sizeof(BhRow)));
       DIF_CUDA_OK(cudaMalloc((void**)&aux, n_rows * sizeof(float)));
       DIF_CUDA_OK(cudaMalloc((void**)&compact, n_rows * sizeof(int4)));
-      DIF_CUDA_OK(cudaMalloc((void**)&partials, ((n_rows + 255) / 256) * 5 * sizeof(double)));
+      DIF_CUDA_OK(cudaMalloc((void**)&partials, ((n_rows + 7) / 8) * 5 * sizeof(double)));
       if (!gmax_key) DIF_CUDA_OK(cudaMalloc((void**)&gmax_key, 16));
       row_cap = n_rows;
     }
@@ -953,11 +894,16 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
   const float* cg_dev = nullptr;
   if (tensor_path) {
     DIF_CUDA_OK(cudaMemsetAsync(g_ws.gmax_key, 0, 16, st));
-    if (int rc = bh_mine_tensor<COSINE>(emb, labels, B, D, g_ws.recs, g_ws.aux, g_ws.gmax_key, st)) return rc;
-    const int fb = (B + 255) / 256;
-    bh_finalize_kernel<COSINE><<<fb, 256, 0, st>>>(g_ws.recs, B, alpha, soft, dloss, g_ws.gmax_key, loss, pos_idx, neg_idx,
-                                                  g_ws.rows, g_ws.compact, g_ws.partials);
-    DIF_LAUNCH_OK();
+    // cosine: the re-rank launch finalizes as well (one partial-sum record per 8 anchors); squared-L2 needs max(dists) first
+    BhFinalize fin{alpha, soft, dloss, loss, pos_idx, neg_idx, COSINE ? g_ws.rows : nullptr, g_ws.compact, g_ws.partials};
+    if (int rc = bh_mine_tensor<COSINE>(emb, labels, B, D, g_ws.recs, g_ws.aux, g_ws.gmax_key, fin, st)) return rc;
+    int fb = (B + kBhFusedFinalizeRows - 1) / kBhFusedFinalizeRows;
+    if (!COSINE) {
+      fb = (B + 255) / 256;
+      bh_finalize_kernel<COSINE><<<fb, 256, 0, st>>>(g_ws.recs, B, alpha, soft, dloss, g_ws.gmax_key, loss, pos_idx, neg_idx,
+                                                    g_ws.rows, g_ws.compact, g_ws.partials);
+      DIF_LAUNCH_OK();
+    }
     float* cg = reinterpret_cast<float*>(g_ws.gmax_key + 1);
     cg_dev = cg;
     if (demb && B <= BH_MAP_MAX_B) {

@@ -302,14 +302,12 @@ __device__ __forceinline__ bool rerank_class(const BhCand* __restrict__ cand, in
 }
 
 template <bool COSINE>
-__global__ void __launch_bounds__(128) bh_rerank_kernel(const BhCand* __restrict__ cand, int n_slots,
-                                                        const float* __restrict__ x, const int32_t* __restrict__ labels,
-                                                        const float* __restrict__ aux, const unsigned int* __restrict__ gmax_sq,
-                                                        int B, int D, BhRec* __restrict__ out,
-                                                        unsigned long long* __restrict__ gmax_key) {
+__device__ __forceinline__ void bh_rerank_row(const BhCand* __restrict__ cand, int n_slots, const float* __restrict__ x,
+                                              const int32_t* __restrict__ labels, const float* __restrict__ aux,
+                                              const unsigned int* __restrict__ gmax_sq, int B, int D,
+                                              BhRec* __restrict__ out, unsigned long long* __restrict__ gmax_key,
+                                              const BhFinalize& fin, int r, double* part) {
   const int lane = threadIdx.x & 31;
-  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (r >= B) return;
   // error window of the 3xTF32 pass (measured <= 1.2e-6 of sum |a||b|; 16x margin) plus the fp32 rounding of the sums
   float eps;
   if (COSINE) {
@@ -367,7 +365,43 @@ __global__ void __launch_bounds__(128) bh_rerank_kernel(const BhCand* __restrict
     out[r] = rec;
     if (rec.all_cnt > 0)
       atomicMax(gmax_key, ((unsigned long long)float_orderable(rec.all_max) << 32) | (0xFFFFFFFFu - (unsigned)r));
+    if (COSINE && fin.rows) {
+      double sums[5];
+      bh_finalize_row<COSINE>(rec, r, B, fin.alpha, fin.soft, fin.dloss, 0.f, fin.loss, fin.pos_idx, fin.neg_idx, fin.rows,
+                              fin.compact, sums);
+      sums[4] = 0.0;   // (the filler share is a squared-L2 matter)
+      for (int k = 0; k < 5; ++k) part[k] = sums[k];
+    }
   }
+}
+
+// The cosine loss needs nothing global to finalize an anchor (its fillers are the constants 1 / -1), so the
+// re-rank warp finalizes its anchor on the spot (fin.rows != NULL) and the block leaves one partial-sum record for
+// the statistics; the squared-L2 loss waits for max(dists) and keeps the separate bh_finalize_kernel.
+constexpr int kRerankWarps = 8;
+static_assert(kRerankWarps == kBhFusedFinalizeRows, "one partial-sum record per re-rank block");
+template <bool COSINE>
+__global__ void __launch_bounds__(kRerankWarps * 32) bh_rerank_kernel(const BhCand* __restrict__ cand, int n_slots,
+                                                        const float* __restrict__ x, const int32_t* __restrict__ labels,
+                                                        const float* __restrict__ aux, const unsigned int* __restrict__ gmax_sq,
+                                                        int B, int D, BhRec* __restrict__ out,
+                                                        unsigned long long* __restrict__ gmax_key, BhFinalize fin) {
+  __shared__ double s_part[kRerankWarps][5];
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * kRerankWarps + (threadIdx.x >> 5);
+  if (COSINE && fin.rows) {
+    if (lane == 0)   // (the only lane that writes this record, here and at the end of the row)
+      for (int k = 0; k < 5; ++k) s_part[threadIdx.x >> 5][k] = 0.0;
+    if (r < B) bh_rerank_row<COSINE>(cand, n_slots, x, labels, aux, gmax_sq, B, D, out, gmax_key, fin, r, s_part[threadIdx.x >> 5]);
+    __syncthreads();
+    if (threadIdx.x < 5) {
+      double t = 0.0;
+      for (int w = 0; w < kRerankWarps; ++w) t += s_part[w][threadIdx.x];
+      fin.partials[(size_t)blockIdx.x * 5 + threadIdx.x] = t;
+    }
+    return;
+  }
+  if (r < B) bh_rerank_row<COSINE>(cand, n_slots, x, labels, aux, gmax_sq, B, D, out, gmax_key, fin, r, s_part[0]);
 }
 
 struct TcWorkspace {
@@ -400,7 +434,7 @@ static thread_local TcWorkspace g_tc;
 // (recs [B]) plus aux [B] (inverse norm | sum of squares), exactly what bh_mine_kernel + the split merge produce.
 template <bool COSINE>
 int bh_mine_tensor(const float* emb, const int32_t* labels, int B, int D, BhRec* recs, float* aux,
-                   unsigned long long* gmax_key, cudaStream_t st) {
+                   unsigned long long* gmax_key, const BhFinalize& fin, cudaStream_t st) {
   const int sms = std::max(1, device_sm_count());
   GemmShape shape{};
   shape.m_blocks = (B + GEMM_BM - 1) / GEMM_BM;
@@ -435,12 +469,15 @@ int bh_mine_tensor(const float* emb, const int32_t* labels, int B, int D, BhRec*
   if (int rc = make_tmap_2d(&maps[3], g_tc.lo, B, D, (uint64_t)D * 4, kMineBN, 32, 0)) return rc;
   typename MineEpi<COSINE>::Params ep{g_tc.cand, labels, aux, g_tc.gmax, B};
   if (int rc = launch_nt_gemm<0, kMineBN, 1, 0, MineEpi<COSINE>>(maps, shape, ep, sms, st)) return rc;
-  bh_rerank_kernel<COSINE><<<(B + 3) / 4, 128, 0, st>>>(g_tc.cand, n_slots, emb, labels, aux, g_tc.gmax, B, D, recs, gmax_key);
+  bh_rerank_kernel<COSINE><<<(B + kRerankWarps - 1) / kRerankWarps, kRerankWarps * 32, 0, st>>>(
+      g_tc.cand, n_slots, emb, labels, aux, g_tc.gmax, B, D, recs, gmax_key, fin);
   DIF_LAUNCH_OK();
   return DIF_OK;
 }
 
-template int bh_mine_tensor<true>(const float*, const int32_t*, int, int, BhRec*, float*, unsigned long long*, cudaStream_t);
-template int bh_mine_tensor<false>(const float*, const int32_t*, int, int, BhRec*, float*, unsigned long long*, cudaStream_t);
+template int bh_mine_tensor<true>(const float*, const int32_t*, int, int, BhRec*, float*, unsigned long long*, const BhFinalize&,
+                                  cudaStream_t);
+template int bh_mine_tensor<false>(const float*, const int32_t*, int, int, BhRec*, float*, unsigned long long*, const BhFinalize&,
+                                   cudaStream_t);
 
 }  // namespace dif
