@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #include "bh_tile.cuh"
+#include "canon_mm.cuh"
 #include "dif_ptx.cuh"
 
 namespace dif {
@@ -1133,12 +1134,224 @@ __global__ void __launch_bounds__(BH_WARPS * 32) ba_grad_kernel(const float* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Large batches (B >= 256, D <= 128): the three passes above each recompute S with warp tiles (and the gradient runs
+// on B / 32 blocks).  Here S is produced ONCE by the one-thread-per-entry canonical kernel (canon_mm.cuh, the same
+// products in the same order, so `hp - S < alpha` decides exactly as before), a warp per anchor reduces its row, and
+// the gradient (G + G^T) N is a warp per anchor streaming N: B=1024 516 -> ~40 us.
+// ---------------------------------------------------------------------------------------------
+struct BaDotEpi {
+  __device__ __forceinline__ float operator()(int, int, float dot) const { return dot; }
+};
+
+__global__ void __launch_bounds__(256) ba_norm_kernel(const float* __restrict__ x, int B, int D, float* __restrict__ xn,
+                                                      float* __restrict__ inv_out) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= B) return;
+  float acc = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    const float t = x[(size_t)r * D + d];
+    acc = __fmaf_rn(t, t, acc);
+  }
+  const float inv = canon_inv_norm(canon_tree(acc));
+  for (int d = lane; d < D; d += 32) xn[(size_t)r * D + d] = __fmul_rn(x[(size_t)r * D + d], inv);
+  if (lane == 0) inv_out[r] = inv;
+}
+
+constexpr int BA_ROW_WARPS = 8;
+__global__ void __launch_bounds__(BA_ROW_WARPS * 32) ba_row_kernel(const float* __restrict__ S, int lds,
+                                                                   const int32_t* __restrict__ labels, int B, float alpha,
+                                                                   const float* __restrict__ dloss, float* __restrict__ loss,
+                                                                   BaRow* __restrict__ rows) {
+  const int i = blockIdx.x * BA_ROW_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= B) return;
+  const float* row = S + (size_t)i * lds;
+  const int my_lab = labels[i];
+  float hp = INFINITY, ps = 0.f;
+  int n_pos = 0;
+  for (int j = lane; j < B; j += 32) {
+    if (labels[j] == my_lab) {
+      const float v = row[j];
+      hp = fminf(hp, v);
+      ps += v;
+      ++n_pos;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    hp = fminf(hp, __shfl_xor_sync(0xffffffffu, hp, o));
+    ps += __shfl_xor_sync(0xffffffffu, ps, o);
+    n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
+  }
+  if (n_pos < B) hp = fminf(hp, 1.f);   // the 1.0 fillers of the non-positive columns
+  float sv = 0.f;
+  int nv = 0;
+  for (int j = lane; j < B; j += 32) {
+    const float v = row[j];
+    if (labels[j] != my_lab && __fsub_rn(hp, v) < alpha) {
+      sv += v;
+      ++nv;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    nv += __shfl_xor_sync(0xffffffffu, nv, o);
+  }
+  if (lane == 0) {
+    const float g = dloss ? dloss[i] : 1.f / (float)B;
+    loss[i] = ((float)n_pos - ps) / (float)n_pos + sv / ((float)nv + 1.f);
+    BaRow r;
+    r.hp = hp;
+    r.cp = -g / (float)n_pos;
+    r.cn = g / ((float)nv + 1.f);
+    r.n_pos = n_pos;
+    rows[i] = r;
+  }
+}
+
+// dN = (G + G^T) N as a split-K product: a warp owns 4 anchors and one range of columns j, keeps the weights of a
+// 128-column chunk in shared memory, streams the rows n_j (each load feeds 4 anchors) and leaves a partial sum;
+// ba_grad_reduce_kernel folds the ranges in a fixed order and applies the l2_normalize backward.
+constexpr int BA_GRAD_CHUNK = 128;
+constexpr int BA_GRAD_ROWS = 4;      // anchors per warp
+__global__ void __launch_bounds__(BA_ROW_WARPS * 32) ba_grad_fast_kernel(const float* __restrict__ S, int lds,
+                                                                         const float* __restrict__ xn,
+                                                                         const int32_t* __restrict__ labels, int B, int D,
+                                                                         const BaRow* __restrict__ rows, float alpha,
+                                                                         int cols_per_split, float* __restrict__ part) {
+  __shared__ float s_w[BA_ROW_WARPS][BA_GRAD_ROWS][BA_GRAD_CHUNK];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = (blockIdx.x * BA_ROW_WARPS + warp) * BA_GRAD_ROWS;
+  if (i0 >= B) return;   // warp-uniform; warps never synchronise with each other
+  const int c_begin = blockIdx.y * cols_per_split, c_end = min(B, c_begin + cols_per_split);
+  int my_lab[BA_GRAD_ROWS];
+  BaRow me[BA_GRAD_ROWS];
+#pragma unroll
+  for (int a = 0; a < BA_GRAD_ROWS; ++a) {
+    const int i = min(i0 + a, B - 1);
+    my_lab[a] = labels[i];
+    me[a] = rows[i];
+  }
+  float acc[BA_GRAD_ROWS][4];
+#pragma unroll
+  for (int a = 0; a < BA_GRAD_ROWS; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+  for (int j0 = c_begin; j0 < c_end; j0 += BA_GRAD_CHUNK) {
+    const int n = min(BA_GRAD_CHUNK, c_end - j0);
+    __syncwarp();
+    // w(i, j) = G_ij + G_ji: positives -1/n_pos each way, valid negatives +1/(n_valid + 1) each way
+#pragma unroll
+    for (int q = 0; q < BA_GRAD_CHUNK / 32; ++q) {
+      const int jj = lane + 32 * q, j = j0 + jj;
+      BaRow o;
+      o.hp = o.cp = o.cn = 0.f;
+      o.n_pos = 0;
+      int lab_j = -2;
+      float sim[BA_GRAD_ROWS];
+      if (jj < n) {
+        o = rows[j];
+        lab_j = labels[j];
+#pragma unroll
+        for (int a = 0; a < BA_GRAD_ROWS; ++a) sim[a] = S[(size_t)min(i0 + a, B - 1) * lds + j];
+      }
+#pragma unroll
+      for (int a = 0; a < BA_GRAD_ROWS; ++a) {
+        float w = 0.f;
+        if (jj < n && i0 + a < B) {
+          if (lab_j == my_lab[a]) {
+            w = me[a].cp + o.cp;
+          } else {
+            if (__fsub_rn(me[a].hp, sim[a]) < alpha) w += me[a].cn;   // j is a valid negative of anchor i
+            if (__fsub_rn(o.hp, sim[a]) < alpha) w += o.cn;           // i is a valid negative of anchor j
+          }
+        }
+        s_w[warp][a][jj] = w;
+      }
+    }
+    __syncwarp();
+    for (int jj = 0; jj < n; jj += 4) {
+      float v[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + min(jj + u, n - 1);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[u][c] = c * 32 + lane < D ? xn[(size_t)j * D + c * 32 + lane] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int a = 0; a < BA_GRAD_ROWS; ++a) {
+          const float w = jj + u < n ? s_w[warp][a][jj + u] : 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(w, v[u][c], acc[a][c]);
+        }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < BA_GRAD_ROWS; ++a)
+    if (i0 + a < B)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c * 32 + lane < D) part[((size_t)blockIdx.y * B + i0 + a) * D + c * 32 + lane] = acc[a][c];
+}
+
+// dx = inv * (dn - n (n . dn)), dn = the column ranges' partial sums in ascending order
+__global__ void __launch_bounds__(BA_ROW_WARPS * 32) ba_grad_reduce_kernel(const float* __restrict__ part, int n_splits,
+                                                                           const float* __restrict__ xn,
+                                                                           const float* __restrict__ inv, int B, int D,
+                                                                           float* __restrict__ demb) {
+  const int i = blockIdx.x * BA_ROW_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= B) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, nrm[4], dotp = 0.f;
+  for (int s = 0; s < n_splits; ++s)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c * 32 + lane < D) acc[c] += part[((size_t)s * B + i) * D + c * 32 + lane];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    nrm[c] = c * 32 + lane < D ? xn[(size_t)i * D + c * 32 + lane] : 0.f;
+    dotp += acc[c] * nrm[c];
+  }
+  for (int o = 16; o >= 1; o >>= 1) dotp += __shfl_xor_sync(0xffffffffu, dotp, o);
+  const float iv = inv[i];
+  const bool clamped = iv >= 0.99e6f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    if (c * 32 + lane < D) demb[(size_t)i * D + c * 32 + lane] = clamped ? iv * acc[c] : iv * (acc[c] - nrm[c] * dotp);
+}
+
 struct BaWorkspace {
   BaRow* rows = nullptr;
   float* pos_loss = nullptr;
   size_t row_cap = 0;
   float2* vrec = nullptr;
   size_t v_cap = 0;
+  float *xn = nullptr, *S = nullptr;   // large-batch path: normalised rows [B][D], similarity matrix [B][lds]
+  float* part = nullptr;               // [column ranges][B][D] partial gradients
+  size_t xn_cap = 0, s_cap = 0, part_cap = 0;
+  int ensure_matrix(size_t n_xn, size_t n_s, size_t n_part) {
+    if (n_part > part_cap) {
+      retire_device_block(part);
+      part = nullptr; part_cap = 0;
+      DIF_CUDA_OK(cudaMalloc((void**)&part, n_part * sizeof(float)));
+      part_cap = n_part;
+    }
+    if (n_xn > xn_cap) {
+      retire_device_block(xn);
+      xn = nullptr; xn_cap = 0;
+      DIF_CUDA_OK(cudaMalloc((void**)&xn, n_xn * sizeof(float)));
+      xn_cap = n_xn;
+    }
+    if (n_s > s_cap) {
+      retire_device_block(S);
+      S = nullptr; s_cap = 0;
+      DIF_CUDA_OK(cudaMalloc((void**)&S, n_s * sizeof(float)));
+      s_cap = n_s;
+    }
+    return DIF_OK;
+  }
   int ensure(size_t n_rows, size_t n_v) {
     if (n_rows > row_cap) {
       retire_device_block(rows); retire_device_block(pos_loss);
@@ -1243,6 +1456,33 @@ int dif_batch_all(const float* emb, const int32_t* labels, int B, int D, float a
   int cols = (B + splits - 1) / splits;
   cols = (cols + BH_TJ - 1) / BH_TJ * BH_TJ;
   splits = (B + cols - 1) / cols;
+  static const bool ba_tiles_only = getenv("DIF_BA_TILES") != nullptr;   // A/B switch
+  if (B >= 256 && B <= 16384 && D <= 128 && !ba_tiles_only) {
+    const int lds = (B + 3) & ~3;
+    if (int rc = g_ws.ensure(1, (size_t)B)) return rc;
+    if (int rc = g_ba.ensure((size_t)B, 1)) return rc;
+    // column ranges of the gradient: enough (32-anchor block, range) pairs for ~4 blocks per SM, whole 128-column chunks
+    const int gblocks = (B + BA_ROW_WARPS * BA_GRAD_ROWS - 1) / (BA_ROW_WARPS * BA_GRAD_ROWS);
+    int ks = std::max(1, std::min(16, (4 * sms + gblocks - 1) / gblocks));
+    int gcols = ((B + ks - 1) / ks + BA_GRAD_CHUNK - 1) / BA_GRAD_CHUNK * BA_GRAD_CHUNK;
+    ks = (B + gcols - 1) / gcols;
+    if (int rc = g_ba.ensure_matrix((size_t)B * D, (size_t)B * lds, demb ? (size_t)ks * B * D : 0)) return rc;
+    ba_norm_kernel<<<(B + 7) / 8, 256, 0, st>>>(emb, B, D, g_ba.xn, g_ws.aux);
+    DIF_LAUNCH_OK();
+    if (int rc = canon_mm_launch(g_ba.xn, B, D, BaDotEpi{}, g_ba.S, lds, st)) return rc;
+    ba_row_kernel<<<(B + BA_ROW_WARPS - 1) / BA_ROW_WARPS, BA_ROW_WARPS * 32, 0, st>>>(g_ba.S, lds, labels, B, alpha, dloss, loss,
+                                                                                      g_ba.rows);
+    DIF_LAUNCH_OK();
+    if (demb) {
+      ba_grad_fast_kernel<<<dim3(gblocks, ks), BA_ROW_WARPS * 32, 0, st>>>(g_ba.S, lds, g_ba.xn, labels, B, D, g_ba.rows, alpha,
+                                                                          gcols, g_ba.part);
+      DIF_LAUNCH_OK();
+      ba_grad_reduce_kernel<<<(B + BA_ROW_WARPS - 1) / BA_ROW_WARPS, BA_ROW_WARPS * 32, 0, st>>>(g_ba.part, ks, g_ba.xn, g_ws.aux, B,
+                                                                                              D, demb);
+      DIF_LAUNCH_OK();
+    }
+    return DIF_OK;
+  }
   if (int rc = g_ws.ensure((size_t)splits * B, (size_t)B)) return rc;
   if (int rc = g_ba.ensure((size_t)B, (size_t)splits * B)) return rc;
   const size_t smem = ((size_t)(BH_RB + BH_CB) * D + BH_RB + BH_CB) * sizeof(float) + BH_CB * sizeof(int) + 3 * BH_CB * sizeof(float);

@@ -164,7 +164,8 @@ def test_explicit_triplet_siamese_and_contrastive(gpu):
     assert _accuracy(yt, d[:, 0] / 10, 0.5) == lo.siamese_accuracy(yt, d[:, 0] / 10, 0.5)
 
 
-@pytest.mark.parametrize("P,K,D", [(18, 4, 128), (33, 3, 100), (128, 4, 256), (16, 2, 512)])
+@pytest.mark.parametrize("P,K,D", [(18, 4, 128), (33, 3, 100), (128, 4, 256), (16, 2, 512),
+                                   (256, 4, 128), (100, 3, 96), (67, 5, 50)])   # the last three: B >= 256, D <= 128 (matrix path)
 @pytest.mark.parametrize("noise,alpha", [(0.5, 0.35), (1.5, 0.2)])
 def test_batch_all(gpu, P, K, D, noise, alpha):
     from deep_insight_face_b200.common.losses import BatchAllTripletLoss
@@ -178,6 +179,24 @@ def test_batch_all(gpu, P, K, D, noise, alpha):
     close(got, want["loss"])
     close(grad, want["grad"], scale=max(np.abs(want["grad"]).max(), np.abs(emb).max() / emb.shape[0] * 1e-2))
     close(loss.call(onehot, emb), want["loss"])
+
+
+def test_batch_all_matrix_path_decides_like_the_tile_path(gpu):
+    """B >= 256 builds the similarity matrix once (canon_mm.cuh) instead of three tile passes: the same canonical
+    products, so the valid-negative counts - hence every loss term that is not a float sum - cannot move; the float
+    sums are folded in another order, so losses agree to rounding."""
+    from deep_insight_face_b200.common.losses import BatchAllTripletLoss
+    from oracle import losses_oracle as lo
+
+    emb, lab = pk_batch(128, 4, 128, 1.0)
+    emb[17] = emb[3]          # an exact duplicate
+    emb[200] = 0.0            # a zero row: l2_normalize clamps
+    got, grad, _ = BatchAllTripletLoss(alpha=0.35).loss_and_grad(lab, emb)
+    want = lo.batch_all_cosine(lab, emb, 0.35)
+    close(got, want["loss"])
+    close(grad, want["grad"], scale=max(np.abs(want["grad"]).max(), np.abs(emb).max() / emb.shape[0] * 1e-2))
+    got2, grad2, _ = BatchAllTripletLoss(alpha=0.35).loss_and_grad(lab, emb)
+    assert np.array_equal(got, got2) and np.array_equal(grad, grad2)
 
 
 def test_batch_hard_step_graph(gpu):
