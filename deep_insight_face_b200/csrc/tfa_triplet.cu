@@ -189,91 +189,110 @@ __device__ __forceinline__ void tfa_emit_row(int b, int B, int ldp, const TfaLis
   }
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(TFA_THREADS) tfa_row_kernel(const float* __restrict__ P, int ldp,
-                                                              const int32_t* __restrict__ labels, int B, float margin,
-                                                              int soft, int squared, TfaRow* __restrict__ rows,
-                                                              int32_t* __restrict__ pos_idx, int32_t* __restrict__ neg_idx,
-                                                              float* __restrict__ Cf, TfaLists L) {
+// Semi-hard: values first, like the hard kernel below.  Every sweep of the row is branch-free min / max / count
+// arithmetic; "which column, how many ties" is a second membership sweep against the reduced value, and the rarely
+// needed facts (ties of the row maximum, of the farthest negative) are computed on demand.
+template <int G>
+__device__ __forceinline__ void block_min_g(float (&v)[G], float (*s_gv)[G]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+    for (int g = 0; g < G; ++g) v[g] = fminf(v[g], __shfl_xor_sync(0xffffffffu, v[g], o));
+  __syncthreads();   // scratch free again
+  if (lane == 0)
+#pragma unroll
+    for (int g = 0; g < G; ++g) s_gv[warp][g] = v[g];
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    v[g] = s_gv[0][g];
+#pragma unroll
+    for (int w = 1; w < TFA_WARPS; ++w) v[g] = fminf(v[g], s_gv[w][g]);
+  }
+}
+// (first index, count) of G membership tests
+template <int G>
+__device__ __forceinline__ void block_first_count_g(int (&first)[G], int (&cnt)[G], int (*s_gi)[G], int (*s_gc)[G]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      first[g] = min(first[g], __shfl_xor_sync(0xffffffffu, first[g], o));
+      cnt[g] += __shfl_xor_sync(0xffffffffu, cnt[g], o);
+    }
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      s_gi[warp][g] = first[g];
+      s_gc[warp][g] = cnt[g];
+    }
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    first[g] = s_gi[0][g];
+    cnt[g] = s_gc[0][g];
+#pragma unroll
+    for (int w = 1; w < TFA_WARPS; ++w) {
+      first[g] = min(first[g], s_gi[w][g]);
+      cnt[g] += s_gc[w][g];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TFA_THREADS) tfa_semihard_row_kernel(const float* __restrict__ P, int ldp,
+                                                                       const int32_t* __restrict__ labels, int B, float margin,
+                                                                       int squared, TfaRow* __restrict__ rows,
+                                                                       float* __restrict__ Cf, TfaLists L) {
   extern __shared__ float sm[];
   float* srow = sm;                                          // [B]
   float* scf = srow + B;                                     // [B]
   unsigned char* sflag = reinterpret_cast<unsigned char*>(scf + B);   // [B]
-  __shared__ float s_v[TFA_WARPS];
-  __shared__ int s_i[TFA_WARPS], s_c[TFA_WARPS];
+  unsigned short* spos = reinterpret_cast<unsigned short*>(sflag + ((B + 1) & ~1));   // [n_pos] <= [B]
+  constexpr int G = 4;
+  __shared__ float s_gv[TFA_WARPS][G];
+  __shared__ int s_gi[TFA_WARPS][G], s_gc[TFA_WARPS][G];
+  __shared__ int s_c[TFA_WARPS];
+  __shared__ int s_fill;
   const int b = blockIdx.x, t = threadIdx.x;
   const int my_lab = labels[b];
-  float rmax = -INFINITY;
-  int rmax_i = -1, rmax_c = 0, npos_t = 0;
+  if (t == 0) s_fill = 0;
+  // sweep 1: the row, its flags, row maximum, farthest negative (negatives_inside), number of positives
+  float red[G] = {INFINITY, INFINITY, INFINITY, INFINITY};   // [0] = -rowmax, [1] = -max over negatives
+  int npos_t = 0;
   for (int j = t; j < B; j += TFA_THREADS) {
     const float v = P[(size_t)b * ldp + j];
+    const int f = j == b ? 0 : (labels[j] == my_lab ? 1 : 2);
     srow[j] = v;
     scf[j] = 0.f;
-    const int f = j == b ? 0 : (labels[j] == my_lab ? 1 : 2);
     sflag[j] = (unsigned char)f;
     npos_t += f == 1;
-    fold<false>(v, j, rmax, rmax_i, rmax_c);
+    red[0] = fminf(red[0], -v);
+    red[1] = fminf(red[1], f == 2 ? -v : INFINITY);
   }
-  block_extreme<false>(rmax, rmax_i, rmax_c, s_v, s_i, s_c);
+  block_min_g<G>(red, s_gv);
+  const float rmax = -red[0];
   const int n_pos = block_count(npos_t, s_c);
   const int n_neg = B - 1 - n_pos;
-
-  if (KIND == DIF_TFA_HARD) {
-    float hp_v = -INFINITY, mn_v = INFINITY;
-    int hp_i = -1, hp_c = 0, mn_i = -1, mn_c = 0;
-    for (int j = t; j < B; j += TFA_THREADS) {
-      if (sflag[j] == 1) fold<false>(srow[j], j, hp_v, hp_i, hp_c);
-      if (sflag[j] == 2) fold<true>(__fsub_rn(srow[j], rmax), j, mn_v, mn_i, mn_c);
+  const float in_v = n_neg > 0 ? -red[1] : 0.f;
+  const float inside = in_v;                                 // negatives_inside (row minimum 0 as filler)
+  // ordered list of this anchor's positives (ascending column)
+  if (n_pos <= TFA_THREADS) {
+    // a handful of positives (PK batches): append in any order, then rank-sort
+    __shared__ unsigned short s_tmp[TFA_THREADS];
+    for (int j = t; j < B; j += TFA_THREADS)
+      if (sflag[j] == 1) s_tmp[atomicAdd(&s_fill, 1)] = (unsigned short)j;
+    __syncthreads();
+    if (t < n_pos) {
+      const int c = s_tmp[t];
+      int rank = 0;
+      for (int e = 0; e < n_pos; ++e) rank += s_tmp[e] < c ? 1 : 0;
+      spos[rank] = (unsigned short)c;
     }
-    block_extreme<false>(hp_v, hp_i, hp_c, s_v, s_i, s_c);
-    block_extreme<true>(mn_v, mn_i, mn_c, s_v, s_i, s_c);
-    const float hp = hp_c > 0 ? hp_v : 0.f;                  // _masked_maximum: row minimum (the 0 diagonal) as filler
-    const float vmin = mn_c > 0 ? mn_v : 0.f;                // unmasked entries contribute (P - rowmax) * 0
-    const float hn = __fadd_rn(vmin, rmax);
-    const float xd = __fsub_rn(hp, hn);
-    float loss, g;
-    if (soft) {
-      loss = log1pf(expf(xd));
-      g = 1.f / (1.f + expf(-xd));
-    } else {
-      const float basic = __fadd_rn(xd, margin);
-      loss = fmaxf(basic, 0.f);
-      g = basic >= 0.f ? 1.f : 0.f;
-    }
-    if (t == 0) {
-      rows[b].loss_sum = (double)loss;
-      rows[b].n_pos = n_pos;
-      if (pos_idx) pos_idx[b] = hp_c > 0 ? hp_i : -1;
-      if (neg_idx) neg_idx[b] = mn_c > 0 ? mn_i : -1;
-    }
-    if (Cf) {
-      // reduce_min tie set: masked entries at vmin, plus every unmasked entry when vmin == 0
-      const int m_tied = (mn_c > 0 && mn_v == vmin) ? mn_c : 0;
-      const int n_tied = vmin == 0.f ? m_tied + (B - n_neg) : m_tied;
-      const float c_pos = hp_c > 0 ? g / (float)hp_c : 0.f;
-      const float c_neg = m_tied > 0 ? g / (float)n_tied : 0.f;
-      const float c_max = vmin == 0.f ? g * (1.f - (float)m_tied / (float)n_tied) / (float)rmax_c : 0.f;
-      tfa_emit_row(b, B, ldp, L, Cf, [&](int j) {
-        float cf = 0.f;
-        if (sflag[j] == 1 && srow[j] == hp_v) cf += c_pos;
-        if (sflag[j] == 2 && __fsub_rn(srow[j], rmax) == vmin) cf -= c_neg;
-        if (srow[j] == rmax) cf -= c_max;                   // gradient through the rowmax term of _masked_minimum
-        return tfa_weight(cf, srow[j], squared);
-      });
-    }
-    return;
-  }
-
-  // ---- semi-hard
-  float in_v = -INFINITY;
-  int in_i = -1, in_c = 0;
-  for (int j = t; j < B; j += TFA_THREADS)
-    if (sflag[j] == 2) fold<false>(srow[j], j, in_v, in_i, in_c);
-  block_extreme<false>(in_v, in_i, in_c, s_v, s_i, s_c);
-  const float inside = in_c > 0 ? in_v : 0.f;                // negatives_inside (row minimum 0 as filler)
-  // ordered list of this anchor's positives (ascending column), built chunk by chunk with warp ballots
-  unsigned short* spos = reinterpret_cast<unsigned short*>(sflag + ((B + 1) & ~1));   // [n_pos] <= [B]
-  {
+    __syncthreads();
+  } else {
     const int lane = t & 31, warp = t >> 5;
     int filled = 0;
     for (int c0 = 0; c0 < B; c0 += TFA_THREADS) {
@@ -294,54 +313,107 @@ __global__ void __launch_bounds__(TFA_THREADS) tfa_row_kernel(const float* __res
     }
     __syncthreads();
   }
-  double loss_sum = 0.0;
-  for (int ia = 0; ia < n_pos; ++ia) {
-    const int a = spos[ia];
-    const float pa = srow[a];
-    float out_v = INFINITY;
-    int out_i = -1, out_c = 0, n_mask_t = 0;
+  // on demand (block-uniform): ties of the farthest negative, ties of the row maximum
+  int in_i = -1, in_c = -1, rmax_c = -1;
+  auto need_inside = [&]() {
+    if (in_c >= 0) return;
+    int first[G] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff}, cnt[G] = {0, 0, 0, 0};
     for (int k = t; k < B; k += TFA_THREADS) {
-      if (sflag[k] == 2 && srow[k] > pa) {
-        ++n_mask_t;
-        fold<true>(__fsub_rn(srow[k], rmax), k, out_v, out_i, out_c);
+      const bool hit = sflag[k] == 2 && srow[k] == in_v;
+      cnt[0] += hit;
+      first[0] = hit ? min(first[0], k) : first[0];
+      cnt[1] += srow[k] == rmax;
+    }
+    block_first_count_g<G>(first, cnt, s_gi, s_gc);
+    in_i = first[0];
+    in_c = cnt[0];
+    rmax_c = cnt[1];
+  };
+  double loss_sum = 0.0;
+  for (int ia0 = 0; ia0 < n_pos; ia0 += G) {
+    int a_g[G];
+    float pa_g[G], ov[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      a_g[g] = ia0 + g < n_pos ? spos[ia0 + g] : -1;
+      pa_g[g] = a_g[g] >= 0 ? srow[a_g[g]] : INFINITY;   // nothing is farther than +inf: an empty slot stays empty
+      ov[g] = INFINITY;
+    }
+    // sweep A: for each of the four positives, the smallest shifted distance among the negatives farther than it
+    for (int k = t; k < B; k += TFA_THREADS) {
+      const float v = sflag[k] == 2 ? srow[k] : -INFINITY;   // (-inf is farther than nothing)
+      const float sh = __fsub_rn(v, rmax);
+#pragma unroll
+      for (int g = 0; g < G; ++g) ov[g] = fminf(ov[g], v > pa_g[g] ? sh : INFINITY);
+    }
+    block_min_g<G>(ov, s_gv);
+    // sweep B: which negative (first column), how many tie with it, how many are farther at all
+    int oi[G], oc[G], nm[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      oi[g] = 0x7fffffff;
+      oc[g] = 0;
+      nm[g] = 0;
+    }
+    for (int k = t; k < B; k += TFA_THREADS) {
+      const float v = sflag[k] == 2 ? srow[k] : -INFINITY;
+      const float sh = __fsub_rn(v, rmax);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const bool far = v > pa_g[g], hit = far && sh == ov[g];
+        nm[g] += far;
+        oc[g] += hit;
+        oi[g] = hit ? min(oi[g], k) : oi[g];
       }
     }
-    block_extreme<true>(out_v, out_i, out_c, s_v, s_i, s_c);
-    const bool outside = out_c > 0;                          // mask_final
-    const float sh = outside ? __fadd_rn(out_v, rmax) : inside;
-    const float lm = __fadd_rn(margin, __fsub_rn(pa, sh));
-    loss_sum += (double)fmaxf(lm, 0.f);
-    if (Cf && lm >= 0.f) {
-      // the usual case touches two entries: +1 on the positive, -1 on the one selected negative
-      if (outside && out_c == 1 && out_v != 0.f) {
-        if (t == 0) {
-          scf[a] += 1.f;
-          scf[out_i] -= 1.f;
-        }
-      } else if (!outside && in_c == 1) {
-        if (t == 0) {
-          scf[a] += 1.f;
-          scf[in_i] -= 1.f;
-        }
-      } else if (outside) {
-        int n_tied = out_c;
-        if (out_v == 0.f) n_tied += B - block_count(n_mask_t, s_c);   // every unmasked entry ties at 0
-        const float c_neg = 1.f / (float)n_tied;
-        const float c_max = out_v == 0.f ? (1.f - (float)out_c / (float)n_tied) / (float)rmax_c : 0.f;
-        for (int k = t; k < B; k += TFA_THREADS) {
-          float cf = scf[k];
-          if (k == a) cf += 1.f;
-          if (sflag[k] == 2 && srow[k] > pa && __fsub_rn(srow[k], rmax) == out_v) cf -= c_neg;
-          if (out_v == 0.f && srow[k] == rmax) cf -= c_max;
-          scf[k] = cf;
-        }
-      } else {
-        const float c_neg = in_c > 0 ? 1.f / (float)in_c : 0.f;
-        for (int k = t; k < B; k += TFA_THREADS) {
-          float cf = scf[k];
-          if (k == a) cf += 1.f;
-          if (sflag[k] == 2 && srow[k] == in_v) cf -= c_neg;
-          scf[k] = cf;
+    block_first_count_g<G>(oi, oc, s_gi, s_gc);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (a_g[g] < 0) continue;   // block-uniform
+      const int a = a_g[g];
+      const float pa = pa_g[g], out_v = ov[g];
+      const int out_i = oi[g], out_c = oc[g];
+      const bool outside = out_c > 0;                          // mask_final
+      const float sh = outside ? __fadd_rn(out_v, rmax) : inside;
+      const float lm = __fadd_rn(margin, __fsub_rn(pa, sh));
+      loss_sum += (double)fmaxf(lm, 0.f);
+      if (Cf && lm >= 0.f) {
+        if (!outside || out_v == 0.f) need_inside();
+        // the usual case touches two entries: +1 on the positive, -1 on the one selected negative
+        if (outside && out_c == 1 && out_v != 0.f) {
+          if (t == 0) {
+            scf[a] += 1.f;
+            scf[out_i] -= 1.f;
+          }
+        } else if (!outside && in_c == 1) {
+          if (t == 0) {
+            scf[a] += 1.f;
+            scf[in_i] -= 1.f;
+          }
+        } else if (outside) {
+          int n_tied = out_c;
+          if (out_v == 0.f) n_tied += B - block_count(nm[g], s_c);   // every unmasked entry ties at 0
+          const float c_neg = 1.f / (float)n_tied;
+          const float c_max = out_v == 0.f ? (1.f - (float)out_c / (float)n_tied) / (float)rmax_c : 0.f;
+          __syncthreads();   // thread 0's two-entry updates above are visible
+          for (int k = t; k < B; k += TFA_THREADS) {
+            float cf = scf[k];
+            if (k == a) cf += 1.f;
+            if (sflag[k] == 2 && srow[k] > pa && __fsub_rn(srow[k], rmax) == out_v) cf -= c_neg;
+            if (out_v == 0.f && srow[k] == rmax) cf -= c_max;
+            scf[k] = cf;
+          }
+          __syncthreads();
+        } else {
+          const float c_neg = in_c > 0 ? 1.f / (float)in_c : 0.f;
+          __syncthreads();
+          for (int k = t; k < B; k += TFA_THREADS) {
+            float cf = scf[k];
+            if (k == a) cf += 1.f;
+            if (sflag[k] == 2 && srow[k] == in_v) cf -= c_neg;
+            scf[k] = cf;
+          }
+          __syncthreads();
         }
       }
     }
@@ -772,8 +844,8 @@ extern "C" int dif_tfa_triplet(const float* emb, const int32_t* labels, int B, i
   static bool configured = false;
   if (!configured) {
     DIF_CUDA_OK(cudaFuncSetAttribute(tfa_pdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    DIF_CUDA_OK(cudaFuncSetAttribute(tfa_row_kernel<DIF_TFA_HARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    DIF_CUDA_OK(cudaFuncSetAttribute(tfa_row_kernel<DIF_TFA_SEMIHARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    DIF_CUDA_OK(cudaFuncSetAttribute(tfa_hard_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
+    DIF_CUDA_OK(cudaFuncSetAttribute(tfa_semihard_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = true;
   }
   // K1
@@ -796,16 +868,11 @@ extern "C" int dif_tfa_triplet(const float* emb, const int32_t* labels, int B, i
   // K2
   const size_t smem2 = (size_t)B * 11 + 32;   // row, coefficient row (fp32), flags (u8), positives list (u16)
   float* cf = demb ? g_tfa.Cf : nullptr;
-  static const bool generic_hard = getenv("DIF_TFA_GENERIC_HARD") != nullptr;   // A/B switch
-  if (base == DIF_TFA_HARD && !generic_hard)
+  if (base == DIF_TFA_HARD)
     tfa_hard_row_kernel<<<B, TFA_THREADS, (size_t)B * 5 + 16, st>>>(g_tfa.P, ldp, labels, B, margin, soft, squared, g_tfa.rows,
                                                                    pos_idx, neg_idx, cf, g_tfa.lists);
-  else if (base == DIF_TFA_HARD)
-    tfa_row_kernel<DIF_TFA_HARD><<<B, TFA_THREADS, smem2, st>>>(g_tfa.P, ldp, labels, B, margin, soft, squared, g_tfa.rows,
-                                                               pos_idx, neg_idx, cf, g_tfa.lists);
   else
-    tfa_row_kernel<DIF_TFA_SEMIHARD><<<B, TFA_THREADS, smem2, st>>>(g_tfa.P, ldp, labels, B, margin, 0, squared, g_tfa.rows,
-                                                                   nullptr, nullptr, cf, g_tfa.lists);
+    tfa_semihard_row_kernel<<<B, TFA_THREADS, smem2, st>>>(g_tfa.P, ldp, labels, B, margin, squared, g_tfa.rows, cf, g_tfa.lists);
   DIF_LAUNCH_OK();
   // K3
   tfa_finalize_kernel<<<1, 1024, 0, st>>>(g_tfa.rows, B, base, dloss, loss, g_tfa.scale);
