@@ -557,6 +557,38 @@ __global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_merge_grad_kernel(
 // Same arithmetic, same records, same gradient code as the two-launch path (bit-identical indices and gradients; the
 // statistics' float sums are folded in a different - fixed - order).
 constexpr int BH_CL_WARPS = 8;    // (sixteen warps were tried: staging 0.7 us faster, mining and exchange 1.7 us slower)
+// canonical dot products of row `gi` with rows lane, lane + 32, ... (NQ of them) out of a chain-major operand
+// [32 chains][n_rows][4] (row index XOR-swizzled by the chain): the 32 chains in bit-reversed order, folded by the
+// counter tree of canon_mm.cuh
+template <int NQ>
+__device__ __forceinline__ void chain_major_dots(const float* __restrict__ s_x, int n_rows, int gi, int lane, float (&dots)[4]) {
+  float st[6][NQ];
+#pragma unroll
+  for (int n = 0; n < 32; ++n) {
+    const int l = ((n & 1) << 4) | ((n & 2) << 2) | (n & 4) | ((n & 8) >> 2) | ((n & 16) >> 4);   // bit reversal
+    const int sw = (l >> 2) & 7;
+    const float4 a = *reinterpret_cast<const float4*>(s_x + ((size_t)l * n_rows + (gi ^ sw)) * 4);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int row = min(lane + 32 * q, n_rows - 1);
+      const float4 bq = *reinterpret_cast<const float4*>(s_x + ((size_t)l * n_rows + (row ^ sw)) * 4);
+      float sacc = __fmaf_rn(a.x, bq.x, 0.f);
+      sacc = __fmaf_rn(a.y, bq.y, sacc);
+      sacc = __fmaf_rn(a.z, bq.z, sacc);
+      sacc = __fmaf_rn(a.w, bq.w, sacc);
+      int lvl = 0;
+#pragma unroll
+      for (int m = n; m & 1; m >>= 1) {
+        sacc = __fadd_rn(st[lvl][q], sacc);
+        ++lvl;
+      }
+      st[lvl][q] = sacc;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) dots[q] = st[5][q];
+}
+
 constexpr int BH_CL_MAX_B = 128;
 template <bool COSINE>
 __global__ void __launch_bounds__(BH_CL_WARPS * 32) bh_cluster_step_kernel(
@@ -574,8 +606,13 @@ __global__ void __launch_bounds__(BH_CL_WARPS * 32) bh_cluster_step_kernel(
   };
   stamp(0);
   const int G = (int)gridDim.x, Bp = G * BH_TI;
-  float* s_x = sm;                                         // [Bp][D] staged rows (cosine: normalised)
-  float* s_raw = COSINE ? s_x + (size_t)Bp * D : s_x;      // [Bp][D] the rows as given (cosine keeps both: the gradient
+  // D <= 128: the mining operand is kept chain-major, [32 chains][Bp rows][4] (element d = l + 32 k of a row at
+  // (l, row ^ swizzle(l), k)), so that ONE thread can run all 32 canonical chains of an entry with one 16-byte load per
+  // chain and row (see canon_mm.cuh); wider rows keep the row-major warp tiles
+  const bool chain_major = D <= 128;
+  const int Dx = chain_major ? 128 : D;
+  float* s_x = sm;                                         // [Bp][Dx] mining operand (cosine: normalised)
+  float* s_raw = (COSINE || chain_major) ? s_x + (size_t)Bp * Dx : s_x;   // [Bp][D] the rows as given (the gradient
                                                            // code recomputes x * inv and must find x where it looks)
   float* s_aux = s_raw + (size_t)Bp * D;                   // [Bp] inverse norm | sum of squares
   int* s_lab = reinterpret_cast<int*>(s_aux + Bp);         // [Bp]
@@ -624,7 +661,15 @@ __global__ void __launch_bounds__(BH_CL_WARPS * 32) bh_cluster_step_kernel(
     }
     const float ss = canon_tree(acc);
     const float inv = canon_inv_norm(ss);
-    if (COSINE) {
+    if (chain_major) {
+      // lane = chain; (padding columns d >= D hold zeros: fma(0, 0, acc) = acc)
+      float4 q;
+      q.x = COSINE ? __fmul_rn(v[0], inv) : v[0];
+      q.y = COSINE ? __fmul_rn(v[1], inv) : v[1];
+      q.z = COSINE ? __fmul_rn(v[2], inv) : v[2];
+      q.w = COSINE ? __fmul_rn(v[3], inv) : v[3];
+      *reinterpret_cast<float4*>(s_x + ((size_t)lane * Bp + (r ^ ((lane >> 2) & 7))) * 4) = q;
+    } else if (COSINE) {
 #pragma unroll
       for (int c = 0; c < BH_MAX_KD; ++c) {
         const int d = c * 32 + lane;
@@ -636,8 +681,68 @@ __global__ void __launch_bounds__(BH_CL_WARPS * 32) bh_cluster_step_kernel(
   __syncthreads();
   stamp(1);
 
-  // 2. mine anchors 8g .. 8g + 7: warp w takes the column steps 4w, 4w + 32, ...
-  {
+  // 2. mine anchors 8g .. 8g + 7
+  if (chain_major) {
+    // warp w = anchor 8g + w, lane t = columns t, t + 32, ... : every thread runs the 32 chains of its (up to four)
+    // entries in bit-reversed order and folds them with the counter tree of canon_mm.cuh - 128 fma + 31 add per entry,
+    // no shuffles, no dependent tile steps (the warp-tile code below spends 4.5 us here at B = 72).  The anchor's
+    // record is then one butterfly over the warp.
+    const int gi = g * BH_TI + warp;
+    const int my_lab = gi < B ? s_lab[gi] : -1;
+    const float my_aux = s_aux[gi];
+    const int nq = (B + 31) >> 5;   // <= 4
+    float dots[4] = {0.f, 0.f, 0.f, 0.f};
+    // (the column count is a template argument: straight-line code, so the loads of later chains overlap the fma
+    // chains of earlier ones - with a run-time bound every chain waited for its own loads: 5.8 us instead of 4.5)
+    if (nq <= 1) chain_major_dots<1>(s_x, Bp, gi, lane, dots);
+    else if (nq == 2) chain_major_dots<2>(s_x, Bp, gi, lane, dots);
+    else if (nq == 3) chain_major_dots<3>(s_x, Bp, gi, lane, dots);
+    else chain_major_dots<4>(s_x, Bp, gi, lane, dots);
+    float pos_val = COSINE ? INFINITY : -INFINITY, neg_val = COSINE ? -INFINITY : INFINITY, all_max = -INFINITY;
+    int pos_idx = -1, neg_idx = -1, all_idx = -1, pos_cnt = 0, neg_cnt = 0, all_cnt = 0, n_pos = 0;
+    float row_sum = 0.f, pos_sum = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int gj = lane + 32 * q;
+      if (q < nq && gj < B && gi < B) {
+        const float dot = dots[q];
+        const float dist = COSINE ? dot : __fsub_rn(__fadd_rn(my_aux, s_aux[gj]), __fmul_rn(2.f, dot));
+        row_sum += dist;
+        fold<false>(dist, gj, all_max, all_idx, all_cnt);
+        if (s_lab[gj] == my_lab) {
+          ++n_pos;
+          pos_sum += dist;
+          fold<COSINE>(dist, gj, pos_val, pos_idx, pos_cnt);
+        } else {
+          fold<!COSINE>(dist, gj, neg_val, neg_idx, neg_cnt);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 1; o <= 16; o <<= 1) {
+      const float pv = __shfl_xor_sync(0xffffffffu, pos_val, o);
+      const int pi = __shfl_xor_sync(0xffffffffu, pos_idx, o), pc = __shfl_xor_sync(0xffffffffu, pos_cnt, o);
+      const float nv = __shfl_xor_sync(0xffffffffu, neg_val, o);
+      const int ni = __shfl_xor_sync(0xffffffffu, neg_idx, o), nc = __shfl_xor_sync(0xffffffffu, neg_cnt, o);
+      const float av = __shfl_xor_sync(0xffffffffu, all_max, o);
+      const int ai = __shfl_xor_sync(0xffffffffu, all_idx, o), ac = __shfl_xor_sync(0xffffffffu, all_cnt, o);
+      merge<COSINE>(pv, pi, pc, pos_val, pos_idx, pos_cnt);
+      merge<!COSINE>(nv, ni, nc, neg_val, neg_idx, neg_cnt);
+      merge<false>(av, ai, ac, all_max, all_idx, all_cnt);
+      row_sum = __fadd_rn(row_sum, __shfl_xor_sync(0xffffffffu, row_sum, o));
+      pos_sum = __fadd_rn(pos_sum, __shfl_xor_sync(0xffffffffu, pos_sum, o));
+      n_pos += __shfl_xor_sync(0xffffffffu, n_pos, o);
+    }
+    if (lane == 0) {   // already the anchor's merged record: the eight-warp merge below has nothing to add
+      BhRec r;
+      r.pos_val = pos_val; r.pos_idx = pos_idx; r.pos_cnt = pos_cnt;
+      r.neg_val = neg_val; r.neg_idx = neg_idx; r.neg_cnt = neg_cnt;
+      r.all_max = all_max; r.all_idx = all_idx; r.all_cnt = all_cnt;
+      r.row_sum = row_sum; r.n_pos = n_pos; r.pos_sum = pos_sum;
+      s_part[warp] = r;
+    }
+  } else {
+    // warp w takes the column steps 4w, 4w + 32, ...
     const int my_i = lane >> 2, gi = g * BH_TI + my_i;
     const int my_lab = gi < B ? s_lab[gi] : -1;
     const float my_aux = s_aux[gi];
@@ -687,7 +792,7 @@ __global__ void __launch_bounds__(BH_CL_WARPS * 32) bh_cluster_step_kernel(
   __syncthreads();
   stamp(2);
   // merge the eight warps' partials of each anchor (fixed warp order), then hand the record to every CTA
-  if (threadIdx.x < BH_TI) {
+  if (!chain_major && threadIdx.x < BH_TI) {
     const int a = threadIdx.x;
     BhRec m = s_part[a];
     for (int w = 1; w < BH_CL_WARPS; ++w) {
@@ -835,8 +940,10 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
   // small batches: the whole step in one cluster launch
   if (g_bh_force_path == 0 || g_bh_force_path == 3) {
     const int G = (B + BH_TI - 1) / BH_TI;
-    const size_t cl_smem = ((size_t)G * BH_TI * D * (COSINE ? 2 : 1) + 2 * (size_t)G * BH_TI) * 4 +
-                           ((size_t)G * BH_TI + BH_CL_WARPS * BH_TI) * sizeof(BhRec);
+    // mining operand (chain-major, padded to 128 columns, for D <= 128) + the rows as given (shared with the operand
+    // only for the squared-L2 loss on wide rows) + norms, labels, records
+    const size_t cl_rows = D <= 128 ? (size_t)G * BH_TI * (128 + D) : (size_t)G * BH_TI * D * (COSINE ? 2 : 1);
+    const size_t cl_smem = (cl_rows + 2 * (size_t)G * BH_TI) * 4 + ((size_t)G * BH_TI + BH_CL_WARPS * BH_TI) * sizeof(BhRec);
     if (B <= BH_CL_MAX_B && G <= 16 && D <= 32 * BH_MAX_KD && cl_smem <= 160 * 1024 && ((size_t)B * D * 4) % 16 == 0 &&
         (reinterpret_cast<uintptr_t>(emb) & 15u) == 0) {
       static int cluster_ok = -1;   // per instantiation: can a cluster of this kernel be scheduled at all?
