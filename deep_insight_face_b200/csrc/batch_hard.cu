@@ -130,6 +130,29 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return s;
 }
 
+// three sums for the price of one barrier pair (same per-sum order as block_sum)
+__device__ __forceinline__ void block_sum3(double& a, double& b, double& c, double* red) {
+  for (int o = 16; o >= 1; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  __syncthreads();
+  const int w = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
+  if ((threadIdx.x & 31) == 0) {
+    red[w] = a;
+    red[32 + w] = b;
+    red[64 + w] = c;
+  }
+  __syncthreads();
+  a = b = c = 0.0;
+  for (int i = 0; i < nw; ++i) {
+    a += red[i];
+    b += red[32 + i];
+    c += red[64 + i];
+  }
+}
+
 // One block.  stats = {mean(dists), mean(hardest_pos), mean(hardest_neg), max(dists)}
 // Body shared by bh_merge_kernel (one block) and the fused small-batch kernel (every block redoes it into its own
 // shared memory; `write_out` selects the block that also writes loss / indices / statistics).
@@ -138,7 +161,7 @@ __device__ __forceinline__ void bh_merge_body(const BhRec* __restrict__ recs, in
                                               const float* __restrict__ dloss, float* __restrict__ loss,
                                               int32_t* __restrict__ pos_idx_out, int32_t* __restrict__ neg_idx_out,
                                               float* __restrict__ stats, BhRow* rows, int4* compact, bool write_out) {
-  __shared__ double red[32];
+  __shared__ double red[96];
   __shared__ unsigned long long gmax_key;   // orderable(value) << 32 | ~first row
   __shared__ int gmax_cnt_s;
   if (threadIdx.x == 0) {
@@ -215,9 +238,8 @@ __device__ __forceinline__ void bh_merge_body(const BhRec* __restrict__ recs, in
       gm_share += (double)(-g) * (double)n_pos / (double)tie_n;
     rows[i] = r;
   }
-  const double tot_hp = block_sum(sum_hp, red);
-  const double tot_hn = block_sum(sum_hn, red);
-  const double tot_gm = block_sum(gm_share, red);
+  double tot_hp = sum_hp, tot_hn = sum_hn, tot_gm = gm_share;
+  block_sum3(tot_hp, tot_hn, tot_gm, red);
   if (threadIdx.x == 0 && write_out) {
     stats[0] = B > 0 ? (float)(tot_d / ((double)B * (double)B)) : 0.f;
     stats[1] = B > 0 ? (float)(tot_hp / (double)B) : 0.f;
@@ -650,6 +672,44 @@ __global__ void __launch_bounds__(BH_CL_WARPS * 32) bh_cluster_step_kernel(
   for (int r = threadIdx.x; r < Bp; r += blockDim.x) s_lab[r] = r < B ? labels[r] : -2;
   __syncthreads();                                             // the barrier is initialised for everyone
   mbar_wait(&s_bar, 0);
+  if (chain_major) {
+    // three rows per trip: their load -> fma -> butterfly -> sqrt / divide chains run side by side (one row at a time
+    // the nine rows of a warp were nine dependent chains in a row)
+    constexpr int U = 3;
+    for (int r0 = warp; r0 < Bp; r0 += U * BH_CL_WARPS) {
+      float v[U][4], acc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = min(r0 + u * BH_CL_WARPS, Bp - 1);
+        acc[u] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int d = c * 32 + lane;
+          v[u][c] = (c < kd && d < D) ? s_raw[(size_t)r * D + d] : 0.f;
+          if (c < kd) acc[u] = __fmaf_rn(v[u][c], v[u][c], acc[u]);   // chain `lane`: d = lane, lane + 32, ... (dif_canon.cuh)
+        }
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1)
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[u] = __fadd_rn(acc[u], __shfl_xor_sync(0xffffffffu, acc[u], o));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = r0 + u * BH_CL_WARPS;
+        if (r >= Bp) break;   // warp-uniform
+        const float ss = acc[u];
+        const float inv = canon_inv_norm(ss);
+        // lane = chain; (padding columns d >= D hold zeros: fma(0, 0, acc) = acc)
+        float4 q;
+        q.x = COSINE ? __fmul_rn(v[u][0], inv) : v[u][0];
+        q.y = COSINE ? __fmul_rn(v[u][1], inv) : v[u][1];
+        q.z = COSINE ? __fmul_rn(v[u][2], inv) : v[u][2];
+        q.w = COSINE ? __fmul_rn(v[u][3], inv) : v[u][3];
+        *reinterpret_cast<float4*>(s_x + ((size_t)lane * Bp + (r ^ ((lane >> 2) & 7))) * 4) = q;
+        if (lane == 0) s_aux[r] = COSINE ? inv : ss;
+      }
+    }
+  } else
   for (int r = warp; r < Bp; r += BH_CL_WARPS) {
     float v[BH_MAX_KD];
     float acc = 0.f;
@@ -661,15 +721,7 @@ __global__ void __launch_bounds__(BH_CL_WARPS * 32) bh_cluster_step_kernel(
     }
     const float ss = canon_tree(acc);
     const float inv = canon_inv_norm(ss);
-    if (chain_major) {
-      // lane = chain; (padding columns d >= D hold zeros: fma(0, 0, acc) = acc)
-      float4 q;
-      q.x = COSINE ? __fmul_rn(v[0], inv) : v[0];
-      q.y = COSINE ? __fmul_rn(v[1], inv) : v[1];
-      q.z = COSINE ? __fmul_rn(v[2], inv) : v[2];
-      q.w = COSINE ? __fmul_rn(v[3], inv) : v[3];
-      *reinterpret_cast<float4*>(s_x + ((size_t)lane * Bp + (r ^ ((lane >> 2) & 7))) * 4) = q;
-    } else if (COSINE) {
+    if (COSINE) {
 #pragma unroll
       for (int c = 0; c < BH_MAX_KD; ++c) {
         const int d = c * 32 + lane;
