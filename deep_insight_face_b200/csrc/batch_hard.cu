@@ -611,6 +611,48 @@ __device__ __forceinline__ void chain_major_dots(const float* __restrict__ s_x, 
   for (int q = 0; q < NQ; ++q) dots[q] = st[5][q];
 }
 
+// The same for TWO anchors (gi0, gi0 + 1) and HALF of the chains: half 0 = the sixteen even chains = the first sixteen
+// of the bit-reversed order, whose counter tree ends in y_0 of the canonical butterfly; half 1 = the odd chains, y_1.
+// The canonical total is y_0 + y_1.  Two anchors per thread halve the shared-memory traffic of the column operand
+// (the mining bound at C1: every B-row quad was read by all eight warps).
+template <int NQ>
+__device__ __forceinline__ void chain_major_half_dots(const float* __restrict__ s_x, int n_rows, int gi0, int half, int lane,
+                                                      float (&y)[2][4]) {
+  float st[5][2][NQ];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) {
+    const int n = half * 16 + m;   // position in the bit-reversed order; the low four bits drive the counter
+    const int l = ((n & 1) << 4) | ((n & 2) << 2) | (n & 4) | ((n & 8) >> 2) | ((n & 16) >> 4);
+    const int sw = (l >> 2) & 7;
+    float4 a[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) a[i] = *reinterpret_cast<const float4*>(s_x + ((size_t)l * n_rows + ((gi0 + i) ^ sw)) * 4);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int row = min(lane + 32 * q, n_rows - 1);
+      const float4 bq = *reinterpret_cast<const float4*>(s_x + ((size_t)l * n_rows + (row ^ sw)) * 4);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float sacc = __fmaf_rn(a[i].x, bq.x, 0.f);
+        sacc = __fmaf_rn(a[i].y, bq.y, sacc);
+        sacc = __fmaf_rn(a[i].z, bq.z, sacc);
+        sacc = __fmaf_rn(a[i].w, bq.w, sacc);
+        int lvl = 0;
+#pragma unroll
+        for (int mm = m; mm & 1; mm >>= 1) {
+          sacc = __fadd_rn(st[lvl][i][q], sacc);
+          ++lvl;
+        }
+        st[lvl][i][q] = sacc;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) y[i][q] = st[4][i][q];
+}
+
 constexpr int BH_CL_MAX_B = 128;
 template <bool COSINE>
 __global__ void __launch_bounds__(BH_CL_WARPS * 32) bh_cluster_step_kernel(
@@ -746,10 +788,25 @@ __global__ void __launch_bounds__(BH_CL_WARPS * 32) bh_cluster_step_kernel(
     float dots[4] = {0.f, 0.f, 0.f, 0.f};
     // (the column count is a template argument: straight-line code, so the loads of later chains overlap the fma
     // chains of earlier ones - with a run-time bound every chain waited for its own loads: 5.8 us instead of 4.5)
-    if (nq <= 1) chain_major_dots<1>(s_x, Bp, gi, lane, dots);
-    else if (nq == 2) chain_major_dots<2>(s_x, Bp, gi, lane, dots);
-    else if (nq == 3) chain_major_dots<3>(s_x, Bp, gi, lane, dots);
-    else chain_major_dots<4>(s_x, Bp, gi, lane, dots);
+    {
+      // warp (pair p, half h) runs half of the chains for anchors 2p, 2p + 1; the halves meet in shared memory
+      __shared__ float s_y[2][BH_TI][BH_CL_MAX_B];
+      const int pair = warp & 3, half = warp >> 2;
+      float y[2][4];
+      if (nq <= 1) chain_major_half_dots<1>(s_x, Bp, g * BH_TI + 2 * pair, half, lane, y);
+      else if (nq == 2) chain_major_half_dots<2>(s_x, Bp, g * BH_TI + 2 * pair, half, lane, y);
+      else if (nq == 3) chain_major_half_dots<3>(s_x, Bp, g * BH_TI + 2 * pair, half, lane, y);
+      else chain_major_half_dots<4>(s_x, Bp, g * BH_TI + 2 * pair, half, lane, y);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nq) s_y[half][2 * pair + i][lane + 32 * q] = y[i][q];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < nq) dots[q] = __fadd_rn(s_y[0][warp][lane + 32 * q], s_y[1][warp][lane + 32 * q]);
+    }
     float pos_val = COSINE ? INFINITY : -INFINITY, neg_val = COSINE ? -INFINITY : INFINITY, all_max = -INFINITY;
     int pos_idx = -1, neg_idx = -1, all_idx = -1, pos_cnt = 0, neg_cnt = 0, all_cnt = 0, n_pos = 0;
     float row_sum = 0.f, pos_sum = 0.f;
