@@ -439,7 +439,7 @@ def run_reference(args):
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def load_traffic(precision, workload, world, overridden):
@@ -783,10 +783,22 @@ def main():
         "modes": modes,
         "secondary": secondary,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def _emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
+    # Libraries chat on stdout (NCCL prints its version banner there when the first communicator is made): keep file
+    # descriptor 1 for the JSON line alone and send everything else to stderr.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     main()

@@ -69,6 +69,7 @@ SIGNATURES = {
     "dif_sync": (_i32, [_vp]),
     "dif_version": (C.c_char_p, []),
     "dif_launch_count": (_i64, []),
+    "dif_release_retired": (_i64, []),
     "dif_gallery_create": (_vp, [_i32, _i64, _i32, _i32, _i32]),
     "dif_gallery_destroy": (None, [_vp]),
     "dif_gallery_add": (_i32, [_vp, _vp, _vp, _i64, _vp]),
@@ -176,6 +177,12 @@ def init(device=None) -> None:
 
 def launch_count() -> int:
     return int(load_library().dif_launch_count())
+
+
+def release_retired() -> int:
+    """Free workspace blocks the loss entry points outgrew (kept alive for CUDA graphs captured at smaller sizes);
+    call when no such graph is alive, e.g. after a sweep over batch sizes.  Returns the number of blocks freed."""
+    return int(load_library().dif_release_retired())
 
 
 _c_char = C.c_char

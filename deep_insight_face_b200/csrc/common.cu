@@ -29,12 +29,23 @@ int count_launch(int n) {
 
 int device_sm_count() { return g_sm_count; }
 
+// Outgrown workspace blocks are parked, not freed: a CUDA graph captured earlier may still replay kernels that
+// point at them.  dif_release_retired() frees the lot when the caller knows no such graph is alive.
+static std::mutex g_retired_mu;
+static std::vector<void*>* g_retired = new std::vector<void*>();   // lives until the process exits
 void retire_device_block(void* p) {
-  static std::mutex mu;
-  static std::vector<void*>* retired = new std::vector<void*>();   // lives until the process exits
   if (!p) return;
-  std::lock_guard<std::mutex> lock(mu);
-  retired->push_back(p);
+  std::lock_guard<std::mutex> lock(g_retired_mu);
+  g_retired->push_back(p);
+}
+int64_t release_retired_blocks() {
+  std::vector<void*> blocks;
+  {
+    std::lock_guard<std::mutex> lock(g_retired_mu);
+    blocks.swap(*g_retired);
+  }
+  for (void* p : blocks) cudaFree(p);
+  return (int64_t)blocks.size();
 }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -107,5 +118,6 @@ int dif_sync(void* stream) {
 const char* dif_version(void) { return "dif_b200 0.1.0 (sm_100a)"; }
 
 int64_t dif_launch_count(void) { return dif::g_launches.load(); }
+int64_t dif_release_retired(void) { return dif::release_retired_blocks(); }
 
 }  // extern "C"

@@ -58,5 +58,6 @@ int device_sm_count();
 // Loss workspaces only grow.  A block that is outgrown is retired, not freed: CUDA graphs captured earlier
 // (BatchHardStep / ArcFaceStep of another shape) hold its address in their kernel nodes and must stay valid.
 void retire_device_block(void* p);
+int64_t release_retired_blocks();
 
 }  // namespace dif

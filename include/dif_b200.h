@@ -56,6 +56,11 @@ const char* dif_last_error(void);
 int dif_sync(void* stream);
 const char* dif_version(void);
 int64_t dif_launch_count(void);       /* kernels launched by this library since load (bench evidence) */
+/* The loss entry points keep per-thread workspaces sized for the largest batch seen; a block that is outgrown is parked
+ * rather than freed, because a CUDA graph captured at the smaller size may still replay kernels that point at it.  A
+ * sweep over batch sizes therefore holds every size's blocks until this call frees the parked ones: call it when no
+ * captured graph that contains library kernels is alive.  Returns the number of blocks freed. */
+int64_t dif_release_retired(void);
 
 /* ---- 1:N gallery search -------------------------------------------------------------------
  * New API (the reference only has 1:1 verify: predictions.py:104-150 `TripletPrediction.verify`,

@@ -199,6 +199,27 @@ def test_batch_all_matrix_path_decides_like_the_tile_path(gpu):
     assert np.array_equal(got, got2) and np.array_equal(grad, grad2)
 
 
+def test_outgrown_workspaces_can_be_released(gpu):
+    """A sweep over batch sizes parks every outgrown workspace block (a captured CUDA graph may still point at it);
+    dif_release_retired frees them and the next call allocates afresh."""
+    from deep_insight_face_b200 import _ffi
+    from deep_insight_face_b200.common.losses import BatchAllTripletLoss, BatchHardTripletLoss
+    from oracle import losses_oracle as lo
+
+    _ffi.release_retired()
+    for P in (130, 160, 200, 260):        # growing B: 520 .. 1040 rows, tensor-core miner and matrix batch-all
+        emb, lab = pk_batch(P, 4, 64, 1.0)
+        BatchHardTripletLoss().loss_and_grad(lab, emb)
+        BatchAllTripletLoss().loss_and_grad(lab, emb)
+    assert _ffi.release_retired() > 0
+    assert _ffi.release_retired() == 0
+    emb, lab = pk_batch(300, 4, 64, 1.0)
+    got, grad, _ = BatchHardTripletLoss().loss_and_grad(lab, emb)
+    want = lo.batch_hard_cosine(lab, emb, 0.35)
+    close(got, want["loss"], scale=1.0)
+    close(grad, want["grad"])
+
+
 def test_batch_hard_step_graph(gpu):
     import torch
 
