@@ -1431,6 +1431,7 @@ __global__ void __launch_bounds__(BA_ROW_WARPS * 32) ba_row_kernel(const float* 
 // ba_grad_reduce_kernel folds the ranges in a fixed order and applies the l2_normalize backward.
 constexpr int BA_GRAD_CHUNK = 128;
 constexpr int BA_GRAD_ROWS = 4;      // anchors per warp
+template <int KQ>   // 32-float chunks per row: 4 (D <= 128), 8 (<= 256), 16 (<= 512)
 __global__ void __launch_bounds__(BA_ROW_WARPS * 32) ba_grad_fast_kernel(const float* __restrict__ S, int lds,
                                                                          const float* __restrict__ xn,
                                                                          const int32_t* __restrict__ labels, int B, int D,
@@ -1449,11 +1450,12 @@ __global__ void __launch_bounds__(BA_ROW_WARPS * 32) ba_grad_fast_kernel(const f
     my_lab[a] = labels[i];
     me[a] = rows[i];
   }
-  float acc[BA_GRAD_ROWS][4];
+  constexpr int U = 16 / KQ;   // rows n_j in flight per trip
+  float acc[BA_GRAD_ROWS][KQ];
 #pragma unroll
   for (int a = 0; a < BA_GRAD_ROWS; ++a)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+    for (int c = 0; c < KQ; ++c) acc[a][c] = 0.f;
   for (int j0 = c_begin; j0 < c_end; j0 += BA_GRAD_CHUNK) {
     const int n = min(BA_GRAD_CHUNK, c_end - j0);
     __syncwarp();
@@ -1487,21 +1489,21 @@ __global__ void __launch_bounds__(BA_ROW_WARPS * 32) ba_grad_fast_kernel(const f
       }
     }
     __syncwarp();
-    for (int jj = 0; jj < n; jj += 4) {
-      float v[4][4];
+    for (int jj = 0; jj < n; jj += U) {
+      float v[U][KQ];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         const int j = j0 + min(jj + u, n - 1);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) v[u][c] = c * 32 + lane < D ? xn[(size_t)j * D + c * 32 + lane] : 0.f;
+        for (int c = 0; c < KQ; ++c) v[u][c] = c * 32 + lane < D ? xn[(size_t)j * D + c * 32 + lane] : 0.f;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int a = 0; a < BA_GRAD_ROWS; ++a) {
           const float w = jj + u < n ? s_w[warp][a][jj + u] : 0.f;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(w, v[u][c], acc[a][c]);
+          for (int c = 0; c < KQ; ++c) acc[a][c] = fmaf(w, v[u][c], acc[a][c]);
         }
     }
   }
@@ -1509,24 +1511,27 @@ __global__ void __launch_bounds__(BA_ROW_WARPS * 32) ba_grad_fast_kernel(const f
   for (int a = 0; a < BA_GRAD_ROWS; ++a)
     if (i0 + a < B)
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < KQ; ++c)
         if (c * 32 + lane < D) part[((size_t)blockIdx.y * B + i0 + a) * D + c * 32 + lane] = acc[a][c];
 }
 
 // dx = inv * (dn - n (n . dn)), dn = the column ranges' partial sums in ascending order
+template <int KQ>
 __global__ void __launch_bounds__(BA_ROW_WARPS * 32) ba_grad_reduce_kernel(const float* __restrict__ part, int n_splits,
                                                                            const float* __restrict__ xn,
                                                                            const float* __restrict__ inv, int B, int D,
                                                                            float* __restrict__ demb) {
   const int i = blockIdx.x * BA_ROW_WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= B) return;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, nrm[4], dotp = 0.f;
+  float acc[KQ], nrm[KQ], dotp = 0.f;
+#pragma unroll
+  for (int c = 0; c < KQ; ++c) acc[c] = 0.f;
   for (int s = 0; s < n_splits; ++s)
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < KQ; ++c)
       if (c * 32 + lane < D) acc[c] += part[((size_t)s * B + i) * D + c * 32 + lane];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < KQ; ++c) {
     nrm[c] = c * 32 + lane < D ? xn[(size_t)i * D + c * 32 + lane] : 0.f;
     dotp += acc[c] * nrm[c];
   }
@@ -1534,7 +1539,7 @@ __global__ void __launch_bounds__(BA_ROW_WARPS * 32) ba_grad_reduce_kernel(const
   const float iv = inv[i];
   const bool clamped = iv >= 0.99e6f;
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int c = 0; c < KQ; ++c)
     if (c * 32 + lane < D) demb[(size_t)i * D + c * 32 + lane] = clamped ? iv * acc[c] : iv * (acc[c] - nrm[c] * dotp);
 }
 
@@ -1673,7 +1678,7 @@ int dif_batch_all(const float* emb, const int32_t* labels, int B, int D, float a
   cols = (cols + BH_TJ - 1) / BH_TJ * BH_TJ;
   splits = (B + cols - 1) / cols;
   static const bool ba_tiles_only = getenv("DIF_BA_TILES") != nullptr;   // A/B switch
-  if (B >= 256 && B <= 16384 && D <= 128 && !ba_tiles_only) {
+  if (B >= 256 && B <= 16384 && D <= kCanonMmMaxD && !ba_tiles_only) {
     const int lds = (B + 3) & ~3;
     if (int rc = g_ws.ensure(1, (size_t)B)) return rc;
     if (int rc = g_ba.ensure((size_t)B, 1)) return rc;
@@ -1690,11 +1695,19 @@ int dif_batch_all(const float* emb, const int32_t* labels, int B, int D, float a
                                                                                       g_ba.rows);
     DIF_LAUNCH_OK();
     if (demb) {
-      ba_grad_fast_kernel<<<dim3(gblocks, ks), BA_ROW_WARPS * 32, 0, st>>>(g_ba.S, lds, g_ba.xn, labels, B, D, g_ba.rows, alpha,
-                                                                          gcols, g_ba.part);
-      DIF_LAUNCH_OK();
-      ba_grad_reduce_kernel<<<(B + BA_ROW_WARPS - 1) / BA_ROW_WARPS, BA_ROW_WARPS * 32, 0, st>>>(g_ba.part, ks, g_ba.xn, g_ws.aux, B,
-                                                                                              D, demb);
+      const dim3 gg(gblocks, ks), rg((B + BA_ROW_WARPS - 1) / BA_ROW_WARPS);
+      const int th = BA_ROW_WARPS * 32;
+      if (D <= 128) {
+        ba_grad_fast_kernel<4><<<gg, th, 0, st>>>(g_ba.S, lds, g_ba.xn, labels, B, D, g_ba.rows, alpha, gcols, g_ba.part);
+        ba_grad_reduce_kernel<4><<<rg, th, 0, st>>>(g_ba.part, ks, g_ba.xn, g_ws.aux, B, D, demb);
+      } else if (D <= 256) {
+        ba_grad_fast_kernel<8><<<gg, th, 0, st>>>(g_ba.S, lds, g_ba.xn, labels, B, D, g_ba.rows, alpha, gcols, g_ba.part);
+        ba_grad_reduce_kernel<8><<<rg, th, 0, st>>>(g_ba.part, ks, g_ba.xn, g_ws.aux, B, D, demb);
+      } else {
+        ba_grad_fast_kernel<16><<<gg, th, 0, st>>>(g_ba.S, lds, g_ba.xn, labels, B, D, g_ba.rows, alpha, gcols, g_ba.part);
+        ba_grad_reduce_kernel<16><<<rg, th, 0, st>>>(g_ba.part, ks, g_ba.xn, g_ws.aux, B, D, demb);
+      }
+      count_launch(1);   // (DIF_LAUNCH_OK counts the other one)
       DIF_LAUNCH_OK();
     }
     return DIF_OK;

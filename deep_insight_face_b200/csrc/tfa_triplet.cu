@@ -851,7 +851,7 @@ extern "C" int dif_tfa_triplet(const float* emb, const int32_t* labels, int B, i
   // K1
   const int sms = std::max(1, device_sm_count());
   static const bool slow_pdist = getenv("DIF_TFA_SLOW_PDIST") != nullptr;   // A/B switch
-  if (D <= 128 && B >= 256 && !slow_pdist) {
+  if (D <= kCanonMmMaxD && B >= 256 && !slow_pdist) {
     tfa_sqnorm_kernel<<<(B + 7) / 8, 256, 0, st>>>(emb, B, D, g_tfa.sq);
     DIF_LAUNCH_OK();
     if (int rc = canon_mm_launch(emb, B, D, TfaDistEpi{g_tfa.sq, squared}, g_tfa.P, ldp, st)) return rc;

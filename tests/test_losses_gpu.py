@@ -165,7 +165,7 @@ def test_explicit_triplet_siamese_and_contrastive(gpu):
 
 
 @pytest.mark.parametrize("P,K,D", [(18, 4, 128), (33, 3, 100), (128, 4, 256), (16, 2, 512),
-                                   (256, 4, 128), (100, 3, 96), (67, 5, 50)])   # the last three: B >= 256, D <= 128 (matrix path)
+                                   (256, 4, 128), (100, 3, 96), (67, 5, 50), (64, 4, 512), (90, 3, 200)])   # B >= 256: matrix path
 @pytest.mark.parametrize("noise,alpha", [(0.5, 0.35), (1.5, 0.2)])
 def test_batch_all(gpu, P, K, D, noise, alpha):
     from deep_insight_face_b200.common.losses import BatchAllTripletLoss

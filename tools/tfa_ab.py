@@ -17,7 +17,7 @@ from deep_insight_face_b200.common.tfa_losses import TFA_HARD, TFA_SEMIHARD, tfa
 
 out = {}
 rng = np.random.default_rng(7)
-for (P, K, D) in ((18, 4, 128), (83, 4, 128), (256, 4, 128), (100, 3, 64), (50, 5, 100), (40, 2, 32), (33, 3, 20), (512, 4, 96)):
+for (P, K, D) in ((18, 4, 128), (83, 4, 128), (256, 4, 128), (100, 3, 64), (50, 5, 100), (40, 2, 32), (33, 3, 20), (512, 4, 96), (150, 2, 256), (70, 4, 512), (90, 3, 200), (300, 1, 300)):
     B = P * K
     cent = 0.05 * rng.standard_normal((P, D)).astype(np.float32)
     x = (np.repeat(cent, K, 0) + 0.5 * rng.standard_normal((B, D))).astype(np.float32)
