@@ -579,40 +579,10 @@ __global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_merge_grad_kernel(
 // Same arithmetic, same records, same gradient code as the two-launch path (bit-identical indices and gradients; the
 // statistics' float sums are folded in a different - fixed - order).
 constexpr int BH_CL_WARPS = 8;    // (sixteen warps were tried: staging 0.7 us faster, mining and exchange 1.7 us slower)
-// canonical dot products of row `gi` with rows lane, lane + 32, ... (NQ of them) out of a chain-major operand
-// [32 chains][n_rows][4] (row index XOR-swizzled by the chain): the 32 chains in bit-reversed order, folded by the
-// counter tree of canon_mm.cuh
-template <int NQ>
-__device__ __forceinline__ void chain_major_dots(const float* __restrict__ s_x, int n_rows, int gi, int lane, float (&dots)[4]) {
-  float st[6][NQ];
-#pragma unroll
-  for (int n = 0; n < 32; ++n) {
-    const int l = ((n & 1) << 4) | ((n & 2) << 2) | (n & 4) | ((n & 8) >> 2) | ((n & 16) >> 4);   // bit reversal
-    const int sw = (l >> 2) & 7;
-    const float4 a = *reinterpret_cast<const float4*>(s_x + ((size_t)l * n_rows + (gi ^ sw)) * 4);
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int row = min(lane + 32 * q, n_rows - 1);
-      const float4 bq = *reinterpret_cast<const float4*>(s_x + ((size_t)l * n_rows + (row ^ sw)) * 4);
-      float sacc = __fmaf_rn(a.x, bq.x, 0.f);
-      sacc = __fmaf_rn(a.y, bq.y, sacc);
-      sacc = __fmaf_rn(a.z, bq.z, sacc);
-      sacc = __fmaf_rn(a.w, bq.w, sacc);
-      int lvl = 0;
-#pragma unroll
-      for (int m = n; m & 1; m >>= 1) {
-        sacc = __fadd_rn(st[lvl][q], sacc);
-        ++lvl;
-      }
-      st[lvl][q] = sacc;
-    }
-  }
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) dots[q] = st[5][q];
-}
-
-// The same for TWO anchors (gi0, gi0 + 1) and HALF of the chains: half 0 = the sixteen even chains = the first sixteen
-// of the bit-reversed order, whose counter tree ends in y_0 of the canonical butterfly; half 1 = the odd chains, y_1.
+// Canonical dot products out of a chain-major operand [32 chains][n_rows][4] (row index XOR-swizzled by the chain, see
+// canon_mm.cuh) for TWO anchors (gi0, gi0 + 1) against rows lane, lane + 32, ... (NQ of them), HALF of the chains:
+// half 0 = the sixteen even chains = the first sixteen of the bit-reversed order, whose counter tree ends in y_0 of the
+// canonical butterfly; half 1 = the odd chains, y_1.
 // The canonical total is y_0 + y_1.  Two anchors per thread halve the shared-memory traffic of the column operand
 // (the mining bound at C1: every B-row quad was read by all eight warps).
 template <int NQ>

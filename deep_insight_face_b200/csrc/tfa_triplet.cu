@@ -8,8 +8,9 @@
 //   semihard : for every positive pair (b, a): the closest negative farther than P_ba (same rowmax form), else the
 //              farthest negative;  sum max(margin + (P_ba - sh_ba), 0) / #positive pairs
 // Layout: P [B][ldp] fp32 (canonical arithmetic of dif_canon.cuh, so selections match oracle/tfa_oracle.py bit
-// for bit) and the coefficient matrix Cf = dL/dP [B][ldp], both in a library-owned workspace; the backward pass
-// folds Cf + Cf^T and 1/P into P in place and scatters w_ij (x_i - x_j) from the few non-zero entries of each row.
+// for bit) in a library-owned workspace; one block per anchor turns its row into a loss term and a short sorted
+// list of (column, weight = dL/dP * 1/P | 2) - a dense row of Cf only past TFA_LIST_CAP non-zeros - and the backward
+// pass gathers dX_r = scale * sum_j (W_rj + W_jr)(x_r - x_j) from the lists (own list, then the anchors that list r).
 // Every reduction has a fixed order: results are run-to-run identical.
 #include <algorithm>
 #include <cmath>
@@ -88,30 +89,7 @@ struct TfaDistEpi {
   }
 };
 
-// ---------------------------------------------------------------- block-wide (value, first index, tie count)
-template <bool MIN>
-__device__ __forceinline__ void block_extreme(float& v, int& i, int& c, float* s_v, int* s_i, int* s_c) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, i, o), oc = __shfl_xor_sync(0xffffffffu, c, o);
-    merge<MIN>(ov, oi, oc, v, i, c);
-  }
-  __syncthreads();   // scratch free again
-  if (lane == 0) {
-    s_v[warp] = v;
-    s_i[warp] = i;
-    s_c[warp] = c;
-  }
-  __syncthreads();
-  v = s_v[0];
-  i = s_i[0];
-  c = s_c[0];
-#pragma unroll
-  for (int w = 1; w < TFA_WARPS; ++w) merge<MIN>(s_v[w], s_i[w], s_c[w], v, i, c);
-}
-
+// ---------------------------------------------------------------- block-wide count
 __device__ __forceinline__ int block_count(int n, int* s_c) {
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
