@@ -351,6 +351,21 @@ __device__ __forceinline__ void axpy_row(float (&acc)[BH_MAX_KD], float w, const
 constexpr int BH_GRAD_WARPS = 8;
 constexpr int BH_GRAD_CHUNK = 1024;   // compact records staged per pass (16 KB)
 
+// bh_grad_map_kernel's scan also keeps, per row of the block, the (anchor, weight) pairs of the anchors that mined it
+constexpr int BH_MAP_LIST = 32;
+struct BhMapLists {
+  int cnt[BH_GRAD_WARPS];
+  int anchor[BH_GRAD_WARPS][BH_MAP_LIST];
+  float weight[BH_GRAD_WARPS][BH_MAP_LIST];
+  int any_tied;
+  // squared-L2: the share of the max(dists) filler gradient is folded from the finalize kernel's partial sums by the
+  // (one or two) warps whose row holds the maximum, not by every block
+  const double* partials;
+  int n_parts;
+  const unsigned long long* gmax_key;
+  float cg[BH_GRAD_WARPS];
+};
+
 // MODE 0: every block stages the compact records of all anchors and its warps scan them (O(B) per row);
 // MODE 2: the rows that mined r come from the bitmaps bh_grad_map_kernel built in shared memory (O(in-degree) per row).
 // Both visit the contributing anchors in ascending order, so the two variants give bit-identical gradients.
@@ -358,7 +373,8 @@ template <bool COSINE, int MODE>
 __device__ __forceinline__ void bh_grad_body(const float* __restrict__ x, const int32_t* __restrict__ labels, int B, int D,
                                              const float* __restrict__ aux,   // inv norm | sum sq
                                              const BhRow* rows, const int4* compact, const float* __restrict__ cg_dev,
-                                             float* __restrict__ demb, const unsigned* s_bits = nullptr) {
+                                             float* __restrict__ demb, const unsigned* s_bits = nullptr,
+                                             const BhMapLists* lists = nullptr) {
   __shared__ int4 s_c[MODE != 0 ? 1 : BH_GRAD_CHUNK];
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * BH_GRAD_WARPS + (threadIdx.x >> 5);
@@ -373,16 +389,129 @@ __device__ __forceinline__ void bh_grad_body(const float* __restrict__ x, const 
   if (active) me = rows[r];
   const int my_lab = active ? labels[r] : -1;
   if (cg_dev) me.coef_gmax = me.coef_gmax != 0.f ? *cg_dev : 0.f;   // multi-block finalize leaves a flag here
+  if (MODE == 2 && !COSINE && active && me.coef_gmax != 0.f) {      // warp-uniform: this row holds max(dists)
+    BhMapLists* wl = const_cast<BhMapLists*>(lists);
+    bh_stats_body(wl->partials, wl->n_parts, B, wl->gmax_key, nullptr, &wl->cg[threadIdx.x >> 5]);
+    __syncwarp();
+    me.coef_gmax = wl->cg[threadIdx.x >> 5];
+  }
 
+  // MODE 2, the usual case (no ties anywhere, D <= 128, a short list): the warp's whole work is a list of (row, weight)
+  // pairs - own positive, own negative, then the anchors that mined r in ascending order, the order of the code below -
+  // so the rows are fetched four at a time instead of one dependent load after the other
+  bool gathered = false;
+  if (MODE == 2) {
+    const int wid = threadIdx.x >> 5;
+    const int n_inv = lists->cnt[wid];
+    const bool untied = active && D <= 128 && !lists->any_tied && (me.coef_pos == 0.f || me.pos_cnt == 1) &&
+                        (me.coef_neg == 0.f || me.neg_cnt == 1);
+    if (untied) {   // warp-uniform
+      const float* xr = x + (size_t)r * D;
+      float a_r[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) a_r[c] = (!COSINE && c * 32 + lane < D) ? xr[c * 32 + lane] : 0.f;
+      // n list entries, one per lane: rows fetched four at a time, added in list order (the expressions of axpy_row)
+      auto gather = [&](int n, int my_j, float my_w) {
+        for (int e0 = 0; e0 < n; e0 += 4) {
+          float v[4][4], w[4], ib[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int src = min(e0 + u, n - 1);
+            const int j = __shfl_sync(0xffffffffu, my_j, src);
+            w[u] = __shfl_sync(0xffffffffu, my_w, src);
+            ib[u] = COSINE ? aux[j] : 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) v[u][c] = c * 32 + lane < D ? x[(size_t)j * D + c * 32 + lane] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (e0 + u < n) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+                if (c * 32 + lane < D) acc[c] += COSINE ? w[u] * (v[u][c] * ib[u]) : w[u] * 2.f * (a_r[c] - v[u][c]);
+            }
+        }
+      };
+      const int has_p = me.coef_pos != 0.f ? 1 : 0, has_n = me.coef_neg != 0.f ? 1 : 0;
+      int my_j = 0;
+      float my_w = 0.f;
+      if (lane < has_p) {
+        my_j = me.pos_idx;
+        my_w = me.coef_pos;
+      } else if (lane < has_p + has_n) {
+        my_j = me.neg_idx;
+        my_w = me.coef_neg;
+      }
+      if (n_inv <= BH_MAP_LIST - 2) {
+        // the scan's entries, ranked by anchor: lane t >= has_p + has_n takes the entry whose rank is t - has_p - has_n
+        const int want = lane - has_p - has_n;
+        const int a_in = lane < n_inv ? lists->anchor[wid][lane] : 0x7fffffff;
+        const float w_in = lane < n_inv ? lists->weight[wid][lane] : 0.f;
+        int rank_in = 0;
+        if (lane < n_inv)
+          for (int e = 0; e < n_inv; ++e) rank_in += lists->anchor[wid][e] < a_in ? 1 : 0;
+        for (int e = 0; e < n_inv; ++e) {
+          const int re = __shfl_sync(0xffffffffu, rank_in, e), ae = __shfl_sync(0xffffffffu, a_in, e);
+          const float we = __shfl_sync(0xffffffffu, w_in, e);
+          if (re == want) {
+            my_j = ae;
+            my_w = we;
+          }
+        }
+        gather(has_p + has_n + n_inv, my_j, my_w);
+      } else {
+        // a hub row (the hardest negative of dozens or hundreds of anchors: squared-L2 batches have them): own entries,
+        // then the bitmap 32 words at a time, its set bits handed to the lanes in ascending order, 32 anchors per
+        // round; every lane fetches its own anchor's record, then the rows are gathered as above
+        gather(has_p + has_n, my_j, my_w);
+        const int W = (B + 31) >> 5;
+        const unsigned* bm = s_bits + wid * W;
+        int* slot = const_cast<int*>(lists->anchor[wid]);   // (the scan's truncated list is not needed any more)
+        for (int w0 = 0; w0 < W; w0 += 32) {
+          const int wi = w0 + lane;
+          const unsigned word = wi < W ? bm[wi] : 0u;
+          const int cnt = __popc(word);
+          int incl = cnt;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+          }
+          const int total = __shfl_sync(0xffffffffu, incl, 31), first = incl - cnt;
+          for (int base = 0; base < total; base += 32) {
+            __syncwarp();
+            unsigned u = word;
+            for (int k = first; u; ++k) {
+              const int bit = __ffs((int)u) - 1;
+              u &= u - 1;
+              if (k >= base && k < base + 32) slot[k - base] = wi * 32 + bit;
+            }
+            __syncwarp();
+            const int n = min(32, total - base);
+            int a = 0;
+            float w = 0.f;
+            if (lane < n) {
+              a = slot[lane];
+              const int4 c = compact[a];
+              if (c.x == r) w += __int_as_float(c.z);
+              if (c.y == r) w += __int_as_float(c.w);
+            }
+            gather(n, a, w);
+          }
+        }
+      }
+      gathered = true;
+    }
+  }
   // --- own row: tied real positive / negative columns
-  if (active && me.coef_pos != 0.f) {
+  if (!gathered && active && me.coef_pos != 0.f) {
     if (me.pos_cnt == 1) axpy_row<COSINE>(acc, me.coef_pos, x, aux, D, r, me.pos_idx);
     else
       for (int j = 0; j < B; ++j)
         if (labels[j] == my_lab && warp_dist<COSINE>(x, aux, D, r, j) == me.pos_val)
           axpy_row<COSINE>(acc, me.coef_pos, x, aux, D, r, j);
   }
-  if (active && me.coef_neg != 0.f) {
+  if (!gathered && active && me.coef_neg != 0.f) {
     if (me.neg_cnt == 1) axpy_row<COSINE>(acc, me.coef_neg, x, aux, D, r, me.neg_idx);
     else
       for (int j = 0; j < B; ++j)
@@ -392,7 +521,7 @@ __device__ __forceinline__ void bh_grad_body(const float* __restrict__ x, const 
   if (MODE == 2) {
     // --- rows that mined r, from this warp's bitmap over the anchors (bit a set = anchor a mined r, or a is tied):
     // set bits come out in ascending anchor order, the order of the staged scan below
-    if (active) {
+    if (active && !gathered) {
       const int W = (B + 31) >> 5;
       const unsigned* bm = s_bits + (threadIdx.x >> 5) * W;
       const unsigned* tm = s_bits + BH_GRAD_WARPS * W;
@@ -529,22 +658,54 @@ __global__ void __launch_bounds__(BH_GRAD_WARPS * 32) bh_grad_map_kernel(
     const unsigned long long* __restrict__ gmax_key, float* __restrict__ stats, float* __restrict__ demb) {
   extern __shared__ unsigned s_map[];   // [BH_GRAD_WARPS + 1][W]
   __shared__ float s_cg;
+  __shared__ BhMapLists s_lists;
   const int W = (B + 31) >> 5;
   const int r0 = blockIdx.x * BH_GRAD_WARPS;
   for (int i = threadIdx.x; i < (BH_GRAD_WARPS + 1) * W; i += blockDim.x) s_map[i] = 0u;
-  if ((threadIdx.x >> 5) == 0 && (!COSINE || blockIdx.x == 0))
-    bh_stats_body(partials, n_parts, B, gmax_key, blockIdx.x == 0 ? stats : nullptr, &s_cg);
+  if (threadIdx.x < BH_GRAD_WARPS) s_lists.cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_lists.any_tied = 0;
+  if (threadIdx.x == 0) {
+    s_lists.partials = partials;
+    s_lists.n_parts = n_parts;
+    s_lists.gmax_key = gmax_key;
+  }
+  if ((threadIdx.x >> 5) == 0 && blockIdx.x == 0) bh_stats_body(partials, n_parts, B, gmax_key, stats, &s_cg);
   __syncthreads();
 #pragma unroll 4
   for (int a = threadIdx.x; a < B; a += BH_GRAD_WARPS * 32) {
     const int4 c = compact[a];
     const unsigned ux = (unsigned)(c.x - r0), uy = (unsigned)(c.y - r0), bit = 1u << (a & 31);
-    if (ux < (unsigned)BH_GRAD_WARPS) atomicOr(&s_map[ux * W + (a >> 5)], bit);
-    if (uy < (unsigned)BH_GRAD_WARPS) atomicOr(&s_map[uy * W + (a >> 5)], bit);
-    if (c.x == -2 || c.y == -2) atomicOr(&s_map[BH_GRAD_WARPS * W + (a >> 5)], bit);
+    if (ux < (unsigned)BH_GRAD_WARPS) {
+      atomicOr(&s_map[ux * W + (a >> 5)], bit);
+      // (a hub row - the hardest negative of hundreds of anchors - must not serialise the block on its counter: once the
+      // list is past its cap the row walks its bitmap anyway)
+      if (*reinterpret_cast<volatile int*>(&s_lists.cnt[ux]) <= BH_MAP_LIST) {
+        const int slot = atomicAdd(&s_lists.cnt[ux], 1);
+        if (slot < BH_MAP_LIST) {
+          s_lists.anchor[ux][slot] = a;
+          s_lists.weight[ux][slot] = __int_as_float(c.z);
+        }
+      }
+    }
+    if (uy < (unsigned)BH_GRAD_WARPS) {
+      atomicOr(&s_map[uy * W + (a >> 5)], bit);
+      // (a hub row - the hardest negative of hundreds of anchors - must not serialise the block on its counter: once the
+      // list is past its cap the row walks its bitmap anyway)
+      if (*reinterpret_cast<volatile int*>(&s_lists.cnt[uy]) <= BH_MAP_LIST) {
+        const int slot = atomicAdd(&s_lists.cnt[uy], 1);
+        if (slot < BH_MAP_LIST) {
+          s_lists.anchor[uy][slot] = a;
+          s_lists.weight[uy][slot] = __int_as_float(c.w);
+        }
+      }
+    }
+    if (c.x == -2 || c.y == -2) {
+      atomicOr(&s_map[BH_GRAD_WARPS * W + (a >> 5)], bit);
+      s_lists.any_tied = 1;
+    }
   }
   __syncthreads();
-  bh_grad_body<COSINE, 2>(x, labels, B, D, aux, rows, compact, COSINE ? nullptr : &s_cg, demb, s_map);
+  bh_grad_body<COSINE, 2>(x, labels, B, D, aux, rows, compact, nullptr, demb, s_map, &s_lists);
 }
 
 // Small batches (B <= 256): merge + gradient in one launch.  Every block redoes the (tiny) merge of all anchors
