@@ -656,7 +656,23 @@ __global__ void __launch_bounds__(TFA_GRAD_WARPS * 32) tfa_grad_sparse_kernel(Tf
   // a list held one entry per lane: rows are fetched four at a time, added in list order
   auto gather = [&](int n, int my_j, float my_w) {
     if (D <= 128) {
-      for (int e0 = 0; e0 < n; e0 += 4) {
+      int e0 = 0;
+      // long lists (hub rows): eight rows in flight per trip
+      for (; e0 + 8 <= n; e0 += 8) {
+        float v[8][4], w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int j = __shfl_sync(0xffffffffu, my_j, e0 + u);
+          w[u] = __shfl_sync(0xffffffffu, my_w, e0 + u);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[u][c] = c * 32 + lane < D ? x[(size_t)j * D + c * 32 + lane] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) acc[c] = __fmaf_rn(w[u], xr[c] - v[u][c], acc[c]);
+      }
+      for (; e0 < n; e0 += 4) {
         float v[4][4], w[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
