@@ -7,8 +7,14 @@ bit for bit with the GPU.  TensorFlow semantics that the reference relies on but
   reduce_min / reduce_max gradient = cotangent split evenly over every tied position;
   tf.where gradient flows only into the selected branch;  tf.maximum(x, 0) passes the gradient to x when x >= 0;
   Keras AUTO reduction = mean over the batch (default dloss = 1/B).
-PARITY UNPINNED by the reference: TensorFlow cannot be installed here and the reference ships no golden
-vectors; tests/test_oracle_cpu.py cross-checks these rules against torch autograd.
+PINNED AGAINST THE REFERENCE'S OWN SOURCE (round 2): TensorFlow cannot be installed here and the reference ships
+no golden vectors, so tests/golden/make_golden_losses.py IMPORTS deep_insight_face/common/
+losses.py (and cuts triplet_loss / euclidean_distance / contrastive_loss / _accuracy out of networks/*.py) and runs
+that code on a float64 torch stand-in for the two dozen TensorFlow / Keras-backend entry points it calls; the outputs
+(losses, gradients of mean(loss) by autograd through the reference's own op sequence, AutoAlpha state) are committed
+as tests/golden/losses_reference.npz and tests/test_parity_cpu.py holds these functions to them (2e-5).  What stays
+an assumption is that the stand-in's one-liners mean what TensorFlow's ops mean (listed above).  ArcFace (absent from
+the reference) remains parity-unpinned: its oracle is cross-checked against torch autograd only.
 """
 from __future__ import annotations
 

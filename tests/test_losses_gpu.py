@@ -199,6 +199,57 @@ def test_batch_all_matrix_path_decides_like_the_tile_path(gpu):
     assert np.array_equal(got, got2) and np.array_equal(grad, grad2)
 
 
+def test_cuda_losses_match_the_reference_source(gpu):
+    """The CUDA path against tests/golden/losses_reference.npz directly: what deep_insight_face/common/losses.py (imported
+    and run in the build container on a float64 stand-in for its TensorFlow calls), networks/triplet.py:triplet_loss and
+    networks/siamese.py compute, with the gradient of mean(loss) from autograd through the reference's own op sequence."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden_losses import CASES, pk_batch as ref_batch
+
+    from deep_insight_face_b200.common.losses import (BatchAllTripletLoss, BatchHardTripletLoss, BatchHardTripletLossEuclidean,
+                                                      BatchHardTripletLossEuclideanAutoAlpha)
+    from deep_insight_face_b200.networks.siamese import _accuracy, contrastive_loss, euclidean_distance
+    from deep_insight_face_b200.networks.triplet import triplet_loss
+
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "losses_reference.npz"))
+
+    def near(got, want, what, floor):
+        got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+        scale = max(np.abs(want).max(), floor)
+        assert np.abs(got - want).max() <= RTOL * scale, f"{what}: {np.abs(got - want).max():.3e} vs {scale:.3e}"
+
+    for name, P, K, D, noise, seed, flags in CASES:
+        emb, lab = ref_batch(P, K, D, noise, seed, **flags)
+        onehot = np.eye(int(lab.max()) + 1, dtype=np.float32)[lab]
+        for key, obj in (("bh_cos", BatchHardTripletLoss(alpha=0.35)), ("bh_euc", BatchHardTripletLossEuclidean(alpha=0.3 * D)),
+                         ("ball", BatchAllTripletLoss(alpha=0.35))):
+            loss, grad, _ = obj.loss_and_grad(onehot, emb)
+            near(loss, ref[f"{name}/{key}/loss"], f"{name}/{key} loss", 1.0)
+            near(grad, ref[f"{name}/{key}/grad"], f"{name}/{key} grad", 1e-3)
+        auto = BatchHardTripletLossEuclideanAutoAlpha(alpha=0.1, init_auto_alpha=1)
+        for step in range(2):
+            loss, grad, _ = auto.loss_and_grad(onehot, emb)
+            near(loss, ref[f"{name}/bh_auto{step}/loss"], f"{name}/auto{step} loss", 1.0)
+            near(grad, ref[f"{name}/bh_auto{step}/grad"], f"{name}/auto{step} grad", 1e-3)   # (single identity: +g and -g cancel in fp32)
+            want_alpha = float(ref[f"{name}/bh_auto{step}/auto_alpha_after"])
+            assert abs(float(auto.auto_alpha) - want_alpha) <= RTOL * abs(want_alpha)
+    for name in ("apn_a", "apn_b"):
+        y = ref[f"{name}/y"]
+        loss, grad = triplet_loss(None, y, alpha=0.4, return_grad=True)
+        near(loss, ref[f"{name}/loss"], name + " loss", 1.0)
+        near(grad / y.shape[0], ref[f"{name}/grad"], name + " grad", 1e-3)
+    a, b = ref["siamese/a"], ref["siamese/b"]
+    d = euclidean_distance([a, b])
+    near(d, ref["siamese/dist"], "euclidean_distance", 1.0)
+    y = (np.arange(50) % 2).astype(np.float32)
+    val, _ = contrastive_loss(y, d / 10, return_grad=True)
+    assert abs(val - float(ref["siamese/contrastive"])) <= RTOL * abs(val)
+    assert _accuracy(y, d[:, 0] / 10) == float(ref["siamese/accuracy_default"])
+
+
 def test_outgrown_workspaces_can_be_released(gpu):
     """A sweep over batch sizes parks every outgrown workspace block (a captured CUDA graph may still point at it);
     dif_release_retired frees them and the next call allocates afresh."""

@@ -135,3 +135,64 @@ def test_arcface_oracle_against_torch_autograd(s, m):
     np.testing.assert_allclose(want["loss"], loss, rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(want["dX"], dX, rtol=1e-7, atol=1e-10)
     np.testing.assert_allclose(want["dW"], dW, rtol=1e-7, atol=1e-10)
+
+
+# ------------------------------------------------------------------ losses: the reference's own source under an op stand-in
+@pytest.fixture(scope="module")
+def losses_ref():
+    return np.load(os.path.join(HERE, "golden", "losses_reference.npz"))
+
+
+def _close(got, want, rtol, what, floor=1e-4):
+    """|got - want| <= rtol * max(max |want|, floor).  Losses are O(1) quantities (cosines, margins): floor 1, so that a
+    loss that is zero up to fp32 rounding (all-singleton batches) is not held to 1e-5 of nothing; gradients get a
+    floor a tenth of their usual size (single-identity and all-singleton batches have analytically zero gradients)."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = max(np.abs(want).max(), floor)
+    err = np.abs(got - want).max()
+    assert err <= rtol * scale, f"{what}: max error {err:.3e} vs scale {scale:.3e}"
+
+
+def test_losses_oracle_matches_the_reference_source(losses_ref):
+    """tests/golden/losses_reference.npz holds what deep_insight_face/common/losses.py itself computes (the module is
+    imported and its classes called, on a float64 torch stand-in for the TensorFlow entry points it uses; gradients
+    of mean(loss) by autograd through the reference's own op sequence).  The oracle - the checker of every GPU test -
+    must agree: losses to fp32 rounding, gradients to 1e-5 of their scale, on PK batches incl. exact duplicates (tied
+    extremes split the cotangent), a zero row (l2_normalize clamp), a single identity and all-singleton batches."""
+    from make_golden_losses import CASES, pk_batch
+
+    from oracle import losses_oracle as lo
+
+    for name, P, K, D, noise, seed, flags in CASES:
+        emb, lab = pk_batch(P, K, D, noise, seed, **flags)
+        for key, got in (("bh_cos", lo.batch_hard_cosine(lab, emb, 0.35)),
+                         ("bh_euc", lo.batch_hard_euclidean(lab, emb, 0.3 * D)),
+                         ("ball", lo.batch_all_cosine(lab, emb, 0.35))):
+            _close(got["loss"], losses_ref[f"{name}/{key}/loss"], 2e-5, f"{name}/{key} loss", floor=1.0)
+            _close(got["grad"], losses_ref[f"{name}/{key}/grad"], 2e-5, f"{name}/{key} grad")
+        # AutoAlpha (losses.py:88-128): step 0 runs with the initial margin 1, then margin = mean(dists) * alpha
+        margin = 1.0
+        for step in range(2):
+            got = lo.batch_hard_euclidean(lab, emb, margin)
+            _close(got["loss"], losses_ref[f"{name}/bh_auto{step}/loss"], 2e-5, f"{name}/auto{step} loss", floor=1.0)
+            _close(got["grad"], losses_ref[f"{name}/bh_auto{step}/grad"], 2e-5, f"{name}/auto{step} grad")
+            margin = float(got["stats"][0]) * 0.1
+            assert abs(margin - float(losses_ref[f"{name}/bh_auto{step}/auto_alpha_after"])) <= 1e-5 * abs(margin)
+
+
+def test_apn_and_siamese_oracles_match_the_reference_source(losses_ref):
+    """networks/triplet.py:16-46 and networks/siamese.py:22-45, source cut out of the reference and executed."""
+    from oracle import losses_oracle as lo
+
+    for name in ("apn_a", "apn_b"):
+        got = lo.triplet_apn(losses_ref[f"{name}/y"], 0.4)
+        _close(got["loss"], losses_ref[f"{name}/loss"], 2e-5, name + " loss", floor=1.0)
+        _close(got["grad"] / got["loss"].shape[0], losses_ref[f"{name}/grad"], 2e-5, name + " grad")   # mean reduction
+    a, b = losses_ref["siamese/a"], losses_ref["siamese/b"]
+    d = lo.euclidean_distance(a, b)
+    _close(d, losses_ref["siamese/dist"], 2e-5, "euclidean_distance")
+    assert d[7, 0] == np.float32(np.sqrt(np.float32(1e-7)))            # the K.epsilon() clamp on a zero distance
+    y = (np.arange(50) % 2).astype(np.float64)
+    cl, dcl = lo.contrastive_loss(y, d / 10.0)
+    assert abs(cl - float(losses_ref["siamese/contrastive"])) <= 2e-5 * abs(cl)
+    assert lo.siamese_accuracy(y, d / 10.0) == float(losses_ref["siamese/accuracy_default"])
