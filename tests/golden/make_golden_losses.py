@@ -10,7 +10,8 @@ expressions in float64 with autograd.  What is executed is the reference's text,
    `tensorflow.python.ops`): BatchHardTripletLoss, BatchHardTripletLossEuclidean,
    BatchHardTripletLossEuclideanAutoAlpha, BatchAllTripletLoss are instantiated and `call(labels, embeddings)`ed;
  * networks/triplet.py:triplet_loss and networks/siamese.py:{euclidean_distance, contrastive_loss, _accuracy} live in
-   modules that import the whole Keras model zoo, so their source is cut out with `ast` and executed as is.
+   modules that import the whole Keras model zoo, so their source is cut out with `ast` and executed as is;
+ * networks/utils.py (numpy only) is imported; api.py:{face_distance, compare_faces} are cut out and executed.
 
 The stand-in follows TensorFlow where the two libraries differ: `maximum(x, y)` sends the gradient to x where x >= y
 (torch.maximum splits it at ties), `reduce_min / reduce_max` split the cotangent evenly over tied positions (torch.amin /
@@ -270,6 +271,31 @@ def main():
     out["siamese/a"], out["siamese/b"], out["siamese/dist"] = a, b, d.detach().numpy()
     out["siamese/contrastive"], out["siamese/grad_a"], out["siamese/grad_b"] = cl.detach().numpy(), at.grad.numpy(), bt.grad.numpy()
     out["siamese/accuracy_default"] = ns["_accuracy"](yt, (d / 10.0).detach()).numpy()
+    # networks/utils.py imports as is (numpy only); api.py:face_distance / compare_faces are cut out (the module builds a
+    # Keras model at import time) and executed with the reference's own helpers in scope
+    spec = importlib.util.spec_from_file_location("ref_utils", os.path.join(REF, "deep_insight_face/networks/utils.py"))
+    ru = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ru)
+    api_ns = {"np": np, "gaussian_kernel_dist_to_prob": ru.gaussian_kernel_dist_to_prob, "distance_to_proba": ru.distance_to_proba}
+    for fn in ("face_distance", "compare_faces"):
+        exec(function_source(os.path.join(REF, "deep_insight_face/api.py"), fn), api_ns)
+    e = rng.standard_normal((6, 128)).astype(np.float32)
+    e /= np.linalg.norm(e, axis=1, keepdims=True)
+    e[1] = e[0] + 0.02 * e[2]                                # a pair inside the 0.6 tolerance
+    out["api/enc"] = e
+    out["api/face_distance"] = np.array([api_ns["face_distance"](e[i], e[j]) for i in range(6) for j in range(6)])
+    cf = [api_ns["compare_faces"]([e[i]], [e[j]]) for i in range(6) for j in range(6)]
+    out["api/compare_faces"] = np.array(cf, dtype=np.float64)
+    out["api/face_distance_empty_shape"] = np.array(api_ns["face_distance"]([], e[0]).shape)
+    out["utils/distance"] = np.array([ru.distance(e[i], e[j]) for i in range(6) for j in range(6)], dtype=np.float64)
+    dgrid = np.linspace(0.0, 3.0, 13)
+    out["utils/dgrid"] = dgrid
+    out["utils/distance_to_proba"] = ru.distance_to_proba(dgrid)
+    out["utils/gaussian_kernel_1"] = ru.gaussian_kernel_dist_to_prob(dgrid)
+    out["utils/gaussian_kernel_half"] = ru.gaussian_kernel_dist_to_prob(dgrid, 0.5)
+    scores = rng.random(10)
+    out["utils/scores"] = scores
+    out["utils/calc_mean_score"] = np.float64(ru.calc_mean_score(scores))
     np.savez_compressed(os.path.join(HERE, "losses_reference.npz"), **out)
     print("wrote", len(out), "arrays to tests/golden/losses_reference.npz")
 

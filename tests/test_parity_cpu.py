@@ -196,3 +196,17 @@ def test_apn_and_siamese_oracles_match_the_reference_source(losses_ref):
     cl, dcl = lo.contrastive_loss(y, d / 10.0)
     assert abs(cl - float(losses_ref["siamese/contrastive"])) <= 2e-5 * abs(cl)
     assert lo.siamese_accuracy(y, d / 10.0) == float(losses_ref["siamese/accuracy_default"])
+
+
+def test_scalar_helpers_match_the_reference_module(losses_ref):
+    """networks/utils.py of the reference (imported as is by the golden generator) vs the drop-in's own-words versions."""
+    from deep_insight_face_b200.networks import utils as U
+
+    e = losses_ref["api/enc"]
+    got = np.array([U.distance(e[i], e[j]) for i in range(6) for j in range(6)], dtype=np.float64)
+    assert np.allclose(got, losses_ref["utils/distance"], rtol=1e-6, atol=1e-7)
+    d = losses_ref["utils/dgrid"]
+    assert np.array_equal(U.distance_to_proba(d), losses_ref["utils/distance_to_proba"])
+    assert np.array_equal(U.gaussian_kernel_dist_to_prob(d), losses_ref["utils/gaussian_kernel_1"])
+    assert np.array_equal(U.gaussian_kernel_dist_to_prob(d, 0.5), losses_ref["utils/gaussian_kernel_half"])
+    assert abs(U.calc_mean_score(losses_ref["utils/scores"]) - float(losses_ref["utils/calc_mean_score"])) <= 1e-12
