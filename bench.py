@@ -226,6 +226,27 @@ def secondary_metrics(torch, device, peaks, lib):
                                       "sample": f"{cpu_n} full steps (fwd + bwd), oracle/cpu_paths.py:batch_hard_step "
                                                 "(torch-CPU sgemm + where/amin/amax + autograd: the reference's TF-CPU op sequence)"},
                      "note": "fwd + bwd; steps_per_s = CUDA-graphed BatchHardStep, e2e = numpy in/out through dif_batch_hard_host"}
+    # C4 sweep (B = 72 ... 4096, D = 128): the graphed fwd + bwd step at every size, both metrics
+    sweep = {}
+    for Bs in (72, 128, 256, 512, 1024, 2048, 4096):
+        P = Bs // 4
+        cent = rng.standard_normal((P, 128)).astype(np.float32)
+        emb = (np.repeat(cent, 4, 0) + 1.0 * rng.standard_normal((P * 4, 128))).astype(np.float32)
+        lab = np.repeat(np.arange(P), 4).astype(np.int32)
+        row = {}
+        for key, variant in (("cosine_us", _ffi.LOSS_BH_COSINE), ("squared_l2_us", _ffi.LOSS_BH_EUCLIDEAN)):
+            step = BatchHardStep(P * 4, 128, variant, 0.35, device, graph=True)
+            step.emb.copy_(torch.from_numpy(emb).to(device))
+            step.labels.copy_(torch.from_numpy(lab).to(device))
+            row[key] = timed(step, 100) * 1e3
+        sweep[str(P * 4)] = row
+    out["c4_batch_hard_sweep_D128"] = {
+        "us_per_step": sweep,
+        "note": "CUDA-graphed fwd + bwd; B <= 128 one cluster launch, then the CUDA-core tile miner, then the tcgen05 filter + "
+                "canonical re-rank (cosine from B = 320, squared-L2 from B = 512); back-to-back graph launches land on a ~2 us grid",
+        "roofline": {"bound": "latency", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None,
+                     "note": "launch-chain latency below B ~ 2048 (see c4_batch_hard_B4096_D128 for the tensor roofline)"},
+        "cpu_baseline": out["c4_batch_hard_B4096_D128"]["cpu_baseline"]}
     # a5: batch-all (common/losses.py:131-148), fwd + bwd
     for name, P, K, D, iters in (("c4_batch_all_B1024_D128", 256, 4, 128, 30),):
         B = P * K

@@ -1238,7 +1238,9 @@ static int run_batch_hard(const float* emb, const int32_t* labels, int B, int D,
     }
   }
   // large batches: tensor-core filter + canonical re-rank (bh_tc.cu), then a multi-block finalize
-  const bool tensor_path = (g_bh_force_path == 2 || (g_bh_force_path == 0 && B >= 512)) && D >= 32 && D % 4 == 0;
+  // (measured, D = 128: cosine B = 256 30.8 us either way, B = 384 32.6 us on the tensor cores vs 39.0; squared-L2 B = 384
+  // 36.7 vs 32.3 - its epilogue and finalize are heavier - so the two losses switch at different sizes)
+  const bool tensor_path = (g_bh_force_path == 2 || (g_bh_force_path == 0 && B >= (COSINE ? 320 : 512))) && D >= 32 && D % 4 == 0;
   const float* cg_dev = nullptr;
   if (tensor_path) {
     DIF_CUDA_OK(cudaMemsetAsync(g_ws.gmax_key, 0, 16, st));

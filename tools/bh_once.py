@@ -1,4 +1,5 @@
-"""Time the CUDA-graphed batch-hard step (fwd + bwd) - development aid.   python tools/bh_once.py [B] [D] [variant]"""
+"""Time the CUDA-graphed batch-hard step (fwd + bwd) - development aid.   python tools/bh_once.py [B] [D] [variant] [path]
+(path: 0 auto, 1 CUDA-core miner, 2 tensor-core miner, 3 one-launch cluster step - dif_batch_hard_set_path)"""
 import os
 import sys
 
@@ -12,6 +13,9 @@ from deep_insight_face_b200.common.losses import BatchHardStep
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 variant = int(sys.argv[3]) if len(sys.argv) > 3 else _ffi.LOSS_BH_COSINE
+if len(sys.argv) > 4:
+    _ffi.init(0)
+    _ffi.check(_ffi.load_library().dif_batch_hard_set_path(int(sys.argv[4])))
 rng = np.random.default_rng(1)
 P, K = B // 4, 4
 emb = (np.repeat(rng.standard_normal((P, D)), K, 0) + rng.standard_normal((B, D))).astype(np.float32)
