@@ -266,7 +266,7 @@ def secondary_metrics(torch, device, peaks, lib):
                                       "sample": f"{cpu_n} full steps, oracle/cpu_paths.py:batch_all_step"},
                      "note": "fwd + bwd, device tensors in/out"}
     # a8: the tensorflow_addons losses the reference compiles its triplet models with (networks/triplet.py:196,209,211)
-    from deep_insight_face_b200.common.tfa_losses import TFA_HARD, TFA_SEMIHARD, tfa_triplet
+    from deep_insight_face_b200.common.tfa_losses import TFA_HARD, TFA_SEMIHARD, TfaTripletStep, tfa_triplet
 
     for name, P, K, D, iters in (("tfa_triplet_B72_D128", 18, 4, 128, 200), ("tfa_triplet_B4096_D128", 1024, 4, 128, 20)):
         B = P * K
@@ -277,8 +277,15 @@ def secondary_metrics(torch, device, peaks, lib):
         ld = torch.from_numpy(lab).to(device)
         ms_h = timed(lambda: tfa_triplet(ld, xd, TFA_HARD, 1.0), iters)
         ms_s = timed(lambda: tfa_triplet(ld, xd, TFA_SEMIHARD, 1.0), iters)
+        graphed = {}
+        for key, kind in (("hard_graphed_ms", TFA_HARD), ("semihard_graphed_ms", TFA_SEMIHARD)):
+            step = TfaTripletStep(B, D, kind, 1.0, device, graph=True)
+            step.emb.copy_(xd)
+            step.labels.copy_(ld)
+            graphed[key] = timed(step, iters * 3)
         cpu_s, cpu_n = cpu_timed(lambda: cp.tfa_hard_step(lab, emb, 1.0))
         out[name] = {"hard_steps_per_s": 1e3 / ms_h, "semihard_steps_per_s": 1e3 / ms_s, "hard_ms": ms_h, "semihard_ms": ms_s,
+                     **graphed, "hard_graphed_steps_per_s": 1e3 / graphed["hard_graphed_ms"],
                      "roofline": fp32_roofline(2.0 * B * B * D, ms_h, "hard loss; the full B x B distance matrix counted (the "
                                                "kernel computes the upper triangle once: P is symmetric bit for bit), plus 31 "
                                                "adds per entry for the canonical 32-chain tree that are not counted"),
@@ -288,7 +295,8 @@ def secondary_metrics(torch, device, peaks, lib):
                              "canonical fp32 warp tiles (bh_tile.cuh), row kernel, sorted weight lists, bitmap gather gradient",
                      "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "steps/s (hard)", "cores": cores, "kind": "port",
                                       "sample": f"{cpu_n} full steps, oracle/cpu_paths.py:tfa_hard_step"},
-                     "note": "fwd + bwd, device tensors in/out"}
+                     "note": "fwd + bwd, device tensors in/out; *_ms = one Python call per step (tensor allocation included), "
+                             "*_graphed_ms = TfaTripletStep (preallocated, one cudaGraphLaunch per step)"}
     # C4: verification sweep, 6000 LFW-style pairs, 10 folds, 400 + 4000 thresholds (evaluation/utility.py:10-33)
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     from synth import pairs as synth_pairs

@@ -80,12 +80,15 @@ __global__ void __launch_bounds__(256) tfa_sqnorm_kernel(const float* __restrict
 struct TfaDistEpi {
   const float* sq;   // [B] canonical sum of squares
   int squared;
-  __device__ __forceinline__ float operator()(int gi, int gj, float dot) const {
-    float v = __fsub_rn(__fadd_rn(sq[gi], sq[gj]), __fmul_rn(2.f, dot));   // (a + b == b + a: symmetric bit for bit)
+  __device__ __forceinline__ float from_norms(float sq_i, float sq_j, float dot, bool diagonal) const {
+    float v = __fsub_rn(__fadd_rn(sq_i, sq_j), __fmul_rn(2.f, dot));       // (a + b == b + a: symmetric bit for bit)
     v = fmaxf(v, 0.f);
     const bool err = v <= 0.f;                           // error_mask of metric_learning.pairwise_distance
     const float d = squared ? v : __fsqrt_rn(__fadd_rn(v, err ? 1e-16f : 0.f));
-    return (err || gj == gi) ? 0.f : d;
+    return (err || diagonal) ? 0.f : d;
+  }
+  __device__ __forceinline__ float operator()(int gi, int gj, float dot) const {
+    return from_norms(sq[gi], sq[gj], dot, gj == gi);
   }
 };
 
@@ -551,30 +554,43 @@ __global__ void __launch_bounds__(TFA_THREADS) tfa_hard_row_kernel(const float* 
 }
 
 // ---------------------------------------------------------------- K3: scalar loss and the backward scale
-__global__ void __launch_bounds__(1024) tfa_finalize_kernel(const TfaRow* __restrict__ rows, int B, int kind, float dloss,
-                                                            float* __restrict__ loss, float* __restrict__ scale) {
-  __shared__ double s_sum[1024];
-  __shared__ long long s_cnt[1024];
-  double sum = 0.0;
-  long long cnt = 0;
-  for (int b = threadIdx.x; b < B; b += 1024) {
-    sum += rows[b].loss_sum;
-    cnt += rows[b].n_pos;
+// All threads of a block of >= 256 threads call this; the first 256 fold the per-anchor terms in a fixed tree, so the
+// stand-alone kernel and the gradient kernel that does it for itself (small batches) produce the same bits.
+__device__ __forceinline__ void tfa_reduce_rows(const TfaRow* __restrict__ rows, int B, int kind, float dloss, float& loss,
+                                                float& scale) {
+  __shared__ double s_sum[256];
+  __shared__ long long s_cnt[256];
+  const int t = threadIdx.x;
+  if (t < 256) {
+    double sum = 0.0;
+    long long cnt = 0;
+    for (int b = t; b < B; b += 256) {
+      sum += rows[b].loss_sum;
+      cnt += rows[b].n_pos;
+    }
+    s_sum[t] = sum;
+    s_cnt[t] = cnt;
   }
-  s_sum[threadIdx.x] = sum;
-  s_cnt[threadIdx.x] = cnt;
   __syncthreads();
-  for (int o = 512; o >= 1; o >>= 1) {
-    if ((int)threadIdx.x < o) {
-      s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
-      s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o];
+  for (int o = 128; o >= 1; o >>= 1) {
+    if (t < o) {
+      s_sum[t] += s_sum[t + o];
+      s_cnt[t] += s_cnt[t + o];
     }
     __syncthreads();
   }
+  const double denom = kind == DIF_TFA_HARD ? (double)B : (double)s_cnt[0];   // 0 positive pairs: 0 / 0 = NaN as in tfa
+  loss = (float)(s_sum[0] / denom);
+  scale = (float)((double)dloss / denom);
+}
+
+__global__ void __launch_bounds__(256) tfa_finalize_kernel(const TfaRow* __restrict__ rows, int B, int kind, float dloss,
+                                                           float* __restrict__ loss, float* __restrict__ scale) {
+  float l, sc;
+  tfa_reduce_rows(rows, B, kind, dloss, l, sc);
   if (threadIdx.x == 0) {
-    const double denom = kind == DIF_TFA_HARD ? (double)B : (double)s_cnt[0];   // 0 positive pairs: 0 / 0 = NaN as in tfa
-    loss[0] = (float)(s_sum[0] / denom);
-    scale[0] = (float)((double)dloss / denom);
+    loss[0] = l;
+    scale[0] = sc;
   }
 }
 
@@ -588,8 +604,17 @@ constexpr int TFA_INV_CAP = 32;   // listing anchors kept per row in shared memo
 __global__ void __launch_bounds__(TFA_GRAD_WARPS * 32) tfa_grad_sparse_kernel(TfaLists L, const float* __restrict__ Cf, int ldp,
                                                                               const float* __restrict__ x, int B, int D,
                                                                               const float* __restrict__ scale,
-                                                                              float* __restrict__ dX) {
+                                                                              float* __restrict__ dX,
+                                                                              const TfaRow* __restrict__ fin_rows, int fin_kind,
+                                                                              float fin_dloss, float* __restrict__ fin_loss) {
   extern __shared__ unsigned s_map[];   // [TFA_GRAD_WARPS + 1][W]
+  // small batches: no separate finalize launch - every block folds the per-anchor terms itself (block 0 writes the loss)
+  float fused_scale = 0.f;
+  if (fin_rows) {
+    float l;
+    tfa_reduce_rows(fin_rows, B, fin_kind, fin_dloss, l, fused_scale);
+    if (blockIdx.x == 0 && threadIdx.x == 0) fin_loss[0] = l;
+  }
   __shared__ int s_cnt[TFA_GRAD_WARPS];
   __shared__ int s_anchor[TFA_GRAD_WARPS][TFA_INV_CAP];
   __shared__ float s_weight[TFA_GRAD_WARPS][TFA_INV_CAP];
@@ -769,7 +794,7 @@ __global__ void __launch_bounds__(TFA_GRAD_WARPS * 32) tfa_grad_sparse_kernel(Tf
       }
     }
   }
-  const float sc = scale[0];
+  const float sc = fin_rows ? fused_scale : scale[0];
 #pragma unroll
   for (int c = 0; c < BH_MAX_KD; ++c) {
     const int d = c * 32 + lane;
@@ -785,10 +810,11 @@ struct TfaWorkspace {
   float* sq = nullptr;   // [rows] canonical sum of squares (fast pairwise kernel)
   TfaLists lists{nullptr, nullptr, nullptr};
   size_t mat_cap = 0, row_cap = 0;
+  // (outgrown blocks are parked, not freed: a CUDA graph captured at the smaller size - TfaTripletStep - may still use them)
   int ensure(size_t mat, size_t n_rows, bool want_cf) {
     if (mat > mat_cap) {
-      cudaFree(P);
-      cudaFree(Cf);
+      retire_device_block(P);
+      retire_device_block(Cf);
       P = Cf = nullptr;
       mat_cap = 0;
       DIF_CUDA_OK(cudaMalloc((void**)&P, mat * sizeof(float)));
@@ -796,11 +822,11 @@ struct TfaWorkspace {
     }
     if (want_cf && !Cf) DIF_CUDA_OK(cudaMalloc((void**)&Cf, mat_cap * sizeof(float)));
     if (n_rows > row_cap) {
-      cudaFree(rows);
-      cudaFree(sq);
-      cudaFree(lists.count);
-      cudaFree(lists.cols);
-      cudaFree(lists.wts);
+      retire_device_block(rows);
+      retire_device_block(sq);
+      retire_device_block(lists.count);
+      retire_device_block(lists.cols);
+      retire_device_block(lists.wts);
       rows = nullptr;
       sq = nullptr;
       lists = TfaLists{nullptr, nullptr, nullptr};
@@ -844,7 +870,13 @@ extern "C" int dif_tfa_triplet(const float* emb, const int32_t* labels, int B, i
   }
   // K1
   const int sms = std::max(1, device_sm_count());
-  static const bool slow_pdist = getenv("DIF_TFA_SLOW_PDIST") != nullptr;   // A/B switch
+  static const bool slow_pdist = getenv("DIF_TFA_SLOW_PDIST") != nullptr;   // A/B switches
+  static const bool no_fuse = getenv("DIF_TFA_UNFUSED") != nullptr;
+  // small batches (the reference's own: 18 x 4) are launch chains: the gradient blocks fold the loss terms themselves, one
+  // launch less.  (Letting every row block compute its own row of the matrix as well - two launches - was measured and
+  // dropped: 29.5 us graphed at B = 72 against 24.6, each block repeats 2 B warp-dots.)
+  const bool small = B <= 128 && !no_fuse;
+  const float* Pm = g_tfa.P;
   if (D <= kCanonMmMaxD && B >= 256 && !slow_pdist) {
     tfa_sqnorm_kernel<<<(B + 7) / 8, 256, 0, st>>>(emb, B, D, g_tfa.sq);
     DIF_LAUNCH_OK();
@@ -863,19 +895,22 @@ extern "C" int dif_tfa_triplet(const float* emb, const int32_t* labels, int B, i
   const size_t smem2 = (size_t)B * 11 + 32;   // row, coefficient row (fp32), flags (u8), positives list (u16)
   float* cf = demb ? g_tfa.Cf : nullptr;
   if (base == DIF_TFA_HARD)
-    tfa_hard_row_kernel<<<B, TFA_THREADS, (size_t)B * 5 + 16, st>>>(g_tfa.P, ldp, labels, B, margin, soft, squared, g_tfa.rows,
+    tfa_hard_row_kernel<<<B, TFA_THREADS, (size_t)B * 5 + 16, st>>>(Pm, ldp, labels, B, margin, soft, squared, g_tfa.rows,
                                                                    pos_idx, neg_idx, cf, g_tfa.lists);
   else
-    tfa_semihard_row_kernel<<<B, TFA_THREADS, smem2, st>>>(g_tfa.P, ldp, labels, B, margin, squared, g_tfa.rows, cf, g_tfa.lists);
+    tfa_semihard_row_kernel<<<B, TFA_THREADS, smem2, st>>>(Pm, ldp, labels, B, margin, squared, g_tfa.rows, cf, g_tfa.lists);
   DIF_LAUNCH_OK();
-  // K3
-  tfa_finalize_kernel<<<1, 1024, 0, st>>>(g_tfa.rows, B, base, dloss, loss, g_tfa.scale);
-  DIF_LAUNCH_OK();
+  // K3 (folded into K4 for small batches with a backward pass)
+  const bool fuse_fin = small && demb != nullptr;
+  if (!fuse_fin) {
+    tfa_finalize_kernel<<<1, 256, 0, st>>>(g_tfa.rows, B, base, dloss, loss, g_tfa.scale);
+    DIF_LAUNCH_OK();
+  }
   if (!demb) return DIF_OK;
   // K4
   const size_t map_smem = (size_t)(TFA_GRAD_WARPS + 1) * ((B + 31) / 32) * sizeof(unsigned);
   tfa_grad_sparse_kernel<<<(B + TFA_GRAD_WARPS - 1) / TFA_GRAD_WARPS, TFA_GRAD_WARPS * 32, map_smem, st>>>(
-      g_tfa.lists, g_tfa.Cf, ldp, emb, B, D, g_tfa.scale, demb);
+      g_tfa.lists, g_tfa.Cf, ldp, emb, B, D, g_tfa.scale, demb, fuse_fin ? g_tfa.rows : nullptr, base, dloss, loss);
   DIF_LAUNCH_OK();
   return DIF_OK;
 }

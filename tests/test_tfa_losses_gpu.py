@@ -186,3 +186,28 @@ def test_torch_autograd_and_config_roundtrip():
         assert _close(e.grad.cpu().numpy(), 3.0 * g64)
     with pytest.raises(NotImplementedError):
         TripletHardLoss(distance_metric="angular")
+
+
+def test_preallocated_and_graphed_step_equals_the_call():
+    """TfaTripletStep (fixed buffers, optionally one CUDA graph launch per step) gives the bits of tfa_triplet, also after
+    the library workspace has grown for a larger batch in between (outgrown blocks stay alive for captured graphs)."""
+    import torch
+
+    from deep_insight_face_b200.common.tfa_losses import TFA_HARD, TFA_SEMIHARD, TfaTripletStep, tfa_triplet
+
+    lab, x = _pk(18, 4, 128, seed=31, scale=0.1)
+    xd, ld = torch.from_numpy(x).cuda(), torch.from_numpy(lab.astype(np.int32)).cuda()
+    for kind in (TFA_HARD, TFA_SEMIHARD):
+        want_loss, want_grad, want_info = tfa_triplet(ld, xd, kind, 1.0)
+        for graph in (False, True):
+            step = TfaTripletStep(72, 128, kind, 1.0, "cuda:0", graph=graph)
+            step.emb.copy_(xd)
+            step.labels.copy_(ld)
+            big_lab, big_x = _pk(128, 4, 128, seed=32)          # grows the workspace (B = 512) between capture and replay
+            tfa_triplet(torch.from_numpy(big_lab.astype(np.int32)).cuda(), torch.from_numpy(big_x).cuda(), kind, 1.0)
+            for _ in range(3):
+                loss, grad = step()
+            torch.cuda.synchronize()
+            assert torch.equal(loss[0], want_loss) and torch.equal(grad, want_grad)
+            if kind == TFA_HARD:
+                assert torch.equal(step.pos_idx, want_info["pos_idx"]) and torch.equal(step.neg_idx, want_info["neg_idx"])
