@@ -212,12 +212,24 @@ def secondary_metrics(torch, device, peaks, lib):
         for _ in range(n_host):
             loss.loss_and_grad(lab, emb)
         host_ms = (time.perf_counter() - t0) / n_host * 1e3
+        # the same host-to-host step without copies: the caller works in the library's page-locked block
+        from deep_insight_face_b200.common.losses import BatchHardHostStep
+        hstep = BatchHardHostStep(P * K, D, _ffi.LOSS_BH_COSINE, 0.35)
+        hstep.emb[:] = emb
+        hstep.labels[:] = lab
+        for _ in range(3):
+            hstep()
+        t0 = time.perf_counter()
+        for _ in range(n_host):
+            hstep()
+        host_step_ms = (time.perf_counter() - t0) / n_host * 1e3
         cpu_s, cpu_n = cpu_timed(lambda: cp.batch_hard_step(lab, emb, 0.35, cosine=True))
         flops = 2.0 * B * B * D
         roof = tensor_roofline(flops, ms, "forward GEMM only counted; B = 72 is launch-latency bound (1.3 MFLOP), the "
                                "fraction only means something at B = 4096")
         out[name] = {"steps_per_s": 1e3 / ms, "ms_per_step": ms, "ungraphed_call_steps_per_s": 1e3 / ms_call,
-                     "e2e_steps_per_s": 1e3 / host_ms, "e2e_ms": host_ms, "launches_per_step": n_launch,
+                     "e2e_steps_per_s": 1e3 / host_ms, "e2e_ms": host_ms, "e2e_host_step_ms": host_step_ms,
+                     "launches_per_step": n_launch,
                      "path": "tcgen05 3xTF32 filter + canonical re-rank + finalize + bitmap gather gradient (statistics in the same launch)" if B >= 512 else
                              "one thread-block-cluster launch: bulk-copy staging, chain-major one-thread-per-entry canonical mining, DSMEM record exchange, "
                              "finalize + gradient out of shared memory",
@@ -225,7 +237,8 @@ def secondary_metrics(torch, device, peaks, lib):
                      "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "steps/s", "cores": cores, "kind": "port",
                                       "sample": f"{cpu_n} full steps (fwd + bwd), oracle/cpu_paths.py:batch_hard_step "
                                                 "(torch-CPU sgemm + where/amin/amax + autograd: the reference's TF-CPU op sequence)"},
-                     "note": "fwd + bwd; steps_per_s = CUDA-graphed BatchHardStep, e2e = numpy in/out through dif_batch_hard_host"}
+                     "note": "fwd + bwd; steps_per_s = CUDA-graphed BatchHardStep, e2e = numpy in/out through dif_batch_hard_host (loss_and_grad: "
+                             "fresh output arrays per call), e2e_host_step = BatchHardHostStep (numpy views of the page-locked block, no copies)"}
     # C4 sweep (B = 72 ... 4096, D = 128): the graphed fwd + bwd step at every size, both metrics
     sweep = {}
     for Bs in (72, 128, 256, 512, 1024, 2048, 4096):

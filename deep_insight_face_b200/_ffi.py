@@ -103,6 +103,7 @@ SIGNATURES = {
     "dif_debug_gemm_time": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _i32, C.POINTER(_f32)]),
     "dif_batch_hard": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "dif_batch_hard_host": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i32]),
+    "dif_batch_hard_host_buffers": (_i32, [_i32, _i32, C.POINTER(_vp)]),
     "dif_batch_hard_set_path": (_i32, [_i32]),
     "dif_batch_all": (_i32, [_vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp]),
     "dif_tfa_triplet": (_i32, [_vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _f32, _vp, _vp]),

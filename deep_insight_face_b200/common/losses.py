@@ -148,6 +148,48 @@ class BatchHardStep:
         return self.loss, self.grad
 
 
+class BatchHardHostStep:
+    """Host-array batch-hard step without copies: the embeddings are written straight into the library's page-locked
+    staging block and the results are read out of it.
+
+    `emb`, `labels` (and `dloss`) are numpy views of that block; `__call__` is ONE foreign call = one kernel launch + one
+    wait at B <= 128 (the kernel reads and writes the block across PCIe), ~30 us host to host for 72 x 128 floats.  The
+    views belong to the calling thread and stay valid until it asks the library for a larger block.
+
+        step = BatchHardHostStep(72, 128, variant=LOSS_BH_COSINE, alpha=0.35)
+        step.emb[:] = embeddings; step.labels[:] = int_labels
+        loss, grad = step()            # numpy views: step.loss [B], step.grad [B, D], step.pos_idx, step.neg_idx, step.stats
+    """
+
+    def __init__(self, B: int, D: int, variant: int = _ffi.LOSS_BH_COSINE, alpha: float = 0.35, use_dloss: bool = False):
+        import ctypes as C
+
+        _ffi.init()
+        self._lib = _ffi.load_library()
+        self.B, self.D, self.variant, self.alpha = int(B), int(D), int(variant), float(alpha)
+        bufs = (C.c_void_p * 8)()
+        _ffi.check(self._lib.dif_batch_hard_host_buffers(self.B, self.D, bufs))
+
+        def view(i, n, dtype):
+            return np.ctypeslib.as_array(C.cast(bufs[i], C.POINTER(C.c_float if dtype == np.float32 else C.c_int32)), shape=(n,))
+
+        self.emb = view(0, B * D, np.float32).reshape(B, D)
+        self.labels = view(1, B, np.int32)
+        self.dloss = view(2, B, np.float32) if use_dloss else None
+        self.loss = view(3, B, np.float32)
+        self.pos_idx, self.neg_idx = view(4, B, np.int32), view(5, B, np.int32)
+        self.stats = view(6, 4, np.float32)
+        self.grad = view(7, B * D, np.float32).reshape(B, D)
+        self._args = (bufs[0], bufs[1], self.B, self.D, self.variant, self.alpha, bufs[3], bufs[4], bufs[5], bufs[6],
+                      bufs[2] if use_dloss else None, bufs[7], _ffi.PREC_TF32X3)
+
+    def __call__(self):
+        rc = self._lib.dif_batch_hard_host(*self._args)
+        if rc:
+            _ffi.check(rc)
+        return self.loss, self.grad
+
+
 def _torch_function():
     import torch
 

@@ -1762,9 +1762,10 @@ int dif_batch_hard_host(const float* emb_host, const int32_t* labels_host, int B
   if (int rc = g_bh_stage.ensure(in_bytes + out_bytes)) return rc;
   char* h = (char*)g_bh_stage.h;
   char* d = (char*)g_bh_stage.d;
-  memcpy(h, emb_host, (size_t)B * D * 4);
-  memcpy(h + eb, labels_host, (size_t)B * 4);
-  if (dloss_host) memcpy(h + eb + lb, dloss_host, (size_t)B * 4);
+  // (a caller that works in the staging block itself - dif_batch_hard_host_buffers - needs no copies)
+  if ((const char*)emb_host != h) memcpy(h, emb_host, (size_t)B * D * 4);
+  if ((const char*)labels_host != h + eb) memcpy(h + eb, labels_host, (size_t)B * 4);
+  if (dloss_host && (const char*)dloss_host != h + eb + lb) memcpy(h + eb + lb, dloss_host, (size_t)B * 4);
   cudaStream_t st = g_bh_stage.st;
   // The reference's own batch (18 x 4 rows of 128 floats) is one cluster launch of ~16 us: two DMA copies around it
   // would cost more than the step.  The page-locked staging block is device-visible (unified addressing), so the
@@ -1787,11 +1788,31 @@ int dif_batch_hard_host(const float* emb_host, const int32_t* labels_host, int B
   if (!zero_copy) DIF_CUDA_OK(cudaMemcpyAsync(h + in_bytes, o, back, cudaMemcpyDeviceToHost, st));
   DIF_CUDA_OK(cudaStreamSynchronize(st));
   char* ho = h + in_bytes;
-  memcpy(loss_host, ho, (size_t)B * 4);
-  if (pos_idx_host) memcpy(pos_idx_host, ho + lb, (size_t)B * 4);
-  if (neg_idx_host) memcpy(neg_idx_host, ho + 2 * lb, (size_t)B * 4);
-  memcpy(stats_host, ho + 3 * lb, 16);
-  if (demb_host) memcpy(demb_host, ho + 3 * lb + 256, (size_t)B * D * 4);
+  if ((char*)loss_host != ho) memcpy(loss_host, ho, (size_t)B * 4);
+  if (pos_idx_host && (char*)pos_idx_host != ho + lb) memcpy(pos_idx_host, ho + lb, (size_t)B * 4);
+  if (neg_idx_host && (char*)neg_idx_host != ho + 2 * lb) memcpy(neg_idx_host, ho + 2 * lb, (size_t)B * 4);
+  if ((char*)stats_host != ho + 3 * lb) memcpy(stats_host, ho + 3 * lb, 16);
+  if (demb_host && (char*)demb_host != ho + 3 * lb + 256) memcpy(demb_host, ho + 3 * lb + 256, (size_t)B * D * 4);
+  return DIF_OK;
+}
+
+int dif_batch_hard_host_buffers(int B, int D, void** bufs) {
+  DIF_REQUIRE(bufs && B >= 1 && D >= 1 && B <= 65536 && D <= 32 * BH_MAX_KD, DIF_ERR_INVALID,
+              "dif_batch_hard_host_buffers: invalid argument");
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t eb = al((size_t)B * D * 4), lb = al((size_t)B * 4);
+  const size_t in_bytes = eb + 2 * lb, out_bytes = 3 * lb + 256 + eb;
+  if (int rc = g_bh_stage.ensure(in_bytes + out_bytes)) return rc;
+  char* h = (char*)g_bh_stage.h;
+  char* ho = h + in_bytes;
+  bufs[0] = h;                  // emb    [B * D] float
+  bufs[1] = h + eb;             // labels [B] int32
+  bufs[2] = h + eb + lb;        // dloss  [B] float
+  bufs[3] = ho;                 // loss   [B] float
+  bufs[4] = ho + lb;            // pos_idx [B] int32
+  bufs[5] = ho + 2 * lb;        // neg_idx [B] int32
+  bufs[6] = ho + 3 * lb;        // stats  [4] float
+  bufs[7] = ho + 3 * lb + 256;  // demb   [B * D] float
   return DIF_OK;
 }
 

@@ -219,6 +219,12 @@ int dif_batch_hard(const float* emb, const int32_t* labels, int B, int D, int va
 int dif_batch_hard_host(const float* emb_host, const int32_t* labels_host, int B, int D, int variant, float alpha,
                         float* loss_host, int32_t* pos_idx_host, int32_t* neg_idx_host, float* stats_host,
                         const float* dloss_host, float* demb_host, int precision);
+/* The calling thread's page-locked staging block for a B x D step, as eight pointers the caller may work in directly:
+ * bufs[0..7] = emb [B*D] float, labels [B] int32, dloss [B] float (inputs); loss [B] float, pos_idx [B] int32, neg_idx [B]
+ * int32, stats [4] float, demb [B*D] float (outputs).  dif_batch_hard_host called with these very pointers skips its
+ * copy-in / copy-out: at B <= 128 a step is then one kernel launch and one wait, nothing else (the kernel reads and writes
+ * the block across PCIe).  The pointers stay valid until the thread asks for a larger block. */
+int dif_batch_hard_host_buffers(int B, int D, void** bufs);
 /* test knob: 0 = automatic (B <= 128: the whole step in one thread-block-cluster launch; B >= 512: tensor-core filter +
  * canonical re-rank; CUDA-core miner + fused merge / gradient in between), 1 = always the CUDA-core miner (two
  * launches), 2 = always the tensor-core miner, 3 = the cluster step where it fits.  Mined indices, losses and

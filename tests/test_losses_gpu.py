@@ -250,6 +250,30 @@ def test_cuda_losses_match_the_reference_source(gpu):
     assert _accuracy(y, d[:, 0] / 10) == float(ref["siamese/accuracy_default"])
 
 
+def test_host_step_in_the_staging_block_equals_the_copying_call(gpu):
+    """BatchHardHostStep works in the library's page-locked block (dif_batch_hard_host_buffers): no copy-in / copy-out,
+    the same bits as loss_and_grad on separate arrays, for both metrics and with a per-sample cotangent."""
+    from deep_insight_face_b200 import _ffi
+    from deep_insight_face_b200.common.losses import BatchHardHostStep, batch_hard
+
+    emb, lab = pk_batch(18, 4, 128, 1.0, seed=5)
+    rng = np.random.default_rng(9)
+    dl = rng.random(72).astype(np.float32)
+    for variant, alpha in ((_ffi.LOSS_BH_COSINE, 0.35), (_ffi.LOSS_BH_EUCLIDEAN, 40.0)):
+        for use_dl in (False, True):
+            want_loss, want_grad, info = batch_hard(lab, emb, variant, alpha, dloss=dl if use_dl else None)
+            step = BatchHardHostStep(72, 128, variant, alpha, use_dloss=use_dl)
+            step.emb[:] = emb
+            step.labels[:] = lab
+            if use_dl:
+                step.dloss[:] = dl
+            for _ in range(2):
+                loss, grad = step()
+            assert np.array_equal(loss, want_loss) and np.array_equal(grad, want_grad)
+            assert np.array_equal(step.pos_idx, info["pos_idx"]) and np.array_equal(step.neg_idx, info["neg_idx"])
+            assert np.array_equal(step.stats, info["stats"])
+
+
 def test_outgrown_workspaces_can_be_released(gpu):
     """A sweep over batch sizes parks every outgrown workspace block (a captured CUDA graph may still point at it);
     dif_release_retired frees them and the next call allocates afresh."""
