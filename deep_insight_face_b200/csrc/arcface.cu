@@ -376,7 +376,8 @@ static int run_arcface(const float* X, const float* W, const int32_t* y, int B, 
   const bool side_by_side = bwd && !serial && units >= 8;
   // (46 % of the pairs to dxh measured best at C2: 36 % 131.5 us, 41 % 125.6, 46 % 123.5, 52 % 150.5 - there dwh's 120
   // items need a fourth wave on the remaining 36 pairs)
-  const int units_x = side_by_side ? std::max(2, (units * 46) / 100) : units, units_w = side_by_side ? units - units_x : units;
+  static const int x_pct = getenv("DIF_ARC_XPCT") ? atoi(getenv("DIF_ARC_XPCT")) : 46;   // development aid
+  const int units_x = side_by_side ? std::max(2, (units * x_pct) / 100) : units, units_w = side_by_side ? units - units_x : units;
   GemmShape gx{};   // dxh [B, D] = dcos [B, C] x wh [C, D], split over K = classes
   gx.m_blocks = fwd.m_blocks;
   gx.bn = D <= 128 ? 128 : 256;
@@ -502,17 +503,30 @@ static int run_arcface(const float* X, const float* W, const int32_t* y, int B, 
   if (int rc = operand_maps<T>(&maps[2], &maps[3], P(o_xh), P(o_xl), D, B, D, 0, true)) return rc;
   StoreEpi::Params sw{F(o_gw), C, D, D, gw.n_splits, 0};
   if (int rc = launch_nt_gemm<PREC, kArcBN, kArcCtas, 0, StoreEpi, 1, 1>(maps, gw, sw, units_w, st_w)) return rc;
-  if (side_by_side) {
-    DIF_CUDA_OK(cudaEventRecord(ev_join, st_w));
-    DIF_CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));
-  }
-  mark();
 
-  // ---- 5. l2_normalize backward, X rows and W rows in one launch
+  // ---- 5. l2_normalize backward.  Side by side: each half follows its own GEMM on its own stream (the 10 000 W rows are
+  //         60 MB of traffic: they start when dwh is done, under the tail of dxh, instead of after both); else one launch.
   NormBwdJob jx{F(o_gx), gx.k_splits, (size_t)B * D, X, F(o_xi), B, dX};
   NormBwdJob jw{F(o_gw), 1, 0, W, F(o_wi), C, dW};
-  launch_norm_bwd(jx, jw, D, st);
-  DIF_LAUNCH_OK();
+  static const bool joint_norm = getenv("DIF_ARC_JOINT_NORM") != nullptr;   // A/B switch
+  if (side_by_side && !joint_norm) {
+    NormBwdJob none{nullptr, 0, 0, nullptr, nullptr, 0, nullptr};
+    launch_norm_bwd(none, jw, D, st_w);
+    DIF_LAUNCH_OK();
+    DIF_CUDA_OK(cudaEventRecord(ev_join, st_w));
+    launch_norm_bwd(jx, none, D, st);
+    DIF_LAUNCH_OK();
+    DIF_CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));
+    mark();
+  } else {
+    if (side_by_side) {
+      DIF_CUDA_OK(cudaEventRecord(ev_join, st_w));
+      DIF_CUDA_OK(cudaStreamWaitEvent(st, ev_join, 0));
+    }
+    mark();
+    launch_norm_bwd(jx, jw, D, st);
+    DIF_LAUNCH_OK();
+  }
   mark();
   if (profile) {
     cudaStreamSynchronize(st);
