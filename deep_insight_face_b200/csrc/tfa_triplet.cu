@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(TFA_THREADS) tfa_hard_row_kernel(const float* 
                                                                    int soft, int squared, TfaRow* __restrict__ rows,
                                                                    int32_t* __restrict__ pos_idx, int32_t* __restrict__ neg_idx,
                                                                    float* __restrict__ Cf, TfaLists L) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];   // (16-byte row stores below)
   float* srow = sm;                                                    // [B]
   unsigned char* sflag = reinterpret_cast<unsigned char*>(srow + B);   // [B] 0 diagonal, 1 positive, 2 negative
   __shared__ TfaHardRed s_red[TFA_WARPS];
@@ -434,15 +434,32 @@ __global__ void __launch_bounds__(TFA_THREADS) tfa_hard_row_kernel(const float* 
   if (t == 0) s_n = 0;
   // pass 1: values only
   TfaHardRed me{-INFINITY, -INFINITY, INFINITY, 0};
-  for (int j = t; j < B; j += TFA_THREADS) {
-    const float v = P[(size_t)b * ldp + j];
-    const int f = j == b ? 0 : (labels[j] == my_lab ? 1 : 2);
-    srow[j] = v;
-    sflag[j] = (unsigned char)f;
+  auto visit1 = [&](int j, float v, int lab_j) {
+    const int f = j == b ? 0 : (lab_j == my_lab ? 1 : 2);
     me.rmax = fmaxf(me.rmax, v);
     me.hp = fmaxf(me.hp, f == 1 ? v : -INFINITY);
     me.nmin = fminf(me.nmin, f == 2 ? v : INFINITY);
     me.n_pos += f == 1;
+    return f;
+  };
+  // four columns per trip where the alignment allows (the kernel is instruction bound: 46 per entry one at a time)
+  const int B4 = ((reinterpret_cast<uintptr_t>(labels) & 15u) == 0) ? (B & ~3) : 0;
+  {
+    const float4* P4 = reinterpret_cast<const float4*>(P + (size_t)b * ldp);   // ldp % 4 == 0, P from cudaMalloc
+    const int4* L4 = reinterpret_cast<const int4*>(labels);
+    for (int q = t; q < (B4 >> 2); q += TFA_THREADS) {
+      const float4 v = P4[q];
+      const int4 l = L4[q];
+      const int j = q << 2;
+      const int f0 = visit1(j, v.x, l.x), f1 = visit1(j + 1, v.y, l.y), f2 = visit1(j + 2, v.z, l.z), f3 = visit1(j + 3, v.w, l.w);
+      *reinterpret_cast<float4*>(srow + j) = v;
+      *reinterpret_cast<uint32_t*>(sflag + j) = (uint32_t)f0 | ((uint32_t)f1 << 8) | ((uint32_t)f2 << 16) | ((uint32_t)f3 << 24);
+    }
+  }
+  for (int j = B4 + t; j < B; j += TFA_THREADS) {
+    const float v = P[(size_t)b * ldp + j];
+    srow[j] = v;
+    sflag[j] = (unsigned char)visit1(j, v, labels[j]);
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {
@@ -469,9 +486,7 @@ __global__ void __launch_bounds__(TFA_THREADS) tfa_hard_row_kernel(const float* 
   // pass 2: membership.  bit 0: a positive at hp; bit 1: a negative whose shifted value is vmin; bit 2: a row maximum
   // (only when the gradient reaches the rowmax term)
   int c_p = 0, c_n = 0, c_m = 0, f_p = 0x7fffffff, f_n = 0x7fffffff;
-  for (int j = t; j < B; j += TFA_THREADS) {
-    const float v = srow[j];
-    const int f = sflag[j];
+  auto visit2 = [&](int j, float v, int f) {
     const bool pt = f == 1 && v == hp_v;
     const bool nt = f == 2 && __fsub_rn(v, rmax) == vmin;
     const bool mt = through_max && v == rmax;
@@ -489,7 +504,17 @@ __global__ void __launch_bounds__(TFA_THREADS) tfa_hard_row_kernel(const float* 
         }
       }
     }
+  };
+  for (int q = t; q < (B4 >> 2); q += TFA_THREADS) {
+    const int j = q << 2;
+    const float4 v = *reinterpret_cast<const float4*>(srow + j);
+    const uint32_t f = *reinterpret_cast<const uint32_t*>(sflag + j);
+    visit2(j, v.x, (int)(f & 255u));
+    visit2(j + 1, v.y, (int)((f >> 8) & 255u));
+    visit2(j + 2, v.z, (int)((f >> 16) & 255u));
+    visit2(j + 3, v.w, (int)(f >> 24));
   }
+  for (int j = B4 + t; j < B; j += TFA_THREADS) visit2(j, srow[j], sflag[j]);
   if (c_p) atomicAdd(&s_cnt[0], c_p);
   if (c_n) atomicAdd(&s_cnt[1], c_n);
   if (c_m) atomicAdd(&s_cnt[2], c_m);
