@@ -30,27 +30,58 @@ struct CanonMmGeom {
 // operand slot of (quad group kg, chain l, row): [KG][32 chains][T rows][4]
 template <int T>
 __device__ __forceinline__ int pf_slot(int kg, int l, int row) { return ((kg * 32 + l) * T + (row ^ ((l >> 2) & 7))) * 4; }
+// Row operand, PAIRED layout [KG][32 chains][T / 2 row pairs][4 k][2 rows]: the two rows of a pair sit side by side for
+// every k, so a 16-byte load yields two ready-made (row 2p, row 2p + 1) operand pairs of the packed fp32 pipe below.
+template <int T>
+__device__ __forceinline__ int pf_pair_slot(int kg, int l, int pair) {
+  return ((kg * 32 + l) * (T / 2) + (pair ^ ((l >> 2) & 7))) * 8;
+}
+
+// Packed fp32 arithmetic (sm_100: FFMA2 / FADD2).  Each half is an ordinary IEEE fma.rn / add.rn, so results are the
+// bits of the scalar instructions - and the fp32 pipe retires two of them per issue slot (a scalar FFMA occupies its
+// SMSP's fma pipe for two cycles: the scalar version of this kernel was bound by exactly that).
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long dup2(float v) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(v));
+  return d;
+}
+__device__ __forceinline__ void unpack2(unsigned long long p, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p));
+}
 
 // rows [row0, row0 + T) -> dst: element d = l + 32 k of a row lands at (k / 4, l, row) [k % 4]
-template <int KG, int T>
+template <int KG, int T, bool PAIR = false>
 __device__ __forceinline__ void pf_stage(const float* __restrict__ x, int B, int D, int row0, float* __restrict__ dst,
                                          bool vec) {
   constexpr int DP = 128 * KG;   // padded row length
+  auto at = [](int kg, int l, int row, int k) {
+    return PAIR ? pf_pair_slot<T>(kg, l, row >> 1) + 2 * k + (row & 1) : pf_slot<T>(kg, l, row) + k;
+  };
   if (vec) {   // D % 4 == 0, 16-byte aligned rows: one float4 per lane, four conflict-free scalar stores
     for (int idx = threadIdx.x; idx < T * (DP / 4); idx += PF_THREADS) {
       const int row = idx / (DP / 4), q = idx % (DP / 4), d0 = q * 4, gr = row0 + row;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gr < B && d0 < D) v = *reinterpret_cast<const float4*>(x + (size_t)gr * D + d0);
       const int kg = d0 >> 7, k = (d0 & 127) >> 5, l0 = d0 & 31;
-      dst[pf_slot<T>(kg, l0, row) + k] = v.x;
-      dst[pf_slot<T>(kg, l0 + 1, row) + k] = v.y;
-      dst[pf_slot<T>(kg, l0 + 2, row) + k] = v.z;
-      dst[pf_slot<T>(kg, l0 + 3, row) + k] = v.w;
+      dst[at(kg, l0, row, k)] = v.x;
+      dst[at(kg, l0 + 1, row, k)] = v.y;
+      dst[at(kg, l0 + 2, row, k)] = v.z;
+      dst[at(kg, l0 + 3, row, k)] = v.w;
     }
   } else {
     for (int idx = threadIdx.x; idx < T * DP; idx += PF_THREADS) {
       const int row = idx / DP, d = idx % DP, gr = row0 + row;
-      dst[pf_slot<T>(d >> 7, d & 31, row) + ((d & 127) >> 5)] = (gr < B && d < D) ? x[(size_t)gr * D + d] : 0.f;
+      dst[at(d >> 7, d & 31, row, (d & 127) >> 5)] = (gr < B && d < D) ? x[(size_t)gr * D + d] : 0.f;
     }
   }
 }
@@ -73,7 +104,8 @@ canon_mm_kernel(const float* __restrict__ x, int B, int D, int tiles_per_block, 
   // P is symmetric bit for bit (products and the two norms commute): only tiles on or above the diagonal are
   // computed, each off-diagonal tile is also written transposed
   if ((int)(blockIdx.x + 1) * tiles_per_block <= bi) return;
-  pf_stage<KG, T>(x, B, D, row0, sA, vec != 0);
+  pf_stage<KG, T, true>(x, B, D, row0, sA, vec != 0);   // row operand: paired layout
+  constexpr int TP = TM / 2;                            // row pairs per thread
   for (int t = 0; t < tiles_per_block; ++t) {
     const int bj = blockIdx.x * tiles_per_block + t;
     if (bj >= n_tiles) break;   // block-uniform
@@ -82,49 +114,61 @@ canon_mm_kernel(const float* __restrict__ x, int B, int D, int tiles_per_block, 
     __syncthreads();            // the previous tile's readers are done
     pf_stage<KG, T>(x, B, D, c0, sB, vec != 0);
     __syncthreads();
-    float st[6][TM][TN];
+    unsigned long long st[6][TP][TN];   // (row 2p, row 2p + 1) pairs of pending partial sums
 #pragma unroll
     for (int n = 0; n < 32; ++n) {
       const int l = ((n & 1) << 4) | ((n & 2) << 2) | (n & 4) | ((n & 8) >> 2) | ((n & 16) >> 4);   // bit reversal
-      float s[TM][TN];
+      unsigned long long s2[TP][TN];
 #pragma unroll
       for (int kg = 0; kg < KG; ++kg) {   // chain l: k = 0, 1, 2, ... in ascending order
-        float4 b[TN];
+        unsigned long long bd[TN][4];     // the column operand, each value duplicated into both halves
 #pragma unroll
-        for (int j = 0; j < TN; ++j) b[j] = *reinterpret_cast<const float4*>(sB + pf_slot<T>(kg, l, tx + 32 * j));
+        for (int j = 0; j < TN; ++j) {
+          const float4 b = *reinterpret_cast<const float4*>(sB + pf_slot<T>(kg, l, tx + 32 * j));
+          bd[j][0] = dup2(b.x);
+          bd[j][1] = dup2(b.y);
+          bd[j][2] = dup2(b.z);
+          bd[j][3] = dup2(b.w);
+        }
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-          const float4 a = *reinterpret_cast<const float4*>(sA + pf_slot<T>(kg, l, ty * TM + i));
+        for (int p2 = 0; p2 < TP; ++p2) {
+          const ulonglong2* ap = reinterpret_cast<const ulonglong2*>(sA + pf_pair_slot<T>(kg, l, ty * TP + p2));
+          const ulonglong2 a01 = ap[0], a23 = ap[1];   // (k0 pair, k1 pair), (k2 pair, k3 pair)
 #pragma unroll
           for (int j = 0; j < TN; ++j) {
-            float v = __fmaf_rn(a.x, b[j].x, kg == 0 ? 0.f : s[i][j]);
-            v = __fmaf_rn(a.y, b[j].y, v);
-            v = __fmaf_rn(a.z, b[j].z, v);
-            s[i][j] = __fmaf_rn(a.w, b[j].w, v);
+            unsigned long long v = fma2(a01.x, bd[j][0], kg == 0 ? 0ull : s2[p2][j]);
+            v = fma2(a01.y, bd[j][1], v);
+            v = fma2(a23.x, bd[j][2], v);
+            s2[p2][j] = fma2(a23.y, bd[j][3], v);
           }
         }
       }
 #pragma unroll
-      for (int i = 0; i < TM; ++i)
+      for (int p2 = 0; p2 < TP; ++p2)
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-          float v = s[i][j];
+          unsigned long long v = s2[p2][j];
           int lvl = 0;
 #pragma unroll
           for (int m = n; m & 1; m >>= 1) {
-            v = __fadd_rn(st[lvl][i][j], v);
+            v = add2(st[lvl][p2][j], v);
             ++lvl;
           }
-          st[lvl][i][j] = v;
+          st[lvl][p2][j] = v;
         }
     }
+    float out[TM][TN];
+#pragma unroll
+    for (int p2 = 0; p2 < TP; ++p2)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) unpack2(st[5][p2][j], out[2 * p2][j], out[2 * p2 + 1][j]);
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
         const int gi = row0 + ty * TM + i, gj = c0 + tx + 32 * j;
-        const float d = (gi < B && gj < B) ? epi(gi, gj, st[5][i][j]) : 0.f;
-        st[5][i][j] = d;
+        const float d = (gi < B && gj < B) ? epi(gi, gj, out[i][j]) : 0.f;
+        out[i][j] = d;
         if (gi < B && gj < B) P[(size_t)gi * ldp + gj] = d;
       }
     if (bj > bi) {
@@ -132,7 +176,7 @@ canon_mm_kernel(const float* __restrict__ x, int B, int D, int tiles_per_block, 
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) sB[(tx + 32 * j) * (T + 1) + ty * TM + i] = st[5][i][j];
+        for (int j = 0; j < TN; ++j) sB[(tx + 32 * j) * (T + 1) + ty * TM + i] = out[i][j];
       __syncthreads();
       for (int r = ty; r < T; r += PF_THREADS / 32) {
         const int gj = c0 + r;
