@@ -1584,11 +1584,11 @@ __global__ void __launch_bounds__(BA_ROW_WARPS * 32) ba_grad_fast_kernel(const f
     me[a] = rows[i];
   }
   constexpr int U = 16 / KQ;   // rows n_j in flight per trip
-  float acc[BA_GRAD_ROWS][KQ];
+  unsigned long long acc[BA_GRAD_ROWS][KQ / 2];   // (d, d + 1) pairs
 #pragma unroll
   for (int a = 0; a < BA_GRAD_ROWS; ++a)
 #pragma unroll
-    for (int c = 0; c < KQ; ++c) acc[a][c] = 0.f;
+    for (int c = 0; c < KQ / 2; ++c) acc[a][c] = 0ull;
   for (int j0 = c_begin; j0 < c_end; j0 += BA_GRAD_CHUNK) {
     const int n = min(BA_GRAD_CHUNK, c_end - j0);
     __syncwarp();
@@ -1622,21 +1622,24 @@ __global__ void __launch_bounds__(BA_ROW_WARPS * 32) ba_grad_fast_kernel(const f
       }
     }
     __syncwarp();
+    // lane t owns the column pairs d = 64 c + 2 t, + 1 (D is even): one 8-byte load per pair, one packed fma
+    // (fma.rn.f32x2: both halves plain IEEE fma, two per issue slot of the fp32 pipe) per anchor and pair
     for (int jj = 0; jj < n; jj += U) {
-      float v[U][KQ];
+      unsigned long long v[U][KQ / 2];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int j = j0 + min(jj + u, n - 1);
 #pragma unroll
-        for (int c = 0; c < KQ; ++c) v[u][c] = c * 32 + lane < D ? xn[(size_t)j * D + c * 32 + lane] : 0.f;
+        for (int c = 0; c < KQ / 2; ++c)
+          v[u][c] = c * 64 + 2 * lane < D ? *reinterpret_cast<const unsigned long long*>(xn + (size_t)j * D + c * 64 + 2 * lane) : 0ull;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int a = 0; a < BA_GRAD_ROWS; ++a) {
-          const float w = jj + u < n ? s_w[warp][a][jj + u] : 0.f;
+          const unsigned long long w2 = dup2(jj + u < n ? s_w[warp][a][jj + u] : 0.f);
 #pragma unroll
-          for (int c = 0; c < KQ; ++c) acc[a][c] = fmaf(w, v[u][c], acc[a][c]);
+          for (int c = 0; c < KQ / 2; ++c) acc[a][c] = fma2(w2, v[u][c], acc[a][c]);
         }
     }
   }
@@ -1644,8 +1647,9 @@ __global__ void __launch_bounds__(BA_ROW_WARPS * 32) ba_grad_fast_kernel(const f
   for (int a = 0; a < BA_GRAD_ROWS; ++a)
     if (i0 + a < B)
 #pragma unroll
-      for (int c = 0; c < KQ; ++c)
-        if (c * 32 + lane < D) part[((size_t)blockIdx.y * B + i0 + a) * D + c * 32 + lane] = acc[a][c];
+      for (int c = 0; c < KQ / 2; ++c)
+        if (c * 64 + 2 * lane < D)
+          *reinterpret_cast<unsigned long long*>(part + ((size_t)blockIdx.y * B + i0 + a) * D + c * 64 + 2 * lane) = acc[a][c];
 }
 
 // dx = inv * (dn - n (n . dn)), dn = the column ranges' partial sums in ascending order
@@ -1832,7 +1836,7 @@ int dif_batch_all(const float* emb, const int32_t* labels, int B, int D, float a
   cols = (cols + BH_TJ - 1) / BH_TJ * BH_TJ;
   splits = (B + cols - 1) / cols;
   static const bool ba_tiles_only = getenv("DIF_BA_TILES") != nullptr;   // A/B switch
-  if (B >= 256 && B <= 16384 && D <= kCanonMmMaxD && !ba_tiles_only) {
+  if (B >= 256 && B <= 16384 && D <= kCanonMmMaxD && D % 2 == 0 && !ba_tiles_only) {   // (even D: 8-byte row pairs)
     const int lds = (B + 3) & ~3;
     if (int rc = g_ws.ensure(1, (size_t)B)) return rc;
     if (int rc = g_ba.ensure((size_t)B, 1)) return rc;
