@@ -328,23 +328,24 @@ __global__ void __launch_bounds__(TFA_THREADS) tfa_semihard_row_kernel(const flo
       for (int g = 0; g < G; ++g) ov[g] = fminf(ov[g], v > pa_g[g] ? sh : INFINITY);
     }
     block_min_g<G>(ov, s_gv);
-    // sweep B: which negative (first column), how many tie with it, how many are farther at all
-    int oi[G], oc[G], nm[G];
+    // sweep B: which negative (first column) and how many tie with it.  An entry can only matter if its shifted value
+    // equals one of the four minima: one OR of four compares sorts out all but a handful of columns
+    int oi[G], oc[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       oi[g] = 0x7fffffff;
       oc[g] = 0;
-      nm[g] = 0;
     }
     for (int k = t; k < B; k += TFA_THREADS) {
       const float v = sflag[k] == 2 ? srow[k] : -INFINITY;
       const float sh = __fsub_rn(v, rmax);
+      if ((sh == ov[0]) | (sh == ov[1]) | (sh == ov[2]) | (sh == ov[3])) {
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const bool far = v > pa_g[g], hit = far && sh == ov[g];
-        nm[g] += far;
-        oc[g] += hit;
-        oi[g] = hit ? min(oi[g], k) : oi[g];
+        for (int g = 0; g < G; ++g) {
+          const bool hit = v > pa_g[g] && sh == ov[g];
+          oc[g] += hit;
+          oi[g] = hit ? min(oi[g], k) : oi[g];
+        }
       }
     }
     block_first_count_g<G>(oi, oc, s_gi, s_gc);
@@ -373,7 +374,11 @@ __global__ void __launch_bounds__(TFA_THREADS) tfa_semihard_row_kernel(const flo
           }
         } else if (outside) {
           int n_tied = out_c;
-          if (out_v == 0.f) n_tied += B - block_count(nm[g], s_c);   // every unmasked entry ties at 0
+          if (out_v == 0.f) {   // (rare: the selected negative is the row maximum) every unmasked entry ties at 0
+            int n_mask = 0;
+            for (int k = t; k < B; k += TFA_THREADS) n_mask += (sflag[k] == 2 && srow[k] > pa) ? 1 : 0;
+            n_tied += B - block_count(n_mask, s_c);
+          }
           const float c_neg = 1.f / (float)n_tied;
           const float c_max = out_v == 0.f ? (1.f - (float)out_c / (float)n_tied) / (float)rmax_c : 0.f;
           __syncthreads();   // thread 0's two-entry updates above are visible
