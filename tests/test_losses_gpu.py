@@ -373,6 +373,52 @@ def test_soft_margin_extension(gpu, P, K, D):
         assert (got > 0).all() and cls.from_config(loss.get_config()).soft
 
 
+@pytest.mark.parametrize("variant", ["cosine", "euclid"])
+def test_hub_rows_on_the_tensor_core_path(gpu, lib, variant):
+    """A row that is the hardest negative of hundreds of anchors (a sample near the centre of the batch): the gradient
+    launch takes its anchors off the shared-memory bitmap 32 per round instead of the 30-entry list.  Forced tensor-core
+    path against the oracle and against the CUDA-core path, B = 640 (also with exact duplicates, which switch every row
+    to the tie-aware walk)."""
+    import torch
+
+    from deep_insight_face_b200 import _ffi
+    from deep_insight_face_b200.common.losses import batch_hard
+    from oracle import losses_oracle as lo
+
+    rng = np.random.default_rng(17)
+    B, D = 640, 64
+    lab = np.repeat(np.arange(B // 4), 4).astype(np.int32)
+    emb = (rng.standard_normal((B // 4, D))[lab] * 3.0 + rng.standard_normal((B, D))).astype(np.float32)
+    if variant == "cosine":
+        emb += 4.0      # a common offset: every row looks alike in angle, row 5 (the offset direction itself) most of all
+        emb[5] = 7.0 + 0.01 * rng.standard_normal(D).astype(np.float32)
+    else:
+        emb[5] = emb.mean(0) + 0.01 * rng.standard_normal(D).astype(np.float32)   # the centre of the batch
+    code = _ffi.LOSS_BH_COSINE if variant == "cosine" else _ffi.LOSS_BH_EUCLIDEAN
+    alpha = 0.35 if variant == "cosine" else 500.0
+    fn = lo.batch_hard_cosine if variant == "cosine" else lo.batch_hard_euclidean
+    for dup in (False, True):
+        x = emb.copy()
+        if dup:
+            x[77] = x[12]
+        want = fn(lab, x, alpha)
+        hub = np.bincount(want["neg_idx"][want["neg_idx"] >= 0], minlength=B).max()
+        assert hub > 64, hub      # the batch really has a hub
+        xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(lab).cuda()
+        out = {}
+        try:
+            for path in (1, 2):
+                _ffi.check(lib.dif_batch_hard_set_path(path))
+                loss, grad, info = batch_hard(yd, xd, code, alpha)
+                out[path] = (loss.cpu().numpy(), grad.cpu().numpy(), info["neg_idx"].cpu().numpy())
+        finally:
+            _ffi.check(lib.dif_batch_hard_set_path(0))
+        assert np.array_equal(out[2][2], want["neg_idx"]) and np.array_equal(out[1][2], want["neg_idx"])
+        close(out[2][0], want["loss"], scale=max(1.0, np.abs(want["loss"]).max()))
+        close(out[2][1], want["grad"])
+        close(out[2][1], out[1][1], scale=np.abs(out[1][1]).max())
+
+
 def test_graphed_steps_survive_workspace_growth():
     """A CUDA-graphed step keeps the library workspace addresses in its kernel nodes: a later, larger step makes the
     workspace grow, and the outgrown block must stay valid (retired, not freed) for the earlier graph."""

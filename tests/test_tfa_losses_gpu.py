@@ -211,3 +211,24 @@ def test_preallocated_and_graphed_step_equals_the_call():
             assert torch.equal(loss[0], want_loss) and torch.equal(grad, want_grad)
             if kind == TFA_HARD:
                 assert torch.equal(step.pos_idx, want_info["pos_idx"]) and torch.equal(step.neg_idx, want_info["neg_idx"])
+
+
+def test_hub_row_in_the_list_gather():
+    """A sample at the centre of the batch is the closest negative of almost every anchor: its row of the gradient
+    gather walks its bitmap 32 anchors per round (the per-row list holds 32 entries).  Hard and semi-hard, B = 320."""
+    from deep_insight_face_b200.common.tfa_losses import TripletHardLoss, TripletSemiHardLoss
+    from oracle import tfa_oracle as orc
+
+    rng = np.random.default_rng(23)
+    lab = np.repeat(np.arange(80), 4).astype(np.int32)
+    x = (3.0 * rng.standard_normal((80, 48))[lab] + rng.standard_normal((320, 48))).astype(np.float32)
+    x[9] = x.mean(0) + 0.01 * rng.standard_normal(48).astype(np.float32)
+    want = orc.triplet_hard(lab, x)
+    assert np.bincount(want["neg_idx"][want["neg_idx"] >= 0], minlength=320).max() > 64
+    loss, grad, info = TripletHardLoss().loss_and_grad(lab, x)
+    assert np.array_equal(info["neg_idx"], want["neg_idx"]) and np.array_equal(info["pos_idx"], want["pos_idx"])
+    l64, g64 = orc.torch_shadow("hard", lab, x)
+    assert abs(loss - l64) <= RTOL * max(abs(l64), 1e-6) and _close(grad, g64)
+    loss, grad, _ = TripletSemiHardLoss().loss_and_grad(lab, x)
+    l64, g64 = orc.torch_shadow("semihard", lab, x)
+    assert abs(loss - l64) <= RTOL * max(abs(l64), 1e-6) and _close(grad, g64)
