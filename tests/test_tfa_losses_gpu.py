@@ -24,7 +24,7 @@ def _close(a, b, rtol=RTOL):
 
 
 @pytest.mark.parametrize("P,K,D,scale", [(18, 4, 128, 0.05), (18, 4, 128, 1.0), (16, 8, 64, 0.1), (33, 3, 100, 0.2),
-                                          (64, 4, 512, 0.05)])
+                                          (64, 4, 512, 0.05), (70, 4, 201, 0.2), (65, 4, 260, 0.1), (90, 3, 30, 0.3)])
 @pytest.mark.parametrize("soft", [False, True])
 def test_hard_matches_oracle(P, K, D, scale, soft):
     from deep_insight_face_b200.common.tfa_losses import TripletHardLoss
