@@ -66,3 +66,38 @@ def test_threshold_counts_equal_the_reference_formulas(orc, seed, n, t):
         pred = np.less(dist, th)                                        # evaluation/utility.py:37
         want = (np.sum(pred & same), np.sum(pred & ~same), np.sum(~pred & ~same), np.sum(~pred & same))
         assert tuple(int(c) for c in counts[i]) == tuple(int(w) for w in want)
+
+
+def test_bit_reversed_counter_tree_is_the_canonical_butterfly():
+    """csrc/canon_mm.cuh lets ONE thread fold the 32 chain sums of the canonical dot product: it visits the chains in
+    bit-reversed order and keeps a binary counter of pending partial sums.  That must be, addition for addition, the
+    butterfly t[i] += t[i ^ o], o = 16 .. 1, of dif_canon.cuh / oracle/dif_oracle.c (fp32 addition is commutative, not
+    associative: the PAIRING is what has to match).  Checked here in numpy float32 on adversarial magnitudes; the
+    half-chain variant of the cluster kernel (even chains -> y0, odd chains -> y1, total y0 + y1) as well."""
+    rng = np.random.default_rng(0)
+    f32 = np.float32
+    for trial in range(200):
+        t = (rng.standard_normal(32) * 10.0 ** rng.integers(-6, 7, size=32)).astype(f32)
+        bt = t.copy()
+        for o in (16, 8, 4, 2, 1):
+            bt = (bt + bt[np.arange(32) ^ o]).astype(f32)
+        want = bt[0]
+        assert all(bt[i] == want or (np.isnan(bt[i]) and np.isnan(want)) for i in range(32))   # every lane agrees
+
+        def counter_tree(order):
+            stack = {}
+            for n, chain in enumerate(order):
+                v = t[chain]
+                lvl, m = 0, n
+                while m & 1:
+                    v = f32(stack[lvl] + v)
+                    m >>= 1
+                    lvl += 1
+                stack[lvl] = v
+            return stack[lvl]
+
+        bitrev = [int(format(n, "05b")[::-1], 2) for n in range(32)]
+        assert counter_tree(bitrev).tobytes() == want.tobytes()
+        y0, y1 = counter_tree(bitrev[:16]), counter_tree(bitrev[16:])
+        assert all(c % 2 == 0 for c in bitrev[:16]) and all(c % 2 == 1 for c in bitrev[16:])
+        assert f32(y0 + y1).tobytes() == want.tobytes()
