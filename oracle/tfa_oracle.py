@@ -4,11 +4,18 @@ The reference calls `tfa.losses.TripletHardLoss()` and `tfa.losses.TripletSemiHa
 (deep_insight_face/networks/triplet.py:196,209,211; sparse integer labels from training/triplet.py:72).  The
 arithmetic lives in the third-party package tensorflow_addons (version UNPINNED: the reference's
 requirements.txt is empty), files tensorflow_addons/losses/triplet.py and losses/metric_learning.py, which are
-not under the reference tree and cannot be installed here -> PARITY UNPINNED.  The functions below restate the
-published algorithm of those two files operation by operation (names kept), on the canonical fp32 pairwise
-matrix of oracle/dif_oracle.c so mined indices compare bit for bit with the GPU; gradients come from torch
-autograd (fp64) over the same literal forward, whose amax/amin split the cotangent over ties like
-tf.reduce_max / reduce_min.
+not under the reference tree and cannot be installed here.  The functions below restate the published algorithm
+of those two files operation by operation (names kept), on the canonical fp32 pairwise matrix of
+oracle/dif_oracle.c so mined indices compare bit for bit with the GPU; gradients come from torch autograd (fp64)
+over the same literal forward, whose amax/amin split the cotangent over ties like tf.reduce_max / reduce_min.
+
+PIN STATUS.  Semi-hard loss, pairwise_distance, _masked_maximum / _masked_minimum: PINNED against the one text of
+this algorithm the reference holds - its copy of tf.contrib's triplet_semihard_loss, the function tensorflow_addons
+ported (deep_insight_face/common/losses.py:151-308; executed by tests/golden/make_golden_semihard.py both as it is
+and with its dangling `- 2.0 * matmul` line repaired, goldens in tests/golden/semihard_reference.npz, held by
+tests/test_parity_cpu.py).  TripletHardLoss and the soft margin have no text in the reference: PARITY UNPINNED for
+those (cross-checked against the fp64 autograd shadow only); the step from tf.contrib's function to tfa's (sparse
+labels instead of one-hot, `distance_metric`) is likewise taken from tfa's published source, not from the reference.
 """
 from __future__ import annotations
 
@@ -71,13 +78,16 @@ def triplet_hard(labels, emb, margin=1.0, soft=False, squared=False):
             "neg_idx": neg_idx, "hard_positives": hard_positives, "hard_negatives": hard_negatives}
 
 
-def triplet_semihard(labels, emb, margin=1.0, squared=False):
-    """triplet.triplet_semihard_loss, anchor by anchor (the [B*B, B] tiling of the original is the same
-    arithmetic per (anchor b, positive a) pair): semi-hard negative = the closest negative farther than the
-    positive (negatives_outside) or, when none is, the farthest negative (negatives_inside)."""
+def semihard_from_matrix(P, labels, margin=1.0):
+    """The semi-hard rule of triplet.triplet_semihard_loss on a given pairwise matrix P (any float dtype), anchor
+    by anchor (the [B*B, B] tiling of the original is the same arithmetic per (anchor b, positive a) pair):
+    semi-hard negative = the closest negative farther than the positive (negatives_outside) or, when none is, the
+    farthest negative (negatives_inside); sum of the hinges / number of positive pairs.  Pinned against the
+    reference's copy of the tf.contrib ancestor of this function (deep_insight_face/common/losses.py:249-308,
+    executed by tests/golden/make_golden_semihard.py) in tests/test_parity_cpu.py."""
     lab = np.asarray(labels).reshape(-1).astype(np.int64)
     B = lab.shape[0]
-    P = pairwise_distance(emb, squared)
+    T = P.dtype.type
     total = 0.0
     num_positives = 0
     for b in range(B):
@@ -90,19 +100,24 @@ def triplet_semihard(labels, emb, margin=1.0, squared=False):
         row = P[b]
         rowmax = row.max()
         rowmin = row.min()
-        inside = ((row - rowmin) * neg.astype(F32)).max() + rowmin
+        inside = ((row - rowmin) * neg.astype(T)).max() + rowmin
         shifted = row - rowmax
         for a in np.flatnonzero(pos):
             mask = neg & (row > row[a])
             if mask.any():
-                sh = (shifted * mask.astype(F32)).min() + rowmax
+                sh = (shifted * mask.astype(T)).min() + rowmax
             else:
                 sh = inside
-            lm = F32(margin) + (row[a] - sh)
-            total += float(max(lm, F32(0.0)))
+            lm = T(margin) + (row[a] - sh)
+            total += float(max(lm, T(0.0)))
     with np.errstate(invalid="ignore", divide="ignore"):
-        loss = F32(np.float64(total) / np.float64(num_positives)) if num_positives else F32(np.nan)
+        loss = T(np.float64(total) / np.float64(num_positives)) if num_positives else T(np.nan)
     return {"loss": loss, "num_positives": num_positives}
+
+
+def triplet_semihard(labels, emb, margin=1.0, squared=False):
+    """triplet.triplet_semihard_loss: the semi-hard rule on the canonical fp32 pairwise matrix."""
+    return semihard_from_matrix(pairwise_distance(emb, squared), labels, margin)
 
 
 # ------------------------------------------------------------------ fp64 autograd shadow (torch CPU)

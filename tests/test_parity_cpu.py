@@ -210,3 +210,79 @@ def test_scalar_helpers_match_the_reference_module(losses_ref):
     assert np.array_equal(U.gaussian_kernel_dist_to_prob(d), losses_ref["utils/gaussian_kernel_1"])
     assert np.array_equal(U.gaussian_kernel_dist_to_prob(d, 0.5), losses_ref["utils/gaussian_kernel_half"])
     assert abs(U.calc_mean_score(losses_ref["utils/scores"]) - float(losses_ref["utils/calc_mean_score"])) <= 1e-12
+
+
+# ------------------------------------------------------------------ a8: the tfa oracle against the reference's tf.contrib text
+@pytest.fixture(scope="module")
+def semihard_ref():
+    return np.load(os.path.join(HERE, "golden", "semihard_reference.npz"))
+
+
+def test_masked_extremes_match_the_reference_source(semihard_ref):
+    """deep_insight_face/common/losses.py:211-246 (masked_maximum / masked_minimum, imported and called by
+    tests/golden/make_golden_semihard.py) are the functions tensorflow_addons kept as _masked_maximum / _masked_minimum;
+    the oracle's restatements compute the same numbers, empty masks and one-signed rows included."""
+    from oracle import tfa_oracle as t
+
+    data, mask = semihard_ref["masked/data"], semihard_ref["masked/mask"].astype(np.float64)
+    assert np.array_equal(t._masked_maximum(data, mask), semihard_ref["masked/maximum"])
+    assert np.array_equal(t._masked_minimum(data, mask), semihard_ref["masked/minimum"])
+
+
+def test_semihard_oracle_matches_the_reference_text_as_it_is(semihard_ref):
+    """triplet_loss_adapted_from_tf (common/losses.py:249-308) executed unmodified.  Its pairwise_distance loses the
+    -2ab term (line 183 is a discarded expression), so the matrix it ranks is |a|^2 + |b|^2 off the diagonal; on
+    that same matrix the oracle's semi-hard rule (anchor by anchor, fp32 and fp64) and the literal tiled forward the
+    gradient oracle differentiates give the reference's loss, and autograd through the tiled forward gives the
+    reference's gradient."""
+    import torch
+    from make_golden_semihard import CASES, case_inputs
+
+    from oracle import tfa_oracle as t
+
+    for case in CASES:
+        name = case[0]
+        emb, lab = case_inputs(*case)
+        B = emb.shape[0]
+        want_P = semihard_ref[f"{name}/as_is/pdist_squared"]
+        sq32 = (emb * emb).sum(1, dtype=np.float32)
+        P32 = ((sq32[:, None] + sq32[None, :]) * (1 - np.eye(B, dtype=np.float32))).astype(np.float32)
+        _close(P32, want_P, 2e-6, name + " matrix as is")
+        want = float(semihard_ref[f"{name}/as_is/loss"])
+        got64 = t.semihard_from_matrix(want_P, lab, 1.0)
+        assert abs(float(got64["loss"]) - want) <= 1e-12 * max(1.0, abs(want)), name
+        assert abs(float(t.semihard_from_matrix(P32, lab, 1.0)["loss"]) - want) <= 2e-5 * max(1.0, abs(want)), name
+        x = torch.tensor(emb.astype(np.float64), requires_grad=True)
+        sq = (x * x).sum(1, keepdim=True)
+        P = (sq + sq.t()) * (1.0 - torch.eye(B, dtype=torch.float64))
+        loss = t._torch_loss("semihard", P, torch.tensor(lab), 1.0, False)
+        loss.backward()
+        assert abs(float(loss.detach()) - want) <= 1e-12 * max(1.0, abs(want)), name
+        _close(x.grad.numpy(), semihard_ref[f"{name}/as_is/grad"], 1e-9, name + " gradient as is")
+
+
+def test_tfa_oracle_matches_the_repaired_reference_text(semihard_ref):
+    """The same module with the dangling `- 2.0 * matmul` line joined to its statement (one text repair, asserted to
+    match once by the generator) is tf.contrib's triplet_semihard_loss as published - the function tensorflow_addons
+    ported.  The oracle's pairwise_distance (squared and not: clamp, error mask, zero diagonal), its semi-hard loss
+    with distance_metric='squared-L2', margin 1, and both gradient oracles agree with it: fp64 shadow to 1e-9, the
+    canonical fp32 forward to fp32 rounding."""
+    from make_golden_semihard import CASES, case_inputs
+
+    from oracle import tfa_oracle as t
+
+    for case in CASES:
+        name = case[0]
+        emb, lab = case_inputs(*case)
+        _close(t.pairwise_distance(emb, True), semihard_ref[f"{name}/repaired/pdist_squared"], 4e-6, name + " squared matrix")
+        # sqrt near zero amplifies the rounding of d^2: duplicates are exactly 0 on both sides, the rest is off zero
+        _close(t.pairwise_distance(emb, False), semihard_ref[f"{name}/repaired/pdist"], 4e-6, name + " matrix")
+        want, want_g = float(semihard_ref[f"{name}/repaired/loss"]), semihard_ref[f"{name}/repaired/grad"]
+        got = float(t.triplet_semihard(lab, emb, 1.0, squared=True)["loss"])
+        assert abs(got - want) <= 2e-5 * max(1.0, abs(want)), (name, got, want)
+        l64, g64 = t.torch_shadow_fp64("semihard", lab, emb, 1.0, False, True)
+        assert abs(l64 - want) <= 1e-12 * max(1.0, abs(want)), name
+        _close(g64, want_g, 1e-9, name + " fp64 gradient")
+        l32, g32 = t.torch_shadow("semihard", lab, emb, 1.0, False, True)
+        assert abs(l32 - want) <= 2e-5 * max(1.0, abs(want)), name
+        _close(g32, want_g, 2e-5, name + " fp32-faithful gradient")
