@@ -1,8 +1,11 @@
 """ctypes binding of oracle/dif_oracle.c (canonical fp32 reductions, 1:N search, pair distance, sweep).
 
-TEST INFRASTRUCTURE ONLY - see oracle/__init__.py.  PARITY UNPINNED by the reference for the 1:N
-search (the reference has no such routine); pair distance / threshold counts are pinned against
-the live reference functions by tests/golden (see tests/golden/make_golden.py).
+TEST INFRASTRUCTURE ONLY - see oracle/__init__.py.  Pair distance / threshold counts are pinned against
+the live reference functions by tests/golden (see tests/golden/make_golden.py).  The reference has no 1:N
+routine; the search is pinned as "rank the gallery by the reference's own distance function"
+(evaluation/utility.py:52-66 run over every query x row pair by tests/golden/make_golden_gallery.py:
+same rows, same order, same numbers); its tie rule (lower row first) and the id / empty-slot conventions are
+this build's.
 """
 from __future__ import annotations
 

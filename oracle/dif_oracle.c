@@ -12,7 +12,9 @@
  *   - Gram / distance matrix   common/losses.py:40 (cosine) and :63-65 (squared L2)
  *   - 1:N top-k search         ABSENT from the reference (predictions.py:126 is 1:1 only); the
  *                              semantics are this build's: k best rows by (score best-first,
- *                              row index ascending).  PARITY UNPINNED by the reference.
+ *                              row index ascending).  Pinned as a ranking by the reference's
+ *                              distance() (utility.py:52-66, tests/golden/make_golden_gallery.py);
+ *                              the tie rule is this build's.
  *
  * Canonical fp32 arithmetic.  The GPU library promises bit-identical "exact" results, so every
  * reduction here uses the same fixed order as csrc/dif_canon.cuh:

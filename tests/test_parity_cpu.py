@@ -286,3 +286,25 @@ def test_tfa_oracle_matches_the_repaired_reference_text(semihard_ref):
         l32, g32 = t.torch_shadow("semihard", lab, emb, 1.0, False, True)
         assert abs(l32 - want) <= 2e-5 * max(1.0, abs(want)), name
         _close(g32, want_g, 2e-5, name + " fp32-faithful gradient")
+
+
+# ------------------------------------------------------------------ a15: 1:N ranking against the reference's distance function
+def test_gallery_oracle_ranks_like_the_reference_distance():
+    """The reference has no 1:N search; a search by ITS distance (evaluation/utility.py:52-66, imported and run on
+    every (query, gallery row) pair by tests/golden/make_golden_gallery.py) keeps the k smallest.  The oracle's
+    gallery_search returns those rows in that order and the same numbers: squared-L2 scores are the reference's
+    metric-0 distances, cosine scores are cos(pi * metric-1 distance)."""
+    from synth import GALLERY_CASES, check_ranking, gallery_case
+
+    from oracle import c_oracle as orc
+
+    ref = np.load(os.path.join(HERE, "golden", "gallery_reference.npz"))
+    for name, seed, N, Q, D, k in GALLERY_CASES:
+        rows, q, pick = gallery_case(seed, N, Q, D)
+        chk = np.array([rows.astype(np.float64).sum(), q.astype(np.float64).sum(), float(pick.sum())])
+        assert np.array_equal(chk, ref[f"{name}/checksum"]), "the inputs are not the ones the golden was made from"
+        for metric in (0, 1):
+            s, r = orc.gallery_search(rows, q, k, metric)
+            share = check_ranking(ref[f"{name}/metric{metric}/dist"], ref[f"{name}/metric{metric}/rows"], s, r, metric)
+            assert share > 0.97, (name, metric, share)
+            assert (r[:, 0] == pick).all()
