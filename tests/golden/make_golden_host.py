@@ -6,6 +6,13 @@
    broken imports), so the function's source is cut out of the file with `ast` and executed as is
    under fixed `np.random.seed`s;
  * `write_pairs_to_file` (scripts/generate_pairs.py:60-76): the module imports here; its output text is recorded;
+ * `facematch_image_pairs`, `triplet_image_pairs`, `create_pairs` (generator.py:43-124): cut out with `ast` like
+   `sample_people` and executed as they are on an image tree built by `image_tree()` below, with the names the
+   module's (broken) imports would have bound: `add_extension` is the reference's own (evaluation/utility.py:247,
+   imported), `read_pairs` the reference's loop without its final np.array() (which raises on mixed 3/4-field rows
+   under numpy >= 1.24), `to_categorical` = np.eye(num_classes)[idx], `InvalidPairsError` an Exception subclass
+   (common/utils.py defines none of the four); `os.listdir` is wrapped to return sorted names so that the shuffle of
+   triplet_image_pairs is reproducible across filesystems.  Paths are recorded relative to the tree;
  * default arguments of the functions / constructors the drop-in mirrors, read from the reference's AST.
 /root/reference does not exist on the GPU box; only the .json travels.
 """
@@ -59,8 +66,71 @@ def dataset(seed, n_people):
     return [PersonClass(f"person{p:03d}", int(rng.integers(1, 9))) for p in range(n_people)]
 
 
+TREE = {"ann": [1, 2, 3, 5], "bob": [1, 2], "cat": [1], "dan": [2, 4, 6], "eve": [1, 3]}      # name -> image numbers
+PAIR_ROWS = [["ann", "1", "2"], ["ann", "2", "bob", "1"], ["dan", "2", "6"], ["bob", "1", "cat", "1"], ["cat", "1", "ann", "5"],
+             ["eve", "1", "3"], ["dan", "4", "eve", "3"], ["bob", "2", "dan", "6"], ["ann", "3", "5"], ["ann", "1"]]
+
+
+def image_tree(root):
+    """<root>/<name>/<name>_%04d.(jpg|png) (odd numbers .jpg, even .png), a hidden file per directory, pairs.txt."""
+    for name, numbers in TREE.items():
+        os.makedirs(os.path.join(root, name))
+        open(os.path.join(root, name, ".hidden"), "w").close()
+        for n in numbers:
+            open(os.path.join(root, name, "%s_%04d.%s" % (name, n, "jpg" if n % 2 else "png")), "w").close()
+    with open(os.path.join(root, "pairs.txt"), "w") as f:
+        f.write("1\t%d\n" % len(PAIR_ROWS))
+        for row in PAIR_ROWS:
+            f.write("\t".join(row) + "\n")
+    return os.path.join(root, "pairs.txt")
+
+
+class _SortedListdirOs:
+    """`os` as the cut-out functions see it: listdir returns sorted names."""
+    path = os.path
+
+    @staticmethod
+    def listdir(d):
+        return sorted(os.listdir(d))
+
+
+def _pair_listing_goldens():
+    import sys
+
+    sys.path.insert(0, REF)
+    from deep_insight_face.evaluation import utility as ref_util
+
+    def read_pairs(fn):                       # utility.py:256-262 without the final np.array()
+        with open(fn) as f:
+            return [line.strip().split("\t") for line in f.readlines()[1:]]
+
+    gen = os.path.join(REF, "deep_insight_face/datagen/generator.py")
+    ns = {"np": np, "os": _SortedListdirOs, "add_extension": ref_util.add_extension, "read_pairs": read_pairs,
+          "InvalidPairsError": type("InvalidPairsError", (Exception,), {}),
+          "to_categorical": lambda idx, num_classes: np.eye(num_classes, dtype=np.float32)[np.asarray(idx)]}
+    for name in ("facematch_image_pairs", "triplet_image_pairs", "create_pairs"):
+        exec(function_source(gen, name)[0], ns)   # the reference's functions, verbatim
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        pairs_txt = image_tree(td)
+        rel = lambda p: os.path.relpath(p, td)
+        pairs, names = ns["facematch_image_pairs"](td, PAIR_ROWS)
+        out["facematch"] = {"pairs": [[rel(a), rel(b), bool(s)] for a, b, s in pairs], "names": sorted(names)}
+        out["triplet"] = []
+        for seed in (0, 1, 2):
+            np.random.seed(seed)
+            trip, names = ns["triplet_image_pairs"](td, PAIR_ROWS)
+            out["triplet"].append({"seed": seed, "triplets": [[rel(x) for x in t] for t in trip], "names": sorted(names)})
+        for key, func in (("create_facematch", "facematch_image_pairs"), ("create_triplet", "triplet_image_pairs")):
+            np.random.seed(5)
+            pairs, names, one_hot = ns["create_pairs"](td, func=ns[func], pairs_txt=pairs_txt)
+            out[key] = {"n_pairs": len(pairs), "one_hot_of": {n: [float(v) for v in one_hot[i]] for i, n in enumerate(names)}}
+    return out
+
+
 def main():
     out = {"sample_people": [], "defaults": {}}
+    out["pair_listing"] = _pair_listing_goldens()
     src, _ = function_source(os.path.join(REF, "deep_insight_face/datagen/generator.py"), "sample_people")
     ns = {"np": np}
     exec(src, ns)  # the reference's function, verbatim

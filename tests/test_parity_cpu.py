@@ -308,3 +308,38 @@ def test_gallery_oracle_ranks_like_the_reference_distance():
             share = check_ranking(ref[f"{name}/metric{metric}/dist"], ref[f"{name}/metric{metric}/rows"], s, r, metric)
             assert share > 0.97, (name, metric, share)
             assert (r[:, 0] == pick).all()
+
+
+# ------------------------------------------------------------------ f1: pairs.txt expansion and one-hot labels
+def test_pair_listings_and_one_hot_labels_match_the_reference(host_ref, tmp_path, capsys):
+    """generator.py:43-124 (facematch_image_pairs / triplet_image_pairs / create_pairs, cut out of the reference and
+    executed by make_golden_host.py on the image tree rebuilt here): same pairs in the same order, same triplets
+    under the same np.random.seed, same class names, same name -> one-hot row mapping."""
+    from make_golden_host import PAIR_ROWS, image_tree
+
+    from deep_insight_face_b200 import datagen
+
+    ref = host_ref["pair_listing"]
+    root = str(tmp_path / "tree")
+    os.makedirs(root)
+    pairs_txt = image_tree(root)
+    rel = lambda p: os.path.relpath(p, root)
+
+    pairs, names = datagen.facematch_image_pairs(root, PAIR_ROWS)
+    assert [[rel(a), rel(b), s] for a, b, s in pairs] == ref["facematch"]["pairs"]
+    assert sorted(names) == ref["facematch"]["names"]
+    for case in ref["triplet"]:
+        np.random.seed(case["seed"])
+        trip, names = datagen.triplet_image_pairs(root, PAIR_ROWS)
+        assert [[rel(x) for x in t] for t in trip] == case["triplets"], case["seed"]
+        assert sorted(names) == case["names"]
+    for key, func in (("create_facematch", datagen.facematch_image_pairs), ("create_triplet", datagen.triplet_image_pairs)):
+        np.random.seed(5)
+        pairs, names, one_hot = datagen.create_pairs(root, func=func, pairs_txt=pairs_txt)
+        assert len(pairs) == ref[key]["n_pairs"] and one_hot.dtype == np.float32
+        assert {n: one_hot[i].tolist() for i, n in enumerate(names)} == ref[key]["one_hot_of"]
+    # a missing image skips the row and says so (the reference aborts with add_extension's RuntimeError instead)
+    pairs, _ = datagen.facematch_image_pairs(root, [["ann", "1", "9"], ["ann", "1", "2"]])
+    assert len(pairs) == 1 and "Skipped 1 image pairs" in capsys.readouterr().out
+    with pytest.raises(AssertionError):
+        datagen.create_pairs(root, pairs_txt=pairs_txt)
