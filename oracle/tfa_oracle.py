@@ -13,9 +13,13 @@ PIN STATUS.  Semi-hard loss, pairwise_distance, _masked_maximum / _masked_minimu
 this algorithm the reference holds - its copy of tf.contrib's triplet_semihard_loss, the function tensorflow_addons
 ported (deep_insight_face/common/losses.py:151-308; executed by tests/golden/make_golden_semihard.py both as it is
 and with its dangling `- 2.0 * matmul` line repaired, goldens in tests/golden/semihard_reference.npz, held by
-tests/test_parity_cpu.py).  TripletHardLoss and the soft margin have no text in the reference: PARITY UNPINNED for
-those (cross-checked against the fp64 autograd shadow only); the step from tf.contrib's function to tfa's (sparse
-labels instead of one-hot, `distance_metric`) is likewise taken from tfa's published source, not from the reference.
+tests/test_parity_cpu.py).  Hard loss: the reference holds no text of tfa's function, but with
+distance_metric='squared-L2' it is anchor by anchor the reference's own BatchHardTripletLossEuclidean
+(common/losses.py:54-85) whenever every anchor has a negative - PINNED in that mode against the goldens that class
+produced (losses_reference.npz: loss to 1e-12, gradient to 1e-9 in fp64; same test file).  What stays PARITY
+UNPINNED: the soft margin, and the step from these functions to tfa's defaults (sparse labels instead of one-hot,
+the non-squared `distance_metric='L2'` the reference's call sites use - the sqrt / error-mask convention is pinned
+through pairwise_distance above, its composition with the hard rule is taken from tfa's published source).
 """
 from __future__ import annotations
 

@@ -343,3 +343,30 @@ def test_pair_listings_and_one_hot_labels_match_the_reference(host_ref, tmp_path
     assert len(pairs) == 1 and "Skipped 1 image pairs" in capsys.readouterr().out
     with pytest.raises(AssertionError):
         datagen.create_pairs(root, pairs_txt=pairs_txt)
+
+
+def test_tfa_hard_oracle_meets_the_reference_euclidean_batch_hard_goldens(losses_ref):
+    """a8 hard rule: tfa's TripletHardLoss(distance_metric='squared-L2', margin=alpha) is, anchor by anchor, the
+    reference's BatchHardTripletLossEuclidean (common/losses.py:54-85) whenever a negative exists for every anchor
+    (the two differ only in what fills an empty extreme).  So the goldens the reference's own class produced
+    (losses_reference.npz, make_golden_losses.py) pin the tfa oracle's hard rule directly: scalar loss = mean of the
+    reference's per-anchor losses, gradient = the reference's gradient of mean(loss) - fp64 shadow to 1e-12 / 1e-9,
+    the canonical fp32 forward to fp32 rounding.  'one_identity' is left out: no anchor has a negative there."""
+    from make_golden_losses import CASES, pk_batch
+
+    from oracle import tfa_oracle as t
+
+    for name, P, K, D, noise, seed, flags in CASES:
+        if name == "one_identity":
+            continue
+        emb, lab = pk_batch(P, K, D, noise, seed, **flags)
+        margin = 0.3 * D
+        want, want_g = float(losses_ref[f"{name}/bh_euc/loss"].mean()), losses_ref[f"{name}/bh_euc/grad"]
+        l64, g64 = t.torch_shadow_fp64("hard", lab, emb, margin, False, True)
+        assert abs(l64 - want) <= 1e-12 * max(1.0, abs(want)), name
+        _close(g64, want_g, 1e-9, name + " fp64 gradient")
+        got = float(t.triplet_hard(lab, emb, margin=margin, squared=True)["loss"])
+        assert abs(got - want) <= 2e-5 * max(1.0, abs(want)), (name, got, want)
+        l32, g32 = t.torch_shadow("hard", lab, emb, margin, False, True)
+        assert abs(l32 - want) <= 2e-5 * max(1.0, abs(want)), name
+        _close(g32, want_g, 2e-5, name + " fp32-faithful gradient")
