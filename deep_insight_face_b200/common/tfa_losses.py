@@ -5,7 +5,11 @@
 
 Same constructor arguments as tfa (margin=1.0, soft=False, distance_metric="L2" | "squared-L2") and the same
 result: a SCALAR (tfa reduces inside the loss).  The arithmetic runs in libdif_b200.so (csrc/tfa_triplet.cu);
-there is no CPU path.  distance_metric="angular" and callables are not implemented (the reference never passes them).
+there is no CPU path.  distance_metric="angular" (tfa: max(1 - x^ x^T, 0) on l2-normalised rows) is served by the same
+kernels: on unit rows the squared distance is 2 - 2 x^ x^T = 2 * angular, so the angular loss with margin m is HALF the
+squared-L2 loss of the normalised rows with margin 2m, and its gradient goes back through dif_l2_normalize_bwd (three
+launches more; hinge losses only - softplus is not homogeneous, soft=True with "angular" raises).  Callables are not
+implemented (the reference passes neither).
 
     loss(y_true, y_pred)                numpy in -> python float; torch-CUDA in -> differentiable 0-d tensor
     loss.loss_and_grad(y_true, y_pred)  (loss, d loss / d y_pred [B, D], info) in one fused call
@@ -18,6 +22,7 @@ from .. import _ffi
 from .losses import _LossBase
 
 TFA_HARD, TFA_SEMIHARD, TFA_SOFT, TFA_SQUARED = 0, 1, 4, 8
+TFA_ANGULAR = 16   # host-side flag: never reaches the C ABI (angular_via_squared turns it into TFA_SQUARED on unit rows)
 
 
 def _metric_flag(distance_metric) -> int:
@@ -25,7 +30,29 @@ def _metric_flag(distance_metric) -> int:
         return 0
     if distance_metric == "squared-L2":
         return TFA_SQUARED
-    raise NotImplementedError(f"distance_metric {distance_metric!r}: only 'L2' and 'squared-L2' run on the GPU path")
+    if distance_metric == "angular":
+        return TFA_ANGULAR
+    raise NotImplementedError(f"distance_metric {distance_metric!r}: only 'L2', 'squared-L2' and 'angular' run on the GPU path")
+
+
+def angular_via_squared(kind: int, margin: float, dloss: float, normalize, squared_loss, normalize_bwd):
+    """tfa's angular metric out of the squared-L2 step on unit rows.  With x^ = l2_normalize(x):
+    angular_ij = max(1 - x^_i x^_j, 0) = |x^_i - x^_j|^2 / 2, every comparison the mining makes is unchanged by the
+    factor 2, and hinge(a_p - a_n + m) = hinge(s_p - s_n + 2m) / 2.  So
+        loss(x; angular, m) = 0.5 * loss(x^; squared-L2, 2m),   d loss / d x = J_normalize^T (0.5 * d loss_sq / d x^).
+    The three steps are passed in (the CUDA entry points in tfa_triplet; CPU stand-ins in tests/test_oracle_cpu.py):
+        normalize()                         -> (unit rows, saved state)
+        squared_loss(unit, code, m, dloss)  -> (loss, d loss / d unit or None, info)
+        normalize_bwd(g, unit, state)       -> d / d x
+    Returns (loss, grad or None, info).  Known divergence: a row with |x|^2 < 1e-12 stays (near) zero under
+    tf.math.l2_normalize, so it is not a unit row - tfa gives it the angular distance 1 to every sample, this path 1/2."""
+    if kind & TFA_SOFT:
+        raise NotImplementedError("soft=True with distance_metric='angular': log1p(exp(.)) does not commute with the "
+                                  "factor 2 between angular and squared-L2 distances of unit rows")
+    code = (kind & ~TFA_ANGULAR) | TFA_SQUARED
+    unit, state = normalize()
+    loss2, g2, info = squared_loss(unit, code, 2.0 * float(margin), 0.5 * float(dloss))
+    return 0.5 * loss2, (None if g2 is None else normalize_bwd(g2, unit, state)), info
 
 
 class TfaTripletStep:
@@ -47,6 +74,9 @@ class TfaTripletStep:
         dev = torch.device(device)
         _ffi.init(dev.index or 0)
         self._lib = _ffi.load_library()
+        if int(kind) & TFA_ANGULAR:
+            raise NotImplementedError("TfaTripletStep runs the 'L2' / 'squared-L2' metrics; for 'angular' normalise the "
+                                      "batch (networks.head.l2_normalize) and step on squared-L2 with twice the margin")
         self.B, self.D, self.kind, self.margin, self.dloss = int(B), int(D), int(kind), float(margin), float(dloss)
         self.emb = torch.zeros((B, D), dtype=torch.float32, device=dev)
         self.labels = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -94,6 +124,20 @@ def tfa_triplet(labels, embeddings, kind: int, margin: float = 1.0, dloss: float
         _ffi.host_array(embeddings, np.float32)).cuda()
     if emb.dim() != 2:
         raise ValueError("embeddings must be [B, D]")
+    if kind & TFA_ANGULAR:
+        from ..networks.head import _launch_bwd, _launch_fwd
+
+        dev_labels = labels if _ffi.is_device_tensor(labels) else torch.from_numpy(
+            np.ascontiguousarray(np.asarray(_ffi.host_array(labels, None)).reshape(-1), dtype=np.int32)).to(emb.device)
+        loss, grad, info = angular_via_squared(
+            kind, margin, dloss, lambda: _launch_fwd(emb),
+            lambda unit, code, m, dl: tfa_triplet(dev_labels, unit, code, m, dloss=dl, want_grad=want_grad,
+                                                  want_indices=want_indices),
+            lambda g, unit, inv: _launch_bwd(g, unit, inv))
+        if on_dev:
+            return loss, grad, info
+        info = {k: v.cpu().numpy() for k, v in info.items()}
+        return float(loss.cpu()), (None if grad is None else grad.cpu().numpy()), info
     dev = emb.device
     _ffi.init(dev.index or 0)
     B, D = emb.shape
@@ -186,6 +230,8 @@ class TripletHardLoss(_TfaTripletBase):
     def __init__(self, margin=1.0, soft=False, distance_metric="L2", name=None, **kwargs):
         super().__init__(margin=margin, distance_metric=distance_metric, name=name, **kwargs)
         self.soft = bool(soft)
+        if self.soft and self._flag == TFA_ANGULAR:
+            raise NotImplementedError("soft=True with distance_metric='angular' is not on the GPU path")
 
     def _code(self) -> int:
         return super()._code() | (TFA_SOFT if self.soft else 0)

@@ -21,6 +21,17 @@ def _launch_fwd(x):
     return y, inv
 
 
+def _launch_bwd(g, y, inv):
+    """d / dx of y = l2_normalize(x) applied to the cotangent g [n, D] (device tensors; y, inv from _launch_fwd)."""
+    import torch
+
+    g = g.contiguous().float()
+    dx = torch.empty_like(y)
+    _ffi.check(_ffi.load_library().dif_l2_normalize_bwd(_ffi.ptr(g), _ffi.ptr(y), _ffi.ptr(inv), y.shape[0], y.shape[1],
+                                                        _ffi.ptr(dx), _ffi.current_stream_ptr(y.device)))
+    return dx
+
+
 def l2_normalize(x, axis=1):
     """x [n, D] -> x * rsqrt(max(sum(x^2, axis=1), 1e-12)).  numpy in -> numpy out; torch-CUDA in -> torch out,
     differentiable (the backward is dif_l2_normalize_bwd)."""
@@ -46,11 +57,6 @@ def l2_normalize(x, axis=1):
         @staticmethod
         def backward(ctx, g):
             y, inv = ctx.saved_tensors
-            g = g.contiguous().float()
-            dx = torch.empty_like(y)
-            _ffi.check(_ffi.load_library().dif_l2_normalize_bwd(_ffi.ptr(g), _ffi.ptr(y), _ffi.ptr(inv), y.shape[0],
-                                                                y.shape[1], _ffi.ptr(dx),
-                                                                _ffi.current_stream_ptr(y.device)))
-            return dx
+            return _launch_bwd(g, y, inv)
 
     return _Fn.apply(x)

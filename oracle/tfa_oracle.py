@@ -208,3 +208,27 @@ def torch_shadow(kind, labels, emb, margin=1.0, soft=False, squared=False):
         fac = np.where(P64 > 0, 2.0 if squared else 1.0 / P64, 0.0)
     W = (G + G.T) * fac
     return float(loss.detach()), W.sum(1)[:, None] * x - W @ x
+
+
+# ------------------------------------------------------------------ distance_metric="angular"
+def _torch_angular(x):
+    """metric_learning.angular_distance: l2_normalize the rows (x * rsqrt(max(sum x^2, 1e-12))),
+    1 - x^ x^T, clamp at 0, zero diagonal."""
+    import torch
+
+    unit = x * torch.rsqrt(torch.clamp_min((x * x).sum(1, keepdim=True), 1e-12))
+    a = torch.clamp_min(1.0 - unit @ unit.t(), 0.0)
+    return a * (1.0 - torch.eye(x.shape[0], dtype=x.dtype))
+
+
+def torch_shadow_angular_fp64(kind, labels, emb, margin=1.0, soft=False):
+    """tfa's losses with distance_metric='angular', fp64 end to end (autograd through the normalisation too).
+    The reference never passes this metric and holds no text of it: tfa's published source, PARITY UNPINNED."""
+    import torch
+
+    x = torch.tensor(np.asarray(emb, dtype=np.float64), requires_grad=True)
+    lab = torch.tensor(np.asarray(labels).reshape(-1).astype(np.int64))
+    loss = _torch_loss(kind, _torch_angular(x), lab, margin, soft)
+    loss.backward()
+    return float(loss.detach()), x.grad.numpy()
+

@@ -185,7 +185,9 @@ def test_torch_autograd_and_config_roundtrip():
         assert abs(float(out.detach()) - l64) <= RTOL * max(abs(l64), 1e-6)
         assert _close(e.grad.cpu().numpy(), 3.0 * g64)
     with pytest.raises(NotImplementedError):
-        TripletHardLoss(distance_metric="angular")
+        TripletHardLoss(distance_metric="manhattan")
+    with pytest.raises(NotImplementedError):
+        TripletHardLoss(soft=True, distance_metric="angular")
 
 
 def test_preallocated_and_graphed_step_equals_the_call():
