@@ -8,8 +8,8 @@ result: a SCALAR (tfa reduces inside the loss).  The arithmetic runs in libdif_b
 there is no CPU path.  distance_metric="angular" (tfa: max(1 - x^ x^T, 0) on l2-normalised rows) is served by the same
 kernels: on unit rows the squared distance is 2 - 2 x^ x^T = 2 * angular, so the angular loss with margin m is HALF the
 squared-L2 loss of the normalised rows with margin 2m, and its gradient goes back through dif_l2_normalize_bwd (three
-launches more; hinge losses only - softplus is not homogeneous, soft=True with "angular" raises).  Callables are not
-implemented (the reference passes neither).
+launches more; with soft=True the unit rows are scaled by sqrt(1/2) instead, whose squared distances are the angular
+ones).  Callables are not implemented (the reference passes neither).
 
     loss(y_true, y_pred)                numpy in -> python float; torch-CUDA in -> differentiable 0-d tensor
     loss.loss_and_grad(y_true, y_pred)  (loss, d loss / d y_pred [B, D], info) in one fused call
@@ -37,20 +37,24 @@ def _metric_flag(distance_metric) -> int:
 
 def angular_via_squared(kind: int, margin: float, dloss: float, normalize, squared_loss, normalize_bwd):
     """tfa's angular metric out of the squared-L2 step on unit rows.  With x^ = l2_normalize(x):
-    angular_ij = max(1 - x^_i x^_j, 0) = |x^_i - x^_j|^2 / 2, every comparison the mining makes is unchanged by the
-    factor 2, and hinge(a_p - a_n + m) = hinge(s_p - s_n + 2m) / 2.  So
-        loss(x; angular, m) = 0.5 * loss(x^; squared-L2, 2m),   d loss / d x = J_normalize^T (0.5 * d loss_sq / d x^).
+    angular_ij = max(1 - x^_i x^_j, 0) = |x^_i - x^_j|^2 / 2, and every comparison the mining makes is unchanged by
+    the factor 2.  Hinge losses: hinge(a_p - a_n + m) = hinge(s_p - s_n + 2m) / 2, so
+        loss(x; angular, m) = 0.5 * loss(x^; squared-L2, 2m),   d loss / d x = J_normalize^T (0.5 * d loss_sq / d x^)
+    with both factors exact in fp32.  soft=True (log1p(exp(a_p - a_n)) does not commute with a factor): the unit rows
+    are scaled by sqrt(1/2) instead, whose squared distances ARE the angular ones (one rounding per element),
+        loss(x; angular, soft) = loss(x^ * sqrt(1/2); squared-L2, soft),   d / d x^ = sqrt(1/2) * d / d (x^ sqrt(1/2)).
     The three steps are passed in (the CUDA entry points in tfa_triplet; CPU stand-ins in tests/test_oracle_cpu.py):
         normalize()                         -> (unit rows, saved state)
-        squared_loss(unit, code, m, dloss)  -> (loss, d loss / d unit or None, info)
+        squared_loss(rows, code, m, dloss)  -> (loss, d loss / d rows or None, info)
         normalize_bwd(g, unit, state)       -> d / d x
     Returns (loss, grad or None, info).  Known divergence: a row with |x|^2 < 1e-12 stays (near) zero under
     tf.math.l2_normalize, so it is not a unit row - tfa gives it the angular distance 1 to every sample, this path 1/2."""
-    if kind & TFA_SOFT:
-        raise NotImplementedError("soft=True with distance_metric='angular': log1p(exp(.)) does not commute with the "
-                                  "factor 2 between angular and squared-L2 distances of unit rows")
     code = (kind & ~TFA_ANGULAR) | TFA_SQUARED
     unit, state = normalize()
+    if kind & TFA_SOFT:
+        r = float(np.sqrt(0.5))
+        loss, g, info = squared_loss(unit * r, code, float(margin), float(dloss))
+        return loss, (None if g is None else normalize_bwd(g * r, unit, state)), info
     loss2, g2, info = squared_loss(unit, code, 2.0 * float(margin), 0.5 * float(dloss))
     return 0.5 * loss2, (None if g2 is None else normalize_bwd(g2, unit, state)), info
 
@@ -230,8 +234,6 @@ class TripletHardLoss(_TfaTripletBase):
     def __init__(self, margin=1.0, soft=False, distance_metric="L2", name=None, **kwargs):
         super().__init__(margin=margin, distance_metric=distance_metric, name=name, **kwargs)
         self.soft = bool(soft)
-        if self.soft and self._flag == TFA_ANGULAR:
-            raise NotImplementedError("soft=True with distance_metric='angular' is not on the GPU path")
 
     def _code(self) -> int:
         return super()._code() | (TFA_SOFT if self.soft else 0)

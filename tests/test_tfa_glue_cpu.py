@@ -131,3 +131,26 @@ def test_plain_routes_pass_the_flags_through(fake, metric, flag):
     fake.calls.clear()
     TripletHardLoss(soft=True, distance_metric=metric).loss_and_grad(lab, x)
     assert fake.calls[0][1] == 4 | flag
+
+
+def test_soft_angular_route_scales_the_unit_rows(fake):
+    """soft=True with 'angular': unit rows times sqrt(1/2) through the squared-L2 soft loss, margin and cotangent as
+    they are, gradient times sqrt(1/2) back through the normalisation."""
+    import torch
+
+    from deep_insight_face_b200.common.tfa_losses import TripletHardLoss
+    from oracle import tfa_oracle as orc
+
+    lab, x = _pk(12, 4, 48, seed=9)
+    fn = TripletHardLoss(soft=True, distance_metric="angular")
+    want, want_g = orc.torch_shadow_angular_fp64("hard", lab, x, 1.0, soft=True)
+    scale = np.abs(want_g).max()
+    loss, grad, _ = fn.loss_and_grad(lab, x)
+    assert fake.calls == [("l2_normalize",), ("tfa_triplet", 4 | 8, 1.0, 1.0), ("l2_normalize_bwd",)]
+    assert abs(loss - want) <= 1e-5 * max(1.0, abs(want)) and np.abs(grad - want_g).max() <= 1e-4 * scale
+    e = torch.from_numpy(x.copy()).requires_grad_(True)
+    out = fn(torch.from_numpy(lab), e)
+    out.backward()
+    assert abs(float(out.detach()) - want) <= 1e-5 * max(1.0, abs(want))
+    assert np.abs(e.grad.numpy() - want_g).max() <= 1e-4 * scale
+

@@ -186,8 +186,6 @@ def test_torch_autograd_and_config_roundtrip():
         assert _close(e.grad.cpu().numpy(), 3.0 * g64)
     with pytest.raises(NotImplementedError):
         TripletHardLoss(distance_metric="manhattan")
-    with pytest.raises(NotImplementedError):
-        TripletHardLoss(soft=True, distance_metric="angular")
 
 
 def test_preallocated_and_graphed_step_equals_the_call():

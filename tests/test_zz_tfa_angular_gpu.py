@@ -40,3 +40,15 @@ def test_angular_matches_the_tfa_formula(gpu, kind, P, K, D, margin):
     (2.0 * out).backward()
     assert abs(float(out.detach()) - want) <= TOL * max(1.0, abs(want))
     assert np.abs(e.grad.cpu().numpy() - 2.0 * want_g).max() <= 2.0 * TOL * scale
+
+
+def test_soft_angular_matches_the_tfa_formula(gpu):
+    from deep_insight_face_b200.common.tfa_losses import TripletHardLoss
+    from oracle import tfa_oracle as orc
+
+    lab, x = _pk(18, 4, 128, seed=31)
+    want, want_g = orc.torch_shadow_angular_fp64("hard", lab, x, 1.0, soft=True)
+    loss, grad, _ = TripletHardLoss(soft=True, distance_metric="angular").loss_and_grad(lab, x)
+    assert abs(loss - want) <= TOL * max(1.0, abs(want)), (loss, want)
+    assert np.abs(grad - want_g).max() <= TOL * max(np.abs(want_g).max(), 1e-6)
+
