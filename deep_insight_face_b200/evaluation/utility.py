@@ -61,7 +61,10 @@ def distance(embeddings1, embeddings2, distance_metric=0, _mean=None):
 
 
 def get_emd_distance(embeddings1, embeddings2, distance_metric=0):
-    """utility.py:174-188, the single-pair twin (1-D inputs for metric 0)."""
+    """utility.py:174-188, the single-pair twin: two 1-D embeddings and metric 0 give a scalar, which is the form the
+    reference calls it in (evals.py:119).  For 2-D inputs the reference's metric 0 sums over axis 0 (one number per
+    embedding dimension, summed over the pairs - an artefact of the 1-D twin); here 2-D inputs give the per-pair
+    distances of `distance`, which is also what the reference's metric 1 branch returns."""
     e1 = np.atleast_2d(_ffi.host_array(embeddings1, np.float32))
     e2 = np.atleast_2d(_ffi.host_array(embeddings2, np.float32))
     d = distance(e1, e2, distance_metric)

@@ -1,0 +1,41 @@
+"""Entry points no other GPU test reaches: the single-pair twin get_emd_distance (evaluation/utility.py:174-188)
+and Gallery.reset (dif_gallery_reset).  Written after the round's GPU budget was spent; first run is the driver's."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_get_emd_distance_is_the_single_pair_twin(gpu, golden):
+    from synth import pairs
+
+    from deep_insight_face_b200.evaluation import utility as U
+
+    emb, _ = pairs(4, 600, 128)
+    e1, e2 = emb[0::2], emb[1::2]
+    for i in (0, 7, 599):      # the reference's call form (evals.py:119): two 1-D embeddings, metric 0 -> a scalar
+        want = np.sum(np.square(np.subtract(e1[i].astype(np.float64), e2[i].astype(np.float64))), 0)
+        got = U.get_emd_distance(e1[i], e2[i], 0)
+        assert np.ndim(got) == 0 and abs(float(got) - want) <= 1e-6 * max(1.0, want)
+    np.testing.assert_allclose(U.get_emd_distance(e1, e2, 1), golden["small_dist1"], rtol=1e-4, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        U.get_emd_distance(e1, e2, 2)
+
+
+def test_reset_empties_the_gallery_and_it_fills_again(gpu, orc):
+    from deep_insight_face_b200.gallery import Gallery
+
+    first, second = orc.synth_rows(5, 0, 3000, 128), orc.synth_rows(6, 0, 1000, 128)
+    pick = np.random.default_rng(1).integers(0, 1000, size=40)
+    q = second[pick] + 0.3 * orc.synth_rows(36, 0, 40, 128)
+    with Gallery(4000, 128, "cosine", "tf32x3") as g:
+        g.add(first, np.arange(3000, dtype=np.int64) * 3 + 7)
+        g.search(q, 10)
+        g.reset()
+        assert len(g) == 0
+        g.add(second)                      # ids are the row numbers again, no explicit ids required after a reset
+        assert len(g) == 1000
+        s, ids, r = g.search(q, 10, return_rows=True)
+        ws, wr = orc.gallery_search(second, q, 10, 1)
+        assert np.array_equal(r.astype(np.int64), wr) and np.array_equal(s.view(np.uint32), ws.view(np.uint32))
+        assert np.array_equal(np.asarray(ids).astype(np.int64), wr)
