@@ -19,7 +19,7 @@ TOL = 3e-4
 
 def _close(got, want, what):
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
-    scale = max(np.abs(want).max(), 1e-6)
+    scale = max(np.abs(want).max(), 1e-3)      # batches whose hinges are all inactive have an all-zero gradient
     err = np.abs(got - want).max()
     assert err <= TOL * scale, f"{what}: max error {err:.3e} vs scale {scale:.3e}"
 
