@@ -97,7 +97,7 @@ def tfa_hard_step(labels, emb, margin=1.0):
     hp = torch.where(adj & ~torch.eye(P.shape[0], dtype=torch.bool), P, torch.zeros_like(P)).amax(dim=1)
     loss = torch.clamp(hp - hn + margin, min=0).mean()
     loss.backward()
-    return float(loss), x.grad.numpy()
+    return float(loss.detach()), x.grad.numpy()
 
 
 def pair_distance(e1, e2, metric=0):
