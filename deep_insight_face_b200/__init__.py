@@ -13,6 +13,9 @@ ctypes (_ffi.py) and exposed through the reference's own names:
     api                  face_distance, compare_faces
     predictions          TripletPrediction.verify, SiamesePrediction.verify
     gallery              Gallery, ShardedGallery (1:N top-k search, new)
+    arcface              arcface_loss, ArcFaceLoss (new)
+    datagen              sample_people, pk_labels, create_pairs, facematch_image_pairs, triplet_image_pairs,
+                         write_pairs_to_file (host-side callers of the losses)
 
 There is no CPU fallback: importing is cheap, but any compute call needs libdif_b200.so and a B200.
 """
