@@ -137,6 +137,28 @@ def test_arcface_oracle_against_torch_autograd(s, m):
     np.testing.assert_allclose(want["dW"], dW, rtol=1e-7, atol=1e-10)
 
 
+def test_arcface_oracle_without_margin_is_cosine_softmax_cross_entropy():
+    """m = 0 removes the margin: the ArcFace loss must then be the library cross-entropy (torch's fused
+    F.cross_entropy) of the scaled cosine logits, and its gradients autograd's through F.normalize - a second anchor
+    that shares no line with the oracle or with the acos formulation above."""
+    import torch
+    import torch.nn.functional as F
+
+    from oracle import losses_oracle as lo
+
+    rng = np.random.default_rng(12)
+    B, C, D, s = 40, 29, 16, 30.0
+    X, W, y = rng.standard_normal((B, D)), rng.standard_normal((C, D)), rng.integers(0, C, size=B)
+    want = lo.arcface(X, W, y, s, 0.0)
+    x = torch.tensor(X, dtype=torch.float64, requires_grad=True)
+    w = torch.tensor(W, dtype=torch.float64, requires_grad=True)
+    loss = F.cross_entropy(s * (F.normalize(x, dim=1) @ F.normalize(w, dim=1).T), torch.tensor(y), reduction="none")
+    loss.mean().backward()
+    np.testing.assert_allclose(want["loss"], loss.detach().numpy(), rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(want["dX"], x.grad.numpy(), rtol=1e-7, atol=1e-10)
+    np.testing.assert_allclose(want["dW"], w.grad.numpy(), rtol=1e-7, atol=1e-10)
+
+
 # ------------------------------------------------------------------ losses: the reference's own source under an op stand-in
 @pytest.fixture(scope="module")
 def losses_ref():
