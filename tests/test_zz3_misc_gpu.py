@@ -39,3 +39,28 @@ def test_reset_empties_the_gallery_and_it_fills_again(gpu, orc):
         ws, wr = orc.gallery_search(second, q, 10, 1)
         assert np.array_equal(r.astype(np.int64), wr) and np.array_equal(s.view(np.uint32), ws.view(np.uint32))
         assert np.array_equal(np.asarray(ids).astype(np.int64), wr)
+
+
+@pytest.mark.parametrize("name,seed,noise", [("hard10", 5, 1.0), ("hard15", 6, 1.5)])
+def test_val_at_far_matches_the_reference(gpu, golden, name, seed, noise):
+    """calculate_val / evaluate (utility.py:80-119, :10-33) on overlapping classes against the reference's own run
+    (make_golden.py; its interp1d call repaired for repeated x, named in the keys).  Distances here are the canonical
+    fp32 ones, the reference's are numpy's: a pair within an ulp of the selected threshold may change sides, which
+    moves VAL or FAR of one fold by 1/60 - hence 2 pairs of 600 on the means."""
+    from synth import pairs
+
+    from deep_insight_face_b200.evaluation import utility as U
+
+    emb, issame = pairs(seed, 1200, 64, noise=noise)
+    e1, e2 = emb[0::2], emb[1::2]
+    thr = np.arange(0, 4, 0.001)
+    for metric in (0, 1):
+        for sm in (False, True):
+            for far_target in (1e-3, 1e-2):
+                val, std, far = U.calculate_val(thr, e1, e2, issame, far_target, 10, metric, subtract_mean=sm)
+                want = golden[f"{name}_val_repaired{metric}_{int(sm)}_far{far_target:g}"]
+                assert abs(val - want[0]) <= 2.0 / 600 and abs(far - want[2]) <= 2.0 / 600, (metric, sm, far_target, val, far, want)
+                assert abs(std - want[1]) <= 1e-2
+    out = U.evaluate(emb, issame)
+    want = golden[f"{name}_evaluate_repaired"]
+    assert abs(np.mean(out[2]) - want[0]) <= 2.0 / 120 and abs(out[4] - want[2]) <= 2.0 / 600 and abs(out[6] - want[4]) <= 2.0 / 600
