@@ -13,6 +13,8 @@
    under numpy >= 1.24), `to_categorical` = np.eye(num_classes)[idx], `InvalidPairsError` an Exception subclass
    (common/utils.py defines none of the four); `os.listdir` is wrapped to return sorted names so that the shuffle of
    triplet_image_pairs is reproducible across filesystems.  Paths are recorded relative to the tree;
+ * `TripletPrediction.verify` / `SiamesePrediction.verify` (predictions.py:104-150, :52-89): cut out and executed on a stub
+   `self` (see _verify_goldens);
  * default arguments of the functions / constructors the drop-in mirrors, read from the reference's AST.
 /root/reference does not exist on the GPU box; only the .json travels.
 """
@@ -128,9 +130,54 @@ def _pair_listing_goldens():
     return out
 
 
+def verify_cases():
+    """(encoding [1, D], stored encodings [n, 1, D], threshold) triples around both default thresholds; regenerated by
+    the tests from the same seed."""
+    rng = np.random.default_rng(77)
+    cases = []
+    for i, (gap, thr) in enumerate([(0.02, 0.7), (0.06, 0.7), (0.2, 0.7), (0.01, 0.3), (0.04, 0.3), (0.0, 0.3), (0.05, 0.5)]):
+        D = 128
+        enc = rng.standard_normal((1, D)).astype(np.float32)
+        enc /= np.linalg.norm(enc)
+        stored = np.stack([enc + gap * (j + 1) * rng.standard_normal((1, D)).astype(np.float32) for j in range(3)])
+        cases.append((f"case{i}", enc, stored.astype(np.float32), thr))
+    return cases
+
+
+def _verify_goldens():
+    """predictions.py:104-150 (TripletPrediction.verify) and :52-89 (SiamesePrediction.verify), cut out with `ast` and
+    executed as they are on a stub `self`: `_embedding` returns the case's encoding, the siamese `model.predict` is the
+    euclidean_distance head of networks/siamese.py:22-24 written out in numpy (the CNN is out of scope)."""
+    import contextlib
+    import io
+    import types
+
+    pred = os.path.join(REF, "deep_insight_face/predictions.py")
+    ns = {"np": np}
+    exec(function_source(pred, "verify", "TripletPrediction")[0].replace("def verify", "def triplet_verify"), ns)
+    exec(function_source(pred, "verify", "SiamesePrediction")[0].replace("def verify", "def siamese_verify"), ns)
+
+    def head(pair):
+        a, b = (np.asarray(p, dtype=np.float32).reshape(len(p), -1) for p in pair)
+        return np.sqrt(np.maximum(np.sum(np.square(a - b), axis=1, keepdims=True), 1e-7))
+
+    out = []
+    for name, enc, stored, thr in verify_cases():
+        me = types.SimpleNamespace(_embedding=lambda _p, e=enc: e, model=types.SimpleNamespace(predict=head))
+        rec = {"name": name, "threshold": thr}
+        for key, fn, db in (("triplet", ns["triplet_verify"], {"who": stored[0]}), ("siamese", ns["siamese_verify"], {"who": stored})):
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                dist, ok = fn(me, "img.jpg", "who", db, threshold=thr)
+            rec[key] = {"dist": float(dist), "is_valid": bool(ok), "printed": buf.getvalue()}
+        out.append(rec)
+    return out
+
+
 def main():
     out = {"sample_people": [], "defaults": {}}
     out["pair_listing"] = _pair_listing_goldens()
+    out["verify"] = _verify_goldens()
     src, _ = function_source(os.path.join(REF, "deep_insight_face/datagen/generator.py"), "sample_people")
     ns = {"np": np}
     exec(src, ns)  # the reference's function, verbatim

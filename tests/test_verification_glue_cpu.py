@@ -79,3 +79,42 @@ def test_val_threshold_is_zero_when_the_target_far_is_out_of_reach(monkeypatch, 
     monkeypatch.setattr(_ffi, "init", lambda device=None: None)
     val, std, far = U.calculate_val(np.arange(0, 0.05, 0.01), emb[0::2], emb[1::2], issame, 0.5)
     assert (val, std, far) == (0.0, 0.0, 0.0)
+
+
+def test_verify_methods_reproduce_the_reference(monkeypatch, capsys):
+    """TripletPrediction.verify / SiamesePrediction.verify against the reference's own methods (predictions.py:104-150,
+    :52-89, cut out and executed on a stub self by make_golden_host.py): same distance, same decision, same printed
+    line - including the identical-encoding case, where the triplet path reports exactly 0 and the siamese head
+    sqrt(K.epsilon()).  dif_euclidean_distance is a numpy stand-in working through the pointers it is handed."""
+    import json
+    import os
+
+    import torch
+    from make_golden_host import verify_cases
+
+    from deep_insight_face_b200 import _ffi
+    from deep_insight_face_b200.predictions import SiamesePrediction, TripletPrediction
+
+    class Lib:
+        def dif_euclidean_distance(self, x, y, B, D, eps, out, stream):
+            a, b = _view(x, (B, D), C.c_float), _view(y, (B, D), C.c_float)
+            _view(out, (B,), C.c_float)[:] = np.sqrt(np.maximum(np.sum(np.square(a - b), axis=1), np.float32(eps)))
+            return 0
+
+    lib = Lib()
+    monkeypatch.setattr(_ffi, "load_library", lambda: lib)
+    monkeypatch.setattr(_ffi, "init", lambda device=None: None)
+    monkeypatch.setattr(_ffi, "current_stream_ptr", lambda device=None: 0)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "golden", "host_reference.json")) as f:
+        ref = {r["name"]: r for r in json.load(f)["verify"]}
+    for name, enc, stored, thr in verify_cases():
+        for key, obj, db in (("triplet", TripletPrediction(), {"who": stored[0]}), ("siamese", SiamesePrediction(), {"who": stored})):
+            capsys.readouterr()
+            dist, ok = obj.verify(enc, "who", db, threshold=thr)
+            want = ref[name][key]
+            assert capsys.readouterr().out == want["printed"] and ok is want["is_valid"], (name, key)
+            assert abs(dist - want["dist"]) <= 1e-6 * max(want["dist"], 1e-3), (name, key, dist, want["dist"])
+            if want["dist"] == 0.0:
+                assert dist == 0.0

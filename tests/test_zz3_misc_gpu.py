@@ -64,3 +64,24 @@ def test_val_at_far_matches_the_reference(gpu, golden, name, seed, noise):
     out = U.evaluate(emb, issame)
     want = golden[f"{name}_evaluate_repaired"]
     assert abs(np.mean(out[2]) - want[0]) <= 2.0 / 120 and abs(out[4] - want[2]) <= 2.0 / 600 and abs(out[6] - want[4]) <= 2.0 / 600
+
+
+def test_verify_methods_match_the_reference(gpu, capsys):
+    """TripletPrediction.verify / SiamesePrediction.verify against the reference's own methods executed on a stub self
+    (tests/golden/make_golden_host.py): distance, decision and printed line."""
+    import json
+    import os
+
+    from make_golden_host import verify_cases
+
+    from deep_insight_face_b200.predictions import SiamesePrediction, TripletPrediction
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "host_reference.json")) as f:
+        ref = {r["name"]: r for r in json.load(f)["verify"]}
+    for name, enc, stored, thr in verify_cases():
+        for key, obj, db in (("triplet", TripletPrediction(), {"who": stored[0]}), ("siamese", SiamesePrediction(), {"who": stored})):
+            capsys.readouterr()
+            dist, ok = obj.verify(enc, "who", db, threshold=thr)
+            want = ref[name][key]
+            assert capsys.readouterr().out == want["printed"] and ok is want["is_valid"], (name, key)
+            assert abs(dist - want["dist"]) <= 1e-5 * max(want["dist"], 1e-3), (name, key, dist, want["dist"])
